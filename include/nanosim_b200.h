@@ -1,0 +1,196 @@
+/*
+ * nanosim_b200 -- C ABI of the B200-native per-read simulation path of NanoSim.
+ *
+ * The reference (bcgsc/NanoSim, pure Python) has no FFI: the seam this library replaces is the Python call
+ *
+ *     simulation(mode, out, dna_type, per, kmer_bias, basecaller, max_l, min_l, num_threads, fastq,
+ *                median_l, sd_l, model_ir, uracil, polya, chimeric)            src/simulator.py:1571-1572
+ *       -> simulation_aligned_genome(dna_type, min_l, max_l, median_l, sd_l, out_reads, out_error,
+ *                                    kmer_bias, fastq, num_simulate, per, chimeric)      :1266-1267
+ *       -> simulation_unaligned(dna_type, min_l, max_l, median_l, sd_l, out_reads, fastq,
+ *                               num_simulate, uracil)                                    :1482
+ *
+ * whose inputs travel as module globals filled by read_profile() (:244-591).  Each entry point below names the
+ * reference interface it stands in for.  Plain pointers and sizes only; all functions return 0 on success and a
+ * negative NS_E* code otherwise, with a human-readable message available from ns_last_error().
+ * Pointers passed to ns_set_* may be host or device pointers (unified addressing); the library copies what it
+ * needs into its own HBM allocations before returning, so the caller keeps ownership of its buffers.
+ */
+#ifndef NANOSIM_B200_H
+#define NANOSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NS_OK 0
+#define NS_EINVAL (-1)
+#define NS_ECUDA (-2)
+#define NS_ESTATE (-3)
+#define NS_ENOMEM (-4)
+
+#define NS_MAX_SEGMENTS 16        /* segments per chimeric read (reference: unbounded Geometric, :1277) */
+#define NS_N_ERR_STATES 7         /* start mis ins del mis0 ins0 del0        (:486-495, :1913-1914)      */
+#define NS_N_QUAL_STATES 5        /* mis ins match ht unmapped               (:580-591)                  */
+#define NS_QUAL_SLOTS 94          /* cdf over q = 0..93                                                   */
+
+typedef struct NsContext NsContext;
+
+/* seq_dict / seq_len / genome_len / dict_dna_type globals (simulator.py:279-356): all chromosomes concatenated,
+ * one ASCII byte per base (case and IUPAC codes kept; case_convert :743-755 is applied per read on the device). */
+typedef struct {
+    const uint8_t* bases;
+    uint64_t n_bases;
+    const uint64_t* chrom_off;   /* n_chrom + 1 offsets into bases, file order */
+    uint32_t n_chrom;
+} NsReference;
+
+/* One joblib KernelDensity pickle (kde_aligned, kde_ht, ... :545-577): gaussian kernel, training samples + bandwidth.
+ * A draw is data[floor(u*n)] + N(0, bandwidth)  (sklearn KernelDensity.sample; call site :235). */
+typedef struct {
+    const float* data;
+    uint32_t n;
+    float bandwidth;
+} NsKde;
+
+/* match_ht_list, match_markov_model, error_par, trans_error_pr, lognorm_base_qual, pw_hp_len/lr_hp_len/hp_mis_rate,
+ * strandness_rate, segment_mean (:247-251, :473-591) as flat tables.  Every discrete distribution is a Walker alias
+ * table over 0..n-1 (built exactly on the host, nanosim_b200/model.py): table t occupies
+ * alias_prob/alias_idx[alias_desc[2t] .. +alias_desc[2t+1]).  Table ids: 0 first match, 1 mismatch length,
+ * 2 insertion length, 3 deletion length, 4+b next-match length given previous-match bin b (last slot = "ECDF miss"). */
+typedef struct {
+    NsKde kde_aligned;        /* _aligned_region.pkl (or _aligned_reads.pkl with perfect=1) */
+    NsKde kde_ht;             /* _ht_length.pkl, log10(x+1) domain */
+    NsKde kde_ht_ratio;       /* _ht_ratio.pkl */
+    NsKde kde_unaligned;      /* _unaligned_length.pkl (n = 0 if absent) */
+    NsKde kde_gap;            /* _gap_length.pkl, log10(x+1) domain (n = 0 if absent) */
+    const uint32_t* alias_prob;
+    const uint32_t* alias_idx;
+    const uint32_t* alias_desc;
+    uint32_t n_tables;
+    uint32_t alias_len;
+    const uint32_t* match_bin_lo;   /* previous-match-length bins [lo, hi) of _match_markov_model's header */
+    const uint32_t* match_bin_hi;
+    uint32_t n_match_bins;
+    uint32_t has_qual;
+    uint32_t trans[NS_N_ERR_STATES][3];                 /* r<t0: mis; r<t1: ins; r>=t2: del; else previous error */
+    uint32_t qual_cdf[NS_N_QUAL_STATES][NS_QUAL_SLOTS]; /* q = first slot with r < cdf[q] (32-bit fixed point)   */
+    double hp[2][6];          /* rows AT, CG: const, alpha1, beta1, breakpoint1, intercept, slope */
+    double hp_mis_rate;
+    uint32_t has_hp;
+    float strandness_rate;
+    float segment_mean;
+    float mean_ref_per_event; /* sizing hint for op slots */
+} NsModel;
+
+/* The scalar arguments of simulation()/simulation_aligned_genome()/simulation_unaligned(). */
+typedef struct {
+    uint32_t mode;            /* 0 genome */
+    uint32_t circular;        /* dna_type == "circular" (single chromosome) */
+    uint32_t perfect;
+    uint32_t fastq;
+    uint32_t chimeric;
+    uint32_t kmer_bias;       /* 0 = off (-k) */
+    uint32_t min_len;
+    uint32_t max_len;         /* caller passes min(max_len, max_chrom) as simulator.py:2318 does */
+    double median_len;        /* 0 = off (-med / -sd) */
+    double sd_len;
+} NsRunConfig;
+
+#define NS_KIND_ALIGNED 0
+#define NS_KIND_UNALIGNED 1
+
+#define NS_PIECE_SEGMENT 0    /* aligned segment (error_list + mutate_read)                  */
+#define NS_PIECE_GAP 1        /* chimeric gap (simulation_gap :1552-1568)                    */
+#define NS_PIECE_UNALIGNED 2  /* unaligned read body (simulation_unaligned :1482-1549)       */
+
+/* What the reference encodes in the read name and FASTQ record (:1390-1402, :1437-1443). */
+typedef struct {
+    uint64_t seq_off;         /* first base of this read in the seq / qual buffers (16-byte aligned slot) */
+    uint32_t seq_len;
+    uint32_t head;
+    uint32_t tail;
+    uint32_t piece_first;     /* index of the read's first piece */
+    uint16_t n_pieces;        /* 2*n_segments-1 for aligned reads, 1 for unaligned */
+    uint8_t reversed;         /* 1 = "_R" */
+    uint8_t flags;            /* bit0 = op slot overflow (read is invalid), bit1 = chimeric */
+    uint32_t attempts;        /* rejection-loop iterations used (:1367, :1429) */
+} NsReadMeta;
+
+typedef struct {
+    uint64_t op_off;          /* first op of the piece in the op buffer */
+    uint32_t n_ops;
+    uint32_t kind;            /* NS_PIECE_* */
+    uint32_t chrom;           /* index into NsReference.chrom_off */
+    uint32_t pos;             /* 0-based start on that chromosome ("{chrom}_{pos}") */
+    uint32_t ref_len;         /* middle_ref: reference bases the piece spans */
+    uint32_t out_len;         /* bases this piece contributes (incl. head/tail carried by the edge pieces) */
+    uint32_t out_rel;         /* offset of the piece inside the forward-strand read */
+    uint32_t l_new;           /* error_list's nominal length (== out_len - head/tail unless an ins/ins collision) */
+    uint32_t ref_req;         /* length drawn from the KDE before error_list extended it (m_ref) */
+    uint32_t read_slot;       /* index of the owning read inside the batch */
+} NsPieceMeta;
+
+/* Edit script element: (type << 28) | length.  The op list of a piece, applied left to right to the reference
+ * segment, is what mutate_read (:1919-2015) computes; it is also the content of <out>_aligned_error_profile. */
+#define NS_OP_COPY 0u    /* copy n reference bases          (match quality)     */
+#define NS_OP_MIS 1u     /* n substituted bases             (mis quality)       */
+#define NS_OP_INS 2u     /* n random inserted bases         (ins quality)       */
+#define NS_OP_DEL 3u     /* skip n reference bases                              */
+#define NS_OP_HT 4u      /* n random head/tail bases        (ht quality)        */
+#define NS_OP_TYPE(op) ((op) >> 28)
+#define NS_OP_LEN(op) ((op) & 0x0fffffffu)
+
+typedef struct {
+    uint64_t seq_bytes;       /* size of the seq (and qual) buffer for this batch */
+    uint64_t n_ops;
+    uint64_t total_bases;     /* sum of seq_len */
+    uint32_t n_reads;
+    uint32_t n_pieces;
+    uint32_t n_overflow;      /* reads whose op slot overflowed (0 unless the sizing hint was too small) */
+    float ms_draw, ms_chain, ms_emit, ms_total;   /* CUDA-event durations on the library's stream */
+} NsBatchInfo;
+
+/* --- lifetime --------------------------------------------------------------------------------------------- */
+/* replaces: process start + random.seed/np.random.seed (:2236-2238).  The stream of read `i` depends only on
+ * (seed, kind, i), so output is invariant to batch size and GPU count. */
+int ns_create(int device, uint64_t seed, NsContext** out);
+int ns_destroy(NsContext* ctx);
+const char* ns_last_error(const NsContext* ctx);
+
+/* --- read_profile() (:244-591): reference + model tables into HBM, once ------------------------------------- */
+int ns_set_reference(NsContext* ctx, const NsReference* ref);
+int ns_set_model(NsContext* ctx, const NsModel* model);
+int ns_configure(NsContext* ctx, const NsRunConfig* cfg);
+
+/* --- simulation_aligned_genome / simulation_unaligned worker bodies (:1266-1454, :1482-1549) ---------------- */
+/* Simulates reads [first_read_id, first_read_id + n_reads) of `kind`; results stay in HBM until the next call. */
+int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_reads, NsBatchInfo* info);
+
+/* Device->host copy of the last batch into caller buffers (pinned memory recommended).  qual / pieces / ops may be
+ * NULL.  seq and qual need info.seq_bytes bytes, reads n_reads entries, pieces n_pieces, ops n_ops uint32. */
+int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
+
+/* Device pointers of the last batch (for consumers that stay on the GPU, e.g. torch tensors / NCCL gathers). */
+int ns_device_buffers(NsContext* ctx, const uint8_t** seq, const uint8_t** qual, const NsReadMeta** reads,
+                      const NsPieceMeta** pieces, const uint32_t** ops);
+
+/* Histograms of the last batch's edit scripts, computed on the device (what tests compare with the statistics of
+ * the reference's <out>_aligned_error_profile).  out must hold NS_STATS_WORDS uint64. */
+#define NS_STATS_EV_CAP 64
+#define NS_STATS_RUN_CAP 512
+#define NS_STATS_WORDS (8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1))
+int ns_op_stats(NsContext* ctx, uint64_t* out);
+
+/* Host-side record formatting of a fetched batch into the reference's FASTA/FASTQ text (:1437-1443); multi-threaded.
+ * names: n_reads NUL-terminated strings laid out back to back, name_off[i] = start of read i's name. */
+int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads, uint32_t n_reads,
+                          const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
+                          int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

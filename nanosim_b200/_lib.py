@@ -1,0 +1,118 @@
+"""ctypes binding of libnanosim_b200.so (include/nanosim_b200.h).  No CPU fallback: if the shared library is
+missing, importing this module's ``lib()`` raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnanosim_b200.so")
+
+NS_MAX_SEGMENTS = 16
+NS_N_ERR_STATES = 7
+NS_N_QUAL_STATES = 5
+NS_QUAL_SLOTS = 94
+NS_KIND_ALIGNED, NS_KIND_UNALIGNED = 0, 1
+NS_PIECE_SEGMENT, NS_PIECE_GAP, NS_PIECE_UNALIGNED = 0, 1, 2
+NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT = 0, 1, 2, 3, 4
+NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
+NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
+
+EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_set_reference", "ns_set_model", "ns_configure",
+           "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records"]
+
+
+class NsReference(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("n_bases", C.c_uint64), ("chrom_off", C.c_void_p), ("n_chrom", C.c_uint32)]
+
+
+class NsKde(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_uint32), ("bandwidth", C.c_float)]
+
+
+class NsModel(C.Structure):
+    _fields_ = [
+        ("kde_aligned", NsKde), ("kde_ht", NsKde), ("kde_ht_ratio", NsKde), ("kde_unaligned", NsKde), ("kde_gap", NsKde),
+        ("alias_prob", C.c_void_p), ("alias_idx", C.c_void_p), ("alias_desc", C.c_void_p),
+        ("n_tables", C.c_uint32), ("alias_len", C.c_uint32),
+        ("match_bin_lo", C.c_void_p), ("match_bin_hi", C.c_void_p),
+        ("n_match_bins", C.c_uint32), ("has_qual", C.c_uint32),
+        ("trans", (C.c_uint32 * 3) * NS_N_ERR_STATES),
+        ("qual_cdf", (C.c_uint32 * NS_QUAL_SLOTS) * NS_N_QUAL_STATES),
+        ("hp", (C.c_double * 6) * 2), ("hp_mis_rate", C.c_double),
+        ("has_hp", C.c_uint32), ("strandness_rate", C.c_float), ("segment_mean", C.c_float),
+        ("mean_ref_per_event", C.c_float),
+    ]
+
+
+class NsRunConfig(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("circular", C.c_uint32), ("perfect", C.c_uint32), ("fastq", C.c_uint32),
+                ("chimeric", C.c_uint32), ("kmer_bias", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32),
+                ("median_len", C.c_double), ("sd_len", C.c_double)]
+
+
+class NsReadMeta(C.Structure):
+    _fields_ = [("seq_off", C.c_uint64), ("seq_len", C.c_uint32), ("head", C.c_uint32), ("tail", C.c_uint32),
+                ("piece_first", C.c_uint32), ("n_pieces", C.c_uint16), ("reversed", C.c_uint8), ("flags", C.c_uint8),
+                ("attempts", C.c_uint32)]
+
+
+class NsPieceMeta(C.Structure):
+    _fields_ = [("op_off", C.c_uint64), ("n_ops", C.c_uint32), ("kind", C.c_uint32), ("chrom", C.c_uint32),
+                ("pos", C.c_uint32), ("ref_len", C.c_uint32), ("out_len", C.c_uint32), ("out_rel", C.c_uint32),
+                ("l_new", C.c_uint32), ("ref_req", C.c_uint32), ("read_slot", C.c_uint32)]
+
+
+class NsBatchInfo(C.Structure):
+    _fields_ = [("seq_bytes", C.c_uint64), ("n_ops", C.c_uint64), ("total_bases", C.c_uint64),
+                ("n_reads", C.c_uint32), ("n_pieces", C.c_uint32), ("n_overflow", C.c_uint32),
+                ("ms_draw", C.c_float), ("ms_chain", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float)]
+
+
+# numpy views of the two record types
+import numpy as np  # noqa: E402
+
+READ_DTYPE = np.dtype([("seq_off", "<u8"), ("seq_len", "<u4"), ("head", "<u4"), ("tail", "<u4"),
+                       ("piece_first", "<u4"), ("n_pieces", "<u2"), ("reversed", "u1"), ("flags", "u1"),
+                       ("attempts", "<u4")], align=True)
+PIECE_DTYPE = np.dtype([("op_off", "<u8"), ("n_ops", "<u4"), ("kind", "<u4"), ("chrom", "<u4"), ("pos", "<u4"),
+                        ("ref_len", "<u4"), ("out_len", "<u4"), ("out_rel", "<u4"), ("l_new", "<u4"),
+                        ("ref_req", "<u4"), ("read_slot", "<u4")], align=True)
+assert READ_DTYPE.itemsize == C.sizeof(NsReadMeta) == 32
+assert PIECE_DTYPE.itemsize == C.sizeof(NsPieceMeta) == 48
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library.  Fails loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("nanosim_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
+                           "g.build()'`; there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    L.ns_create.argtypes = [C.c_int, C.c_uint64, C.POINTER(P)]
+    L.ns_create.restype = C.c_int
+    L.ns_destroy.argtypes = [P]
+    L.ns_destroy.restype = C.c_int
+    L.ns_last_error.argtypes = [P]
+    L.ns_last_error.restype = C.c_char_p
+    L.ns_set_reference.argtypes = [P, C.POINTER(NsReference)]
+    L.ns_set_reference.restype = C.c_int
+    L.ns_set_model.argtypes = [P, C.POINTER(NsModel)]
+    L.ns_set_model.restype = C.c_int
+    L.ns_configure.argtypes = [P, C.POINTER(NsRunConfig)]
+    L.ns_configure.restype = C.c_int
+    L.ns_simulate.argtypes = [P, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(NsBatchInfo)]
+    L.ns_simulate.restype = C.c_int
+    L.ns_fetch.argtypes = [P, P, P, P, P, P]
+    L.ns_fetch.restype = C.c_int
+    L.ns_device_buffers.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]
+    L.ns_device_buffers.restype = C.c_int
+    L.ns_op_stats.argtypes = [P, P]
+    L.ns_op_stats.restype = C.c_int
+    L.ns_format_records.argtypes = [P, P, P, C.c_uint32, P, P, C.c_int, P, C.c_uint64, C.c_int]
+    L.ns_format_records.restype = C.c_int64
+    _lib = L
+    return L

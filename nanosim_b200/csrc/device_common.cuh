@@ -1,0 +1,133 @@
+// Shared device-side definitions: counter-based RNG, table samplers, device mirrors of the C-ABI structs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nanosim_b200.h"
+
+#define NS_MAX_BINS 24
+#define NS_MAX_TABLES (4 + NS_MAX_BINS)
+
+struct DevKde {
+    const float* data;
+    uint32_t n;
+    float bw;
+};
+
+struct DevModel {
+    DevKde aligned, ht, ratio, unaligned, gap;
+    const uint2* alias;                 // interleaved (accept threshold, alias index)
+    uint32_t tab_off[NS_MAX_TABLES];
+    uint32_t tab_n[NS_MAX_TABLES];
+    uint32_t n_bins;
+    uint32_t bin_lo[NS_MAX_BINS];
+    uint32_t bin_hi[NS_MAX_BINS];
+    uint32_t trans[NS_N_ERR_STATES][3];
+    float strandness;
+    double seg_p;                       // 1 / segment_mean
+};
+
+struct DevRef {
+    const uint8_t* bases;
+    const uint64_t* chrom_off;          // n_chrom + 1
+    uint64_t genome_len;
+    uint32_t n_chrom;
+};
+
+struct DevCfg {
+    uint32_t circular, perfect, fastq, chimeric, kmer_bias;
+    uint32_t min_len, max_len;
+    uint64_t seed;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Counter = (read id lo, read id hi, stream word, block index); key = seed.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+// stream word layout: [31:28] purpose, [27] kind, [26:0] attempt / generation
+enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6 };
+
+__device__ __forceinline__ uint32_t stream_word(uint32_t purpose, uint32_t kind, uint32_t sub) {
+    return (purpose << 28) | ((kind & 1u) << 27) | (sub & 0x07ffffffu);
+}
+
+struct Rng {
+    uint2 key;
+    uint4 ctr;
+    uint4 buf;
+    int have;
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t id, uint32_t stream) {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        ctr = make_uint4((uint32_t)id, (uint32_t)(id >> 32), stream, 0u);
+        have = 0;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) {
+            buf = philox4x32_10(ctr, key);
+            ctr.w++;
+            have = 4;
+        }
+        uint32_t r = buf.x;
+        buf.x = buf.y;
+        buf.y = buf.z;
+        buf.z = buf.w;
+        --have;
+        return r;
+    }
+    // fresh block of four words (drops leftovers); used by the event loop: one Philox call per event
+    __device__ __forceinline__ uint4 next4() {
+        uint4 r = philox4x32_10(ctr, key);
+        ctr.w++;
+        have = 0;
+        return r;
+    }
+    __device__ __forceinline__ uint64_t next64() {
+        uint64_t a = next();
+        return (a << 32) | next();
+    }
+};
+
+__device__ __forceinline__ float u01_open_low(uint32_t r) {   // (0, 1]
+    return ((float)(r >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ double u01_double(uint64_t r) {    // [0, 1)
+    return (double)(r >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Walker alias draw from table t with one 32-bit word.
+__device__ __forceinline__ uint32_t alias_draw(const DevModel& m, uint32_t t, uint32_t r) {
+    uint32_t n = m.tab_n[t];
+    uint64_t p = (uint64_t)r * n;
+    uint32_t j = (uint32_t)(p >> 32);
+    uint32_t frac = (uint32_t)p;
+    uint2 e = __ldg(&m.alias[m.tab_off[t] + j]);
+    return (frac < e.x || e.x == 0xffffffffu) ? j : e.y;
+}
+
+// sklearn KernelDensity.sample (gaussian): data[floor(u*N)] + N(0, bw)
+__device__ __forceinline__ double kde_draw(const DevKde& k, Rng& rng) {
+    uint64_t r0 = rng.next64();
+    uint32_t r1 = rng.next(), r2 = rng.next();
+    uint32_t i = (uint32_t)__umul64hi(r0, (uint64_t)k.n);
+    float u1 = u01_open_low(r1);
+    float u2 = (float)(r2 >> 8) * (1.0f / 16777216.0f);
+    float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    return (double)__ldg(&k.data[i]) + (double)k.bw * (double)z;
+}
+
+// base <-> index helpers: A C G T -> 0 1 3 2 via (c >> 1) & 3 ; complement = idx ^ 2
+__device__ __forceinline__ uint32_t base_idx(uint32_t c) { return (c >> 1) & 3u; }
+__device__ __forceinline__ uint32_t idx_base(uint32_t i) { return (0x47544341u >> (8u * i)) & 0xffu; }
+__device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }

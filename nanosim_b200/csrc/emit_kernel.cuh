@@ -1,0 +1,252 @@
+// Emit kernel: applies each piece's edit script to the reference and writes bases + base qualities.
+//
+// This is extract_read's slice (/root/reference/src/simulator.py:1750-1781), case_convert (:743-755), mutate_read's
+// string edits and quality interleaving (:1957-2015), the head/tail synthesis (:1421-1427), reverse_complement
+// (:1433-1435, :1675-1680) and the per-state quality draws (model_base_qualities.py:120-130) in ONE pass:
+//
+//   * a warp owns one piece (an aligned segment with its head/tail, a chimeric gap, or an unaligned read) and
+//     streams its ops 32 at a time; a warp-wide scan turns op lengths into (output start, reference start) pairs
+//     kept in a shared-memory ring;
+//   * every lane produces one 16-byte output chunk per step: it binary-searches the ring for the op covering its
+//     first base, then walks ops/reference bytes sequentially, so global stores are 16-byte vectors, 512 B per
+//     warp and fully coalesced for both the base and the quality stream;
+//   * reverse-strand reads are produced directly in output order by walking the edit script and the reference
+//     backwards and complementing (no second pass over the read);
+//   * all randomness is Philox keyed by (seed, read id, chunk index), so the bytes do not depend on the batch,
+//     the launch geometry or the GPU count.
+#pragma once
+#include "device_common.cuh"
+
+#define EMIT_WARPS 8
+#define EMIT_RING 256
+#define QLUT_BITS 11
+#define QLUT_SIZE (1 << QLUT_BITS)
+
+struct EmitArgs {
+    DevRef ref;
+    DevCfg cfg;
+    uint32_t kind;
+    uint64_t first_id;
+    const NsReadMeta* reads;
+    const NsPieceMeta* pieces;
+    const uint32_t* ops;
+    uint32_t n_pieces;
+    uint8_t* seq;
+    uint8_t* qual;
+    const uint32_t* qlut;        // [5][QLUT_SIZE] packed bucket table (built on the host from qual_cdf)
+    const uint32_t* qcdf;        // [5][94]
+    uint32_t* counter;
+};
+
+// IUPAC resolution of case_convert (:744-746): members in the reference's list order, picked uniformly.
+__device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r16) {
+    uint32_t n, set;   // set: up to 4 members packed one byte each
+    switch (c) {
+    case 'Y': n = 2; set = 'C' | ('T' << 8); break;
+    case 'R': n = 2; set = 'A' | ('G' << 8); break;
+    case 'W': n = 2; set = 'A' | ('T' << 8); break;
+    case 'S': n = 2; set = 'G' | ('C' << 8); break;
+    case 'K': n = 2; set = 'T' | ('G' << 8); break;
+    case 'M': n = 2; set = 'C' | ('A' << 8); break;
+    case 'D': n = 3; set = 'A' | ('G' << 8) | ('T' << 16); break;
+    case 'V': n = 3; set = 'A' | ('C' << 8) | ('G' << 16); break;
+    case 'H': n = 3; set = 'A' | ('C' << 8) | ('T' << 16); break;
+    case 'B': n = 3; set = 'C' | ('G' << 8) | ('T' << 16); break;
+    case 'N':
+    case 'X': n = 4; set = 'A' | ('T' << 8) | ('C' << 16) | ('G' << 24); break;
+    default: return c;
+    }
+    uint32_t k = (r16 * n) >> 16;
+    return (set >> (8 * k)) & 0xffu;
+}
+
+struct Bits16 {
+    Rng rng;
+    uint32_t w;
+    int half;
+    __device__ __forceinline__ uint32_t next16() {
+        if (half == 0) {
+            w = rng.next();
+            half = 1;
+            return w & 0xffffu;
+        }
+        half = 0;
+        return w >> 16;
+    }
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+template <bool FASTQ>
+__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_constant__ EmitArgs a) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* lut = smem;                                        // FASTQ only
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* ring = smem + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0) + warp * (3 * EMIT_RING);
+    uint32_t* ring_out = ring;
+    uint32_t* ring_ref = ring + EMIT_RING;
+    uint32_t* ring_op = ring + 2 * EMIT_RING;
+    if (FASTQ) {
+        for (int i = threadIdx.x; i < NS_N_QUAL_STATES * QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[i];
+        __syncthreads();
+    }
+
+    for (;;) {
+        uint32_t piece = 0;
+        if (lane == 0) piece = atomicAdd(a.counter, 1u);
+        piece = __shfl_sync(0xffffffffu, piece, 0);
+        if (piece >= a.n_pieces) break;
+        const NsPieceMeta pm = a.pieces[piece];
+        if (pm.out_len == 0) continue;
+        const NsReadMeta rm = a.reads[pm.read_slot];
+        const uint64_t rid = a.first_id + pm.read_slot;
+        const bool rev = rm.reversed != 0;
+        const uint32_t out_len = pm.out_len, n_ops = pm.n_ops, ref_len = pm.ref_len;
+        const uint32_t A = rev ? rm.seq_len - pm.out_rel - out_len : pm.out_rel;   // piece start in read coordinates
+        const uint64_t cstart = a.ref.chrom_off[pm.chrom];
+        const uint64_t clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
+        const uint8_t* __restrict__ cbase = a.ref.bases + cstart;
+        const uint32_t* __restrict__ ops = a.ops + pm.op_off;
+        uint8_t* seq_out = a.seq + rm.seq_off;
+        uint8_t* qual_out = FASTQ ? a.qual + rm.seq_off : nullptr;
+        const bool unmapped = pm.kind != NS_PIECE_SEGMENT;
+
+        uint32_t t_loaded = 0, t_ret = 0, out_loaded = 0, ref_loaded = 0, prog = 0;
+        while (prog < out_len) {
+            // ---- 1. stream ops into the ring until the next 32 chunks are covered or the ring is full
+            const uint32_t first_chunk = (A + prog) >> 4;
+            uint32_t target = (first_chunk + 32) * 16 - A;
+            if (target > out_len) target = out_len;
+            while (out_loaded < target && t_loaded < n_ops && (t_loaded - t_ret) + 32 <= EMIT_RING) {
+                uint32_t t = t_loaded + lane;
+                uint32_t op = 0;
+                if (t < n_ops) op = __ldg(&ops[rev ? n_ops - 1 - t : t]);
+                uint32_t ty = op >> 28, len = op & 0x0fffffffu;
+                uint32_t o = (ty == NS_OP_DEL) ? 0u : len;
+                uint32_t r = (ty == NS_OP_INS || ty == NS_OP_HT) ? 0u : len;
+                uint32_t so = warp_incl_scan(o, lane), sr = warp_incl_scan(r, lane);
+                if (t < n_ops) {
+                    ring_out[t % EMIT_RING] = out_loaded + so - o;
+                    ring_ref[t % EMIT_RING] = ref_loaded + sr - r;
+                    ring_op[t % EMIT_RING] = op;
+                }
+                out_loaded += __shfl_sync(0xffffffffu, so, 31);
+                ref_loaded += __shfl_sync(0xffffffffu, sr, 31);
+                t_loaded += (n_ops - t_loaded < 32u) ? n_ops - t_loaded : 32u;
+            }
+            __syncwarp();
+            // ---- 2. what can be produced now: whole chunks up to the loaded frontier (or the piece end)
+            uint32_t lim = out_loaded < target ? out_loaded : target;
+            if (lim < out_len) lim = ((A + lim) & ~15u) > A + prog ? ((A + lim) & ~15u) - A : prog;
+            // (ring holds >= 64 ops beyond t_ret, i.e. >= 1 whole chunk, so lim > prog whenever ops remain)
+            // ---- 3. one 16-byte chunk per lane
+            const uint32_t chunk = first_chunk + lane;
+            uint32_t cs = chunk * 16;                                  // chunk start, read coordinates
+            uint32_t lo = cs > A + prog ? cs : A + prog;
+            uint32_t hi = cs + 16 < A + lim ? cs + 16 : A + lim;
+            if (lo < hi) {
+                const uint32_t plo = lo - A;                           // piece coordinates
+                // upper_bound over ring_out in [t_ret, t_loaded): last op whose output start <= plo
+                uint32_t l = t_ret, h = t_loaded;
+                while (h - l > 1) {
+                    uint32_t mid = (l + h) >> 1;
+                    if (ring_out[mid % EMIT_RING] <= plo) l = mid; else h = mid;
+                }
+                uint32_t k = l;
+                uint32_t op = ring_op[k % EMIT_RING];
+                uint32_t ty = op >> 28;
+                uint32_t within = plo - ring_out[k % EMIT_RING];
+                uint32_t rem = (op & 0x0fffffffu) - within;
+                uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty == NS_OP_INS || ty == NS_OP_HT) ? 0u : within);
+
+                Bits16 bb;
+                bb.rng.init(a.cfg.seed, rid, stream_word(ST_EMIT_B, a.kind, chunk));
+                bb.half = 0;
+                Rng qr;
+                if (FASTQ) qr.init(a.cfg.seed, rid, stream_word(ST_EMIT_Q, a.kind, chunk));
+
+                uint32_t sb[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+                const uint32_t i0 = lo - cs, i1 = hi - cs;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if ((uint32_t)i >= i0 && (uint32_t)i < i1) {
+                        while (rem == 0) {
+                            ++k;
+                            op = ring_op[k % EMIT_RING];
+                            ty = op >> 28;
+                            rem = (ty == NS_OP_DEL) ? 0u : (op & 0x0fffffffu);
+                            rpos = ring_ref[k % EMIT_RING];
+                        }
+                        uint32_t c;
+                        uint32_t qs;   // quality state: 0 mis 1 ins 2 match 3 ht 4 unmapped
+                        if (ty == NS_OP_COPY || ty == NS_OP_MIS) {
+                            uint32_t f = rev ? ref_len - 1 - rpos : rpos;
+                            uint64_t ab = (uint64_t)pm.pos + f;
+                            if (ab >= clen) ab -= clen;                   // circular wrap (:1756-1760)
+                            c = __ldg(&cbase[ab]);
+                            ++rpos;
+                            if (c >= 'a' && c <= 'z') c -= 32;
+                            if (!is_acgt(c)) c = resolve_iupac(c, bb.next16());
+                            if (ty == NS_OP_MIS) {
+                                uint32_t j = (base_idx(c) + 1 + ((bb.next16() * 3u) >> 16)) & 3u;   // one of the 3 others
+                                c = idx_base(j);
+                                qs = 0;
+                            } else {
+                                qs = 2;
+                            }
+                            if (rev && is_acgt(c)) c = idx_base(base_idx(c) ^ 2u);
+                        } else {
+                            c = idx_base(bb.next16() & 3u);               // random.choice(BASES) / np.random.choice
+                            qs = (ty == NS_OP_INS) ? 1 : 3;
+                        }
+                        --rem;
+                        sb[i >> 2] |= c << (8 * (i & 3));
+                        if (FASTQ) {
+                            if (unmapped) qs = 4;
+                            uint32_t r = qr.next();
+                            uint32_t e = lut[qs * QLUT_SIZE + (r >> (32 - QLUT_BITS))];
+                            uint32_t q = e & 0xffu;
+                            if (e >> 31) {                                // bucket spans >2 quality values: exact scan
+                                const uint32_t* cdf = a.qcdf + qs * NS_QUAL_SLOTS;
+                                while (q < NS_QUAL_SLOTS - 1 && r >= __ldg(&cdf[q])) ++q;
+                            } else {
+                                q += ((r & ((1u << (32 - QLUT_BITS)) - 1u)) >= ((e >> 8) & 0x3fffffu)) ? 1u : 0u;
+                            }
+                            sq[i >> 2] |= (q + 33u) << (8 * (i & 3));
+                        }
+                    }
+                }
+                if (i0 == 0 && i1 == 16) {
+                    *reinterpret_cast<uint4*>(seq_out + cs) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
+                    if (FASTQ) *reinterpret_cast<uint4*>(qual_out + cs) = make_uint4(sq[0], sq[1], sq[2], sq[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if ((uint32_t)i >= i0 && (uint32_t)i < i1) {
+                            seq_out[cs + i] = (uint8_t)(sb[i >> 2] >> (8 * (i & 3)));
+                            if (FASTQ) qual_out[cs + i] = (uint8_t)(sq[i >> 2] >> (8 * (i & 3)));
+                        }
+                    }
+                }
+            }
+            // ---- 4. retire ops that end before the new frontier
+            prog = lim;
+            {
+                uint32_t l = t_ret, h = t_loaded;
+                while (h - l > 1) {
+                    uint32_t mid = (l + h) >> 1;
+                    if (ring_out[mid % EMIT_RING] <= prog) l = mid; else h = mid;
+                }
+                t_ret = l;
+            }
+            __syncwarp();
+        }
+    }
+}

@@ -1,0 +1,631 @@
+// C ABI of libnanosim_b200.so (include/nanosim_b200.h): context, HBM residency of reference + model tables,
+// batch orchestration (plan -> scan -> script -> emit) on one CUDA stream, device->host fetch.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "nanosim_b200.h"
+#include "device_common.cuh"
+#include "plan_kernel.cuh"
+#include "emit_kernel.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct NsContext {
+    int device = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    int sm_count = 148;
+
+    bool have_ref = false, have_model = false, have_cfg = false;
+    DevBuf ref_bases, ref_off;
+    DevRef dref{};
+    std::vector<uint64_t> h_chrom_off;
+
+    DevBuf kde[5], alias, qlut, qcdf;
+    DevModel dmodel{};
+    NsModel hmodel{};
+    NsRunConfig hcfg{};
+    DevCfg dcfg{};
+
+    // batch state
+    DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
+        stats;
+    uint64_t* h_totals = nullptr;   // pinned
+    NsBatchInfo last{};
+    int last_kind = 0;
+    uint64_t last_first_id = 0;
+    bool have_batch = false;
+};
+
+namespace {
+
+int fail(NsContext* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, NS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+__global__ void gather_piece_ops(const NsPieceMeta* pieces, uint32_t n, uint64_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pieces[i].n_ops;
+}
+__global__ void scatter_piece_off(NsPieceMeta* pieces, uint32_t n, const uint64_t* off) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pieces[i].op_off = off[i];
+}
+__global__ void gather_read_bytes(const NsReadMeta* reads, uint32_t n, uint64_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((uint64_t)reads[i].seq_len + 15u) & ~(uint64_t)15u;
+}
+__global__ void scatter_read_off(NsReadMeta* reads, uint32_t n, const uint64_t* off) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) reads[i].seq_off = off[i];
+}
+__global__ void widen_u32(const uint32_t* in, uint32_t n, uint64_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void narrow_u64(const uint64_t* in, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+// totals[k] = off[n-1] + in[n-1]
+__global__ void last_total(const uint64_t* in, const uint64_t* off, uint32_t n, uint64_t* totals, int k) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) totals[k] = n ? off[n - 1] + in[n - 1] : 0;
+}
+__global__ void sum_bases(const NsReadMeta* reads, uint32_t n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += reads[i].seq_len;
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// op-list histograms (ns_op_stats)
+__global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* reads, const uint32_t* ops, uint32_t n,
+                                unsigned long long* st) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const NsPieceMeta pm = pieces[i];
+    unsigned long long* ev = st + 8;
+    unsigned long long* evlen = st + 16;
+    unsigned long long* run_h = evlen + 3 * (NS_STATS_EV_CAP + 1);
+    unsigned long long* first_h = run_h + (NS_STATS_RUN_CAP + 1);
+    if (pm.kind != NS_PIECE_SEGMENT) {
+        atomicAdd(&st[4], 1ull);
+        atomicAdd(&st[5], (unsigned long long)pm.out_len);
+        return;
+    }
+    atomicAdd(&st[0], 1ull);
+    atomicAdd(&st[1], (unsigned long long)pm.ref_len);
+    uint64_t run = 0, ht = 0, n_ev = 0;
+    bool first = true;
+    for (uint32_t k = 0; k < pm.n_ops; ++k) {
+        uint32_t op = ops[pm.op_off + k];
+        uint32_t ty = op >> 28, len = op & 0x0fffffffu;
+        if (ty == NS_OP_HT) {
+            ht += len;
+        } else if (ty == NS_OP_COPY) {
+            run += len;
+        } else {
+            uint32_t t = ty - 1;   // 0 mis 1 ins 2 del
+            atomicAdd(&ev[t], 1ull);
+            atomicAdd(&ev[3 + t], (unsigned long long)len);
+            atomicAdd(&evlen[t * (NS_STATS_EV_CAP + 1) + (len < NS_STATS_EV_CAP ? len : NS_STATS_EV_CAP)], 1ull);
+            unsigned long long* h = first ? first_h : run_h;
+            atomicAdd(&h[run < NS_STATS_RUN_CAP ? run : NS_STATS_RUN_CAP], 1ull);
+            first = false;
+            run = 0;
+            ++n_ev;
+        }
+    }
+    atomicAdd(&st[2], (unsigned long long)(pm.out_len - ht));
+    atomicAdd(&st[3], (unsigned long long)ht);
+    atomicAdd(&st[6], (unsigned long long)n_ev);
+}
+
+cudaError_t upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
+    cudaError_t e = b.ensure(bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, s);
+}
+
+void build_qlut(const uint32_t cdf[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut) {
+    lut.assign((size_t)NS_N_QUAL_STATES * QLUT_SIZE, 0);
+    const uint32_t shift = 32 - QLUT_BITS;
+    auto qof = [&](int s, uint32_t r) {
+        uint32_t q = 0;
+        while (q < NS_QUAL_SLOTS - 1 && r >= cdf[s][q]) ++q;
+        return q;
+    };
+    for (int s = 0; s < NS_N_QUAL_STATES; ++s) {
+        for (uint32_t b = 0; b < QLUT_SIZE; ++b) {
+            uint32_t lo = b << shift, hi = lo + ((1u << shift) - 1u);
+            uint32_t qlo = qof(s, lo), qhi = qof(s, hi);
+            uint32_t e;
+            if (qhi == qlo) e = qlo | ((1u << shift) << 8);
+            else if (qhi == qlo + 1) e = qlo | ((cdf[s][qlo] - lo) << 8);
+            else e = qlo | 0x80000000u;
+            lut[(size_t)s * QLUT_SIZE + b] = e;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ns_create(int device, uint64_t seed, NsContext** out) {
+    if (!out) return NS_EINVAL;
+    *out = nullptr;
+    NsContext* ctx = new NsContext();
+    ctx->device = device;
+    ctx->seed = seed;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_totals, 8 * sizeof(uint64_t));
+    if (e == cudaSuccess) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    }
+    if (e != cudaSuccess) {
+        fprintf(stderr, "nanosim_b200: ns_create failed: %s\n", cudaGetErrorString(e));
+        delete ctx;
+        return NS_ECUDA;
+    }
+    *out = ctx;
+    return NS_OK;
+}
+
+int ns_destroy(NsContext* ctx) {
+    if (!ctx) return NS_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
+                      &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
+                      &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& k : ctx->kde) k.release();
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return NS_OK;
+}
+
+const char* ns_last_error(const NsContext* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ns_set_reference(NsContext* ctx, const NsReference* ref) {
+    if (!ctx || !ref || !ref->bases || !ref->chrom_off || ref->n_chrom == 0)
+        return fail(ctx, NS_EINVAL, "ns_set_reference: null argument or empty reference");
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_chrom_off.resize(ref->n_chrom + 1);
+    CK(cudaMemcpy(ctx->h_chrom_off.data(), ref->chrom_off, (ref->n_chrom + 1) * sizeof(uint64_t), cudaMemcpyDefault));
+    if (ctx->h_chrom_off[0] != 0 || ctx->h_chrom_off[ref->n_chrom] != ref->n_bases)
+        return fail(ctx, NS_EINVAL, "ns_set_reference: chrom_off must start at 0 and end at n_bases");
+    for (uint32_t i = 0; i < ref->n_chrom; ++i) {
+        uint64_t len = ctx->h_chrom_off[i + 1] - ctx->h_chrom_off[i];
+        if (ctx->h_chrom_off[i + 1] < ctx->h_chrom_off[i] || len > 0xffffffffull)
+            return fail(ctx, NS_EINVAL, "ns_set_reference: chromosome %u has an invalid length", i);
+    }
+    CK(upload(ctx->ref_bases, ref->bases, ref->n_bases, ctx->stream));
+    CK(upload(ctx->ref_off, ctx->h_chrom_off.data(), (ref->n_chrom + 1) * sizeof(uint64_t), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dref.bases = ctx->ref_bases.as<uint8_t>();
+    ctx->dref.chrom_off = ctx->ref_off.as<uint64_t>();
+    ctx->dref.genome_len = ref->n_bases;
+    ctx->dref.n_chrom = ref->n_chrom;
+    ctx->have_ref = true;
+    ctx->have_batch = false;
+    return NS_OK;
+}
+
+int ns_set_model(NsContext* ctx, const NsModel* m) {
+    if (!ctx || !m) return fail(ctx, NS_EINVAL, "ns_set_model: null argument");
+    if (m->n_match_bins == 0 || m->n_match_bins > NS_MAX_BINS || m->n_tables != 4 + m->n_match_bins)
+        return fail(ctx, NS_EINVAL, "ns_set_model: need 1..%d match bins and 4+bins alias tables", NS_MAX_BINS);
+    if (!m->alias_prob || !m->alias_idx || !m->alias_desc || !m->match_bin_lo || !m->match_bin_hi)
+        return fail(ctx, NS_EINVAL, "ns_set_model: null table pointer");
+    CK(cudaSetDevice(ctx->device));
+    ctx->hmodel = *m;
+    DevModel& d = ctx->dmodel;
+    const NsKde* src[5] = {&m->kde_aligned, &m->kde_ht, &m->kde_ht_ratio, &m->kde_unaligned, &m->kde_gap};
+    DevKde* dst[5] = {&d.aligned, &d.ht, &d.ratio, &d.unaligned, &d.gap};
+    for (int i = 0; i < 5; ++i) {
+        if (src[i]->n && !src[i]->data) return fail(ctx, NS_EINVAL, "ns_set_model: KDE %d has n>0 but no data", i);
+        CK(upload(ctx->kde[i], src[i]->data, (size_t)src[i]->n * sizeof(float), ctx->stream));
+        dst[i]->data = ctx->kde[i].as<float>();
+        dst[i]->n = src[i]->n;
+        dst[i]->bw = src[i]->bandwidth;
+    }
+    if (m->kde_aligned.n == 0 || m->kde_ht.n == 0 || m->kde_ht_ratio.n == 0)
+        return fail(ctx, NS_EINVAL, "ns_set_model: aligned / ht / ht_ratio KDEs are required");
+    // interleave (prob, alias) so that one 8-byte load serves a draw
+    std::vector<uint32_t> hp(m->alias_len), hi(m->alias_len), desc(2 * m->n_tables);
+    CK(cudaMemcpy(hp.data(), m->alias_prob, hp.size() * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(hi.data(), m->alias_idx, hi.size() * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(desc.data(), m->alias_desc, desc.size() * 4, cudaMemcpyDefault));
+    std::vector<uint2> inter(m->alias_len);
+    for (uint32_t i = 0; i < m->alias_len; ++i) inter[i] = make_uint2(hp[i], hi[i]);
+    CK(upload(ctx->alias, inter.data(), inter.size() * sizeof(uint2), ctx->stream));
+    d.alias = ctx->alias.as<uint2>();
+    for (uint32_t t = 0; t < m->n_tables; ++t) {
+        d.tab_off[t] = desc[2 * t];
+        d.tab_n[t] = desc[2 * t + 1];
+        if (d.tab_n[t] == 0 || (uint64_t)d.tab_off[t] + d.tab_n[t] > m->alias_len)
+            return fail(ctx, NS_EINVAL, "ns_set_model: alias table %u out of range", t);
+    }
+    std::vector<uint32_t> blo(m->n_match_bins), bhi(m->n_match_bins);
+    CK(cudaMemcpy(blo.data(), m->match_bin_lo, blo.size() * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(bhi.data(), m->match_bin_hi, bhi.size() * 4, cudaMemcpyDefault));
+    d.n_bins = m->n_match_bins;
+    for (uint32_t b = 0; b < d.n_bins; ++b) {
+        d.bin_lo[b] = blo[b];
+        d.bin_hi[b] = bhi[b];
+    }
+    memcpy(d.trans, m->trans, sizeof d.trans);
+    d.strandness = m->strandness_rate;
+    d.seg_p = m->segment_mean > 1.0f ? 1.0 / (double)m->segment_mean : 1.0;
+    std::vector<uint32_t> lut;
+    build_qlut(m->qual_cdf, lut);
+    CK(upload(ctx->qlut, lut.data(), lut.size() * 4, ctx->stream));
+    CK(upload(ctx->qcdf, m->qual_cdf, sizeof m->qual_cdf, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_model = true;
+    ctx->have_batch = false;
+    return NS_OK;
+}
+
+int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
+    if (!ctx || !cfg) return fail(ctx, NS_EINVAL, "ns_configure: null argument");
+    if (cfg->mode != 0) return fail(ctx, NS_EINVAL, "ns_configure: only genome mode (0) is implemented");
+    if (cfg->max_len < cfg->min_len) return fail(ctx, NS_EINVAL, "Maximum read length must be longer than Minimum read length!");
+    if (cfg->perfect && cfg->chimeric) return fail(ctx, NS_EINVAL, "Perfect reads cannot be chimeric");
+    if (cfg->median_len != 0.0 || cfg->sd_len != 0.0)
+        return fail(ctx, NS_EINVAL, "ns_configure: -med/-sd log-normal lengths are not implemented yet");
+    if (cfg->kmer_bias != 0) return fail(ctx, NS_EINVAL, "ns_configure: homopolymer simulation (-hp/-k) is not implemented yet");
+    ctx->hcfg = *cfg;
+    ctx->dcfg.circular = cfg->circular;
+    ctx->dcfg.perfect = cfg->perfect;
+    ctx->dcfg.fastq = cfg->fastq;
+    ctx->dcfg.chimeric = cfg->chimeric;
+    ctx->dcfg.kmer_bias = cfg->kmer_bias;
+    ctx->dcfg.min_len = cfg->min_len;
+    ctx->dcfg.max_len = cfg->max_len;
+    ctx->dcfg.seed = ctx->seed;
+    ctx->have_cfg = true;
+    ctx->have_batch = false;
+    return NS_OK;
+}
+
+static int exclusive_scan_u64(NsContext* ctx, const uint64_t* in, uint64_t* out, uint32_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, ctx->stream));
+    CK(ctx->scan_tmp.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, in, out, (int)n, ctx->stream));
+    return NS_OK;
+}
+
+int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_reads, NsBatchInfo* info) {
+    if (!ctx) return NS_EINVAL;
+    if (!ctx->have_ref || !ctx->have_model || !ctx->have_cfg)
+        return fail(ctx, NS_ESTATE, "ns_simulate: reference, model and run configuration must be set first");
+    if (kind != NS_KIND_ALIGNED && kind != NS_KIND_UNALIGNED) return fail(ctx, NS_EINVAL, "ns_simulate: bad kind %d", kind);
+    if (kind == NS_KIND_UNALIGNED && ctx->dmodel.unaligned.n == 0)
+        return fail(ctx, NS_ESTATE, "ns_simulate: model has no unaligned-length KDE");
+    if (kind == NS_KIND_ALIGNED && ctx->hcfg.chimeric && ctx->dmodel.gap.n == 0)
+        return fail(ctx, NS_ESTATE, "ns_simulate: chimeric simulation needs the gap-length KDE");
+    if (ctx->hcfg.fastq && !ctx->hmodel.has_qual)
+        return fail(ctx, NS_ESTATE, "ns_simulate: --fastq needs base-quality parameters in the model");
+    if (ctx->hcfg.max_len > 0x0fffffffu) ctx->dcfg.max_len = 0x0fffffffu;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->have_batch = false;
+    memset(&ctx->last, 0, sizeof ctx->last);
+    if (n_reads == 0) {
+        if (info) *info = ctx->last;
+        ctx->have_batch = true;
+        ctx->last_kind = kind;
+        return NS_OK;
+    }
+    const uint32_t n = n_reads;
+    const unsigned tb = 256, gb = (n + tb - 1) / tb;
+    CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
+    CK(ctx->counter.ensure(64));
+    CK(ctx->totals.ensure(8 * sizeof(uint64_t)));
+    CK(ctx->scan_in.ensure((size_t)n * (2 * NS_MAX_SEGMENTS) * sizeof(uint64_t)));
+    CK(ctx->scan_out.ensure((size_t)n * (2 * NS_MAX_SEGMENTS) * sizeof(uint64_t)));
+    CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * sizeof(uint64_t), st));
+    CK(cudaEventRecord(ctx->ev[0], st));
+
+    // ---- pieces per read
+    const bool chim = (kind == NS_KIND_ALIGNED) && ctx->hcfg.chimeric;
+    uint32_t n_pieces = n;
+    const uint32_t* d_nseg = nullptr;
+    const uint32_t* d_pfirst = nullptr;
+    if (chim) {
+        CK(ctx->nseg.ensure((size_t)n * 4));
+        CK(ctx->npieces.ensure((size_t)n * 4));
+        CK(ctx->piece_first.ensure((size_t)n * 4));
+        segments_kernel<<<gb, tb, 0, st>>>(ctx->dmodel, ctx->dcfg, (uint32_t)kind, first_read_id, n, ctx->nseg.as<uint32_t>(),
+                                           ctx->npieces.as<uint32_t>());
+        widen_u32<<<gb, tb, 0, st>>>(ctx->npieces.as<uint32_t>(), n, ctx->scan_in.as<uint64_t>());
+        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
+        if (rc) return rc;
+        narrow_u64<<<gb, tb, 0, st>>>(ctx->scan_out.as<uint64_t>(), n, ctx->piece_first.as<uint32_t>());
+        last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 0);
+        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_pieces = (uint32_t)ctx->h_totals[0];
+        d_nseg = ctx->nseg.as<uint32_t>();
+        d_pfirst = ctx->piece_first.as<uint32_t>();
+    }
+    CK(ctx->pieces.ensure((size_t)n_pieces * sizeof(NsPieceMeta)));
+    CK(cudaMemsetAsync(ctx->pieces.p, 0, (size_t)n_pieces * sizeof(NsPieceMeta), st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- plan pass 1: rejection loops, lengths, op counts, positions
+    PlanArgs pa;
+    pa.m = ctx->dmodel;
+    pa.ref = ctx->dref;
+    pa.cfg = ctx->dcfg;
+    pa.kind = (uint32_t)kind;
+    pa.first_id = first_read_id;
+    pa.n_reads = n;
+    pa.n_seg = d_nseg;
+    pa.piece_first = d_pfirst;
+    pa.reads = ctx->reads.as<NsReadMeta>();
+    pa.pieces = ctx->pieces.as<NsPieceMeta>();
+    pa.ops = nullptr;
+    pa.counter = ctx->counter.as<uint32_t>();
+    const unsigned plan_tb = 128;
+    unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * 16u);
+    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+    plan_kernel<false><<<plan_blocks, plan_tb, 0, st>>>(pa);
+    CK(cudaGetLastError());
+
+    // ---- exclusive scans: op offsets per piece, 16-byte aligned sequence slots per read
+    const unsigned gp = (n_pieces + tb - 1) / tb;
+    gather_piece_ops<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, ctx->scan_in.as<uint64_t>());
+    {
+        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces);
+        if (rc) return rc;
+    }
+    scatter_piece_off<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, ctx->scan_out.as<uint64_t>());
+    last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 1);
+    gather_read_bytes<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_in.as<uint64_t>());
+    {
+        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
+        if (rc) return rc;
+    }
+    scatter_read_off<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_out.as<uint64_t>());
+    last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
+    sum_bases<<<std::min<unsigned>(gb, 1024u), tb, 0, st>>>(pa.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
+    CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t n_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
+    CK(ctx->ops.ensure((size_t)(n_ops + 4) * sizeof(uint32_t)));
+    CK(ctx->seq.ensure((size_t)seq_bytes + 16));
+    if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes + 16));
+    CK(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- plan pass 2: replay the accepted attempt, write the edit scripts
+    pa.ops = ctx->ops.as<uint32_t>();
+    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+    plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- emit
+    EmitArgs ea;
+    ea.ref = ctx->dref;
+    ea.cfg = ctx->dcfg;
+    ea.kind = (uint32_t)kind;
+    ea.first_id = first_read_id;
+    ea.reads = pa.reads;
+    ea.pieces = pa.pieces;
+    ea.ops = pa.ops;
+    ea.n_pieces = n_pieces;
+    ea.seq = ctx->seq.as<uint8_t>();
+    ea.qual = ctx->qual.as<uint8_t>();
+    ea.qlut = ctx->qlut.as<uint32_t>();
+    ea.qcdf = ctx->qcdf.as<uint32_t>();
+    ea.counter = ctx->counter.as<uint32_t>();
+    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+    const size_t ring_bytes = (size_t)EMIT_WARPS * 3 * EMIT_RING * 4;
+    if (ctx->hcfg.fastq) {
+        size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
+        CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<true>, EMIT_WARPS * 32, smem));
+        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
+        emit_kernel<true><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
+    } else {
+        size_t smem = ring_bytes;
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, EMIT_WARPS * 32, smem));
+        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
+        emit_kernel<false><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaStreamSynchronize(st));
+
+    NsBatchInfo& bi = ctx->last;
+    bi.seq_bytes = seq_bytes;
+    bi.n_ops = n_ops;
+    bi.total_bases = total_bases;
+    bi.n_reads = n;
+    bi.n_pieces = n_pieces;
+    bi.n_overflow = 0;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    bi.ms_draw = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[3]);
+    bi.ms_chain = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    bi.ms_emit = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
+    bi.ms_total = ms;
+    ctx->last_kind = kind;
+    ctx->last_first_id = first_read_id;
+    ctx->have_batch = true;
+    if (info) *info = bi;
+    return NS_OK;
+}
+
+int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops) {
+    if (!ctx) return NS_EINVAL;
+    if (!ctx->have_batch) return fail(ctx, NS_ESTATE, "ns_fetch: no simulated batch");
+    CK(cudaSetDevice(ctx->device));
+    const NsBatchInfo& bi = ctx->last;
+    cudaStream_t st = ctx->stream;
+    if (bi.n_reads == 0) return NS_OK;
+    if (seq) CK(cudaMemcpyAsync(seq, ctx->seq.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
+    if (qual) {
+        if (!ctx->hcfg.fastq) return fail(ctx, NS_ESTATE, "ns_fetch: qualities requested but the run is not --fastq");
+        CK(cudaMemcpyAsync(qual, ctx->qual.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (reads) CK(cudaMemcpyAsync(reads, ctx->reads.p, (size_t)bi.n_reads * sizeof(NsReadMeta), cudaMemcpyDeviceToHost, st));
+    if (pieces) CK(cudaMemcpyAsync(pieces, ctx->pieces.p, (size_t)bi.n_pieces * sizeof(NsPieceMeta), cudaMemcpyDeviceToHost, st));
+    if (ops) CK(cudaMemcpyAsync(ops, ctx->ops.p, (size_t)bi.n_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NS_OK;
+}
+
+int ns_device_buffers(NsContext* ctx, const uint8_t** seq, const uint8_t** qual, const NsReadMeta** reads,
+                      const NsPieceMeta** pieces, const uint32_t** ops) {
+    if (!ctx) return NS_EINVAL;
+    if (!ctx->have_batch) return fail(ctx, NS_ESTATE, "ns_device_buffers: no simulated batch");
+    if (seq) *seq = ctx->seq.as<uint8_t>();
+    if (qual) *qual = ctx->hcfg.fastq ? ctx->qual.as<uint8_t>() : nullptr;
+    if (reads) *reads = ctx->reads.as<NsReadMeta>();
+    if (pieces) *pieces = ctx->pieces.as<NsPieceMeta>();
+    if (ops) *ops = ctx->ops.as<uint32_t>();
+    return NS_OK;
+}
+
+int ns_op_stats(NsContext* ctx, uint64_t* out) {
+    if (!ctx || !out) return NS_EINVAL;
+    if (!ctx->have_batch) return fail(ctx, NS_ESTATE, "ns_op_stats: no simulated batch");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)NS_STATS_WORDS * sizeof(uint64_t);
+    CK(ctx->stats.ensure(bytes));
+    CK(cudaMemsetAsync(ctx->stats.p, 0, bytes, ctx->stream));
+    const uint32_t n = ctx->last.n_pieces;
+    if (n) {
+        op_stats_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->pieces.as<NsPieceMeta>(), ctx->reads.as<NsReadMeta>(),
+                                                                   ctx->ops.as<uint32_t>(), n,
+                                                                   (unsigned long long*)ctx->stats.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, ctx->stats.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side FASTA/FASTQ record formatting (simulator.py:1437-1443), multi-threaded memcpy-style assembly
+// ---------------------------------------------------------------------------------------------------------
+int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads, uint32_t n_reads,
+                          const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
+                          int n_threads) {
+    if (!seq || !reads || !names || !name_off || (fastq && !qual)) return NS_EINVAL;
+    std::vector<uint64_t> off((size_t)n_reads + 1, 0);
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        uint64_t nl = strlen(names + name_off[i]);
+        uint64_t rec = 1 + nl + 1 + reads[i].seq_len + 1;
+        if (fastq) rec += 2 + reads[i].seq_len + 1;
+        off[i + 1] = off[i] + rec;
+    }
+    if (!out) return (int64_t)off[n_reads];
+    if (off[n_reads] > out_cap) return NS_ENOMEM;
+    int nt = std::max(1, std::min(n_threads, 64));
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            char* p = out + off[i];
+            const char* nm = names + name_off[i];
+            size_t nl = strlen(nm);
+            *p++ = fastq ? '@' : '>';
+            memcpy(p, nm, nl);
+            p += nl;
+            *p++ = '\n';
+            memcpy(p, seq + reads[i].seq_off, reads[i].seq_len);
+            p += reads[i].seq_len;
+            *p++ = '\n';
+            if (fastq) {
+                *p++ = '+';
+                *p++ = '\n';
+                memcpy(p, qual + reads[i].seq_off, reads[i].seq_len);
+                p += reads[i].seq_len;
+                *p++ = '\n';
+            }
+        }
+    };
+    if (nt == 1 || n_reads < 64) {
+        work(0, n_reads);
+    } else {
+        std::vector<std::thread> th;
+        // split by bytes, not by reads, so threads carry equal copy volume
+        uint32_t lo = 0;
+        for (int t = 0; t < nt; ++t) {
+            uint64_t goal = off[n_reads] * (uint64_t)(t + 1) / nt;
+            uint32_t hi = (uint32_t)(std::upper_bound(off.begin(), off.end(), goal) - off.begin());
+            hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_reads);
+            if (t == nt - 1) hi = n_reads;
+            if (hi > lo) th.emplace_back(work, lo, hi);
+            lo = hi;
+        }
+        for (auto& x : th) x.join();
+    }
+    return (int64_t)off[n_reads];
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// Plan kernel: the per-read control flow of simulation_aligned_genome / simulation_unaligned
+// (/root/reference/src/simulator.py:1266-1454, 1482-1549) with error_list (:1833-1916) and
+// unaligned_error_list (:1784-1830) inside, run as a flattened per-lane state machine.
+//
+// One LANE owns one read at a time and fetches the next read from a global counter as soon as its read is
+// accepted (persistent threads), so lanes of a warp are always in the same hot phase (one error/match event
+// per loop iteration) regardless of how different their read lengths are.
+//
+// The kernel runs twice per batch with identical random streams:
+//   WRITE=false : counts ops / lengths, runs the rejection loops (:1367, :1429, :1503, :1517), draws positions
+//                 (extract_read :1750-1781) and fills NsReadMeta / NsPieceMeta;
+//   WRITE=true  : replays only the accepted attempt and writes the edit script (ops) at the exact offsets an
+//                 exclusive scan of the counts produced.
+#pragma once
+#include "device_common.cuh"
+
+struct PlanArgs {
+    DevModel m;
+    DevRef ref;
+    DevCfg cfg;
+    uint32_t kind;              // NS_KIND_*
+    uint64_t first_id;
+    uint32_t n_reads;
+    const uint32_t* n_seg;      // per read (nullptr => 1)
+    const uint32_t* piece_first;// per read (nullptr => read index)
+    NsReadMeta* reads;
+    NsPieceMeta* pieces;
+    uint32_t* ops;              // WRITE only
+    uint32_t* counter;          // work-fetch counter (zeroed before launch)
+};
+
+enum Phase : int { PH_FETCH = 0, PH_LEN, PH_ATT, PH_PIECE, PH_EVENT, PH_UEVENT, PH_PIECE_END, PH_CHECK, PH_DONE };
+
+template <bool WRITE>
+struct OpSink {
+    uint32_t* base;       // start of this piece's op slot (WRITE)
+    uint32_t n;           // ops emitted so far (flushed)
+    uint32_t pend_type;   // pending (mergeable) op
+    uint32_t pend_len;
+    uint32_t out_len;     // bases produced by flushed + pending ops
+    __device__ __forceinline__ void begin(uint32_t* slot) {
+        base = slot;
+        n = 0;
+        pend_type = 0xffffffffu;
+        pend_len = 0;
+        out_len = 0;
+    }
+    __device__ __forceinline__ void flush() {
+        if (pend_type != 0xffffffffu && pend_len > 0) {
+            if (WRITE) base[n] = (pend_type << 28) | pend_len;
+            ++n;
+        }
+        pend_type = 0xffffffffu;
+        pend_len = 0;
+    }
+    // merge == true: fold into the pending op when the type matches (used where event boundaries carry no meaning)
+    __device__ __forceinline__ void push(uint32_t type, uint32_t len, bool merge) {
+        if (len == 0) return;
+        if (type != NS_OP_DEL) out_len += len;
+        if (merge && type == pend_type) {
+            pend_len += len;
+            return;
+        }
+        flush();
+        pend_type = type;
+        pend_len = len;
+    }
+    // the reference's e_dict[pos - 0.5] overwrite: a second insertion at the same position replaces the first (:1882)
+    __device__ __forceinline__ void replace_pending_ins(uint32_t len) {
+        out_len -= pend_len;
+        pend_len = len;
+        out_len += len;
+    }
+};
+
+__device__ __forceinline__ uint32_t match_bin(const DevModel& m, uint32_t prev_match) {
+    uint32_t b = m.n_bins - 1;          // falls through to the last bin (:1891-1893)
+    for (uint32_t i = 0; i < m.n_bins; ++i) {
+        if (m.bin_lo[i] <= prev_match && prev_match < m.bin_hi[i]) {
+            b = i;
+            break;
+        }
+    }
+    return b;
+}
+
+// extract_read, genome branches (:1750-1781): uniform start over the concatenated genome, redrawn until the
+// segment fits inside one chromosome (linear) / wrap-around on the single chromosome (circular).
+__device__ __forceinline__ void draw_position(const DevRef& ref, const DevCfg& cfg, Rng& rng, uint32_t length,
+                                              uint32_t& chrom, uint32_t& pos) {
+    if (cfg.circular) {
+        chrom = 0;
+        pos = (uint32_t)__umul64hi(rng.next64(), ref.genome_len + 1);
+        return;
+    }
+    for (int iter = 0; iter < 100000; ++iter) {
+        uint64_t p = __umul64hi(rng.next64(), ref.genome_len + 1);
+        if (p >= ref.genome_len) continue;          // walks off the last chromosome -> redraw
+        uint32_t lo = 0, hi = ref.n_chrom;          // chrom_off[lo] <= p < chrom_off[hi]
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&ref.chrom_off[mid]) <= p) lo = mid; else hi = mid;
+        }
+        uint64_t off = p - __ldg(&ref.chrom_off[lo]);
+        uint64_t clen = __ldg(&ref.chrom_off[lo + 1]) - __ldg(&ref.chrom_off[lo]);
+        if (off + length <= clen && length > 0) {
+            chrom = lo;
+            pos = (uint32_t)off;
+            return;
+        }
+    }
+    chrom = 0;
+    pos = 0;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanArgs a) {
+    const DevModel& m = a.m;
+    const DevCfg& cfg = a.cfg;
+    const bool unal_kind = (a.kind == NS_KIND_UNALIGNED);
+
+    int phase = PH_FETCH;
+    uint32_t slot = 0;            // read index inside the batch
+    uint64_t rid = 0;             // global read id
+    uint32_t n_seg = 1, n_pieces = 1, piece_first = 0;
+    uint32_t attempt = 0, gen = 0;
+    Rng rng;                      // attempt stream
+    // attempt state
+    uint32_t remainder = 0, head = 0, tail = 0, reversed = 0;
+    uint64_t total = 0, actual = 0;
+    uint32_t p = 0;               // piece cursor
+    // chain state
+    uint32_t pos = 0, middle_ref = 0, prev_match = 0, err_state = 0, last_err = 3;
+    int64_t l_new = 0;
+    uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
+    bool last_op_was_ins_same_pos = false;
+    OpSink<WRITE> sink;
+    sink.begin(nullptr);
+
+    for (;;) {
+        switch (phase) {
+        case PH_FETCH: {
+            slot = atomicAdd(a.counter, 1u);
+            if (slot >= a.n_reads) {
+                phase = PH_DONE;
+                break;
+            }
+            rid = a.first_id + slot;
+            n_seg = a.n_seg ? a.n_seg[slot] : 1u;
+            piece_first = a.piece_first ? a.piece_first[slot] : slot;
+            n_pieces = unal_kind ? 1u : 2u * n_seg - 1u;
+            if (WRITE) {
+                attempt = a.reads[slot].attempts;
+                phase = PH_ATT;
+            } else {
+                attempt = 0;
+                gen = 0;
+                phase = unal_kind ? PH_ATT : PH_LEN;
+            }
+            break;
+        }
+        case PH_LEN: {   // aligned: ref_lengths / gap_lengths of generation `gen` (:1285-1299, :1309-1310)
+            Rng lr;
+            lr.init(cfg.seed, rid, stream_word(ST_LEN, a.kind, gen));
+            for (uint32_t s = 0; s < n_seg; ++s) {
+                uint32_t len = 0;
+                for (int it = 0; it < 100000; ++it) {
+                    double x = kde_draw(m.aligned, lr);
+                    bool ok = cfg.perfect ? (x >= (double)cfg.min_len && x <= (double)cfg.max_len)
+                                          : (x > 0.0 && x <= (double)cfg.max_len);
+                    // int(x) == 0 makes the reference's extract_read spin forever (:1767-1780); redraw instead
+                    if (ok && (uint32_t)x > 0) {
+                        len = (uint32_t)x;
+                        break;
+                    }
+                }
+                a.pieces[piece_first + 2 * s].ref_req = len;
+                if (s + 1 < n_seg) {
+                    double g = pow(10.0, kde_draw(m.gap, lr)) - 1.0;
+                    int64_t gi = (int64_t)g;
+                    a.pieces[piece_first + 2 * s + 1].ref_req = gi > 0 ? (uint32_t)gi : 0u;
+                }
+            }
+            phase = PH_ATT;
+            break;
+        }
+        case PH_ATT: {
+            rng.init(cfg.seed, rid, stream_word(ST_ATT, a.kind, attempt));
+            p = 0;
+            total = 0;
+            actual = 0;
+            if (unal_kind) {
+                // ref = int(kde_unaligned.sample()) (:1494-1499); <= 0 can never pass the min_l test (:1503)
+                double x = kde_draw(m.unaligned, rng);
+                int64_t r = (int64_t)x;
+                if (!WRITE) a.pieces[piece_first].ref_req = r > 0 ? (uint32_t)r : 0u;
+                head = tail = 0;
+                remainder = 0;
+                if (r <= 0 && !WRITE) {
+                    ++attempt;                      // rejected: middle_ref < min_l
+                    break;
+                }
+            } else if (cfg.perfect) {
+                head = tail = 0;
+                remainder = 0;
+                reversed = u01_double(rng.next64()) > (double)m.strandness;
+            } else {
+                // remainder = 10^x - 1 >= 0, ratio in [0,1] (:1456-1479), strand (:1312)
+                double rem = -1.0;
+                for (int it = 0; it < 100000 && rem < 0.0; ++it) rem = pow(10.0, kde_draw(m.ht, rng)) - 1.0;
+                double ratio = -1.0;
+                for (int it = 0; it < 100000 && (ratio < 0.0 || ratio > 1.0); ++it) ratio = kde_draw(m.ratio, rng);
+                remainder = (uint32_t)rem;
+                reversed = u01_double(rng.next64()) > (double)m.strandness;
+                if (remainder == 0) {
+                    head = tail = 0;
+                } else {
+                    head = (uint32_t)rint((double)remainder * ratio);     // Python round(): half to even (:1381)
+                    tail = remainder - head;
+                }
+                total = remainder;
+            }
+            phase = PH_PIECE;
+            break;
+        }
+        case PH_PIECE: {
+            NsPieceMeta& pm = a.pieces[piece_first + p];
+            uint32_t m_ref = pm.ref_req;
+            sink.begin(WRITE ? a.ops + pm.op_off : nullptr);
+            pos = 0;
+            middle_ref = m_ref;
+            l_new = (int64_t)m_ref;
+            pending_ins = 0;
+            last_op_was_ins_same_pos = false;
+            bool is_gap = unal_kind || (p & 1u);
+            if (!unal_kind && p == 0 && head > 0) sink.push(NS_OP_HT, head, false);
+            if (is_gap) {
+                phase = (m_ref == 0) ? PH_PIECE_END : PH_UEVENT;
+            } else if (cfg.perfect) {
+                sink.push(NS_OP_COPY, m_ref, false);
+                phase = PH_PIECE_END;
+            } else {
+                // first match from _first_match.hist, floor 2 (:1843-1850); no extension when it overshoots
+                uint32_t fm = alias_draw(m, 0, rng.next());
+                prev_match = fm;
+                err_state = 0;     // "start"
+                last_err = 3;
+                pos = fm;
+                sink.push(NS_OP_COPY, fm < middle_ref ? fm : middle_ref, false);
+                phase = (pos < middle_ref) ? PH_EVENT : PH_PIECE_END;
+            }
+            break;
+        }
+        case PH_EVENT: {   // one pass of the while-loop body of error_list (:1858-1914)
+            uint4 r = rng.next4();
+            // error type from the Markov chain keyed by prev_error[+"0"] (:1860-1864)
+            uint32_t e;
+            if (r.x < m.trans[err_state][0]) e = 1;
+            else if (r.x < m.trans[err_state][1]) e = 2;
+            else if (r.x >= m.trans[err_state][2]) e = 3;
+            else e = last_err;                        // dead gap of the (1-p_del, 1) interval: stale value
+            last_err = e;
+            uint32_t step = alias_draw(m, e, r.y);    // tables 1..3: mis / ins / del lengths (:1866-1873)
+            if (e == 2) {
+                l_new += step;
+                if (last_op_was_ins_same_pos) sink.replace_pending_ins(step);
+                else sink.push(NS_OP_INS, step, false);
+            } else {
+                if (e == 3) l_new -= step;
+                sink.push(e == 1 ? NS_OP_MIS : NS_OP_DEL, step, false);
+                pos += step;
+                if (pos >= middle_ref) {
+                    l_new += pos - middle_ref;
+                    middle_ref = pos;
+                }
+            }
+            // next match length given the previous one (:1891-1903)
+            uint32_t b = match_bin(m, prev_match);
+            uint32_t mt = alias_draw(m, 4 + b, r.z);
+            if (mt == m.tab_n[4 + b] - 1) mt = step;  // ECDF miss: `step` keeps the error length (:1895-1898)
+            if (prev_match == 0 && mt == 0) mt = 1;
+            prev_match = mt;
+            if (pos + mt > middle_ref) {
+                l_new += pos + mt - middle_ref;
+                middle_ref = pos + mt;
+            }
+            pos += mt;
+            sink.push(NS_OP_COPY, mt, false);
+            last_op_was_ins_same_pos = (e == 2 && mt == 0);
+            err_state = e + (mt == 0 ? 3u : 0u);      // prev_error += "0" (:1913-1914)
+            if (pos >= middle_ref) phase = PH_PIECE_END;
+            break;
+        }
+        case PH_UEVENT: {  // one pass of unaligned_error_list's loop (:1794-1828) + its effect in mutate_read
+            uint4 r = rng.next4();
+            // fixed type cdf 0.4 / 0.7 / 0.85 / 1 (:1787)
+            uint32_t kind_u = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
+            if (kind_u == 2) {                       // ins: merged at key pos+0.1 (:1808-1815)
+                uint32_t step = alias_draw(m, 2, r.y);
+                pending_ins += step;
+                l_new += step;
+                break;
+            }
+            // mutate_read applies keys right to left; ceil(pos+0.1) = pos+1 puts the insertion AFTER the first
+            // base of the step at `pos`, so a mis/del of length s at pos also eats min(a, s-1) inserted bases.
+            uint32_t a_ins = pending_ins;
+            pending_ins = 0;
+            uint32_t s;
+            if (kind_u == 0) {
+                s = 1;
+                sink.push(NS_OP_COPY, 1, true);
+                sink.push(NS_OP_INS, a_ins, true);
+            } else {
+                s = alias_draw(m, kind_u == 1 ? 1 : 3, r.y);
+                uint32_t covered = a_ins < s - 1 ? a_ins : s - 1;     // inserted bases inside [pos, pos+s)
+                uint32_t rest = (s - 1) - covered;                     // reference bases still hit after them
+                if (kind_u == 1) {
+                    sink.push(NS_OP_MIS, 1, true);
+                    sink.push(NS_OP_INS, a_ins, true);                 // re-randomised inserted bases stay random
+                    sink.push(NS_OP_MIS, rest, true);
+                    sink.push(NS_OP_COPY, covered, true);
+                } else {
+                    l_new -= s;
+                    sink.push(NS_OP_DEL, 1, true);
+                    sink.push(NS_OP_INS, a_ins - covered, true);
+                    sink.push(NS_OP_DEL, rest, true);
+                    sink.push(NS_OP_COPY, covered, true);
+                }
+            }
+            pos += s;
+            if (pos > middle_ref) {
+                l_new += pos - middle_ref;
+                middle_ref = pos;
+            }
+            if (pos >= middle_ref) phase = PH_PIECE_END;
+            break;
+        }
+        case PH_PIECE_END: {
+            NsPieceMeta& pm = a.pieces[piece_first + p];
+            bool is_gap = unal_kind || (p & 1u);
+            if (!unal_kind && p + 1 == n_pieces && tail > 0) sink.push(NS_OP_HT, tail, false);
+            sink.flush();
+            if (!WRITE) {
+                pm.n_ops = sink.n;
+                pm.read_slot = slot;
+                pm.kind = unal_kind ? NS_PIECE_UNALIGNED : (is_gap ? NS_PIECE_GAP : NS_PIECE_SEGMENT);
+                pm.ref_len = middle_ref;
+                pm.out_len = sink.out_len;
+                pm.out_rel = (uint32_t)actual;
+                pm.l_new = (uint32_t)(l_new < 0 ? 0 : l_new);
+            }
+            actual += sink.out_len;
+            if (!is_gap) total += (uint64_t)(l_new < 0 ? 0 : l_new);      // `total += middle` (:1362): segments only
+            ++p;
+            phase = (p < n_pieces) ? PH_PIECE : PH_CHECK;
+            break;
+        }
+        case PH_CHECK: {
+            if (WRITE) {
+                phase = PH_FETCH;
+                break;
+            }
+            bool ok1, ok2;
+            if (unal_kind) {
+                // :1503 middle_ref in range, :1517 len(read_mutated) in range
+                ok1 = middle_ref >= cfg.min_len && middle_ref <= cfg.max_len;
+                ok2 = actual >= cfg.min_len && actual <= cfg.max_len;
+                if (!(ok1 && ok2)) {
+                    ++attempt;
+                    phase = PH_ATT;
+                    break;
+                }
+                reversed = u01_double(rng.next64()) > (double)m.strandness;    // :1526-1527
+            } else if (cfg.perfect) {
+                ok2 = actual >= cfg.min_len && actual <= cfg.max_len;          // :1429
+                if (!ok2) {
+                    ++attempt;
+                    ++gen;
+                    phase = PH_LEN;
+                    break;
+                }
+            } else {
+                ok1 = total >= cfg.min_len && total <= cfg.max_len;            // :1367 keeps the ref lengths
+                if (!ok1) {
+                    ++attempt;
+                    phase = PH_ATT;
+                    break;
+                }
+                ok2 = actual >= cfg.min_len && actual <= cfg.max_len;          // :1429 consumes them
+                if (!ok2) {
+                    ++attempt;
+                    ++gen;
+                    phase = PH_LEN;
+                    break;
+                }
+            }
+            // accepted: positions (extract_read) for every piece, then the read record
+            Rng pr;
+            pr.init(cfg.seed, rid, stream_word(ST_POS, a.kind, attempt));
+            for (uint32_t q = 0; q < n_pieces; ++q) {
+                NsPieceMeta& pm = a.pieces[piece_first + q];
+                uint32_t chrom = 0, ppos = 0;
+                if (pm.ref_len > 0) draw_position(a.ref, cfg, pr, pm.ref_len, chrom, ppos);
+                pm.chrom = chrom;
+                pm.pos = ppos;
+            }
+            NsReadMeta rm;
+            rm.seq_off = 0;
+            rm.seq_len = (uint32_t)actual;
+            rm.head = head;
+            rm.tail = tail;
+            rm.piece_first = piece_first;
+            rm.n_pieces = (uint16_t)n_pieces;
+            rm.reversed = (uint8_t)reversed;
+            rm.flags = (uint8_t)((n_seg > 1) ? 2 : 0);
+            rm.attempts = attempt;
+            a.reads[slot] = rm;
+            phase = PH_FETCH;
+            break;
+        }
+        default:
+            break;
+        }
+        if (phase == PH_DONE) break;
+    }
+}
+
+// n_seg ~ Geometric(1/segment_mean) per read (:1276-1279), fixed across rejection retries.
+__global__ void segments_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t first_id, uint32_t n, uint32_t* n_seg,
+                                uint32_t* n_pieces) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng r;
+    r.init(cfg.seed, first_id + i, stream_word(ST_SEG, kind, 0));
+    double u = 1.0 - u01_double(r.next64());        // (0, 1]
+    uint32_t k = 1;
+    if (m.seg_p < 1.0) {
+        double v = ceil(log(u) / log1p(-m.seg_p));
+        k = v < 1.0 ? 1u : (v > (double)NS_MAX_SEGMENTS ? (uint32_t)NS_MAX_SEGMENTS : (uint32_t)v);
+    }
+    n_seg[i] = k;
+    n_pieces[i] = 2 * k - 1;
+}

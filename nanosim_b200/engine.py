@@ -1,0 +1,169 @@
+"""Thin object wrapper over the C ABI (one context == one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .model import DeviceTables
+
+
+class NanoSimError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Batch:
+    """Host copy of one simulated batch."""
+
+    def __init__(self, info, seq, qual, reads, pieces, ops, kind, first_id):
+        self.info, self.seq, self.qual, self.reads, self.pieces, self.ops = info, seq, qual, reads, pieces, ops
+        self.kind, self.first_id = kind, first_id
+
+    def read_seq(self, i):
+        r = self.reads[i]
+        o = int(r["seq_off"])
+        return self.seq[o:o + int(r["seq_len"])].tobytes().decode()
+
+    def read_qual(self, i):
+        r = self.reads[i]
+        o = int(r["seq_off"])
+        return self.qual[o:o + int(r["seq_len"])]
+
+
+class Engine:
+    def __init__(self, device=0, seed=0):
+        self._lib = L.lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.ns_create(int(device), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.byref(self._ctx))
+        if rc != 0:
+            raise NanoSimError("ns_create failed (rc=%d): no usable CUDA device %d?" % (rc, device))
+        self.device = device
+        self._keep = {}
+        self.fastq = False
+        self.info = None
+
+    def close(self):
+        if self._ctx:
+            self._lib.ns_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NanoSimError(self._lib.ns_last_error(self._ctx).decode() + " (rc=%d)" % rc)
+
+    # ---- read_profile()
+    def set_reference(self, ref):
+        """ref: PackedReference (host) -- or pass device pointers via set_reference_ptr."""
+        self.ref = ref
+        r = L.NsReference(_ptr(ref.bases), ref.genome_len, _ptr(ref.offsets), len(ref.names))
+        self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
+
+    def set_reference_ptr(self, bases_ptr, n_bases, offsets):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1)
+        self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
+
+    def set_model(self, t: DeviceTables, perfect=False):
+        m = L.NsModel()
+        keep = []
+
+        def kde(name):
+            if name not in t.kde:
+                return L.NsKde(None, 0, 0.0)
+            data, bw = t.kde[name]
+            d = np.ascontiguousarray(data.reshape(-1), dtype=np.float32)
+            keep.append(d)
+            return L.NsKde(_ptr(d), len(d), float(bw))
+
+        m.kde_aligned = kde("aligned_reads" if perfect else "aligned_region")
+        m.kde_ht = kde("ht_length")
+        m.kde_ht_ratio = kde("ht_ratio")
+        m.kde_unaligned = kde("unaligned_length")
+        m.kde_gap = kde("gap_length")
+        arrays = dict(prob=np.ascontiguousarray(t.alias_prob, dtype=np.uint32),
+                      idx=np.ascontiguousarray(t.alias_idx, dtype=np.uint32),
+                      desc=np.ascontiguousarray(t.alias_desc.reshape(-1), dtype=np.uint32),
+                      lo=np.ascontiguousarray(t.match_bin_lo, dtype=np.uint32),
+                      hi=np.ascontiguousarray(t.match_bin_hi, dtype=np.uint32))
+        keep.append(arrays)
+        m.alias_prob, m.alias_idx, m.alias_desc = _ptr(arrays["prob"]), _ptr(arrays["idx"]), _ptr(arrays["desc"])
+        m.n_tables, m.alias_len = len(t.alias_desc), len(arrays["prob"])
+        m.match_bin_lo, m.match_bin_hi, m.n_match_bins = _ptr(arrays["lo"]), _ptr(arrays["hi"]), len(arrays["lo"])
+        m.has_qual = 1 if t.has_qual else 0
+        for i in range(L.NS_N_ERR_STATES):
+            for j in range(3):
+                m.trans[i][j] = int(t.trans[i, j])
+        for i in range(L.NS_N_QUAL_STATES):
+            for j in range(L.NS_QUAL_SLOTS):
+                m.qual_cdf[i][j] = int(t.qual_cdf[i, j])
+        for i in range(2):
+            for j in range(6):
+                m.hp[i][j] = float(t.hp[i, j])
+        m.hp_mis_rate = float(t.hp_mis_rate)
+        m.has_hp = 1 if t.has_hp else 0
+        m.strandness_rate = float(t.strandness)
+        m.segment_mean = float(t.segment_mean)
+        m.mean_ref_per_event = float(t.mean_ref_per_event)
+        self._check(self._lib.ns_set_model(self._ctx, C.byref(m)))
+        self.tables = t
+
+    def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
+                  max_len=None, median_len=0.0, sd_len=0.0):
+        if max_len is None or max_len == float("inf"):
+            max_len = 0x0fffffff
+        cfg = L.NsRunConfig(0, int(circular), int(perfect), int(fastq), int(chimeric), int(kmer_bias or 0),
+                            int(min_len), int(min(max_len, 0x0fffffff)), float(median_len or 0.0), float(sd_len or 0.0))
+        self._check(self._lib.ns_configure(self._ctx, C.byref(cfg)))
+        self.fastq = bool(fastq)
+
+    # ---- simulation workers
+    def simulate(self, kind, first_id, n_reads):
+        info = L.NsBatchInfo()
+        self._check(self._lib.ns_simulate(self._ctx, int(kind), C.c_uint64(int(first_id)), int(n_reads), C.byref(info)))
+        self.info = info
+        self._kind, self._first = kind, first_id
+        return info
+
+    def fetch(self, want_ops=False, want_pieces=True):
+        info = self.info
+        seq = np.empty(int(info.seq_bytes), dtype=np.uint8)
+        qual = np.empty(int(info.seq_bytes), dtype=np.uint8) if self.fastq else None
+        reads = np.empty(int(info.n_reads), dtype=L.READ_DTYPE)
+        pieces = np.empty(int(info.n_pieces), dtype=L.PIECE_DTYPE) if want_pieces else None
+        ops = np.empty(int(info.n_ops), dtype=np.uint32) if want_ops else None
+        self._check(self._lib.ns_fetch(self._ctx, _ptr(seq), _ptr(qual), _ptr(reads), _ptr(pieces), _ptr(ops)))
+        return Batch(info, seq, qual, reads, pieces, ops, self._kind, self._first)
+
+    def fetch_into(self, seq_ptr, qual_ptr, reads_ptr, pieces_ptr=None, ops_ptr=None):
+        """Raw-pointer variant for pinned buffers owned by the caller."""
+        def vp(x):
+            return C.c_void_p(int(x)) if x else None
+        self._check(self._lib.ns_fetch(self._ctx, vp(seq_ptr), vp(qual_ptr), vp(reads_ptr), vp(pieces_ptr), vp(ops_ptr)))
+
+    def device_buffers(self):
+        ps = [C.c_void_p() for _ in range(5)]
+        self._check(self._lib.ns_device_buffers(self._ctx, *[C.byref(p) for p in ps]))
+        return dict(zip(("seq", "qual", "reads", "pieces", "ops"), (p.value for p in ps)))
+
+    def op_stats(self):
+        out = np.zeros(L.NS_STATS_WORDS, dtype=np.uint64)
+        self._check(self._lib.ns_op_stats(self._ctx, _ptr(out)))
+        ev, run = L.NS_STATS_EV_CAP + 1, L.NS_STATS_RUN_CAP + 1
+        o = out.astype(np.int64)
+        d = {"n_segments": int(o[0]), "ref_bases": int(o[1]), "segment_out_bases": int(o[2]), "ht_bases": int(o[3]),
+             "n_gaps": int(o[4]), "gap_bases": int(o[5]), "n_events": int(o[6]),
+             "events": {"mis": int(o[8]), "ins": int(o[9]), "del": int(o[10])},
+             "event_bases": {"mis": int(o[11]), "ins": int(o[12]), "del": int(o[13])},
+             "ev_len": {k: o[16 + i * ev: 16 + (i + 1) * ev].copy() for i, k in enumerate(("mis", "ins", "del"))},
+             "match_run": o[16 + 3 * ev: 16 + 3 * ev + run].copy(),
+             "first_match": o[16 + 3 * ev + run: 16 + 3 * ev + 2 * run].copy()}
+        return d

@@ -1,0 +1,112 @@
+"""Host-side text formatting of a fetched batch: read names, FASTA/FASTQ records, error-profile rows.
+
+Formats follow the reference exactly:
+  aligned   {chrom}_{pos}[;{chrom}_{pos}...]_aligned_{idx}[_chimeric]_{F|R}_{head}_{seg[;seg...]}_{tail}
+            (/root/reference/src/simulator.py:1390-1402)
+  perfect   {chrom}_{pos}_perfect_{idx}_{F|R}_0_{len}_0                                   (:1332-1343)
+  unaligned {chrom}_{pos}_unaligned_{idx}_{F|R}_0_{middle_ref}_0                          (:1511, :1529-1534)
+  records   '@'|'>' name, sequence, ['+', chr(q+33)...]                                   (:1437-1443)
+  errors    Seq_name Seq_pos error_type error_length ref_base seq_base, right to left      (:1634, :2006-2008)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in (("A", "T"), ("C", "G")):
+    _COMP[ord(_a)], _COMP[ord(_b)] = ord(_b), ord(_a)
+
+
+def read_names(batch, ref_names, index_base, perfect=False):
+    """index_base: value of the reference's shared ``total_simulated`` counter for the batch's first read."""
+    reads, pieces = batch.reads, batch.pieces
+    names = []
+    unaligned = batch.kind == L.NS_KIND_UNALIGNED
+    for i in range(len(reads)):
+        r = reads[i]
+        p0, npc = int(r["piece_first"]), int(r["n_pieces"])
+        strand = "R" if r["reversed"] else "F"
+        idx = index_base + i
+        if unaligned:
+            pc = pieces[p0]
+            names.append("%s_%d_unaligned_%d_%s_0_%d_0" % (ref_names[pc["chrom"]], pc["pos"], idx, strand, pc["ref_len"]))
+            continue
+        segs = [pieces[p0 + k] for k in range(0, npc, 2)]
+        if perfect:
+            loc = "".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
+            names.append("%s_perfect_%d_%s_0_%d_0" % (loc, idx, strand, sum(int(s["ref_len"]) for s in segs)))
+            continue
+        loc = ";".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
+        nm = "%s_aligned_%d" % (loc, idx)
+        if len(segs) > 1:
+            nm += "_chimeric"
+        nm += "_%s_%d_%s_%d" % (strand, r["head"], ";".join(str(int(s["ref_len"])) for s in segs), r["tail"])
+        names.append(nm)
+    return names
+
+
+def format_records(batch, names, fastq, n_threads=8):
+    """FASTA/FASTQ text of the batch via the library's multi-threaded formatter -> bytes."""
+    lib = L.lib()
+    blob = ("\0".join(names) + "\0").encode()
+    offs = np.zeros(len(names), dtype=np.uint64)
+    pos = 0
+    for i, nm in enumerate(names):
+        offs[i] = pos
+        pos += len(nm.encode()) + 1
+    reads = np.ascontiguousarray(batch.reads)
+    qual_ptr = batch.qual.ctypes.data_as(C.c_void_p) if fastq else None
+    need = lib.ns_format_records(batch.seq.ctypes.data_as(C.c_void_p), qual_ptr, reads.ctypes.data_as(C.c_void_p),
+                                 len(names), blob, offs.ctypes.data_as(C.c_void_p), int(fastq), None, 0, n_threads)
+    if need < 0:
+        raise RuntimeError("ns_format_records failed: %d" % need)
+    out = np.empty(int(need), dtype=np.uint8)
+    got = lib.ns_format_records(batch.seq.ctypes.data_as(C.c_void_p), qual_ptr, reads.ctypes.data_as(C.c_void_p),
+                                len(names), blob, offs.ctypes.data_as(C.c_void_p), int(fastq),
+                                out.ctypes.data_as(C.c_void_p), int(need), n_threads)
+    if got != need:
+        raise RuntimeError("ns_format_records failed: %d" % got)
+    return out.tobytes()
+
+
+def error_profile_rows(batch, names, ref):
+    """The rows mutate_read logs for every aligned segment (needs batch.ops).  ``ref`` is the PackedReference.
+    Reference bases are shown upper-cased as stored (an IUPAC code is shown as the code itself)."""
+    rows = []
+    reads, pieces, ops_all = batch.reads, batch.pieces, batch.ops
+    ref_off = ref.offsets.astype(np.int64)
+    for i in range(len(reads)):
+        r = reads[i]
+        L_read = int(r["seq_len"])
+        so = int(r["seq_off"])
+        fwd = batch.seq[so:so + L_read]
+        if r["reversed"]:
+            fwd = _COMP[fwd[::-1]]
+        p0, npc = int(r["piece_first"]), int(r["n_pieces"])
+        for k in range(0, npc, 2):
+            pc = pieces[p0 + k]
+            if pc["kind"] != L.NS_PIECE_SEGMENT:
+                continue
+            ops = ops_all[int(pc["op_off"]): int(pc["op_off"]) + int(pc["n_ops"])]
+            ty = (ops >> 28).astype(np.int64)
+            ln = (ops & 0x0fffffff).astype(np.int64)
+            out_adv = np.where(ty == L.NS_OP_DEL, 0, ln)
+            ref_adv = np.where((ty == L.NS_OP_INS) | (ty == L.NS_OP_HT), 0, ln)
+            out_start = int(pc["out_rel"]) + np.concatenate([[0], np.cumsum(out_adv)[:-1]])
+            ref_start = np.concatenate([[0], np.cumsum(ref_adv)[:-1]])
+            cstart, clen = int(ref_off[pc["chrom"]]), int(ref_off[pc["chrom"] + 1] - ref_off[pc["chrom"]])
+            base = int(pc["pos"])
+            seg_rows = []
+            for j in np.nonzero((ty >= 1) & (ty <= 3))[0]:
+                t, n, rs, os_ = int(ty[j]), int(ln[j]), int(ref_start[j]), int(out_start[j])
+                if t == L.NS_OP_INS:
+                    refb = "-" * n
+                else:
+                    idx = (base + rs + np.arange(n)) % clen if base + rs + n > clen else np.arange(base + rs, base + rs + n)
+                    refb = ref.bases[cstart + idx].tobytes().decode().upper()
+                seqb = "-" * n if t == L.NS_OP_DEL else fwd[os_:os_ + n].tobytes().decode()
+                seg_rows.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (names[i], rs, ("mis", "ins", "del")[t - 1], n, refb, seqb))
+            rows.extend(reversed(seg_rows))
+    return rows

@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Drop-in driver for the simulation stage: ``simulator.py genome ...`` with the reference's command line
+(/root/reference/src/simulator.py:2070-2531) and output files (``<out>_aligned_reads.{fasta,fastq}``,
+``<out>_aligned_error_profile``, ``<out>_unaligned_reads.{fasta,fastq}``), the per-read work done by the CUDA
+library through the C ABI.
+
+read_profile() / simulation() keep the reference's names and argument meaning:
+  read_profile  -> loads the FASTA and the model directory, compiles the model tables and uploads both to HBM once;
+  simulation    -> the orchestrator (:1571-1672): instead of forking ``num_threads`` workers that each loop over reads
+                   it launches batches on the GPU; with torchrun (WORLD_SIZE>1) every rank simulates its contiguous
+                   shard of read ids and rank 0 concatenates the per-rank sub-files in rank order, exactly like the
+                   reference concatenates its per-worker sub-files (:1626-1639).
+"""
+import argparse
+import os
+import sys
+from textwrap import dedent
+from time import strftime
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+from .model import DeviceTables, load_model
+from .records import error_profile_rows, format_records, read_names
+from .reference_fasta import PackedReference
+
+VERSION = "3.2.2-b200"
+
+
+def _log(msg):
+    sys.stdout.write(strftime("%Y-%m-%d %H:%M:%S") + ": " + msg + "\n")
+    sys.stdout.flush()
+
+
+class Profile:
+    """What read_profile() leaves in module globals in the reference."""
+
+    def __init__(self):
+        self.ref = None
+        self.tables = None
+        self.engine = None
+        self.number_aligned = 0
+        self.number_unaligned = 0
+        self.max_chrom = 0
+        self.perfect = False
+
+
+def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
+                 polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
+                 device=0, seed=0):
+    if mode != "genome":
+        sys.stderr.write("nanosim_b200: only genome mode is implemented in this build\n")
+        sys.exit(1)
+    prof = Profile()
+    _log("Read in reference ")
+    prof.ref = PackedReference.from_fasta(ref_g)
+    prof.max_chrom = prof.ref.max_chrom
+    if len(prof.ref.names) > 1 and dna_type == "circular":
+        sys.stderr.write("Do not choose circular if there is more than one chromosome in the genome!\n")
+        sys.exit(1)
+    _log("Read error profile")
+    cm = load_model(model_prefix)
+    prof.tables = DeviceTables(cm, fastq=fastq, homopolymer=homopolymer, chimeric=chimeric, perfect=per,
+                               strandness=strandness, mode=mode)
+    prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number_list[0], per)
+    prof.perfect = per
+    _log("Read KDF of aligned reads")
+    prof.engine = Engine(device=device, seed=seed)
+    prof.engine.set_reference(prof.ref)
+    prof.engine.set_model(prof.tables, perfect=per)
+    return prof
+
+
+def _shard(n, rank, world):
+    per = n // world
+    lo = rank * per
+    hi = n if rank == world - 1 else lo + per        # remainder goes to the last worker (:1597-1598)
+    return lo, hi
+
+
+def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min_l, num_threads, fastq,
+               median_l=None, sd_l=None, model_ir=False, uracil=False, polya=None, chimeric=False,
+               batch_reads=65536, error_profile=True, rank=0, world=1):
+    eng = prof.engine
+    eng.configure(circular=(dna_type == "circular"), perfect=per, fastq=fastq, chimeric=chimeric,
+                  kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0)
+    ext = ".fastq" if fastq else ".fasta"
+    suffix = "" if world == 1 else str(rank)
+    _log("Start simulation of aligned reads")
+    lo, hi = _shard(prof.number_aligned, rank, world)
+    with open(out + "_aligned_reads" + suffix + ext, "wb") as f_reads, \
+            open(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix), "w") as f_err:
+        if world == 1:
+            f_err.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+        for start in range(lo, hi, batch_reads):
+            n = min(batch_reads, hi - start)
+            eng.simulate(L.NS_KIND_ALIGNED, start, n)
+            b = eng.fetch(want_ops=error_profile and not per)
+            names = read_names(b, prof.ref.names, start, perfect=per)
+            f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
+            if error_profile and not per:
+                f_err.writelines(error_profile_rows(b, names, prof.ref))
+    if not per:
+        _log("Start simulation of random reads")
+        lo, hi = _shard(prof.number_unaligned, rank, world)
+        with open(out + "_unaligned_reads" + suffix + ext, "wb") as f_reads:
+            for start in range(lo, hi, batch_reads):
+                n = min(batch_reads, hi - start)
+                eng.simulate(L.NS_KIND_UNALIGNED, start, n)
+                b = eng.fetch()
+                # the reference's read index keeps counting after the aligned reads (shared total_simulated, :1574)
+                names = read_names(b, prof.ref.names, prof.number_aligned + start)
+                f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
+
+
+def merge_rank_files(out, fastq, per, world):
+    """Rank 0: concatenate per-rank sub-files in rank order and delete them (:1626-1639, :1667-1672)."""
+    ext = ".fastq" if fastq else ".fasta"
+    jobs = [("_aligned_reads%d" + ext, "_aligned_reads" + ext, None)]
+    jobs.append(("_error_profile%d", "_aligned_error_profile", "Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n"))
+    if not per:
+        jobs.append(("_unaligned_reads%d" + ext, "_unaligned_reads" + ext, None))
+    for pat, dst, header in jobs:
+        with open(out + dst, "wb") as o:
+            if header:
+                o.write(header.encode())
+            for r in range(world):
+                p = out + (pat % r)
+                with open(p, "rb") as i:
+                    while True:
+                        blk = i.read(1 << 24)
+                        if not blk:
+                            break
+                        o.write(blk)
+                os.remove(p)
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(
+        description=dedent('''
+        Simulation step
+        -----------------------------------------------------------
+        Given error profiles, reference genome, metagenome,
+        and/or transcriptome, simulate ONT DNA or RNA reads
+        '''), formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument('-v', '--version', action='version', version='NanoSim ' + VERSION)
+    sub = parser.add_subparsers(help="You may run the simulator on genome, transcriptome, or metagenome mode.", dest='mode')
+    g = sub.add_parser('genome', help="Run the simulator on genome mode")
+    g.add_argument('-rg', '--ref_g', help='Input reference genome', required=True)
+    g.add_argument('-c', '--model_prefix', help='Location and prefix of error profiles generated from '
+                   'characterization step (Default = training)', default="training")
+    g.add_argument('-o', '--output', help='Output location and prefix for simulated reads (Default = simulated)',
+                   default="simulated")
+    g.add_argument('-n', '--number', help='Number of reads to be simulated (Default = 20000)', type=int, default=20000)
+    g.add_argument('-x', '--coverage', help='Coverage of the simulated reads, overrides the number of reads', type=float,
+                   default=None)
+    g.add_argument('-max', '--max_len', help='The maximum length for simulated reads (Default = Infinity)', type=int,
+                   default=float("inf"))
+    g.add_argument('-min', '--min_len', help='The minimum length for simulated reads (Default = 50)', type=int, default=50)
+    g.add_argument('-med', '--median_len', help='The median read length (Default = None)', type=int, default=None)
+    g.add_argument('-sd', '--sd_len', help='The standard deviation of read length in log scale (Default = None)',
+                   type=float, default=None)
+    g.add_argument('--seed', help='Manually seeds the pseudo-random number generator', type=int, default=None)
+    g.add_argument('-hp', '--homopolymer', help='Simulate homopolymer lengths (Default = False)', action='store_true',
+                   default=False)
+    g.add_argument('-k', '--KmerBias', help='Minimum homopolymer length to simulate homopolymer contraction and '
+                   'expansion events in, a typical k is 5', type=int, default=None)
+    g.add_argument('-s', '--strandness', help='Proportion of sense sequences. Overrides the value profiled in '
+                   'characterization stage. Should be between 0 and 1', type=float, default=None)
+    g.add_argument('-dna_type', help='Specify the dna type: circular OR linear (Default = linear)',
+                   choices=["linear", "circular"], default="linear")
+    g.add_argument('--perfect', help='Ignore error profiles and simulate perfect reads', action='store_true', default=False)
+    g.add_argument('--fastq', help='Output fastq files instead of fasta files', action='store_true', default=False)
+    g.add_argument('--chimeric', help='Simulate chimeric reads', action='store_true', default=False)
+    g.add_argument('-t', '--num_threads', help='Number of host threads used for record formatting (Default = 1)',
+                   type=int, default=1)
+    # additions of this build
+    g.add_argument('--batch_reads', help='Reads simulated per GPU batch (Default = 65536)', type=int, default=65536)
+    g.add_argument('--no_error_profile', help='Skip writing <out>_aligned_error_profile', action='store_true', default=False)
+    g.add_argument('--device', help='CUDA device index (Default = LOCAL_RANK or 0)', type=int, default=None)
+    for name in ("transcriptome", "metagenome"):
+        sub.add_parser(name, help="Not implemented in this build", add_help=False)
+    return parser, g
+
+
+def coverage_to_reads(prof, cm, coverage):
+    """calculate_read_number_from_coverage (:2024-2068).  The reference estimates the mean read length from 10M KDE
+    samples; gaussian kernel noise has zero mean, so the estimate equals the weighted mean of the training samples."""
+    rate = prof.tables.aligned_ratio
+    w_al = rate / (rate + 1) if rate is not None else 1.0
+    mean = w_al * cm.kde["aligned_reads"][0].mean()
+    if "unaligned_length" in cm.kde:
+        mean += (1 - w_al) * cm.kde["unaligned_length"][0].mean()
+    return int(prof.ref.genome_len / mean * coverage)
+
+
+def main(argv=None):
+    parser, parser_g = build_parser()
+    args = parser.parse_args(argv)
+    if args.mode is None:
+        parser.print_help(sys.stderr)
+        sys.exit(1)
+    if args.mode != "genome":
+        sys.stderr.write("nanosim_b200: %s mode is not implemented in this build (genome only)\n" % args.mode)
+        sys.exit(1)
+    number = [args.number]
+    max_len, min_len = args.max_len, args.min_len
+    if args.homopolymer and (args.KmerBias is None or args.KmerBias < 0):
+        print("\nPlease input proper kmer bias value >= 0 to simulate homopolymer contraction and expansion events from\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+    if args.strandness and (args.strandness < 0 or args.strandness > 1):
+        print("\nPlease input proper strandness value between 0 and 1\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+    if (args.median_len and not args.sd_len) or (args.sd_len and not args.median_len):
+        sys.stderr.write("\nPlease provide both mean and standard deviation of read length!\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+    if args.median_len and args.sd_len and args.chimeric:
+        sys.stderr.write("\nLognormal distributed reads cannot be chimeric!\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+    if max_len < min_len:
+        sys.stderr.write("\nMaximum read length must be longer than Minimum read length!\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+    if args.perfect and args.chimeric:
+        print("\nPerfect reads cannot be chimeric\n")
+        parser_g.print_help(sys.stderr)
+        sys.exit(1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    _log(' '.join(sys.argv))
+    dir_name = os.path.dirname(args.output)
+    if dir_name != '':
+        os.makedirs(dir_name, exist_ok=True)
+
+    prof = read_profile(args.ref_g, number, args.model_prefix, args.perfect, args.mode, args.strandness,
+                        dna_type=args.dna_type, chimeric=args.chimeric, homopolymer=args.homopolymer, fastq=args.fastq,
+                        device=device, seed=args.seed or 0)
+    if args.coverage is not None:
+        number[0] = coverage_to_reads(prof, prof.tables.cm, args.coverage)
+        prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number[0], args.perfect)
+    max_len = min(max_len, prof.max_chrom)
+    simulation(prof, args.mode, args.output, args.dna_type, args.perfect, args.KmerBias if args.homopolymer else None,
+               None, max_len, min_len, max(args.num_threads, 1), args.fastq, args.median_len, args.sd_len,
+               chimeric=args.chimeric, batch_reads=args.batch_reads, error_profile=not args.no_error_profile,
+               rank=rank, world=world)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        dist.barrier()
+        if rank == 0:
+            merge_rank_files(args.output, args.fastq, args.perfect, world)
+        dist.barrier()
+    _log("Finished!")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,375 @@
+"""Shared parity machinery for the GPU tests, __graft_entry__.smoke() and bench.py (test infrastructure).
+
+  * check_edit_scripts : bit-exact.  Re-applies every piece's edit script to the reference on the host with
+    mutate_read's semantics (/root/reference/src/simulator.py:1957-2015) and requires the device's bases to agree.
+  * batch_stats        : the tests/run_stats.py histograms computed from a fetched device batch, so that device
+    output, oracle output and the unmodified reference's output are compared with the same code.
+  * compare_stats      : relative-rate and chi-square comparisons.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import run_stats as rs  # noqa: E402
+
+DATA = os.path.join(ROOT, "nanosim_b200", "data")
+MODELS = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz"}
+
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in (("A", "T"), ("C", "G")):
+    _COMP[ord(_a)], _COMP[ord(_b)] = ord(_b), ord(_a)
+_UPPER = np.arange(256, dtype=np.uint8)
+_UPPER[ord("a"):ord("z") + 1] -= 32
+_IS_ACGT = np.zeros(256, dtype=bool)
+_IS_ACGT[[65, 67, 71, 84]] = True
+_IUPAC = {"Y": "CT", "R": "AG", "W": "AT", "S": "GC", "K": "TG", "M": "CA", "D": "AGT", "V": "ACG", "H": "ACT",
+          "B": "CGT", "N": "ATCG", "X": "ATCG"}
+_MEMBER = np.zeros((256, 256), dtype=bool)     # _MEMBER[ref_code, base]
+for _c in "ACGT":
+    _MEMBER[ord(_c), ord(_c)] = True
+for _k, _v in _IUPAC.items():
+    for _c in _v:
+        _MEMBER[ord(_k), ord(_c)] = True
+_BIDX = np.full(256, -1, dtype=np.int64)
+for _i, _c in enumerate("ACGT"):
+    _BIDX[ord(_c)] = _i
+
+
+def load_tables(model, **kw):
+    from nanosim_b200.model import CompiledModel, DeviceTables
+
+    cm = CompiledModel.load(os.path.join(DATA, MODELS[model]))
+    return cm, DeviceTables(cm, **kw)
+
+
+def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, min_len=50, max_len=None, circular=False,
+                device=0):
+    from nanosim_b200.engine import Engine
+
+    cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect)
+    eng = Engine(device=device, seed=seed)
+    eng.set_reference(ref)
+    eng.set_model(t, perfect=perfect)
+    eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
+                  max_len=min(max_len or ref.max_chrom, ref.max_chrom))
+    return eng, cm, t
+
+
+def _piece_layout(batch, pc):
+    ops = batch.ops[int(pc["op_off"]): int(pc["op_off"]) + int(pc["n_ops"])]
+    ty = (ops >> 28).astype(np.int64)
+    ln = (ops & 0x0fffffff).astype(np.int64)
+    out_adv = np.where(ty == 3, 0, ln)
+    ref_adv = np.where((ty == 2) | (ty == 4), 0, ln)
+    out_start = np.concatenate([[0], np.cumsum(out_adv)[:-1]]) if len(ops) else np.zeros(0, dtype=np.int64)
+    ref_start = np.concatenate([[0], np.cumsum(ref_adv)[:-1]]) if len(ops) else np.zeros(0, dtype=np.int64)
+    return ty, ln, out_adv, ref_adv, out_start, ref_start
+
+
+def check_edit_scripts(batch, ref, fastq, max_reads=None):
+    """Bit-exact structural check of one fetched batch (needs ops + pieces).  Returns number of bases verified."""
+    reads, pieces = batch.reads, batch.pieces
+    ref_off = ref.offsets.astype(np.int64)
+    verified = 0
+    n = len(reads) if max_reads is None else min(len(reads), max_reads)
+    for i in range(n):
+        r = reads[i]
+        Lr, so = int(r["seq_len"]), int(r["seq_off"])
+        assert so % 16 == 0
+        raw = batch.seq[so:so + Lr]
+        fwd = _COMP[raw[::-1]] if r["reversed"] else raw
+        assert _IS_ACGT[fwd].all(), "non-ACGT base in read %d" % i
+        if fastq:
+            q = batch.qual[so:so + Lr]
+            assert q.min() >= 33 + 1 and q.max() <= 33 + 93, "quality out of [1,93] in read %d" % i
+        p0, npc = int(r["piece_first"]), int(r["n_pieces"])
+        cursor = 0
+        for k in range(npc):
+            pc = pieces[p0 + k]
+            assert int(pc["read_slot"]) == i
+            assert int(pc["out_rel"]) == cursor
+            ty, ln, out_adv, ref_adv, out_start, ref_start = _piece_layout(batch, pc)
+            assert int(out_adv.sum()) == int(pc["out_len"])
+            assert int(ref_adv.sum()) == int(pc["ref_len"])
+            assert (ln > 0).all()
+            if k == 0 and int(r["head"]) > 0:
+                assert ty[0] == 4 and ln[0] == int(r["head"])
+            if k == npc - 1 and int(r["tail"]) > 0:
+                assert ty[-1] == 4 and ln[-1] == int(r["tail"])
+            cstart, clen = int(ref_off[pc["chrom"]]), int(ref_off[pc["chrom"] + 1] - ref_off[pc["chrom"]])
+            if int(pc["ref_len"]) > 0:
+                assert int(pc["pos"]) + int(pc["ref_len"]) <= clen or clen == ref.genome_len, "segment leaves its chromosome"
+            seg = fwd[cursor:cursor + int(pc["out_len"])]
+            use = (ty == 0) | (ty == 1)
+            if use.any():
+                per_ty = np.repeat(ty[use], ln[use])
+                ridx = np.repeat(ref_start[use], ln[use]) + (np.arange(int(ln[use].sum())) - np.repeat(np.cumsum(ln[use]) - ln[use], ln[use]))
+                oidx = np.repeat(out_start[use], ln[use]) + (np.arange(int(ln[use].sum())) - np.repeat(np.cumsum(ln[use]) - ln[use], ln[use]))
+                rb = _UPPER[ref.bases[cstart + (int(pc["pos"]) + ridx) % clen]]
+                ob = seg[oidx]
+                cp = per_ty == 0
+                assert _MEMBER[rb[cp], ob[cp]].all(), "copied base differs from the reference (read %d piece %d)" % (i, k)
+                ms = (per_ty == 1) & _IS_ACGT[rb]
+                assert (rb[ms] != ob[ms]).all(), "substituted base equals the reference base (read %d)" % i
+                verified += len(ridx)
+            cursor += int(pc["out_len"])
+        assert cursor == Lr
+    return verified
+
+
+def batch_stats(batch, ref, fastq, s=None):
+    """tests/run_stats.py statistics from a fetched device batch (needs ops for aligned batches)."""
+    from nanosim_b200 import _lib as L
+
+    s = s or rs.empty()
+    reads, pieces = batch.reads, batch.pieces
+    ref_off = ref.offsets.astype(np.int64)
+    aligned = batch.kind == L.NS_KIND_ALIGNED
+    qa = np.zeros(256, dtype=np.int64)
+    qh = np.zeros(256, dtype=np.int64)
+    comp = np.zeros(256, dtype=np.int64)
+    for i in range(len(reads)):
+        r = reads[i]
+        Lr, so = int(r["seq_len"]), int(r["seq_off"])
+        raw = batch.seq[so:so + Lr]
+        if not aligned:
+            s["n_unaligned"] += 1
+            s["unaligned_bases"] += Lr
+            s["strand_R_unaligned"] += int(r["reversed"])
+            s["len_unaligned"][rs._bin(rs.LEN_EDGES, Lr)] += 1
+            if fastq:
+                qa += np.bincount(batch.qual[so:so + Lr], minlength=256)
+            continue
+        head, tail = int(r["head"]), int(r["tail"])
+        p0, npc = int(r["piece_first"]), int(r["n_pieces"])
+        segs = [pieces[p0 + k] for k in range(0, npc, 2)]
+        s["n_aligned"] += 1
+        s["aligned_bases"] += Lr
+        s["ref_bases"] += sum(int(x["ref_len"]) for x in segs)
+        s["head_bases"] += head
+        s["tail_bases"] += tail
+        s["strand_R_aligned"] += int(r["reversed"])
+        s["n_chimeric"] += len(segs) > 1
+        s["n_segments"] += len(segs)
+        s["len_aligned"][rs._bin(rs.LEN_EDGES, Lr)] += 1
+        for x in segs:
+            s["len_middle_ref"][rs._bin(rs.LEN_EDGES, int(x["ref_len"]))] += 1
+        s["len_head"][rs._bin(rs.HT_EDGES, head)] += 1
+        s["len_tail"][rs._bin(rs.HT_EDGES, tail)] += 1
+        comp += np.bincount(raw, minlength=256)
+        if fastq:
+            qq = batch.qual[so:so + Lr]
+            lead, trail = (tail, head) if r["reversed"] else (head, tail)
+            qh += np.bincount(qq[:lead], minlength=256) + np.bincount(qq[Lr - trail:] if trail else qq[:0], minlength=256)
+            qa += np.bincount(qq[lead:Lr - trail], minlength=256)
+        if batch.ops is None:
+            continue
+        fwd = _COMP[raw[::-1]] if r["reversed"] else raw
+        for pc in segs:
+            ty, ln, out_adv, ref_adv, out_start, ref_start = _piece_layout(batch, pc)
+            ev = np.nonzero((ty >= 1) & (ty <= 3))[0]
+            if len(ev) == 0:
+                continue
+            s["events_per_read"][rs._bin(rs.EPR_EDGES, len(ev))] += 1
+            cstart = int(ref_off[pc["chrom"]])
+            clen = int(ref_off[pc["chrom"] + 1]) - cstart
+            cur = 0
+            first = True
+            for j in ev:
+                t, n, rp = int(ty[j]), int(ln[j]), int(ref_start[j])
+                name = ("mis", "ins", "del")[t - 1]
+                s["events"][name] += 1
+                s["event_bases"][name] += n
+                s["ev_len"][name][min(n, rs.EV_CAP)] += 1
+                run = rp - cur
+                (s["first_match"] if first else s["match_run"])[min(run, rs.RUN_CAP)] += 1
+                first = False
+                cur = rp + (n if t != 2 else 0)
+                if t == 1 and n == 1:
+                    a = _BIDX[_UPPER[ref.bases[cstart + (int(pc["pos"]) + rp) % clen]]]
+                    b = _BIDX[fwd[int(pc["out_rel"]) + int(out_start[j])]]
+                    if a >= 0 and b >= 0:
+                        s["mis_sub"][a, b] += 1
+                elif t == 2:
+                    o = int(pc["out_rel"]) + int(out_start[j])
+                    bb = _BIDX[fwd[o:o + n]]
+                    s["ins_base"] += np.bincount(bb[bb >= 0], minlength=4)
+    if aligned:
+        s["qual_middle"] += qa[33:33 + 94]
+        s["qual_ht"] += qh[33:33 + 94]
+        s["base_comp_aligned"] += comp[[65, 67, 71, 84]]
+    else:
+        s["qual_unaligned"] += qa[33:33 + 94]
+    return s
+
+
+def merge_op_stats(s, d):
+    """Fold Engine.op_stats() (device histograms of a whole batch) into a run_stats dict."""
+    for k in ("mis", "ins", "del"):
+        s["events"][k] += d["events"][k]
+        s["event_bases"][k] += d["event_bases"][k]
+        s["ev_len"][k] += d["ev_len"][k]
+    s["match_run"] += d["match_run"]
+    s["first_match"] += d["first_match"]
+    return s
+
+
+def meta_stats(batch, s=None):
+    """Length / strand statistics from read + piece metadata only (no sequence or ops needed): fast for 1M reads."""
+    from nanosim_b200 import _lib as L
+
+    s = s or rs.empty()
+    reads, pieces = batch.reads, batch.pieces
+    Ls = reads["seq_len"].astype(np.int64)
+    if batch.kind != L.NS_KIND_ALIGNED:
+        s["n_unaligned"] += len(reads)
+        s["unaligned_bases"] += int(Ls.sum())
+        s["strand_R_unaligned"] += int(reads["reversed"].sum())
+        s["len_unaligned"] += np.bincount(np.searchsorted(rs.LEN_EDGES, Ls, side="right"), minlength=len(rs.LEN_EDGES) + 1)
+        return s
+    seg = pieces[pieces["kind"] == L.NS_PIECE_SEGMENT]
+    s["n_aligned"] += len(reads)
+    s["aligned_bases"] += int(Ls.sum())
+    s["ref_bases"] += int(seg["ref_len"].astype(np.int64).sum())
+    s["head_bases"] += int(reads["head"].astype(np.int64).sum())
+    s["tail_bases"] += int(reads["tail"].astype(np.int64).sum())
+    s["strand_R_aligned"] += int(reads["reversed"].sum())
+    s["n_chimeric"] += int((reads["n_pieces"] > 1).sum())
+    s["n_segments"] += len(seg)
+    s["len_aligned"] += np.bincount(np.searchsorted(rs.LEN_EDGES, Ls, side="right"), minlength=len(rs.LEN_EDGES) + 1)
+    s["len_middle_ref"] += np.bincount(np.searchsorted(rs.LEN_EDGES, seg["ref_len"].astype(np.int64), side="right"),
+                                       minlength=len(rs.LEN_EDGES) + 1)
+    s["len_head"] += np.bincount(np.searchsorted(rs.HT_EDGES, reads["head"].astype(np.int64), side="right"),
+                                 minlength=len(rs.HT_EDGES) + 1)
+    s["len_tail"] += np.bincount(np.searchsorted(rs.HT_EDGES, reads["tail"].astype(np.int64), side="right"),
+                                 minlength=len(rs.HT_EDGES) + 1)
+    return s
+
+
+# --------------------------------------------------------------------------------------
+# comparisons
+# --------------------------------------------------------------------------------------
+def chi2_two_sample(a, b, min_count=20):
+    """Two-sample chi-square on histograms (bins pooled until both have >= min_count).  Returns (stat, dof, p)."""
+    from scipy.stats import chi2
+
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    pa, pb = [], []
+    ca = cb = 0.0
+    for x, y in zip(a, b):
+        ca += x
+        cb += y
+        if ca + cb >= 2 * min_count:
+            pa.append(ca)
+            pb.append(cb)
+            ca = cb = 0.0
+    if ca + cb > 0 and pa:
+        pa[-1] += ca
+        pb[-1] += cb
+    pa, pb = np.asarray(pa), np.asarray(pb)
+    if len(pa) < 2:
+        return 0.0, 0, 1.0
+    A, B = pa.sum(), pb.sum()
+    stat = float((((np.sqrt(B / A) * pa - np.sqrt(A / B) * pb) ** 2) / (pa + pb)).sum())
+    dof = len(pa) - 1
+    return stat, dof, float(chi2.sf(stat, dof))
+
+
+def rates(s):
+    rb = max(s["ref_bases"], 1)
+    return {k: s["event_bases"][k] / rb for k in ("mis", "ins", "del")}
+
+
+def compare_stats(a, b, rate_tol, p_min, keys=None, label=""):
+    """a, b: run_stats dicts.  Returns list of failure strings (empty == parity)."""
+    fails = []
+    ra, rb_ = rates(a), rates(b)
+    for k in ra:
+        if rb_[k] > 0 and abs(ra[k] / rb_[k] - 1) > rate_tol:
+            fails.append("%s per-base %s rate %.6g vs %.6g (rel %.3g > %.3g)" % (label, k, ra[k], rb_[k], ra[k] / rb_[k] - 1, rate_tol))
+    hist_keys = keys or ["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match",
+                         "events_per_read", "len_unaligned"]
+    for k in hist_keys:
+        if a[k].sum() == 0 or b[k].sum() == 0:
+            continue
+        st, dof, p = chi2_two_sample(a[k], b[k])
+        if p < p_min:
+            fails.append("%s histogram %s: chi2 %.1f dof %d p %.3g" % (label, k, st, dof, p))
+    for k in ("mis", "ins", "del"):
+        if a["ev_len"][k].sum() and b["ev_len"][k].sum():
+            st, dof, p = chi2_two_sample(a["ev_len"][k], b["ev_len"][k])
+            if p < p_min:
+                fails.append("%s event-length %s: chi2 %.1f dof %d p %.3g" % (label, k, st, dof, p))
+    return fails
+
+
+# --------------------------------------------------------------------------------------
+# oracle runs
+# --------------------------------------------------------------------------------------
+def oracle_stats(cm, ref_records, n_aligned, n_unaligned, fastq, chimeric=False, seed=1234, tmpdir=None):
+    """Runs the pure-Python oracle (oracle/nanosim_oracle.py) and returns its run_stats via the same text files the
+    reference would write."""
+    import random
+    import tempfile
+
+    import nanosim_oracle as no
+    from conftest import oracle_model
+
+    tmp = tmpdir or tempfile.mkdtemp(prefix="oracle_run_")
+    m = oracle_model(cm, tmp, fastq=fastq, chimeric=chimeric)
+    oref = no.OracleReference(ref_records)
+    random.seed(seed)
+    np.random.seed(seed)
+    sink = no.ReadSink()
+    no.simulation_aligned_genome(oref, m, sink, "linear", 50, oref.max_chrom, None, None, None, fastq, n_aligned, False, chimeric)
+    ext = ".fastq" if fastq else ".fasta"
+    prefix = os.path.join(tmp, "oracle")
+    with open(prefix + "_aligned_reads" + ext, "w") as f:
+        f.write(no.format_records(sink.records, fastq))
+    with open(prefix + "_aligned_error_profile", "w") as f:
+        f.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+        f.writelines(r + "\n" for r in sink.error_rows)
+    if n_unaligned:
+        sink2 = no.ReadSink()
+        sink2.next_index = sink.next_index
+        no.simulation_unaligned(oref, m, sink2, "linear", 50, oref.max_chrom, None, None, fastq, n_unaligned)
+        with open(prefix + "_unaligned_reads" + ext, "w") as f:
+            f.write(no.format_records(sink2.records, fastq))
+    return rs.stats_from_prefix(prefix, fastq)
+
+
+def smoke_check(verbose=False):
+    from nanosim_b200 import _lib as L
+    from nanosim_b200.reference_fasta import PackedReference
+
+    ref = PackedReference.from_fasta(os.path.join(HERE, "golden", "mini_ref.fa"))
+    eng, cm, t = make_engine("guppy", ref, fastq=True, seed=7)
+    info = eng.simulate(L.NS_KIND_ALIGNED, 0, 3000)
+    b = eng.fetch(want_ops=True)
+    nb = check_edit_scripts(b, ref, True)
+    s_gpu = batch_stats(b, ref, True)
+    info_u = eng.simulate(L.NS_KIND_UNALIGNED, 0, 300)
+    bu = eng.fetch(want_ops=True)
+    nb += check_edit_scripts(bu, ref, True)
+    import nanosim_oracle as no
+
+    recs = no.read_fasta(os.path.join(HERE, "golden", "mini_ref.fa"))
+    s_or = oracle_stats(cm, recs, 250, 0, True)
+    rg, ro = rates(s_gpu), rates(s_or)
+    if verbose:
+        print("smoke: %d reads, %d bases, %d ops, kernels %.2f ms (chain %.2f, emit %.2f); %d bases verified bit-exactly"
+              % (info.n_reads, info.total_bases, info.n_ops, info.ms_total, info.ms_chain, info.ms_emit, nb))
+        print("smoke: per-base rates gpu %s" % {k: round(v, 5) for k, v in rg.items()})
+        print("smoke: per-base rates oracle %s" % {k: round(v, 5) for k, v in ro.items()})
+    for k in rg:
+        assert abs(rg[k] / ro[k] - 1) < 0.15, "rate %s: gpu %g oracle %g" % (k, rg[k], ro[k])
+    eng.close()
+    return True
