@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the per-read simulation hot path (BASELINE.json metric: simulated bases/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch_reads B]
+
+Workload (BASELINE config 2): genome mode, human_NA12878_DNA_FAB49712_guppy error/length model with the
+dorado_v3.2.1 base-quality table (the shipped guppy model has none), FASTQ, on a 3.09 Gb synthetic
+reference (24 chromosomes with hg38 lengths, i.i.d. ACGT).  The whole job is 10M reads; ONE STEP is one batch of
+``--batch_reads`` reads (aligned + unaligned in the model's 8.85:1 ratio) = the unit the job is made of, so
+bases/sec over K steps is the job's throughput.  Under torchrun every rank simulates its own batch per step
+(weak scaling; read ids are disjoint shards) after ONE NCCL broadcast of the reference at init.
+
+Printed JSON line: see the task contract.  ``value`` = bases / device time of the kernels (outputs stay in HBM);
+``e2e`` = the same through ns_simulate + ns_fetch into pinned host buffers (D2H inside the timed region);
+``roofline`` = emit kernel, 3 algorithmic bytes per base (1 reference byte read + 1 base + 1 quality written);
+``cpu_baseline`` = the oracle port (pure Python, like the reference) on a bounded sample with all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+HG38_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+                133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+CHROM_NAMES = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
+MODEL = os.path.join(ROOT, "nanosim_b200", "data", "guppy_fab49712_plusq.npz")
+ALGO_BYTES_PER_BASE = 3.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, device):
+        self.rows = []
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synth_reference_gpu(device, scale=1.0):
+    """24 chromosomes, i.i.d. uniform ACGT, generated on the GPU (torch is plumbing here)."""
+    import torch
+
+    lengths = [max(1000, int(x * scale)) for x in HG38_LENGTHS]
+    total = sum(lengths)
+    g = torch.Generator(device="cuda:%d" % device)
+    g.manual_seed(1)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda:%d" % device)
+    out = torch.empty(total, dtype=torch.uint8, device="cuda:%d" % device)
+    step = 1 << 28
+    for s in range(0, total, step):
+        e = min(total, s + step)
+        idx = torch.randint(0, 4, (e - s,), generator=g, device="cuda:%d" % device, dtype=torch.uint8)
+        out[s:e] = lut[idx.long()]
+        del idx
+    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    return out, offsets
+
+
+def cpu_oracle_sample(ref_strs, n_reads, n_procs, fastq=True):
+    """Times the oracle port (pure Python, same algorithm and data structures as the reference) on ``n_reads`` reads
+    split over ``n_procs`` forked workers, like ``simulator.py -t``.  Returns (bases, seconds)."""
+    import multiprocessing as mp
+
+    from conftest import oracle_model
+    from nanosim_b200.model import CompiledModel
+    import nanosim_oracle as no
+
+    cm = CompiledModel.load(MODEL)
+    tmp = tempfile.mkdtemp(prefix="bench_oracle_")
+    m = oracle_model(cm, tmp, fastq=fastq)
+    oref = no.OracleReference(ref_strs)
+    n_al, n_un = m.split_counts(n_reads)
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def work(i, na, nu):
+        import random
+        random.seed(1000 + i)
+        np.random.seed(1000 + i)
+        s1, s2 = no.ReadSink(), no.ReadSink()
+        no.simulation_aligned_genome(oref, m, s1, "linear", 50, oref.max_chrom, None, None, None, fastq, na, False, False)
+        if nu:
+            no.simulation_unaligned(oref, m, s2, "linear", 50, oref.max_chrom, None, None, fastq, nu)
+        txt = no.format_records(s1.records + s2.records, fastq)      # the reference also formats and writes records
+        q.put((sum(len(r[1]) for r in s1.records + s2.records), len(txt)))
+
+    t0 = time.time()
+    procs = []
+    for i in range(n_procs):
+        na = n_al // n_procs + (n_al % n_procs if i == n_procs - 1 else 0)
+        nu = n_un // n_procs + (n_un % n_procs if i == n_procs - 1 else 0)
+        p = ctx.Process(target=work, args=(i, na, nu))
+        p.start()
+        procs.append(p)
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    dt = time.time() - t0
+    return sum(r[0] for r in res), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch_reads", type=int, default=262144)
+    ap.add_argument("--ref_scale", type=float, default=1.0, help="scale the 3.09 Gb reference (tests only)")
+    ap.add_argument("--cpu_reads", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = "genome FASTQ, guppy FAB49712 model + dorado_v3.2.1 quality table, 3.09 Gb synthetic hg38-sized reference " \
+               "(24 chr, i.i.d. ACGT), 10M-read job, %d reads per step" % args.batch_reads
+
+    import torch
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path == the oracle port (Python, multiprocessing over all cores)
+        if rank != 0:
+            return
+        ref_t, offsets = synth_reference_gpu(local, args.ref_scale) if torch.cuda.is_available() else (None, None)
+        if ref_t is None:
+            rng = np.random.default_rng(1)
+            lengths = [max(1000, int(x * args.ref_scale)) for x in HG38_LENGTHS]
+            host = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n, dtype=np.uint8)] for n in lengths]
+            ref_strs = [(nm, a.tobytes().decode()) for nm, a in zip(CHROM_NAMES, host)]
+        else:
+            host = ref_t.cpu().numpy()
+            ref_strs = [(nm, host[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()) for i, nm in enumerate(CHROM_NAMES)]
+            del ref_t
+        per_step = args.cpu_reads or 40 * cores
+        vals = []
+        for s in range(args.warmup + args.steps):
+            bases, dt = cpu_oracle_sample(ref_strs, per_step, cores)
+            if s >= args.warmup:
+                vals.append((bases, dt))
+        tb, tt = sum(v[0] for v in vals), sum(v[1] for v in vals)
+        v = tb / tt
+        print(json.dumps({"impl": "reference", "metric": "simulated_bases_per_sec", "value": v, "unit": "bases/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * tt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": workload},
+                          "cpu_baseline": {"value": v, "unit": "bases/s", "cores": cores, "kind": "port",
+                                           "sample": "%d reads per step, %d forked workers, pure-Python oracle port of simulator.py "
+                                                     "(same algorithm as the reference, incl. record formatting)" % (per_step, cores)},
+                          "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    from nanosim_b200 import _lib as L
+    from nanosim_b200.engine import Engine
+    from nanosim_b200.model import CompiledModel, DeviceTables
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+
+    # ---- init (not timed): reference generated on rank 0, ONE broadcast over NCCL, model tables to HBM
+    if rank == 0:
+        ref_t, offsets = synth_reference_gpu(local, args.ref_scale)
+    else:
+        lengths = [max(1000, int(x * args.ref_scale)) for x in HG38_LENGTHS]
+        offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+        ref_t = torch.empty(int(offsets[-1]), dtype=torch.uint8, device="cuda:%d" % local)
+    if world > 1:
+        dist.broadcast(ref_t, src=0)
+    torch.cuda.synchronize()
+    cm = CompiledModel.load(MODEL)
+    tables = DeviceTables(cm, fastq=True)
+    eng = Engine(device=local, seed=20260924)
+    eng.set_reference_ptr(ref_t.data_ptr(), int(offsets[-1]), offsets)
+    host_ref = ref_t.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+    del ref_t
+    torch.cuda.empty_cache()
+    eng.set_model(tables)
+    eng.configure(fastq=True, min_len=50, max_len=int(np.diff(offsets.astype(np.int64)).max()))
+
+    n_al, n_un = tables.split_counts(args.batch_reads)
+    total_steps = args.warmup + args.steps
+    job_reads_al = n_al * total_steps * world
+    job_reads_un = n_un * total_steps * world
+
+    def run_step(step, fetch_bufs=None):
+        """One batch of the hot path on this rank: aligned then unaligned reads of the job's next id range."""
+        a0 = (step * world + rank) * n_al
+        u0 = (step * world + rank) * n_un
+        out = []
+        for kind, first, n in ((L.NS_KIND_ALIGNED, a0, n_al), (L.NS_KIND_UNALIGNED, u0, n_un)):
+            if n == 0:
+                continue
+            info = eng.simulate(kind, first, n)
+            if fetch_bufs is not None:
+                need = int(info.seq_bytes)
+                assert need <= fetch_bufs["seq"].numel(), "pinned buffer too small"
+                eng.fetch_into(fetch_bufs["seq"].data_ptr(), fetch_bufs["qual"].data_ptr(), fetch_bufs["reads"].data_ptr(),
+                               fetch_bufs["pieces"].data_ptr())
+            out.append((kind, info.total_bases, info.seq_bytes, info.n_reads, info.n_pieces, info.n_launches,
+                        info.ms_total, info.ms_plan, info.ms_scan, info.ms_script, info.ms_emit, info.ms_setup))
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only arm: outputs stay in HBM.  Every step simulates new read ids; a batch's working set
+    #      (>2 GB of output + the 3 GB reference sampled at random) is far larger than the 126 MB L2.
+    for s in range(args.warmup):
+        run_step(s)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t0 = time.perf_counter()
+    rows = []
+    for s in range(args.warmup, total_steps):
+        rows += run_step(s)
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    bases = sum(r[1] for r in rows)
+    dev_ms = sum(r[6] for r in rows)                 # CUDA events on the library's stream, per batch
+    emit_ms = sum(r[10] for r in rows)
+    launches = sum(r[5] for r in rows)
+    stat = torch.tensor([bases, dev_ms, wall * 1e3, emit_ms, launches], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        mx = stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_bases, t_ms = float(sm[0]), float(mx[1])
+    else:
+        total_bases, t_ms = bases, dev_ms
+    value = total_bases / (t_ms * 1e-3)
+
+    # ---- end-to-end arm: ns_simulate + ns_fetch into pinned host memory every step
+    cap = int(max(r[2] for r in rows) * 1.15) + (1 << 20)
+    bufs = {"seq": torch.empty(cap, dtype=torch.uint8, pin_memory=True), "qual": torch.empty(cap, dtype=torch.uint8, pin_memory=True),
+            "reads": torch.empty(32 * max(n_al, n_un, 1), dtype=torch.uint8, pin_memory=True),
+            "pieces": torch.empty(48 * max(n_al, n_un, 1), dtype=torch.uint8, pin_memory=True)}
+    base_step = total_steps                          # fresh read ids
+    for s in range(min(args.warmup, 2)):
+        run_step(base_step + s, bufs)
+    barrier()
+    t0 = time.perf_counter()
+    rows_e = []
+    for s in range(args.steps):
+        rows_e += run_step(base_step + 2 + s, bufs)
+    barrier()
+    wall_e = time.perf_counter() - t0
+    bases_e = sum(r[1] for r in rows_e)
+    d2h = sum(2 * r[2] + 32 * r[3] + 48 * r[4] for r in rows_e) / max(args.steps, 1)
+    stat = torch.tensor([bases_e, wall_e], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        mx = stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_value = float(sm[0]) / float(mx[1])
+    else:
+        e2e_value = bases_e / wall_e
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    al_rows = [r for r in rows if r[0] == L.NS_KIND_ALIGNED]
+    emit_bases = sum(r[1] for r in rows)
+    achieved = ALGO_BYTES_PER_BASE * emit_bases / (emit_ms * 1e-3) / 1e9
+    line = {
+        "metric": "simulated_bases_per_sec", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload, "reads_per_step_per_gpu": args.batch_reads, "aligned_per_step": n_al,
+                   "unaligned_per_step": n_un, "l2": "inputs larger than L2 (3.09 GB reference sampled at random, >2 GB written per step)",
+                   "timing": "CUDA events on the library stream per batch, summed over K steps, max over ranks"},
+        "reads_per_sec": (sum(r[3] for r in rows) * (world if world > 1 else 1)) / (t_ms * 1e-3),
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": int(d2h),
+                "note": "reference + model are resident in HBM (uploaded once at init); per-step input is the read-id range"},
+        "gpu_launches": int(launches),
+        "phase_ms_per_step": {"plan": sum(r[7] for r in rows) / args.steps, "scan": sum(r[8] for r in rows) / args.steps,
+                              "script": sum(r[9] for r in rows) / args.steps, "emit": emit_ms / args.steps,
+                              "setup": sum(r[11] for r in rows) / args.steps},
+        "roofline": {"bound": "hbm", "kernel": "emit_kernel<FASTQ>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
+                     "whole_path_frac": ALGO_BYTES_PER_BASE * total_bases / (t_ms * 1e-3) / 1e9 / peak / max(world, 1)},
+    }
+    if not args.no_cpu_baseline and host_ref is not None:
+        ref_strs = [(nm, host_ref[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()) for i, nm in enumerate(CHROM_NAMES)]
+        n_cpu = args.cpu_reads or 40 * cores
+        cb, ct = cpu_oracle_sample(ref_strs, n_cpu, cores)
+        line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": cores, "kind": "port",
+                                "sample": "%d reads of the same workload, %d forked workers, pure-Python oracle port of simulator.py "
+                                          "(record formatting included, no file I/O); %.1f s" % (n_cpu, cores, ct)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,8 +63,9 @@ class NsPieceMeta(C.Structure):
 
 class NsBatchInfo(C.Structure):
     _fields_ = [("seq_bytes", C.c_uint64), ("n_ops", C.c_uint64), ("total_bases", C.c_uint64),
-                ("n_reads", C.c_uint32), ("n_pieces", C.c_uint32), ("n_overflow", C.c_uint32),
-                ("ms_draw", C.c_float), ("ms_chain", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float)]
+                ("n_reads", C.c_uint32), ("n_pieces", C.c_uint32), ("n_launches", C.c_uint32),
+                ("ms_setup", C.c_float), ("ms_plan", C.c_float), ("ms_scan", C.c_float), ("ms_script", C.c_float),
+                ("ms_emit", C.c_float), ("ms_total", C.c_float)]
 
 
 # numpy views of the two record types

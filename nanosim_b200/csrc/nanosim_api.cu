@@ -45,7 +45,7 @@ struct NsContext {
     int device = 0;
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int sm_count = 148;
 
@@ -207,7 +207,7 @@ int ns_create(int device, uint64_t seed, NsContext** out) {
     ctx->seed = seed;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_totals, 8 * sizeof(uint64_t));
     if (e == cudaSuccess) {
         cudaDeviceProp prop;
@@ -376,6 +376,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         return NS_OK;
     }
     const uint32_t n = n_reads;
+    uint32_t launches = 0;
     const unsigned tb = 256, gb = (n + tb - 1) / tb;
     CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
     CK(ctx->counter.ensure(64));
@@ -401,6 +402,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         if (rc) return rc;
         narrow_u64<<<gb, tb, 0, st>>>(ctx->scan_out.as<uint64_t>(), n, ctx->piece_first.as<uint32_t>());
         last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 0);
+        launches += 6;
         CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         n_pieces = (uint32_t)ctx->h_totals[0];
@@ -430,6 +432,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
     plan_kernel<false><<<plan_blocks, plan_tb, 0, st>>>(pa);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], st));
+    launches += 1;
 
     // ---- exclusive scans: op offsets per piece, 16-byte aligned sequence slots per read
     const unsigned gp = (n_pieces + tb - 1) / tb;
@@ -454,14 +458,16 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(ctx->ops.ensure((size_t)(n_ops + 4) * sizeof(uint32_t)));
     CK(ctx->seq.ensure((size_t)seq_bytes + 16));
     if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes + 16));
-    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    launches += 11;   // 2 gathers, 2 scans (2 kernels each), 2 scatters, 2 totals, 1 reduction
 
     // ---- plan pass 2: replay the accepted attempt, write the edit scripts
     pa.ops = ctx->ops.as<uint32_t>();
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
     plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaEventRecord(ctx->ev[4], st));
+    launches += 2;    // script pass + emit
 
     // ---- emit
     EmitArgs ea;
@@ -495,7 +501,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         emit_kernel<false><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
 
     NsBatchInfo& bi = ctx->last;
@@ -504,15 +510,19 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     bi.total_bases = total_bases;
     bi.n_reads = n;
     bi.n_pieces = n_pieces;
-    bi.n_overflow = 0;
+    bi.n_launches = launches;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    bi.ms_draw = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[3]);
-    bi.ms_chain = ms;
+    bi.ms_setup = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    bi.ms_plan = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    bi.ms_scan = ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    bi.ms_script = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
     bi.ms_emit = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
     bi.ms_total = ms;
     ctx->last_kind = kind;
     ctx->last_first_id = first_read_id;

@@ -365,8 +365,8 @@ def smoke_check(verbose=False):
     s_or = oracle_stats(cm, recs, 250, 0, True)
     rg, ro = rates(s_gpu), rates(s_or)
     if verbose:
-        print("smoke: %d reads, %d bases, %d ops, kernels %.2f ms (chain %.2f, emit %.2f); %d bases verified bit-exactly"
-              % (info.n_reads, info.total_bases, info.n_ops, info.ms_total, info.ms_chain, info.ms_emit, nb))
+        print("smoke: %d reads, %d bases, %d ops, kernels %.2f ms (plan %.2f, script %.2f, emit %.2f); %d bases verified bit-exactly"
+              % (info.n_reads, info.total_bases, info.n_ops, info.ms_total, info.ms_plan, info.ms_script, info.ms_emit, nb))
         print("smoke: per-base rates gpu %s" % {k: round(v, 5) for k, v in rg.items()})
         print("smoke: per-base rates oracle %s" % {k: round(v, 5) for k, v in ro.items()})
     for k in rg:

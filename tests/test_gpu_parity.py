@@ -1,0 +1,246 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI.
+
+ * bit-exact: every edit script re-applied on the host reproduces the device's bases (mutate_read semantics);
+   same seed -> same bytes; results independent of the batch split;
+ * statistical, vs the oracle run here on a few hundred reads;
+ * statistical, vs the committed histograms of the UNMODIFIED reference (tests/golden/ref_stats_*.json, 1M reads):
+   per-base mis/ins/del counts within +-0.1 % (north_star), length / event histograms by chi-square.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+import parity_checks as pc
+import run_stats as rs
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from nanosim_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def mini_ref():
+    from nanosim_b200.reference_fasta import PackedReference
+    return PackedReference.from_fasta(os.path.join(GOLDEN, "mini_ref.fa"))
+
+
+@pytest.fixture(scope="module")
+def ecoli():
+    from nanosim_b200.reference_fasta import PackedReference
+    return PackedReference.from_records(synth.ecoli5m())
+
+
+CONFIGS = [
+    ("guppy", dict(fastq=True)),
+    ("guppy", dict(fastq=False)),
+    ("dorado", dict(fastq=True, chimeric=True)),
+    ("guppy", dict(fastq=True, perfect=True)),
+]
+
+
+@pytest.mark.parametrize("model,kw", CONFIGS)
+def test_edit_scripts_bit_exact_mini_ref(model, kw, mini_ref, L):
+    """Reference with lower case, IUPAC codes and three chromosomes (reads never span chromosomes)."""
+    eng, cm, t = pc.make_engine(model, mini_ref, seed=3, **kw)
+    info = eng.simulate(L.NS_KIND_ALIGNED, 0, 1500)
+    b = eng.fetch(want_ops=True)
+    assert info.n_reads == 1500 and int(b.reads["seq_len"].astype(np.int64).sum()) == info.total_bases
+    assert pc.check_edit_scripts(b, mini_ref, kw.get("fastq", False)) > 0
+    lens = b.reads["seq_len"]
+    assert lens.min() >= 50 and lens.max() <= mini_ref.max_chrom
+    if kw.get("perfect"):
+        assert (b.reads["head"] == 0).all() and (b.reads["tail"] == 0).all()
+        assert ((b.ops >> 28) == 0).all()
+    if not kw.get("perfect"):
+        eng.simulate(L.NS_KIND_UNALIGNED, 0, 400)
+        bu = eng.fetch(want_ops=True)
+        assert pc.check_edit_scripts(bu, mini_ref, kw.get("fastq", False)) > 0
+        assert bu.reads["seq_len"].min() >= 50
+    eng.close()
+
+
+def test_circular_reference_wraps(L):
+    from nanosim_b200.reference_fasta import PackedReference
+    ref = PackedReference.from_fasta(os.path.join(GOLDEN, "mini_circular.fa"))
+    eng, cm, t = pc.make_engine("dorado", ref, fastq=True, seed=5, circular=True, max_len=4000)
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 2000)
+    b = eng.fetch(want_ops=True)
+    assert pc.check_edit_scripts(b, ref, True) > 0
+    seg = b.pieces[b.pieces["kind"] == L.NS_PIECE_SEGMENT]
+    wrapped = (seg["pos"].astype(np.int64) + seg["ref_len"].astype(np.int64)) > ref.genome_len
+    assert wrapped.any(), "no read wrapped around the circular chromosome"
+    eng.close()
+
+
+def test_same_seed_same_bytes_and_batch_invariance(mini_ref, L):
+    def run(splits, seed):
+        eng, _, _ = pc.make_engine("guppy", mini_ref, fastq=True, seed=seed)
+        out = []
+        start = 0
+        for n in splits:
+            eng.simulate(L.NS_KIND_ALIGNED, start, n)
+            b = eng.fetch()
+            out += [(b.read_seq(i), b.read_qual(i).tobytes()) for i in range(n)]
+            start += n
+        eng.close()
+        return out
+    a = run([600], 42)
+    assert a == run([600], 42)
+    assert a == run([100, 37, 463], 42)            # read i depends on (seed, i) only
+    assert a != run([600], 43)
+
+
+def test_zero_reads_and_state_errors(mini_ref, L):
+    from nanosim_b200.engine import Engine, NanoSimError
+    eng = Engine(0, 1)
+    with pytest.raises(NanoSimError):
+        eng.simulate(L.NS_KIND_ALIGNED, 0, 10)         # nothing configured yet
+    eng.close()
+    eng, _, _ = pc.make_engine("guppy", mini_ref, fastq=False, seed=1)
+    info = eng.simulate(L.NS_KIND_ALIGNED, 0, 0)
+    assert info.n_reads == 0 and info.total_bases == 0
+    with pytest.raises(NanoSimError):
+        eng.configure(min_len=100, max_len=50)
+    with pytest.raises(NanoSimError):
+        eng.configure(perfect=True, chimeric=True)
+    eng.close()
+
+
+def test_min_max_length_window(mini_ref, L):
+    eng, _, _ = pc.make_engine("guppy", mini_ref, fastq=False, seed=9, min_len=2000, max_len=6000)
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 3000)
+    b = eng.fetch()
+    assert b.reads["seq_len"].min() >= 2000 and b.reads["seq_len"].max() <= 6000
+    assert b.reads["attempts"].max() > 0              # the rejection loop (simulator.py:1367) actually ran
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 500)
+    bu = eng.fetch()
+    assert bu.reads["seq_len"].min() >= 2000 and bu.reads["seq_len"].max() <= 6000
+    eng.close()
+
+
+def test_device_op_stats_equal_host_stats(ecoli, L):
+    eng, _, _ = pc.make_engine("guppy", ecoli, fastq=False, seed=2)
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 3000)
+    b = eng.fetch(want_ops=True)
+    host = pc.batch_stats(b, ecoli, False)
+    dev = eng.op_stats()
+    assert dev["events"] == host["events"] and dev["event_bases"] == host["event_bases"]
+    assert dev["ref_bases"] == host["ref_bases"]
+    for k in ("mis", "ins", "del"):
+        assert np.array_equal(dev["ev_len"][k], host["ev_len"][k])
+    assert np.array_equal(dev["match_run"], host["match_run"]) and np.array_equal(dev["first_match"], host["first_match"])
+    eng.close()
+
+
+@pytest.mark.parametrize("model,chim", [("guppy", False), ("dorado", True)])
+def test_statistics_vs_oracle_small(model, chim, mini_ref, L, tmp_path):
+    """Oracle = pure-Python restatement, a few hundred reads (seconds); device = 30k reads.  Loose tolerances sized
+    to the oracle's sampling noise."""
+    import nanosim_oracle as no
+    eng, cm, t = pc.make_engine(model, mini_ref, fastq=True, chimeric=chim, seed=17)
+    s_dev = rs.empty()
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 30000)
+    pc.batch_stats(eng.fetch(want_ops=True), mini_ref, True, s_dev)
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 3000)
+    pc.batch_stats(eng.fetch(), mini_ref, True, s_dev)
+    eng.close()
+    recs = no.read_fasta(os.path.join(GOLDEN, "mini_ref.fa"))
+    s_or = pc.oracle_stats(cm, recs, 500 if model == "guppy" else 250, 150, True, chimeric=chim, tmpdir=str(tmp_path))
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.04 if model == "guppy" else 0.08, p_min=1e-5, label=model)
+    for k in ("qual_middle", "qual_ht", "qual_unaligned"):
+        st, dof, p = pc.chi2_two_sample(s_dev[k], s_or[k])
+        if p < 1e-5:
+            fails.append("%s %s chi2 %.1f dof %d p %.3g" % (model, k, st, dof, p))
+    fr_dev = s_dev["strand_R_aligned"] / s_dev["n_aligned"]
+    assert abs(fr_dev - (1 - t.strandness)) < 0.02
+    assert not fails, "\n".join(fails)
+
+
+def _device_run_stats(eng, ref, L, n_aligned, n_unaligned, batch, fastq):
+    s = rs.empty()
+    for start in range(0, n_aligned, batch):
+        n = min(batch, n_aligned - start)
+        eng.simulate(L.NS_KIND_ALIGNED, start, n)
+        b = eng.fetch(want_ops=False)
+        pc.meta_stats(b, s)
+        pc.merge_op_stats(s, eng.op_stats())
+    for start in range(0, n_unaligned, batch):
+        n = min(batch, n_unaligned - start)
+        eng.simulate(L.NS_KIND_UNALIGNED, start, n)
+        pc.meta_stats(eng.fetch(want_ops=False), s)
+    return s
+
+
+def test_vs_unmodified_reference_1M_reads(ecoli, L):
+    """BASELINE config-1 reference/model at 1M reads, against histograms of the unmodified reference
+    (tests/golden/ref_stats_guppy_fasta.json).  north_star: per-base edit-type counts within +-0.1 %."""
+    path = os.path.join(GOLDEN, "ref_stats_guppy_fasta.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated yet")
+    gold, meta = rs.load(path)
+    n_al, n_un = int(gold["n_aligned"]), int(gold["n_unaligned"])
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=2024)
+    s = _device_run_stats(eng, ecoli, L, n_al, n_un, 125000, False)
+    eng.close()
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    # the reference's own chunk-to-chunk noise bounds what +-0.1 % can mean
+    fails = pc.compare_stats(s, gold, rate_tol=1e-3, p_min=1e-6, label="1M",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match",
+                                   "len_unaligned"])
+    mean_dev, mean_ref = s["aligned_bases"] / s["n_aligned"], gold["aligned_bases"] / gold["n_aligned"]
+    assert abs(mean_dev / mean_ref - 1) < 5e-3, (mean_dev, mean_ref)
+    assert abs(s["strand_R_aligned"] / s["n_aligned"] - gold["strand_R_aligned"] / gold["n_aligned"]) < 3e-3
+    assert not fails, "\n".join(fails)
+
+
+def test_quality_draws_match_model_pmf(ecoli, L):
+    """Device qualities per state against the exact truncated-log-normal pmf (model_base_qualities.py:9-20,120-130)."""
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=True, seed=31)
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 20000)
+    b = eng.fetch(want_ops=False)
+    s = pc.batch_stats(b, ecoli, True)
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 4000)
+    pc.batch_stats(eng.fetch(), ecoli, True, s)
+    eng.close()
+    from nanosim_b200.model import QUAL_STATES
+    for key, st in (("qual_ht", "ht"), ("qual_unaligned", "unmapped")):
+        pm = t.qual_pmf[QUAL_STATES.index(st)]
+        stat, dof, p = pc.chi2_two_sample(s[key], pm * 1e12)
+        assert p > 1e-6, (key, stat, dof, p)
+    # the aligned middle is a mixture of match / mis / ins states weighted by the simulated base counts
+    mix = (t.qual_pmf[QUAL_STATES.index("match")] * (s["aligned_bases"] - s["head_bases"] - s["tail_bases"]))
+    assert s["qual_middle"].sum() == s["aligned_bases"] - s["head_bases"] - s["tail_bases"]
+    assert s["qual_middle"][:1].sum() == 0 and s["qual_middle"][1:].sum() > 0
+    assert abs(np.average(np.arange(94), weights=s["qual_middle"]) - np.average(np.arange(94), weights=mix)) < 1.5
+
+
+def test_cli_end_to_end_config1(tmp_path, L):
+    """BASELINE config 1 through the drop-in command line: file names, formats and read counts of the reference."""
+    from nanosim_b200 import simulator
+    from nanosim_b200.model import CompiledModel
+    ref_path = os.path.join(str(tmp_path), "ecoli5m.fa")
+    synth.ecoli5m(ref_path)
+    out = os.path.join(str(tmp_path), "sim")
+    simulator.main(["genome", "-rg", ref_path, "-c", os.path.join(pc.DATA, pc.MODELS["guppy"]), "-n", "1000", "-o", out,
+                    "--seed", "7"])
+    s = rs.stats_from_prefix(out, False)
+    assert (s["n_aligned"], s["n_unaligned"]) == (898, 102)          # round(1000*8.85/9.85), simulator.py:541
+    assert open(out + "_aligned_error_profile").readline() == "Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n"
+    r = pc.rates(s)
+    assert 0.025 < r["mis"] < 0.036 and 0.019 < r["ins"] < 0.03 and 0.045 < r["del"] < 0.058
+    names = [l[1:].strip() for l in open(out + "_unaligned_reads.fasta") if l.startswith(">")]
+    assert [int(n.split("_unaligned_")[1].split("_")[0]) for n in names] == list(range(898, 1000))
+    out2 = os.path.join(str(tmp_path), "simq")
+    simulator.main(["genome", "-rg", ref_path, "-c", os.path.join(pc.DATA, pc.MODELS["dorado"]), "-n", "300", "-o", out2,
+                    "--fastq", "--chimeric", "-t", "4"])
+    s2 = rs.stats_from_prefix(out2, True)
+    assert s2["n_aligned"] + s2["n_unaligned"] == 300 and s2["qual_middle"].sum() > 0
