@@ -97,7 +97,14 @@ typedef struct {
     uint32_t max_len;         /* caller passes min(max_len, max_chrom) as simulator.py:2318 does */
     double median_len;        /* 0 = off (-med / -sd) */
     double sd_len;
+    uint32_t flags;           /* NS_FLAG_* */
+    uint32_t reserved;
 } NsRunConfig;
+
+/* Unaligned reads normally take the warp-per-read fast path, which writes bases directly and keeps no edit scripts.
+ * With this flag they go through the same plan/script/emit pipeline as aligned reads (identical lengths, strands and
+ * positions; used by the tests to check the fast path against re-applied edit scripts). */
+#define NS_FLAG_UNALIGNED_SCRIPTS 1u
 
 #define NS_KIND_ALIGNED 0
 #define NS_KIND_UNALIGNED 1

@@ -46,7 +46,10 @@ class NsModel(C.Structure):
 class NsRunConfig(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("circular", C.c_uint32), ("perfect", C.c_uint32), ("fastq", C.c_uint32),
                 ("chimeric", C.c_uint32), ("kmer_bias", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32),
-                ("median_len", C.c_double), ("sd_len", C.c_double)]
+                ("median_len", C.c_double), ("sd_len", C.c_double), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+NS_FLAG_UNALIGNED_SCRIPTS = 1
 
 
 class NsReadMeta(C.Structure):

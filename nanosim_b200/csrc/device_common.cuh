@@ -43,18 +43,24 @@ struct DevCfg {
 // ------------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter = (read id lo, read id hi, stream word, block index); key = seed.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    for (int r = 0; r < ROUNDS; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c.x;       // one IMAD.WIDE each
+        uint64_t p1 = (uint64_t)M1 * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
         k.x += W0;
         k.y += W1;
     }
     return c;
 }
+// 10 rounds (the Random123 / cuRAND default) for every structural draw: lengths, error chain, positions.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
+// 7 rounds -- the smallest round count that passes BigCrush in Salmon et al. (SC'11, table 2) -- for the bulk
+// per-base streams of the emit kernel (quality values, substituted / inserted bases).
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
 
 // stream word layout: [31:28] purpose, [27] kind, [26:0] attempt / generation
 enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6 };

@@ -21,6 +21,7 @@
 #define EMIT_RING 256
 #define QLUT_BITS 11
 #define QLUT_SIZE (1 << QLUT_BITS)
+#define QLUT_FRAC_BITS (24 - QLUT_BITS)     // quality uniforms are 24-bit
 
 struct EmitArgs {
     DevRef ref;
@@ -34,12 +35,13 @@ struct EmitArgs {
     uint8_t* seq;
     uint8_t* qual;
     const uint32_t* qlut;        // [5][QLUT_SIZE] packed bucket table (built on the host from qual_cdf)
-    const uint32_t* qcdf;        // [5][94]
+    const uint32_t* qcdf;        // [5][94], 24-bit fixed point
     uint32_t* counter;
 };
 
 // IUPAC resolution of case_convert (:744-746): members in the reference's list order, picked uniformly.
-__device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r16) {
+// r8 is a uniform byte; t3 a uniform value in {0,1,2} derived from it.
+__device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r8, uint32_t t3) {
     uint32_t n, set;   // set: up to 4 members packed one byte each
     switch (c) {
     case 'Y': n = 2; set = 'C' | ('T' << 8); break;
@@ -56,24 +58,15 @@ __device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r16) {
     case 'X': n = 4; set = 'A' | ('T' << 8) | ('C' << 16) | ('G' << 24); break;
     default: return c;
     }
-    uint32_t k = (r16 * n) >> 16;
+    uint32_t k = (n == 3) ? t3 : ((r8 >> 4) & (n - 1));
     return (set >> (8 * k)) & 0xffu;
 }
 
-struct Bits16 {
-    Rng rng;
-    uint32_t w;
-    int half;
-    __device__ __forceinline__ uint32_t next16() {
-        if (half == 0) {
-            w = rng.next();
-            half = 1;
-            return w & 0xffffu;
-        }
-        half = 0;
-        return w >> 16;
-    }
-};
+// bit i of 0x80045 is set for i = 'A'-'A', 'C'-'A', 'G'-'A', 'T'-'A'
+__device__ __forceinline__ bool acgt_fast(uint32_t c) {
+    uint32_t d = c - 'A';
+    return d < 26u && ((0x80045u >> d) & 1u);
+}
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -166,11 +159,24 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                 uint32_t rem = (op & 0x0fffffffu) - within;
                 uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty == NS_OP_INS || ty == NS_OP_HT) ? 0u : within);
 
-                Bits16 bb;
-                bb.rng.init(a.cfg.seed, rid, stream_word(ST_EMIT_B, a.kind, chunk));
-                bb.half = 0;
-                Rng qr;
-                if (FASTQ) qr.init(a.cfg.seed, rid, stream_word(ST_EMIT_Q, a.kind, chunk));
+                // ---- all randomness of the chunk up front, position-indexed, identical in every lane's control flow:
+                //      base i uses byte i of `bw` (substitution / inserted base / IUPAC member) and bits [24i, 24i+24)
+                //      of `qw` (its quality value).
+                const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
+                const uint32_t id_lo = (uint32_t)rid, id_hi = (uint32_t)(rid >> 32);
+                const uint4 bw4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, a.kind, chunk), 0u), key);
+                const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
+                uint32_t qw[13];
+                if (FASTQ) {
+                    const uint32_t sw = stream_word(ST_EMIT_Q, a.kind, chunk);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
+                        qw[4 * j] = t.x; qw[4 * j + 1] = t.y; qw[4 * j + 2] = t.z; qw[4 * j + 3] = t.w;
+                    }
+                    qw[12] = 0;
+                }
+                const uint32_t flip = rev ? 2u : 0u;
 
                 uint32_t sb[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
                 const uint32_t i0 = lo - cs, i1 = hi - cs;
@@ -184,40 +190,36 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                             rem = (ty == NS_OP_DEL) ? 0u : (op & 0x0fffffffu);
                             rpos = ring_ref[k % EMIT_RING];
                         }
-                        uint32_t c;
-                        uint32_t qs;   // quality state: 0 mis 1 ins 2 match 3 ht 4 unmapped
-                        if (ty == NS_OP_COPY || ty == NS_OP_MIS) {
+                        --rem;
+                        const uint32_t r8 = (bw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                        const uint32_t r8n = (bw[((i + 1) & 15) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
+                        const uint32_t rr = (r8 == 255u) ? r8n : r8;           // 0..254 -> exactly uniform mod 3
+                        const uint32_t t3 = rr - 3u * ((rr * 171u) >> 9);
+                        uint32_t oi = r8 & 3u;                                 // random.choice(BASES) / np.random.choice
+                        if (ty < 2u) {                                         // COPY or MIS: reads the reference
                             uint32_t f = rev ? ref_len - 1 - rpos : rpos;
                             uint64_t ab = (uint64_t)pm.pos + f;
-                            if (ab >= clen) ab -= clen;                   // circular wrap (:1756-1760)
-                            c = __ldg(&cbase[ab]);
+                            if (ab >= clen) ab -= clen;                        // circular wrap (:1756-1760)
+                            uint32_t c = __ldg(&cbase[ab]);
                             ++rpos;
-                            if (c >= 'a' && c <= 'z') c -= 32;
-                            if (!is_acgt(c)) c = resolve_iupac(c, bb.next16());
-                            if (ty == NS_OP_MIS) {
-                                uint32_t j = (base_idx(c) + 1 + ((bb.next16() * 3u) >> 16)) & 3u;   // one of the 3 others
-                                c = idx_base(j);
-                                qs = 0;
-                            } else {
-                                qs = 2;
-                            }
-                            if (rev && is_acgt(c)) c = idx_base(base_idx(c) ^ 2u);
-                        } else {
-                            c = idx_base(bb.next16() & 3u);               // random.choice(BASES) / np.random.choice
-                            qs = (ty == NS_OP_INS) ? 1 : 3;
+                            if (c - 'a' < 26u) c -= 32;
+                            if (!acgt_fast(c)) c = resolve_iupac(c, r8n, (r8n == 255u) ? 0u : r8n % 3u);
+                            oi = base_idx(c);
+                            if (ty == NS_OP_MIS) oi = (oi + 1u + t3) & 3u;     // one of the three other bases
                         }
-                        --rem;
-                        sb[i >> 2] |= c << (8 * (i & 3));
+                        sb[i >> 2] |= idx_base(oi ^ flip) << (8 * (i & 3));
                         if (FASTQ) {
-                            if (unmapped) qs = 4;
-                            uint32_t r = qr.next();
-                            uint32_t e = lut[qs * QLUT_SIZE + (r >> (32 - QLUT_BITS))];
+                            // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3); gap/unaligned -> unmapped(4)
+                            const uint32_t qs = unmapped ? 4u : ((0x30102u >> (4u * ty)) & 7u);
+                            const int bit = 24 * i;
+                            const uint32_t u24 = __funnelshift_r(qw[bit >> 5], qw[(bit >> 5) + 1], bit & 31) & 0xffffffu;
+                            const uint32_t e = lut[qs * QLUT_SIZE + (u24 >> QLUT_FRAC_BITS)];
                             uint32_t q = e & 0xffu;
-                            if (e >> 31) {                                // bucket spans >2 quality values: exact scan
+                            if (e >> 31) {                                     // bucket spans >2 quality values: exact scan
                                 const uint32_t* cdf = a.qcdf + qs * NS_QUAL_SLOTS;
-                                while (q < NS_QUAL_SLOTS - 1 && r >= __ldg(&cdf[q])) ++q;
+                                while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf[q])) ++q;
                             } else {
-                                q += ((r & ((1u << (32 - QLUT_BITS)) - 1u)) >= ((e >> 8) & 0x3fffffu)) ? 1u : 0u;
+                                q += ((u24 & ((1u << QLUT_FRAC_BITS) - 1u)) >= ((e >> 8) & 0x3fffu)) ? 1u : 0u;
                             }
                             sq[i >> 2] |= (q + 33u) << (8 * (i & 3));
                         }

@@ -15,6 +15,7 @@
 #include "device_common.cuh"
 #include "plan_kernel.cuh"
 #include "emit_kernel.cuh"
+#include "uread_kernel.cuh"
 
 namespace {
 
@@ -174,21 +175,31 @@ cudaError_t upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, s);
 }
 
-void build_qlut(const uint32_t cdf[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut) {
+// Bucket table over 24-bit quality uniforms: entry = q_lo | threshold << 8 | multi << 31.
+// A draw u24 falls into bucket u24 >> QLUT_FRAC_BITS; when the bucket holds at most one cdf boundary the quality is
+// q_lo + (frac >= threshold); buckets with two or more boundaries (rare tail qualities) are flagged for an exact scan.
+void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut, std::vector<uint32_t>& cdf24) {
     lut.assign((size_t)NS_N_QUAL_STATES * QLUT_SIZE, 0);
-    const uint32_t shift = 32 - QLUT_BITS;
-    auto qof = [&](int s, uint32_t r) {
-        uint32_t q = 0;
-        while (q < NS_QUAL_SLOTS - 1 && r >= cdf[s][q]) ++q;
-        return q;
-    };
+    cdf24.assign((size_t)NS_N_QUAL_STATES * NS_QUAL_SLOTS, 0);
+    const uint32_t shift = QLUT_FRAC_BITS;
     for (int s = 0; s < NS_N_QUAL_STATES; ++s) {
+        uint32_t* c = &cdf24[(size_t)s * NS_QUAL_SLOTS];
+        for (int q = 0; q < NS_QUAL_SLOTS; ++q) {
+            uint64_t v = ((uint64_t)cdf32[s][q] + 128u) >> 8;
+            c[q] = (uint32_t)std::min<uint64_t>(v, 1u << 24);
+        }
+        c[NS_QUAL_SLOTS - 1] = 1u << 24;
+        auto qof = [&](uint32_t u) {
+            uint32_t q = 0;
+            while (q < NS_QUAL_SLOTS - 1 && u >= c[q]) ++q;
+            return q;
+        };
         for (uint32_t b = 0; b < QLUT_SIZE; ++b) {
             uint32_t lo = b << shift, hi = lo + ((1u << shift) - 1u);
-            uint32_t qlo = qof(s, lo), qhi = qof(s, hi);
+            uint32_t qlo = qof(lo), qhi = qof(hi);
             uint32_t e;
             if (qhi == qlo) e = qlo | ((1u << shift) << 8);
-            else if (qhi == qlo + 1) e = qlo | ((cdf[s][qlo] - lo) << 8);
+            else if (qhi == qlo + 1) e = qlo | ((c[qlo] - lo) << 8);
             else e = qlo | 0x80000000u;
             lut[(size_t)s * QLUT_SIZE + b] = e;
         }
@@ -313,10 +324,10 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
     memcpy(d.trans, m->trans, sizeof d.trans);
     d.strandness = m->strandness_rate;
     d.seg_p = m->segment_mean > 1.0f ? 1.0 / (double)m->segment_mean : 1.0;
-    std::vector<uint32_t> lut;
-    build_qlut(m->qual_cdf, lut);
+    std::vector<uint32_t> lut, cdf24;
+    build_qlut(m->qual_cdf, lut, cdf24);
     CK(upload(ctx->qlut, lut.data(), lut.size() * 4, ctx->stream));
-    CK(upload(ctx->qcdf, m->qual_cdf, sizeof m->qual_cdf, ctx->stream));
+    CK(upload(ctx->qcdf, cdf24.data(), cdf24.size() * 4, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_model = true;
     ctx->have_batch = false;
@@ -377,6 +388,85 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     }
     const uint32_t n = n_reads;
     uint32_t launches = 0;
+    if (kind == NS_KIND_UNALIGNED && !(ctx->hcfg.flags & NS_FLAG_UNALIGNED_SCRIPTS)) {
+        // ---- warp-per-read fast path (uread_kernel.cuh): count pass, scan, write pass; no edit scripts
+        const unsigned tbu = 256, gbu = (n + tbu - 1) / tbu;
+        CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
+        CK(ctx->pieces.ensure((size_t)n * sizeof(NsPieceMeta)));
+        CK(ctx->counter.ensure(64));
+        CK(ctx->totals.ensure(8 * sizeof(uint64_t)));
+        CK(ctx->scan_in.ensure((size_t)n * sizeof(uint64_t)));
+        CK(ctx->scan_out.ensure((size_t)n * sizeof(uint64_t)));
+        CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * sizeof(uint64_t), st));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        UreadArgs ua;
+        ua.m = ctx->dmodel;
+        ua.ref = ctx->dref;
+        ua.cfg = ctx->dcfg;
+        ua.first_id = first_read_id;
+        ua.n_reads = n;
+        ua.reads = ctx->reads.as<NsReadMeta>();
+        ua.pieces = ctx->pieces.as<NsPieceMeta>();
+        ua.seq = nullptr;
+        ua.qual = nullptr;
+        ua.qlut = ctx->qlut.as<uint32_t>();
+        ua.qcdf = ctx->qcdf.as<uint32_t>();
+        ua.counter = ctx->counter.as<uint32_t>();
+        const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        CK(cudaEventRecord(ctx->ev[1], st));
+        uread_kernel<false, false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[2], st));
+        gather_read_bytes<<<gbu, tbu, 0, st>>>(ua.reads, n, ctx->scan_in.as<uint64_t>());
+        {
+            int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
+            if (rc) return rc;
+        }
+        scatter_read_off<<<gbu, tbu, 0, st>>>(ua.reads, n, ctx->scan_out.as<uint64_t>());
+        last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
+        sum_bases<<<std::min<unsigned>(gbu, 1024u), tbu, 0, st>>>(ua.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
+        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t seq_bytes_u = ctx->h_totals[2], total_bases_u = ctx->h_totals[3];
+        CK(ctx->ops.ensure(64));
+        CK(ctx->seq.ensure((size_t)seq_bytes_u + 16));
+        if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes_u + 16));
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        ua.seq = ctx->seq.as<uint8_t>();
+        ua.qual = ctx->qual.as<uint8_t>();
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        if (ctx->hcfg.fastq) uread_kernel<true, true><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
+        else uread_kernel<true, false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        NsBatchInfo& bu = ctx->last;
+        bu.seq_bytes = seq_bytes_u;
+        bu.n_ops = 0;
+        bu.total_bases = total_bases_u;
+        bu.n_reads = n;
+        bu.n_pieces = n;
+        bu.n_launches = 2 + 6;
+        float msu = 0;
+        cudaEventElapsedTime(&msu, ctx->ev[0], ctx->ev[1]);
+        bu.ms_setup = msu;
+        cudaEventElapsedTime(&msu, ctx->ev[1], ctx->ev[2]);
+        bu.ms_plan = msu;
+        cudaEventElapsedTime(&msu, ctx->ev[2], ctx->ev[3]);
+        bu.ms_scan = msu;
+        bu.ms_script = 0.f;
+        cudaEventElapsedTime(&msu, ctx->ev[4], ctx->ev[5]);
+        bu.ms_emit = msu;
+        cudaEventElapsedTime(&msu, ctx->ev[0], ctx->ev[5]);
+        bu.ms_total = msu;
+        ctx->last_kind = kind;
+        ctx->last_first_id = first_read_id;
+        ctx->have_batch = true;
+        if (info) *info = bu;
+        return NS_OK;
+    }
     const unsigned tb = 256, gb = (n + tb - 1) / tb;
     CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
     CK(ctx->counter.ensure(64));

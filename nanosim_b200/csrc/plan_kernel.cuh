@@ -29,6 +29,8 @@ struct PlanArgs {
     uint32_t* counter;          // work-fetch counter (zeroed before launch)
 };
 
+#define NS_MAX_SAME_LEN_RETRIES 64
+
 enum Phase : int { PH_FETCH = 0, PH_LEN, PH_ATT, PH_PIECE, PH_EVENT, PH_UEVENT, PH_PIECE_END, PH_CHECK, PH_DONE };
 
 template <bool WRITE>
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
     uint32_t slot = 0;            // read index inside the batch
     uint64_t rid = 0;             // global read id
     uint32_t n_seg = 1, n_pieces = 1, piece_first = 0;
-    uint32_t attempt = 0, gen = 0;
+    uint32_t attempt = 0, gen = 0, gen_fails = 0;
     Rng rng;                      // attempt stream
     // attempt state
     uint32_t remainder = 0, head = 0, tail = 0, reversed = 0;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             } else {
                 attempt = 0;
                 gen = 0;
+                gen_fails = 0;
                 phase = unal_kind ? PH_ATT : PH_LEN;
             }
             break;
@@ -383,13 +386,23 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 ok1 = total >= cfg.min_len && total <= cfg.max_len;            // :1367 keeps the ref lengths
                 if (!ok1) {
                     ++attempt;
-                    phase = PH_ATT;
+                    // The reference retries the same lengths with the following reads of its batch and only redraws
+                    // them when the batch is exhausted (:1283-1299); lengths that can (almost) never pass would
+                    // otherwise spin here, so they are redrawn after NS_MAX_SAME_LEN_RETRIES rejections.
+                    if (++gen_fails >= NS_MAX_SAME_LEN_RETRIES) {
+                        gen_fails = 0;
+                        ++gen;
+                        phase = PH_LEN;
+                    } else {
+                        phase = PH_ATT;
+                    }
                     break;
                 }
                 ok2 = actual >= cfg.min_len && actual <= cfg.max_len;          // :1429 consumes them
                 if (!ok2) {
                     ++attempt;
                     ++gen;
+                    gen_fails = 0;
                     phase = PH_LEN;
                     break;
                 }

@@ -117,11 +117,12 @@ class Engine:
         self.tables = t
 
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
-                  max_len=None, median_len=0.0, sd_len=0.0):
+                  max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
         cfg = L.NsRunConfig(0, int(circular), int(perfect), int(fastq), int(chimeric), int(kmer_bias or 0),
-                            int(min_len), int(min(max_len, 0x0fffffff)), float(median_len or 0.0), float(sd_len or 0.0))
+                            int(min_len), int(min(max_len, 0x0fffffff)), float(median_len or 0.0), float(sd_len or 0.0),
+                            L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0, 0)
         self._check(self._lib.ns_configure(self._ctx, C.byref(cfg)))
         self.fastq = bool(fastq)
 

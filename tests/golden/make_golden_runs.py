@@ -32,6 +32,8 @@ CONFIGS = {
     "dorado_fastq_chimeric": (DORADO, ["--fastq", "--chimeric"], True),
     "dorado_fastq_hp6_chimeric": (DORADO, ["--fastq", "--chimeric", "-hp", "-k", "6"], True),
     "guppy_perfect": (GUPPY, ["--perfect"], False),
+    # eight independent single-threaded processes per chunk (independent numpy streams for the unaligned phase)
+    "guppy_fasta_t1": (GUPPY, [], False),
 }
 
 
@@ -64,10 +66,20 @@ def main():
     while done < total:
         out = os.path.join(work, "sim")
         t0 = time.time()
-        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_shim.py"), "genome", "-rg", ref, "-c", prefix,
-                        "-n", str(chunk), "-t", "8", "-o", out] + flags, check=True, stdout=subprocess.DEVNULL)
-        t1 = time.time()
-        s = rs.stats_from_prefix(out, fastq)
+        if cfg.endswith("_t1"):
+            procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "ref_shim.py"), "genome", "-rg", ref,
+                                       "-c", prefix, "-n", str(chunk // 8), "-t", "1", "-o", out + "_p%d" % i] + flags,
+                                      stdout=subprocess.DEVNULL) for i in range(8)]
+            assert all(p.wait() == 0 for p in procs)
+            t1 = time.time()
+            s = rs.empty()
+            for i in range(8):
+                rs.merge(s, rs.stats_from_prefix(out + "_p%d" % i, fastq, with_errors=False))
+        else:
+            subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_shim.py"), "genome", "-rg", ref, "-c", prefix,
+                            "-n", str(chunk), "-t", "8", "-o", out] + flags, check=True, stdout=subprocess.DEVNULL)
+            t1 = time.time()
+            s = rs.stats_from_prefix(out, fastq)
         for fn in os.listdir(work):
             if fn.startswith("sim_"):
                 os.remove(os.path.join(work, fn))

@@ -50,7 +50,7 @@ def load_tables(model, **kw):
 
 
 def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, min_len=50, max_len=None, circular=False,
-                device=0):
+                device=0, unaligned_scripts=False):
     from nanosim_b200.engine import Engine
 
     cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect)
@@ -58,7 +58,7 @@ def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, m
     eng.set_reference(ref)
     eng.set_model(t, perfect=perfect)
     eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
-                  max_len=min(max_len or ref.max_chrom, ref.max_chrom))
+                  max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts)
     return eng, cm, t
 
 
@@ -122,6 +122,18 @@ def check_edit_scripts(batch, ref, fastq, max_reads=None):
             cursor += int(pc["out_len"])
         assert cursor == Lr
     return verified
+
+
+def check_fast_unaligned(fast, scripted, ref, fastq):
+    """fast: batch from the warp-per-read unaligned path; scripted: same ids/seed through plan/script/emit (with ops)."""
+    from nanosim_b200.engine import Batch
+
+    for k in ("seq_len", "reversed", "attempts", "seq_off"):
+        assert np.array_equal(fast.reads[k], scripted.reads[k]), "unaligned fast path differs in reads.%s" % k
+    for k in ("chrom", "pos", "ref_len", "out_len", "ref_req", "l_new"):
+        assert np.array_equal(fast.pieces[k], scripted.pieces[k]), "unaligned fast path differs in pieces.%s" % k
+    hybrid = Batch(fast.info, fast.seq, fast.qual, scripted.reads, scripted.pieces, scripted.ops, fast.kind, fast.first_id)
+    return check_edit_scripts(hybrid, ref, fastq)
 
 
 def batch_stats(batch, ref, fastq, s=None):
@@ -351,7 +363,7 @@ def smoke_check(verbose=False):
     from nanosim_b200.reference_fasta import PackedReference
 
     ref = PackedReference.from_fasta(os.path.join(HERE, "golden", "mini_ref.fa"))
-    eng, cm, t = make_engine("guppy", ref, fastq=True, seed=7)
+    eng, cm, t = make_engine("guppy", ref, fastq=True, seed=7, unaligned_scripts=True)
     info = eng.simulate(L.NS_KIND_ALIGNED, 0, 3000)
     b = eng.fetch(want_ops=True)
     nb = check_edit_scripts(b, ref, True)
@@ -359,6 +371,12 @@ def smoke_check(verbose=False):
     info_u = eng.simulate(L.NS_KIND_UNALIGNED, 0, 300)
     bu = eng.fetch(want_ops=True)
     nb += check_edit_scripts(bu, ref, True)
+    # the warp-per-read fast path must give the same reads (lengths, strands, positions) and bases that satisfy the
+    # scripted path's edit scripts
+    eng.configure(fastq=True, min_len=50, max_len=ref.max_chrom, unaligned_scripts=False)
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 300)
+    bf = eng.fetch()
+    nb += check_fast_unaligned(bf, bu, ref, True)
     import nanosim_oracle as no
 
     recs = no.read_fasta(os.path.join(HERE, "golden", "mini_ref.fa"))

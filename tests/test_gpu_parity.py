@@ -59,12 +59,26 @@ def test_edit_scripts_bit_exact_mini_ref(model, kw, mini_ref, L):
     if kw.get("perfect"):
         assert (b.reads["head"] == 0).all() and (b.reads["tail"] == 0).all()
         assert ((b.ops >> 28) == 0).all()
-    if not kw.get("perfect"):
-        eng.simulate(L.NS_KIND_UNALIGNED, 0, 400)
-        bu = eng.fetch(want_ops=True)
-        assert pc.check_edit_scripts(bu, mini_ref, kw.get("fastq", False)) > 0
-        assert bu.reads["seq_len"].min() >= 50
     eng.close()
+
+
+@pytest.mark.parametrize("model,fastq", [("guppy", True), ("guppy", False), ("dorado", True)])
+def test_unaligned_fast_path_equals_scripted_path(model, fastq, mini_ref, L):
+    """The warp-per-read unaligned kernel evaluates unaligned_error_list 32 draws at a time; the scripted path runs
+    it sequentially and keeps edit scripts.  Same seed => same lengths, rejections, strands and positions, and the
+    fast path's bases must satisfy the scripted path's edit scripts bit-exactly."""
+    a, _, _ = pc.make_engine(model, mini_ref, fastq=fastq, seed=21, unaligned_scripts=True)
+    a.simulate(L.NS_KIND_UNALIGNED, 100, 1500)
+    bs = a.fetch(want_ops=True)
+    assert pc.check_edit_scripts(bs, mini_ref, fastq) > 0
+    a.close()
+    b, _, _ = pc.make_engine(model, mini_ref, fastq=fastq, seed=21)
+    info = b.simulate(L.NS_KIND_UNALIGNED, 100, 1500)
+    bf = b.fetch()
+    b.close()
+    assert info.n_ops == 0 and bf.reads["seq_len"].min() >= 50
+    assert pc.check_fast_unaligned(bf, bs, mini_ref, fastq) > 0
+    assert bf.reads["attempts"].max() > 0
 
 
 def test_circular_reference_wraps(L):
@@ -194,8 +208,19 @@ def test_vs_unmodified_reference_1M_reads(ecoli, L):
     print("per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
     # the reference's own chunk-to-chunk noise bounds what +-0.1 % can mean
     fails = pc.compare_stats(s, gold, rate_tol=1e-3, p_min=1e-6, label="1M",
-                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match",
-                                   "len_unaligned"])
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    # unaligned lengths: the reference forks its unaligned workers WITHOUT reseeding numpy (simulator.py:1648-1660), so
+    # with -t 8 all eight workers draw the same KDE lengths (8-fold duplicated sample).  They are compared against a
+    # separate golden run made of independent -t 1 processes.
+    p1 = os.path.join(GOLDEN, "ref_stats_guppy_fasta_t1.json")
+    if os.path.exists(p1):
+        g1, _ = rs.load(p1)
+        st, dof, p = pc.chi2_two_sample(s["len_unaligned"], g1["len_unaligned"])
+        print("len_unaligned vs -t 1 golden: chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("1M histogram len_unaligned (vs -t 1 golden): chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        fr_d, fr_g = s["strand_R_unaligned"] / s["n_unaligned"], g1["strand_R_unaligned"] / g1["n_unaligned"]
+        assert abs(fr_d - fr_g) < 0.02
     mean_dev, mean_ref = s["aligned_bases"] / s["n_aligned"], gold["aligned_bases"] / gold["n_aligned"]
     assert abs(mean_dev / mean_ref - 1) < 5e-3, (mean_dev, mean_ref)
     assert abs(s["strand_R_aligned"] / s["n_aligned"] - gold["strand_R_aligned"] / gold["n_aligned"]) < 3e-3

@@ -1,0 +1,19 @@
+"""Small fixed workload for ncu captures: guppy FASTQ on the 5 Mb synthetic reference."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import parity_checks as pc
+import synth
+from nanosim_b200 import _lib as L
+from nanosim_b200.reference_fasta import PackedReference
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 30000
+nu = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
+ref = PackedReference.from_records(synth.ecoli5m())
+eng, cm, t = pc.make_engine("guppy", ref, fastq=True, seed=11)
+for rep in range(2):
+    info = eng.simulate(L.NS_KIND_ALIGNED, 0, n)
+    print("aligned", info.total_bases, info.ms_plan, info.ms_script, info.ms_emit)
+    if nu:
+        info = eng.simulate(L.NS_KIND_UNALIGNED, 0, nu)
+        print("unaligned", info.total_bases, info.ms_plan, info.ms_script, info.ms_emit)
