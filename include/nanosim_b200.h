@@ -160,6 +160,9 @@ typedef struct {
     /* CUDA-event durations on the library's stream: set-up (segment counts, buffer growth), plan pass 1 (rejection
      * loops + counts), scans + host round trip of the totals, plan pass 2 (edit scripts), emit, and the whole batch */
     float ms_setup, ms_plan, ms_scan, ms_script, ms_emit, ms_total;
+    /* begin / end of the batch on the device timeline, in ms since the first ns_create() of this process on this device;
+     * comparable across contexts (streams) of one device, so overlapped pipelines can be timed on the device */
+    double t_begin_ms, t_end_ms;
 } NsBatchInfo;
 
 /* --- lifetime --------------------------------------------------------------------------------------------- */
@@ -168,6 +171,10 @@ typedef struct {
 int ns_create(int device, uint64_t seed, NsContext** out);
 int ns_destroy(NsContext* ctx);
 const char* ns_last_error(const NsContext* ctx);
+/* A second context on the same device that SHARES the parent's reference and model tables in HBM (no copy) but has its
+ * own stream and batch buffers: two or more contexts driven from different host threads overlap one batch's kernels
+ * with another batch's device->host copy.  The parent must outlive its clones. */
+int ns_clone(NsContext* parent, NsContext** out);
 
 /* --- read_profile() (:244-591): reference + model tables into HBM, once ------------------------------------- */
 int ns_set_reference(NsContext* ctx, const NsReference* ref);

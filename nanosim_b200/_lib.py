@@ -16,7 +16,7 @@ NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT = 0, 1, 2, 3, 4
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
-EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_set_reference", "ns_set_model", "ns_configure",
+EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_reference", "ns_set_model", "ns_configure",
            "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records"]
 
 
@@ -68,7 +68,7 @@ class NsBatchInfo(C.Structure):
     _fields_ = [("seq_bytes", C.c_uint64), ("n_ops", C.c_uint64), ("total_bases", C.c_uint64),
                 ("n_reads", C.c_uint32), ("n_pieces", C.c_uint32), ("n_launches", C.c_uint32),
                 ("ms_setup", C.c_float), ("ms_plan", C.c_float), ("ms_scan", C.c_float), ("ms_script", C.c_float),
-                ("ms_emit", C.c_float), ("ms_total", C.c_float)]
+                ("ms_emit", C.c_float), ("ms_total", C.c_float), ("t_begin_ms", C.c_double), ("t_end_ms", C.c_double)]
 
 
 # numpy views of the two record types
@@ -98,6 +98,8 @@ def lib():
     P = C.c_void_p
     L.ns_create.argtypes = [C.c_int, C.c_uint64, C.POINTER(P)]
     L.ns_create.restype = C.c_int
+    L.ns_clone.argtypes = [P, C.POINTER(P)]
+    L.ns_clone.restype = C.c_int
     L.ns_destroy.argtypes = [P]
     L.ns_destroy.restype = C.c_int
     L.ns_last_error.argtypes = [P]

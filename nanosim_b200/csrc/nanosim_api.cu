@@ -50,6 +50,7 @@ struct NsContext {
     std::string err;
     int sm_count = 148;
 
+    bool borrowed = false;          // ns_clone: reference + model buffers belong to the parent
     bool have_ref = false, have_model = false, have_cfg = false;
     DevBuf ref_bases, ref_off;
     DevRef dref{};
@@ -72,6 +73,8 @@ struct NsContext {
 };
 
 namespace {
+
+cudaEvent_t g_base[64] = {};      // per device: origin of the device timeline reported in NsBatchInfo
 
 int fail(NsContext* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -220,6 +223,11 @@ int ns_create(int device, uint64_t seed, NsContext** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_totals, 8 * sizeof(uint64_t));
+    if (e == cudaSuccess && device >= 0 && device < 64 && !g_base[device]) {
+        e = cudaEventCreate(&g_base[device]);
+        if (e == cudaSuccess) e = cudaEventRecord(g_base[device], ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(g_base[device]);
+    }
     if (e == cudaSuccess) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, device);
@@ -241,6 +249,11 @@ int ns_destroy(NsContext* ctx) {
     DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats};
+    if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
+        DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf};
+        for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
+        for (auto& k : ctx->kde) { k.p = nullptr; k.cap = 0; }
+    }
     for (DevBuf* b : bufs) b->release();
     for (auto& k : ctx->kde) k.release();
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -253,9 +266,35 @@ int ns_destroy(NsContext* ctx) {
 
 const char* ns_last_error(const NsContext* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+int ns_clone(NsContext* parent, NsContext** out) {
+    if (!parent || !out) return NS_EINVAL;
+    NsContext* c = nullptr;
+    int rc = ns_create(parent->device, parent->seed, &c);
+    if (rc != NS_OK) return rc;
+    c->borrowed = true;
+    c->have_ref = parent->have_ref;
+    c->have_model = parent->have_model;
+    c->have_cfg = parent->have_cfg;
+    c->ref_bases = parent->ref_bases;      // plain pointer copies; ns_destroy() of a clone does not free them
+    c->ref_off = parent->ref_off;
+    c->alias = parent->alias;
+    c->qlut = parent->qlut;
+    c->qcdf = parent->qcdf;
+    for (int i = 0; i < 5; ++i) c->kde[i] = parent->kde[i];
+    c->dref = parent->dref;
+    c->h_chrom_off = parent->h_chrom_off;
+    c->dmodel = parent->dmodel;
+    c->hmodel = parent->hmodel;
+    c->hcfg = parent->hcfg;
+    c->dcfg = parent->dcfg;
+    *out = c;
+    return NS_OK;
+}
+
 int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     if (!ctx || !ref || !ref->bases || !ref->chrom_off || ref->n_chrom == 0)
         return fail(ctx, NS_EINVAL, "ns_set_reference: null argument or empty reference");
+    if (ctx->borrowed) return fail(ctx, NS_ESTATE, "ns_set_reference: a cloned context shares its parent's reference");
     CK(cudaSetDevice(ctx->device));
     ctx->h_chrom_off.resize(ref->n_chrom + 1);
     CK(cudaMemcpy(ctx->h_chrom_off.data(), ref->chrom_off, (ref->n_chrom + 1) * sizeof(uint64_t), cudaMemcpyDefault));
@@ -280,6 +319,7 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
 
 int ns_set_model(NsContext* ctx, const NsModel* m) {
     if (!ctx || !m) return fail(ctx, NS_EINVAL, "ns_set_model: null argument");
+    if (ctx->borrowed) return fail(ctx, NS_ESTATE, "ns_set_model: a cloned context shares its parent's model");
     if (m->n_match_bins == 0 || m->n_match_bins > NS_MAX_BINS || m->n_tables != 4 + m->n_match_bins)
         return fail(ctx, NS_EINVAL, "ns_set_model: need 1..%d match bins and 4+bins alias tables", NS_MAX_BINS);
     if (!m->alias_prob || !m->alias_idx || !m->alias_desc || !m->match_bin_lo || !m->match_bin_hi)
@@ -461,6 +501,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         bu.ms_emit = msu;
         cudaEventElapsedTime(&msu, ctx->ev[0], ctx->ev[5]);
         bu.ms_total = msu;
+        cudaEventElapsedTime(&msu, g_base[ctx->device], ctx->ev[0]);
+        bu.t_begin_ms = msu;
+        cudaEventElapsedTime(&msu, g_base[ctx->device], ctx->ev[5]);
+        bu.t_end_ms = msu;
         ctx->last_kind = kind;
         ctx->last_first_id = first_read_id;
         ctx->have_batch = true;
@@ -614,6 +658,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     bi.ms_emit = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]);
     bi.ms_total = ms;
+    cudaEventElapsedTime(&ms, g_base[ctx->device], ctx->ev[0]);
+    bi.t_begin_ms = ms;
+    cudaEventElapsedTime(&ms, g_base[ctx->device], ctx->ev[5]);
+    bi.t_end_ms = ms;
     ctx->last_kind = kind;
     ctx->last_first_id = first_read_id;
     ctx->have_batch = true;

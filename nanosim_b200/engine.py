@@ -45,6 +45,19 @@ class Engine:
         self.fastq = False
         self.info = None
 
+    def clone(self):
+        """A context that shares this engine's reference + model in HBM (own stream and batch buffers)."""
+        other = Engine.__new__(Engine)
+        other._lib = self._lib
+        other._ctx = C.c_void_p()
+        self._check(self._lib.ns_clone(self._ctx, C.byref(other._ctx)))
+        other.device, other._keep, other.fastq, other.info = self.device, {}, self.fastq, None
+        other._parent = self            # keep the parent alive
+        for k in ("ref", "tables"):
+            if hasattr(self, k):
+                setattr(other, k, getattr(self, k))
+        return other
+
     def close(self):
         if self._ctx:
             self._lib.ns_destroy(self._ctx)

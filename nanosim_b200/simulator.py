@@ -22,6 +22,7 @@ import numpy as np
 from . import _lib as L
 from .engine import Engine
 from .model import DeviceTables, load_model
+from .pipeline import BatchPipeline
 from .records import error_profile_rows, format_records, read_names
 from .reference_fasta import PackedReference
 
@@ -87,31 +88,38 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                   kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0)
     ext = ".fastq" if fastq else ".fasta"
     suffix = "" if world == 1 else str(rank)
+    want_err = error_profile and not per
+    pipe = BatchPipeline(eng, depth=2, fetch=True, want_ops=want_err)
+
+    def jobs(kind, lo, hi):
+        return [(kind, start, min(batch_reads, hi - start)) for start in range(lo, hi, batch_reads)]
+
     _log("Start simulation of aligned reads")
     lo, hi = _shard(prof.number_aligned, rank, world)
     with open(out + "_aligned_reads" + suffix + ext, "wb") as f_reads, \
             open(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix), "w") as f_err:
         if world == 1:
             f_err.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
-        for start in range(lo, hi, batch_reads):
-            n = min(batch_reads, hi - start)
-            eng.simulate(L.NS_KIND_ALIGNED, start, n)
-            b = eng.fetch(want_ops=error_profile and not per)
-            names = read_names(b, prof.ref.names, start, perfect=per)
+
+        def sink_aligned(info, b, job):
+            names = read_names(b, prof.ref.names, job[1], perfect=per)
             f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
-            if error_profile and not per:
+            if want_err:
                 f_err.writelines(error_profile_rows(b, names, prof.ref))
+
+        pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned)
     if not per:
         _log("Start simulation of random reads")
         lo, hi = _shard(prof.number_unaligned, rank, world)
         with open(out + "_unaligned_reads" + suffix + ext, "wb") as f_reads:
-            for start in range(lo, hi, batch_reads):
-                n = min(batch_reads, hi - start)
-                eng.simulate(L.NS_KIND_UNALIGNED, start, n)
-                b = eng.fetch()
+
+            def sink_unaligned(info, b, job):
                 # the reference's read index keeps counting after the aligned reads (shared total_simulated, :1574)
-                names = read_names(b, prof.ref.names, prof.number_aligned + start)
+                names = read_names(b, prof.ref.names, prof.number_aligned + job[1])
                 f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
+
+            pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned)
+    pipe.close()
 
 
 def merge_rank_files(out, fastq, per, world):
