@@ -286,10 +286,11 @@ def main():
     # ---- end-to-end arm: the public API (BatchPipeline): ns_simulate + ns_fetch into pinned host buffers every batch
     pipe_e = BatchPipeline(eng, depth=args.depth, fetch=True)
     base_step = total_steps                          # fresh read ids
-    pipe_e.run(jobs_for(range(base_step, base_step + 2)))
+    e_warm = max(3, args.depth + 1)                  # every context's pinned buffers must have seen an aligned batch
+    pipe_e.run(jobs_for(range(base_step, base_step + e_warm)))
     barrier()
     t0 = time.perf_counter()
-    rows_e = [row(i) for i in pipe_e.run(jobs_for(range(base_step + 2, base_step + 2 + args.steps)))]
+    rows_e = [row(i) for i in pipe_e.run(jobs_for(range(base_step + e_warm, base_step + e_warm + args.steps)))]
     barrier()
     wall_e = time.perf_counter() - t0
     pipe_e.close()

@@ -38,6 +38,7 @@ struct DevCfg {
     uint32_t circular, perfect, fastq, chimeric, kmer_bias;
     uint32_t min_len, max_len;
     uint64_t seed;
+    double median_len, sd_len;          // -med / -sd (0 = lengths from the KDEs)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -131,6 +132,13 @@ __device__ __forceinline__ double kde_draw(const DevKde& k, Rng& rng) {
     float u2 = (float)(r2 >> 8) * (1.0f / 16777216.0f);
     float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     return (double)__ldg(&k.data[i]) + (double)k.bw * (double)z;
+}
+
+// numpy.random.lognormal(mean, sigma) = exp(mean + sigma * N(0,1))
+__device__ __forceinline__ double lognormal_draw(double mean, double sigma, Rng& rng) {
+    uint32_t r1 = rng.next(), r2 = rng.next();
+    float z = sqrtf(-2.0f * logf(u01_open_low(r1))) * cospif(2.0f * ((float)(r2 >> 8) * (1.0f / 16777216.0f)));
+    return exp(mean + sigma * (double)z);
 }
 
 // base <-> index helpers: A C G T -> 0 1 3 2 via (c >> 1) & 3 ; complement = idx ^ 2

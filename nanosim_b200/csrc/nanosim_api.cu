@@ -1,6 +1,7 @@
 // C ABI of libnanosim_b200.so (include/nanosim_b200.h): context, HBM residency of reference + model tables,
 // batch orchestration (plan -> scan -> script -> emit) on one CUDA stream, device->host fetch.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -30,6 +31,22 @@ struct DevBuf {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    // grow but keep the first `keep` bytes (rare path)
+    cudaError_t ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return cudaSuccess;
+        void* np = nullptr;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = want;
         return e;
     }
     void release() {
@@ -64,7 +81,7 @@ struct NsContext {
 
     // batch state
     DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
-        stats;
+        stats, sort_keys, sort_vals, sort_tmp;
     uint64_t* h_totals = nullptr;   // pinned
     NsBatchInfo last{};
     int last_kind = 0;
@@ -100,6 +117,18 @@ __global__ void gather_piece_ops(const NsPieceMeta* pieces, uint32_t n, uint64_t
 __global__ void scatter_piece_off(NsPieceMeta* pieces, uint32_t n, const uint64_t* off) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pieces[i].op_off = off[i];
+}
+__global__ void set_sentinel_off(NsPieceMeta* pieces, uint32_t n, const uint64_t* total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) pieces[n].op_off = *total;
+}
+// pieces of reads whose script overflowed its slot (NsReadMeta.flags bit 0) get exact offsets behind the primary area
+__global__ void gather_flagged_ops(const NsPieceMeta* pieces, const NsReadMeta* reads, uint32_t n, uint64_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (reads[pieces[i].read_slot].flags & 1u) ? pieces[i].n_ops : 0u;
+}
+__global__ void scatter_flagged_off(NsPieceMeta* pieces, const NsReadMeta* reads, uint32_t n, const uint64_t* off, uint64_t base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (reads[pieces[i].read_slot].flags & 1u)) pieces[i].op_off = base + off[i];
 }
 __global__ void gather_read_bytes(const NsReadMeta* reads, uint32_t n, uint64_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +277,8 @@ int ns_destroy(NsContext* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
-                      &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats};
+                      &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
+                      &ctx->sort_tmp};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
         DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf};
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
@@ -379,8 +409,10 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     if (cfg->mode != 0) return fail(ctx, NS_EINVAL, "ns_configure: only genome mode (0) is implemented");
     if (cfg->max_len < cfg->min_len) return fail(ctx, NS_EINVAL, "Maximum read length must be longer than Minimum read length!");
     if (cfg->perfect && cfg->chimeric) return fail(ctx, NS_EINVAL, "Perfect reads cannot be chimeric");
-    if (cfg->median_len != 0.0 || cfg->sd_len != 0.0)
-        return fail(ctx, NS_EINVAL, "ns_configure: -med/-sd log-normal lengths are not implemented yet");
+    if ((cfg->median_len != 0.0) != (cfg->sd_len != 0.0))
+        return fail(ctx, NS_EINVAL, "Please provide both mean and standard deviation of read length!");
+    if (cfg->median_len != 0.0 && cfg->chimeric) return fail(ctx, NS_EINVAL, "Lognormal distributed reads cannot be chimeric!");
+    if (cfg->median_len < 0.0 || cfg->sd_len < 0.0) return fail(ctx, NS_EINVAL, "ns_configure: negative -med/-sd");
     if (cfg->kmer_bias != 0) return fail(ctx, NS_EINVAL, "ns_configure: homopolymer simulation (-hp/-k) is not implemented yet");
     ctx->hcfg = *cfg;
     ctx->dcfg.circular = cfg->circular;
@@ -391,6 +423,8 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.min_len = cfg->min_len;
     ctx->dcfg.max_len = cfg->max_len;
     ctx->dcfg.seed = ctx->seed;
+    ctx->dcfg.median_len = cfg->median_len;
+    ctx->dcfg.sd_len = cfg->sd_len;
     ctx->have_cfg = true;
     ctx->have_batch = false;
     return NS_OK;
@@ -409,7 +443,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     if (!ctx->have_ref || !ctx->have_model || !ctx->have_cfg)
         return fail(ctx, NS_ESTATE, "ns_simulate: reference, model and run configuration must be set first");
     if (kind != NS_KIND_ALIGNED && kind != NS_KIND_UNALIGNED) return fail(ctx, NS_EINVAL, "ns_simulate: bad kind %d", kind);
-    if (kind == NS_KIND_UNALIGNED && ctx->dmodel.unaligned.n == 0)
+    if (kind == NS_KIND_UNALIGNED && ctx->dmodel.unaligned.n == 0 && ctx->hcfg.median_len == 0.0)
         return fail(ctx, NS_ESTATE, "ns_simulate: model has no unaligned-length KDE");
     if (kind == NS_KIND_ALIGNED && ctx->hcfg.chimeric && ctx->dmodel.gap.n == 0)
         return fail(ctx, NS_ESTATE, "ns_simulate: chimeric simulation needs the gap-length KDE");
@@ -543,11 +577,43 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         d_nseg = ctx->nseg.as<uint32_t>();
         d_pfirst = ctx->piece_first.as<uint32_t>();
     }
-    CK(ctx->pieces.ensure((size_t)n_pieces * sizeof(NsPieceMeta)));
-    CK(cudaMemsetAsync(ctx->pieces.p, 0, (size_t)n_pieces * sizeof(NsPieceMeta), st));
-    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(ctx->pieces.ensure((size_t)(n_pieces + 1) * sizeof(NsPieceMeta)));
+    CK(cudaMemsetAsync(ctx->pieces.p, 0, (size_t)(n_pieces + 1) * sizeof(NsPieceMeta), st));
+    const unsigned gp = (n_pieces + tb - 1) / tb;
 
-    // ---- plan pass 1: rejection loops, lengths, op counts, positions
+    // ---- generation-0 lengths -> op-slot capacities (scan) and processing order (longest reads first)
+    CK(ctx->sort_keys.ensure((size_t)n * 8));
+    CK(ctx->sort_vals.ensure((size_t)n * 8));
+    uint32_t* keys_in = ctx->sort_keys.as<uint32_t>();
+    uint32_t* keys_out = keys_in + n;
+    uint32_t* vals_in = ctx->sort_vals.as<uint32_t>();
+    uint32_t* vals_out = vals_in + n;
+    const bool exact_only = (kind == NS_KIND_UNALIGNED);
+    lengths_kernel<<<gb, tb, 0, st>>>(ctx->dmodel, ctx->dcfg, (uint32_t)kind, first_read_id, n, d_nseg, d_pfirst,
+                                      ctx->pieces.as<NsPieceMeta>(), 1.0f / std::max(1.0f, ctx->hmodel.mean_ref_per_event),
+                                      exact_only ? 1u : 0u, ctx->scan_in.as<uint64_t>(), keys_in, vals_in);
+    CK(cudaGetLastError());
+    {
+        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces);
+        if (rc) return rc;
+    }
+    scatter_piece_off<<<gp, tb, 0, st>>>(ctx->pieces.as<NsPieceMeta>(), n_pieces, ctx->scan_out.as<uint64_t>());
+    last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 4);
+    set_sentinel_off<<<1, 32, 0, st>>>(ctx->pieces.as<NsPieceMeta>(), n_pieces, ctx->totals.as<uint64_t>() + 4);
+    {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, st));
+        CK(ctx->sort_tmp.ensure(tmp));
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, st));
+    }
+    CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t primary_ops = ctx->h_totals[4];
+    CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    launches += 10;
+
+    // ---- plan: rejection loops, positions, edit scripts (single pass)
     PlanArgs pa;
     pa.m = ctx->dmodel;
     pa.ref = ctx->dref;
@@ -559,8 +625,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     pa.piece_first = d_pfirst;
     pa.reads = ctx->reads.as<NsReadMeta>();
     pa.pieces = ctx->pieces.as<NsPieceMeta>();
-    pa.ops = nullptr;
+    pa.ops = ctx->ops.as<uint32_t>();
+    pa.order = vals_out;
     pa.counter = ctx->counter.as<uint32_t>();
+    pa.n_flagged = (uint32_t*)(ctx->totals.as<uint64_t>() + 5);
     const unsigned plan_tb = 128;
     unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * 16u);
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
@@ -569,15 +637,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(cudaEventRecord(ctx->ev[2], st));
     launches += 1;
 
-    // ---- exclusive scans: op offsets per piece, 16-byte aligned sequence slots per read
-    const unsigned gp = (n_pieces + tb - 1) / tb;
-    gather_piece_ops<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, ctx->scan_in.as<uint64_t>());
-    {
-        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces);
-        if (rc) return rc;
-    }
-    scatter_piece_off<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, ctx->scan_out.as<uint64_t>());
-    last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 1);
+    // ---- 16-byte aligned sequence slots per read (scan); exact offsets for scripts that overflowed their slot
     gather_read_bytes<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_in.as<uint64_t>());
     {
         int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
@@ -586,22 +646,33 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     scatter_read_off<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_out.as<uint64_t>());
     last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
     sum_bases<<<std::min<unsigned>(gb, 1024u), tb, 0, st>>>(pa.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
+    gather_flagged_ops<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_in.as<uint64_t>());
+    {
+        int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces);
+        if (rc) return rc;
+    }
+    last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 1);
     CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const uint64_t n_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
-    CK(ctx->ops.ensure((size_t)(n_ops + 4) * sizeof(uint32_t)));
+    const uint64_t overflow_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
+    const uint32_t n_flagged = (uint32_t)(ctx->h_totals[5] & 0xffffffffull);
+    const uint64_t n_ops = primary_ops + overflow_ops;
     CK(ctx->seq.ensure((size_t)seq_bytes + 16));
     if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes + 16));
     CK(cudaEventRecord(ctx->ev[3], st));
-    launches += 11;   // 2 gathers, 2 scans (2 kernels each), 2 scatters, 2 totals, 1 reduction
-
-    // ---- plan pass 2: replay the accepted attempt, write the edit scripts
-    pa.ops = ctx->ops.as<uint32_t>();
-    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-    plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
-    CK(cudaGetLastError());
+    launches += 9;
+    if (n_flagged > 0) {
+        // ---- rare: replay the flagged reads and write their scripts behind the primary area
+        CK(ctx->ops.ensure_keep((size_t)(n_ops + 4) * sizeof(uint32_t), (size_t)primary_ops * sizeof(uint32_t), st));
+        pa.ops = ctx->ops.as<uint32_t>();
+        scatter_flagged_off<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_out.as<uint64_t>(), primary_ops);
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
+        CK(cudaGetLastError());
+        launches += 2;
+    }
     CK(cudaEventRecord(ctx->ev[4], st));
-    launches += 2;    // script pass + emit
+    launches += 1;    // emit
 
     // ---- emit
     EmitArgs ea;

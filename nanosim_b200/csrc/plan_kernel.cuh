@@ -6,11 +6,16 @@
 // accepted (persistent threads), so lanes of a warp are always in the same hot phase (one error/match event
 // per loop iteration) regardless of how different their read lengths are.
 //
-// The kernel runs twice per batch with identical random streams:
-//   WRITE=false : counts ops / lengths, runs the rejection loops (:1367, :1429, :1503, :1517), draws positions
-//                 (extract_read :1750-1781) and fills NsReadMeta / NsPieceMeta;
-//   WRITE=true  : replays only the accepted attempt and writes the edit script (ops) at the exact offsets an
-//                 exclusive scan of the counts produced.
+// Reads are taken in order of decreasing drawn reference length (lengths_kernel + a radix sort), so the 32 lanes of
+// a warp work on reads of almost equal length and finish together, and the longest chains start first.
+//
+//   REPLAY=false : runs the rejection loops (:1367, :1429, :1503, :1517), draws positions (extract_read :1750-1781),
+//                  fills NsReadMeta / NsPieceMeta and writes every edit script into a slot sized from the drawn
+//                  length (mean + 6 sigma of the op count).  A script that does not fit is only counted and the read is
+//                  flagged;
+//   REPLAY=true  : for flagged reads only (normally none; always for unaligned reads in NS_FLAG_UNALIGNED_SCRIPTS
+//                  mode): replays the accepted attempt with identical random streams and writes the script at the
+//                  exact offset an exclusive scan of the counts produced.
 #pragma once
 #include "device_common.cuh"
 
@@ -25,8 +30,10 @@ struct PlanArgs {
     const uint32_t* piece_first;// per read (nullptr => read index)
     NsReadMeta* reads;
     NsPieceMeta* pieces;
-    uint32_t* ops;              // WRITE only
+    uint32_t* ops;
+    const uint32_t* order;      // read slots by decreasing drawn length (nullptr => identity)
     uint32_t* counter;          // work-fetch counter (zeroed before launch)
+    uint32_t* n_flagged;        // REPLAY=false: number of reads whose script overflowed its slot
 };
 
 #define NS_MAX_SAME_LEN_RETRIES 64
@@ -36,12 +43,14 @@ enum Phase : int { PH_FETCH = 0, PH_LEN, PH_ATT, PH_PIECE, PH_EVENT, PH_UEVENT, 
 template <bool WRITE>
 struct OpSink {
     uint32_t* base;       // start of this piece's op slot (WRITE)
+    uint32_t cap;         // slot capacity in ops
     uint32_t n;           // ops emitted so far (flushed)
     uint32_t pend_type;   // pending (mergeable) op
     uint32_t pend_len;
     uint32_t out_len;     // bases produced by flushed + pending ops
-    __device__ __forceinline__ void begin(uint32_t* slot) {
+    __device__ __forceinline__ void begin(uint32_t* slot, uint32_t capacity) {
         base = slot;
+        cap = capacity;
         n = 0;
         pend_type = 0xffffffffu;
         pend_len = 0;
@@ -49,7 +58,7 @@ struct OpSink {
     }
     __device__ __forceinline__ void flush() {
         if (pend_type != 0xffffffffu && pend_len > 0) {
-            if (WRITE) base[n] = (pend_type << 28) | pend_len;
+            if (WRITE && n < cap) base[n] = (pend_type << 28) | pend_len;
             ++n;
         }
         pend_type = 0xffffffffu;
@@ -67,15 +76,21 @@ struct OpSink {
         pend_type = type;
         pend_len = len;
     }
+    // unmerged append (aligned segments: every error event keeps its own op, as in the reference's e_dict)
+    __device__ __forceinline__ void put(uint32_t type, uint32_t len) {
+        if (len == 0) return;
+        if (type != NS_OP_DEL) out_len += len;
+        if (WRITE && n < cap) base[n] = (type << 28) | len;
+        ++n;
+    }
     // the reference's e_dict[pos - 0.5] overwrite: a second insertion at the same position replaces the first (:1882)
-    __device__ __forceinline__ void replace_pending_ins(uint32_t len) {
-        out_len -= pend_len;
-        pend_len = len;
-        out_len += len;
+    __device__ __forceinline__ void replace_last_ins(uint32_t old_len, uint32_t len) {
+        out_len = out_len - old_len + len;
+        if (WRITE && n - 1 < cap) base[n - 1] = (NS_OP_INS << 28) | len;
     }
 };
 
-__device__ __forceinline__ uint32_t match_bin(const DevModel& m, uint32_t prev_match) {
+__device__ __forceinline__ uint32_t match_bin_scan(const DevModel& m, uint32_t prev_match) {
     uint32_t b = m.n_bins - 1;          // falls through to the last bin (:1891-1893)
     for (uint32_t i = 0; i < m.n_bins; ++i) {
         if (m.bin_lo[i] <= prev_match && prev_match < m.bin_hi[i]) {
@@ -84,6 +99,11 @@ __device__ __forceinline__ uint32_t match_bin(const DevModel& m, uint32_t prev_m
         }
     }
     return b;
+}
+#define BIN_LUT_SIZE 1024
+// bin of the previous match length: shared-memory table for short matches, header scan for the rest
+__device__ __forceinline__ uint32_t match_bin(const DevModel& m, const uint8_t* lut, uint32_t prev_match) {
+    return prev_match < BIN_LUT_SIZE ? (uint32_t)lut[prev_match] : match_bin_scan(m, prev_match);
 }
 
 // extract_read, genome branches (:1750-1781): uniform start over the concatenated genome, redrawn until the
@@ -115,11 +135,87 @@ __device__ __forceinline__ void draw_position(const DevRef& ref, const DevCfg& c
     pos = 0;
 }
 
-template <bool WRITE>
+// ref_lengths / gap_lengths of generation `gen` for one aligned read (:1285-1299, :1309-1310) -> pieces[].ref_req
+__device__ __forceinline__ void draw_lengths(const DevModel& m, const DevCfg& cfg, uint32_t kind, uint64_t rid, uint32_t gen,
+                                             uint32_t n_seg, NsPieceMeta* pieces) {
+    Rng lr;
+    lr.init(cfg.seed, rid, stream_word(ST_LEN, kind, gen));
+    for (uint32_t s = 0; s < n_seg; ++s) {
+        uint32_t len = 0;
+        for (int it = 0; it < 100000; ++it) {
+            double x;
+            if (cfg.median_len > 0.0) {
+                // -med/-sd (:1285-1295): perfect reads take the log-normal length itself; otherwise the reference
+                // subtracts a head/tail remainder from a log-normal TOTAL length.  Its list filtering (:1296) breaks
+                // the pairing between that remainder and the one the read later gets, so the subtracted remainder is
+                // an independent kde_ht draw here.
+                if (cfg.perfect) {
+                    x = lognormal_draw(log(cfg.median_len), cfg.sd_len, lr);
+                } else {
+                    double t = lognormal_draw(log(cfg.median_len + cfg.sd_len * cfg.sd_len / 2.0), cfg.sd_len, lr);
+                    double rem = -1.0;
+                    for (int jt = 0; jt < 100000 && rem < 0.0; ++jt) rem = pow(10.0, kde_draw(m.ht, lr)) - 1.0;
+                    x = t - rem;
+                }
+            } else {
+                x = kde_draw(m.aligned, lr);
+            }
+            bool ok = cfg.perfect ? (x >= (double)cfg.min_len && x <= (double)cfg.max_len)
+                                  : (x > 0.0 && x <= (double)cfg.max_len);
+            // int(x) == 0 makes the reference's extract_read spin forever (:1767-1780); redraw instead
+            if (ok && (uint32_t)x > 0) {
+                len = (uint32_t)x;
+                break;
+            }
+        }
+        pieces[2 * s].ref_req = len;
+        if (s + 1 < n_seg) {
+            double g = pow(10.0, kde_draw(m.gap, lr)) - 1.0;
+            int64_t gi = (int64_t)g;
+            pieces[2 * s + 1].ref_req = gi > 0 ? (uint32_t)gi : 0u;
+        }
+    }
+}
+
+// Generation-0 lengths of every read of the batch, op-slot capacities per piece and the sort key (total drawn length).
+// cap = 2 * (E + 6 sqrt(E) + 8) + 4 ops for a segment expected to hold E = m_ref / mean_ref_per_event error events.
+__global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t first_id, uint32_t n, const uint32_t* n_seg,
+                               const uint32_t* piece_first, NsPieceMeta* pieces, float ev_per_base, uint32_t exact_only,
+                               uint64_t* caps, uint32_t* keys, uint32_t* vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t ns = n_seg ? n_seg[i] : 1u;
+    const uint32_t pf = piece_first ? piece_first[i] : i;
+    uint64_t total = 0;
+    if (kind == NS_KIND_ALIGNED) {
+        draw_lengths(m, cfg, kind, first_id + i, 0, ns, pieces + pf);
+        for (uint32_t q = 0; q < 2 * ns - 1; ++q) {
+            const uint32_t len = pieces[pf + q].ref_req;
+            total += len;
+            uint64_t cap;
+            if (q & 1u) cap = 2ull * len + 64;                           // gap: unaligned-type script
+            else if (cfg.perfect) cap = 4;
+            else {
+                float e = (float)len * ev_per_base;
+                cap = (uint64_t)(2.0f * (e + 6.0f * sqrtf(e) + 8.0f)) + 4;
+            }
+            caps[pf + q] = exact_only ? 0 : cap;
+        }
+    } else {
+        caps[pf] = 0;                                                    // scripted unaligned reads: exact pass only
+    }
+    keys[i] = total > 0xffffffffull ? 0xffffffffu : (uint32_t)total;
+    vals[i] = i;
+}
+
+template <bool REPLAY>
 __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanArgs a) {
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const bool unal_kind = (a.kind == NS_KIND_UNALIGNED);
+    __shared__ uint8_t bin_lut[BIN_LUT_SIZE];
+    for (uint32_t i = threadIdx.x; i < BIN_LUT_SIZE; i += blockDim.x) bin_lut[i] = (uint8_t)match_bin_scan(m, i);
+    __syncthreads();
 
     int phase = PH_FETCH;
     uint32_t slot = 0;            // read index inside the batch
@@ -136,8 +232,10 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
     int64_t l_new = 0;
     uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
     bool last_op_was_ins_same_pos = false;
-    OpSink<WRITE> sink;
-    sink.begin(nullptr);
+    uint32_t last_ins_len = 0;
+    OpSink<true> sink;
+    sink.begin(nullptr, 0);
+    bool overflow = false;
 
     for (;;) {
         switch (phase) {
@@ -147,59 +245,43 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 phase = PH_DONE;
                 break;
             }
+            if (a.order) slot = a.order[slot];
+            if (REPLAY && !(a.reads[slot].flags & 1u)) break;      // only flagged reads are replayed
             rid = a.first_id + slot;
             n_seg = a.n_seg ? a.n_seg[slot] : 1u;
             piece_first = a.piece_first ? a.piece_first[slot] : slot;
             n_pieces = unal_kind ? 1u : 2u * n_seg - 1u;
-            if (WRITE) {
+            overflow = false;
+            if (REPLAY) {
                 attempt = a.reads[slot].attempts;
-                phase = PH_ATT;
             } else {
                 attempt = 0;
-                gen = 0;
+                gen = 0;                   // generation-0 lengths were drawn by lengths_kernel
                 gen_fails = 0;
-                phase = unal_kind ? PH_ATT : PH_LEN;
             }
+            phase = PH_ATT;
             break;
         }
-        case PH_LEN: {   // aligned: ref_lengths / gap_lengths of generation `gen` (:1285-1299, :1309-1310)
-            Rng lr;
-            lr.init(cfg.seed, rid, stream_word(ST_LEN, a.kind, gen));
-            for (uint32_t s = 0; s < n_seg; ++s) {
-                uint32_t len = 0;
-                for (int it = 0; it < 100000; ++it) {
-                    double x = kde_draw(m.aligned, lr);
-                    bool ok = cfg.perfect ? (x >= (double)cfg.min_len && x <= (double)cfg.max_len)
-                                          : (x > 0.0 && x <= (double)cfg.max_len);
-                    // int(x) == 0 makes the reference's extract_read spin forever (:1767-1780); redraw instead
-                    if (ok && (uint32_t)x > 0) {
-                        len = (uint32_t)x;
-                        break;
-                    }
-                }
-                a.pieces[piece_first + 2 * s].ref_req = len;
-                if (s + 1 < n_seg) {
-                    double g = pow(10.0, kde_draw(m.gap, lr)) - 1.0;
-                    int64_t gi = (int64_t)g;
-                    a.pieces[piece_first + 2 * s + 1].ref_req = gi > 0 ? (uint32_t)gi : 0u;
-                }
-            }
+        case PH_LEN: {   // aligned: new ref_lengths / gap_lengths after a :1429 rejection (generation >= 1)
+            draw_lengths(m, cfg, a.kind, rid, gen, n_seg, a.pieces + piece_first);
             phase = PH_ATT;
             break;
         }
         case PH_ATT: {
             rng.init(cfg.seed, rid, stream_word(ST_ATT, a.kind, attempt));
+            overflow = false;
             p = 0;
             total = 0;
             actual = 0;
             if (unal_kind) {
                 // ref = int(kde_unaligned.sample()) (:1494-1499); <= 0 can never pass the min_l test (:1503)
-                double x = kde_draw(m.unaligned, rng);
+                double x = cfg.median_len > 0.0 ? lognormal_draw(log(cfg.median_len), cfg.sd_len, rng)
+                                                : kde_draw(m.unaligned, rng);
                 int64_t r = (int64_t)x;
-                if (!WRITE) a.pieces[piece_first].ref_req = r > 0 ? (uint32_t)r : 0u;
+                if (!REPLAY) a.pieces[piece_first].ref_req = r > 0 ? (uint32_t)r : 0u;
                 head = tail = 0;
                 remainder = 0;
-                if (r <= 0 && !WRITE) {
+                if (r <= 0 && !REPLAY) {
                     ++attempt;                      // rejected: middle_ref < min_l
                     break;
                 }
@@ -229,18 +311,19 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
         case PH_PIECE: {
             NsPieceMeta& pm = a.pieces[piece_first + p];
             uint32_t m_ref = pm.ref_req;
-            sink.begin(WRITE ? a.ops + pm.op_off : nullptr);
+            // slot = [op_off, next piece's op_off) ; a replayed (flagged) piece has an exact slot
+            sink.begin(a.ops + pm.op_off, REPLAY ? 0xffffffffu : (uint32_t)(a.pieces[piece_first + p + 1].op_off - pm.op_off));
             pos = 0;
             middle_ref = m_ref;
             l_new = (int64_t)m_ref;
             pending_ins = 0;
             last_op_was_ins_same_pos = false;
             bool is_gap = unal_kind || (p & 1u);
-            if (!unal_kind && p == 0 && head > 0) sink.push(NS_OP_HT, head, false);
+            if (!unal_kind && p == 0 && head > 0) sink.put(NS_OP_HT, head);
             if (is_gap) {
                 phase = (m_ref == 0) ? PH_PIECE_END : PH_UEVENT;
             } else if (cfg.perfect) {
-                sink.push(NS_OP_COPY, m_ref, false);
+                sink.put(NS_OP_COPY, m_ref);
                 phase = PH_PIECE_END;
             } else {
                 // first match from _first_match.hist, floor 2 (:1843-1850); no extension when it overshoots
@@ -249,7 +332,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 err_state = 0;     // "start"
                 last_err = 3;
                 pos = fm;
-                sink.push(NS_OP_COPY, fm < middle_ref ? fm : middle_ref, false);
+                sink.put(NS_OP_COPY, fm < middle_ref ? fm : middle_ref);
                 phase = (pos < middle_ref) ? PH_EVENT : PH_PIECE_END;
             }
             break;
@@ -266,11 +349,12 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             uint32_t step = alias_draw(m, e, r.y);    // tables 1..3: mis / ins / del lengths (:1866-1873)
             if (e == 2) {
                 l_new += step;
-                if (last_op_was_ins_same_pos) sink.replace_pending_ins(step);
-                else sink.push(NS_OP_INS, step, false);
+                if (last_op_was_ins_same_pos) sink.replace_last_ins(last_ins_len, step);
+                else sink.put(NS_OP_INS, step);
+                last_ins_len = step;
             } else {
                 if (e == 3) l_new -= step;
-                sink.push(e == 1 ? NS_OP_MIS : NS_OP_DEL, step, false);
+                sink.put(e == 1 ? NS_OP_MIS : NS_OP_DEL, step);
                 pos += step;
                 if (pos >= middle_ref) {
                     l_new += pos - middle_ref;
@@ -278,7 +362,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 }
             }
             // next match length given the previous one (:1891-1903)
-            uint32_t b = match_bin(m, prev_match);
+            uint32_t b = match_bin(m, bin_lut, prev_match);
             uint32_t mt = alias_draw(m, 4 + b, r.z);
             if (mt == m.tab_n[4 + b] - 1) mt = step;  // ECDF miss: `step` keeps the error length (:1895-1898)
             if (prev_match == 0 && mt == 0) mt = 1;
@@ -288,7 +372,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 middle_ref = pos + mt;
             }
             pos += mt;
-            sink.push(NS_OP_COPY, mt, false);
+            sink.put(NS_OP_COPY, mt);
             last_op_was_ins_same_pos = (e == 2 && mt == 0);
             err_state = e + (mt == 0 ? 3u : 0u);      // prev_error += "0" (:1913-1914)
             if (pos >= middle_ref) phase = PH_PIECE_END;
@@ -341,9 +425,10 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
         case PH_PIECE_END: {
             NsPieceMeta& pm = a.pieces[piece_first + p];
             bool is_gap = unal_kind || (p & 1u);
-            if (!unal_kind && p + 1 == n_pieces && tail > 0) sink.push(NS_OP_HT, tail, false);
             sink.flush();
-            if (!WRITE) {
+            if (!unal_kind && p + 1 == n_pieces && tail > 0) sink.put(NS_OP_HT, tail);
+            if (!REPLAY) {
+                if (sink.n > sink.cap) overflow = true;
                 pm.n_ops = sink.n;
                 pm.read_slot = slot;
                 pm.kind = unal_kind ? NS_PIECE_UNALIGNED : (is_gap ? NS_PIECE_GAP : NS_PIECE_SEGMENT);
@@ -359,7 +444,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             break;
         }
         case PH_CHECK: {
-            if (WRITE) {
+            if (REPLAY) {
                 phase = PH_FETCH;
                 break;
             }
@@ -425,7 +510,8 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             rm.piece_first = piece_first;
             rm.n_pieces = (uint16_t)n_pieces;
             rm.reversed = (uint8_t)reversed;
-            rm.flags = (uint8_t)((n_seg > 1) ? 2 : 0);
+            rm.flags = (uint8_t)(((n_seg > 1) ? 2 : 0) | (overflow ? 1 : 0));
+            if (overflow) atomicAdd(a.n_flagged, 1u);
             rm.attempts = attempt;
             a.reads[slot] = rm;
             phase = PH_FETCH;

@@ -42,6 +42,8 @@ struct UreadArgs {
 template <bool WRITE, bool FASTQ>
 __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_constant__ UreadArgs a) {
     __shared__ uint32_t lut[(WRITE && FASTQ) ? QLUT_SIZE : 1];
+    __shared__ uint32_t dsc_all[WRITE ? UREAD_WARPS : 1][5][32];
+    uint32_t (*dsc)[32] = dsc_all[WRITE ? (threadIdx.x >> 5) : 0];
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const int lane = threadIdx.x & 31;
@@ -70,7 +72,9 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             const uint32_t sw = stream_word(ST_ATT, NS_KIND_UNALIGNED, attempt);
             Rng r0;
             r0.init(cfg.seed, rid, sw);
-            const double x = kde_draw(m.unaligned, r0);          // block 0 of the attempt's stream
+            // block 0 of the attempt's stream; -med/-sd: np.random.lognormal(log(median), sd) (:1494-1495)
+            const double x = cfg.median_len > 0.0 ? lognormal_draw(log(cfg.median_len), cfg.sd_len, r0)
+                                                  : kde_draw(m.unaligned, r0);
             const int64_t mr = (int64_t)x;
             if (mr <= 0) {                                       // middle_ref < min_l (:1503)
                 ++attempt;
@@ -115,23 +119,35 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
                 l_new += delta;
 
-                if (WRITE && nonins && valid && outn > 0) {
-                    // ---- this lane's bases, forward order
-                    const uint32_t R = P - s;                                   // reference offset of the step
+                if (WRITE) {
+                    // ---- emission: publish the draws' descriptors, then the warp writes the block's output bases
+                    //      cooperatively (output index -> owning draw by binary search over the output offsets)
+                    const uint32_t tot = __shfl_sync(0xffffffffu, O + outn, 31) - out_base;
+                    dsc[0][lane] = O - out_base;
+                    dsc[1][lane] = P - s;                                   // reference offset of the step
+                    dsc[2][lane] = kind;
+                    dsc[3][lane] = kind == 3 ? a_ins - covered : a_ins;     // surviving inserted bases
+                    dsc[4][lane] = rest;
+                    __syncwarp();
                     const uint64_t cstart = a.ref.chrom_off[pm.chrom];
                     const uint64_t clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
                     const uint8_t* __restrict__ cb = a.ref.bases + cstart;
                     const bool rev = rm.reversed != 0;
                     uint8_t* sq = a.seq + rm.seq_off;
                     uint8_t* qq = FASTQ ? a.qual + rm.seq_off : nullptr;
-                    Rng br;
-                    br.init(cfg.seed, rid, stream_word(ST_EMIT_B, NS_KIND_UNALIGNED, base + lane));
-                    // segment boundaries inside the lane's output: [first][ins part][mis/extra part][copy part]
-                    const uint32_t n_first = kind == 3 ? 0u : 1u;               // ref[pos] itself (copied or substituted)
-                    const uint32_t n_ins = kind == 3 ? a_ins - covered : a_ins;
-                    const uint32_t n_mid = kind == 1 ? rest : 0u;               // further substituted reference bases
-                    for (uint32_t t = 0; t < outn; ++t) {
-                        const uint32_t w = br.next();
+                    for (uint32_t i = lane; i < tot; i += 32) {
+                        uint32_t l = 0, h = 32;                              // last draw whose output offset <= i
+                        while (h - l > 1) {
+                            uint32_t mid = (l + h) >> 1;
+                            if (dsc[0][mid] <= i) l = mid; else h = mid;
+                        }
+                        const uint32_t t = i - dsc[0][l], R = dsc[1][l], kd = dsc[2][l], n_ins = dsc[3][l], rst = dsc[4][l];
+                        const uint32_t n_first = kd == 3 ? 0u : 1u;          // ref[pos] itself (copied or substituted)
+                        const uint32_t n_mid = kd == 1 ? rst : 0u;           // further substituted reference bases
+                        const uint32_t o = out_base + i;
+                        // one 32-bit word per base: Philox-7 block o>>2, word o&3 of the read's unaligned base stream
+                        const uint4 w4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, NS_KIND_UNALIGNED, 0), o >> 2), key);
+                        const uint32_t w = (o & 2u) ? ((o & 1u) ? w4.w : w4.z) : ((o & 1u) ? w4.y : w4.x);
                         const uint32_t r8 = w >> 24;
                         uint32_t rr = r8 == 255u ? (w & 0xffu) : r8;
                         rr = rr == 255u ? 0u : rr;
@@ -141,14 +157,14 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                         bool sub = false;
                         if (t < n_first) {
                             roff = 0;
-                            sub = kind == 1;
+                            sub = kd == 1;
                         } else if (t < n_first + n_ins) {
                             roff = -1;
                         } else if (t < n_first + n_ins + n_mid) {
                             roff = 1 + (int)(t - n_first - n_ins);
                             sub = true;
                         } else {
-                            roff = 1 + (int)rest + (int)(t - n_first - n_ins - n_mid);
+                            roff = 1 + (int)rst + (int)(t - n_first - n_ins - n_mid);
                         }
                         if (roff >= 0) {
                             uint64_t ab = (uint64_t)pm.pos + R + (uint32_t)roff;
@@ -159,7 +175,6 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                             oi = base_idx(c);
                             if (sub) oi = (oi + 1u + t3) & 3u;
                         }
-                        const uint32_t o = O + t;
                         const uint32_t dst = rev ? rm.seq_len - 1 - o : o;
                         sq[dst] = (uint8_t)idx_base(rev ? oi ^ 2u : oi);
                         if (FASTQ) {
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                             qq[dst] = (uint8_t)(q + 33u);
                         }
                     }
+                    __syncwarp();
                 }
 
                 if (jstop < 32) {

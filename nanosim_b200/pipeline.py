@@ -35,9 +35,9 @@ class _HostBuffers:
             pass
         return np.empty(int(nbytes), dtype=np.uint8)
 
-    def ensure(self, key, nbytes):
+    def ensure(self, key, nbytes, hint=0):
         if nbytes > self.cap[key]:
-            want = int(nbytes * 1.2) + 4096
+            want = int(max(nbytes, hint) * 1.25) + 4096
             self.t[key] = self._alloc(want)
             self.cap[key] = want
         t = self.t[key]
@@ -56,6 +56,7 @@ class BatchPipeline:
         self.bufs = [_HostBuffers(engine.fastq) for _ in self.engines]
         self.pool = ThreadPoolExecutor(max_workers=self.depth)
         self.locks = [threading.Lock() for _ in self.engines]
+        self.hint = {"seq": 0, "reads": 0, "pieces": 0, "ops": 0}     # largest batch seen by any slot (pinned allocs are slow)
 
     def close(self):
         self.pool.shutdown(wait=True)
@@ -69,14 +70,19 @@ class BatchPipeline:
         if not self.fetch:
             return info, None
         fastq = eng.fastq
-        seq = hb.ensure("seq", int(info.seq_bytes))[:int(info.seq_bytes)]
-        qual = hb.ensure("qual", int(info.seq_bytes))[:int(info.seq_bytes)] if fastq else None
-        reads = hb.ensure("reads", int(info.n_reads) * L.READ_DTYPE.itemsize)[:int(info.n_reads) * L.READ_DTYPE.itemsize]
+        nb = {"seq": int(info.seq_bytes), "reads": int(info.n_reads) * L.READ_DTYPE.itemsize,
+              "pieces": int(info.n_pieces) * L.PIECE_DTYPE.itemsize, "ops": int(info.n_ops) * 4}
+        for k, v in nb.items():
+            if v > self.hint[k]:
+                self.hint[k] = v
+        seq = hb.ensure("seq", nb["seq"], self.hint["seq"])[:nb["seq"]]
+        qual = hb.ensure("qual", nb["seq"], self.hint["seq"])[:nb["seq"]] if fastq else None
+        reads = hb.ensure("reads", nb["reads"], self.hint["reads"])[:nb["reads"]]
         pieces = ops = None
         if self.want_pieces:
-            pieces = hb.ensure("pieces", int(info.n_pieces) * L.PIECE_DTYPE.itemsize)[:int(info.n_pieces) * L.PIECE_DTYPE.itemsize]
+            pieces = hb.ensure("pieces", nb["pieces"], self.hint["pieces"])[:nb["pieces"]]
         if self.want_ops and info.n_ops:
-            ops = hb.ensure("ops", int(info.n_ops) * 4)[:int(info.n_ops) * 4]
+            ops = hb.ensure("ops", nb["ops"], self.hint["ops"])[:nb["ops"]]
         eng.fetch_into(hb.ptr("seq"), hb.ptr("qual") if fastq else None, hb.ptr("reads"),
                        hb.ptr("pieces") if pieces is not None else None, hb.ptr("ops") if ops is not None else None)
         b = Batch(info, seq, qual, reads.view(L.READ_DTYPE), pieces.view(L.PIECE_DTYPE) if pieces is not None else None,

@@ -13,7 +13,9 @@ ref = PackedReference.from_records(synth.ecoli5m())
 eng, cm, t = pc.make_engine("guppy", ref, fastq=True, seed=11)
 for rep in range(2):
     info = eng.simulate(L.NS_KIND_ALIGNED, 0, n)
-    print("aligned", info.total_bases, info.ms_plan, info.ms_script, info.ms_emit)
+    b = eng.fetch()
+    print("aligned", info.total_bases, "setup %.2f plan %.2f scan %.2f script %.2f emit %.2f total %.2f" % (info.ms_setup, info.ms_plan, info.ms_scan, info.ms_script, info.ms_emit, info.ms_total),
+          "flagged", int((b.reads["flags"] & 1).sum()), "ops used", int(b.pieces["n_ops"].sum()), "of", info.n_ops)
     if nu:
         info = eng.simulate(L.NS_KIND_UNALIGNED, 0, nu)
         print("unaligned", info.total_bases, info.ms_plan, info.ms_script, info.ms_emit)
