@@ -227,6 +227,83 @@ def test_vs_unmodified_reference_1M_reads(ecoli, L):
     assert not fails, "\n".join(fails)
 
 
+def _run_with_quals(eng, ref, L, n_al, n_un, batch):
+    s = rs.empty()
+    for start in range(0, n_al, batch):
+        n = min(batch, n_al - start)
+        eng.simulate(L.NS_KIND_ALIGNED, start, n)
+        pc.batch_stats(eng.fetch(want_ops=False), ref, True, s)      # lengths, strands, quality histograms
+        pc.merge_op_stats(s, eng.op_stats())                           # event histograms on the device
+    for start in range(0, n_un, batch):
+        n = min(batch, n_un - start)
+        eng.simulate(L.NS_KIND_UNALIGNED, start, n)
+        pc.batch_stats(eng.fetch(), ref, True, s)
+    return s
+
+
+def test_vs_unmodified_reference_dorado_fastq_chimeric(ecoli, L):
+    """100k reads of `simulator.py genome --fastq --chimeric` with the dorado kit-v14 model (unmodified reference) vs
+    the device: chimeric fraction, segments per read, per-base rates, length/event/quality histograms."""
+    path = os.path.join(GOLDEN, "ref_stats_dorado_fastq_chimeric.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    eng, cm, t = pc.make_engine("dorado", ecoli, fastq=True, chimeric=True, seed=77)
+    s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
+    eng.close()
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("dorado per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    fails = pc.compare_stats(s, gold, rate_tol=2.5e-3, p_min=1e-6, label="dorado",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("dorado %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    fc_d, fc_g = s["n_chimeric"] / s["n_aligned"], gold["n_chimeric"] / gold["n_aligned"]
+    assert abs(fc_d - fc_g) < 4 * np.sqrt(fc_g / gold["n_aligned"]) + 1e-4, (fc_d, fc_g)
+    assert abs(s["n_segments"] / s["n_aligned"] - gold["n_segments"] / gold["n_aligned"]) < 3e-3
+    assert abs(s["aligned_bases"] / s["n_aligned"] / (gold["aligned_bases"] / gold["n_aligned"]) - 1) < 1.5e-2
+    assert not fails, "\n".join(fails)
+
+
+def test_qualities_vs_unmodified_reference_guppyq(ecoli, L):
+    """50k FASTQ reads of the unmodified reference with the config-2 model (guppy + dorado quality table): quality
+    histograms of aligned middles (match/mis/ins mixture), head/tail regions and unaligned reads."""
+    path = os.path.join(GOLDEN, "ref_stats_guppyq_fastq.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=True, seed=78)
+    s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
+    eng.close()
+    fails = pc.compare_stats(s, gold, rate_tol=3e-3, p_min=1e-6, label="guppyq",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("qual_middle", "qual_ht", "qual_unaligned"):
+        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("guppyq %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    assert not fails, "\n".join(fails)
+
+
+def test_lognormal_lengths_med_sd(ecoli, L):
+    """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
+    eng.configure(fastq=False, min_len=50, max_len=ecoli.max_chrom, median_len=5000, sd_len=0.4)
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 20000)
+    bu = eng.fetch()
+    # unaligned: ref ~ lognormal(log(5000), 0.4); the read is the mutated copy (ins ~ del in expectation)
+    assert abs(np.median(bu.pieces["ref_req"]) / 5000 - 1) < 0.02
+    assert abs(np.std(np.log(bu.pieces["ref_req"].astype(np.float64))) - 0.4) < 0.01
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 20000)
+    ba = eng.fetch()
+    # aligned: total ~ lognormal(log(5000 + 0.08), 0.4) minus/plus independent remainders, then errors (~ -2.8 % net)
+    med = np.median(ba.reads["seq_len"])
+    assert 4500 < med < 5400, med
+    eng.close()
+
+
 def test_quality_draws_match_model_pmf(ecoli, L):
     """Device qualities per state against the exact truncated-log-normal pmf (model_base_qualities.py:9-20,120-130)."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=True, seed=31)
