@@ -295,7 +295,7 @@ def main():
     wall_e = time.perf_counter() - t0
     pipe_e.close()
     bases_e = sum(r[0] for r in rows_e)
-    d2h = sum(2 * r[1] + 32 * r[2] + 48 * r[3] for r in rows_e) / max(args.steps, 1)
+    d2h = sum(2 * r[1] + 32 * r[2] + 64 * r[3] for r in rows_e) / max(args.steps, 1)
     stat = torch.tensor([bases_e, wall_e], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         mx = stat.clone()

@@ -138,6 +138,9 @@ typedef struct {
     uint32_t l_new;           /* error_list's nominal length (== out_len - head/tail unless an ins/ins collision) */
     uint32_t ref_req;         /* length drawn from the KDE before error_list extended it (m_ref) */
     uint32_t read_slot;       /* index of the owning read inside the batch */
+    uint64_t ev_off;          /* the piece's ERROR-EVENT script (what mutate_read logs, :2006-2008): equal to op_off/n_ops */
+    uint32_t ev_n_ops;        /* unless -hp/-k rewrote the emitted script (mutate_homo); then this is the script before it */
+    uint32_t reserved;
 } NsPieceMeta;
 
 /* Edit script element: (type << 28) | length.  The op list of a piece, applied left to right to the reference
@@ -147,8 +150,10 @@ typedef struct {
 #define NS_OP_INS 2u     /* n random inserted bases         (ins quality)       */
 #define NS_OP_DEL 3u     /* skip n reference bases                              */
 #define NS_OP_HT 4u      /* n random head/tail bases        (ht quality)        */
+#define NS_OP_LIT 5u     /* n copies of a literal base: bits [27:26] base (A C T G = 0 1 2 3), [25:24] quality state
+                            (0 mis, 1 ins, 2 match), [23:0] n.  Only in scripts rewritten by the homopolymer pass. */
 #define NS_OP_TYPE(op) ((op) >> 28)
-#define NS_OP_LEN(op) ((op) & 0x0fffffffu)
+#define NS_OP_LEN(op) (NS_OP_TYPE(op) == NS_OP_LIT ? ((op) & 0x00ffffffu) : ((op) & 0x0fffffffu))
 
 typedef struct {
     uint64_t seq_bytes;       /* size of the seq (and qual) buffer for this batch */

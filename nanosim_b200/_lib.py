@@ -12,7 +12,7 @@ NS_N_QUAL_STATES = 5
 NS_QUAL_SLOTS = 94
 NS_KIND_ALIGNED, NS_KIND_UNALIGNED = 0, 1
 NS_PIECE_SEGMENT, NS_PIECE_GAP, NS_PIECE_UNALIGNED = 0, 1, 2
-NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT = 0, 1, 2, 3, 4
+NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT, NS_OP_LIT = 0, 1, 2, 3, 4, 5
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
@@ -61,7 +61,8 @@ class NsReadMeta(C.Structure):
 class NsPieceMeta(C.Structure):
     _fields_ = [("op_off", C.c_uint64), ("n_ops", C.c_uint32), ("kind", C.c_uint32), ("chrom", C.c_uint32),
                 ("pos", C.c_uint32), ("ref_len", C.c_uint32), ("out_len", C.c_uint32), ("out_rel", C.c_uint32),
-                ("l_new", C.c_uint32), ("ref_req", C.c_uint32), ("read_slot", C.c_uint32)]
+                ("l_new", C.c_uint32), ("ref_req", C.c_uint32), ("read_slot", C.c_uint32),
+                ("ev_off", C.c_uint64), ("ev_n_ops", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class NsBatchInfo(C.Structure):
@@ -79,9 +80,10 @@ READ_DTYPE = np.dtype([("seq_off", "<u8"), ("seq_len", "<u4"), ("head", "<u4"), 
                        ("attempts", "<u4")], align=True)
 PIECE_DTYPE = np.dtype([("op_off", "<u8"), ("n_ops", "<u4"), ("kind", "<u4"), ("chrom", "<u4"), ("pos", "<u4"),
                         ("ref_len", "<u4"), ("out_len", "<u4"), ("out_rel", "<u4"), ("l_new", "<u4"),
-                        ("ref_req", "<u4"), ("read_slot", "<u4")], align=True)
+                        ("ref_req", "<u4"), ("read_slot", "<u4"), ("ev_off", "<u8"), ("ev_n_ops", "<u4"),
+                        ("reserved", "<u4")], align=True)
 assert READ_DTYPE.itemsize == C.sizeof(NsReadMeta) == 32
-assert PIECE_DTYPE.itemsize == C.sizeof(NsPieceMeta) == 48
+assert PIECE_DTYPE.itemsize == C.sizeof(NsPieceMeta) == 64
 
 _lib = None
 

@@ -64,7 +64,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox
 __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
 
 // stream word layout: [31:28] purpose, [27] kind, [26:0] attempt / generation
-enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6 };
+enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6, ST_IUPAC = 7, ST_HP = 8 };
 
 __device__ __forceinline__ uint32_t stream_word(uint32_t purpose, uint32_t kind, uint32_t sub) {
     return (purpose << 28) | ((kind & 1u) << 27) | (sub & 0x07ffffffu);
@@ -145,3 +145,46 @@ __device__ __forceinline__ double lognormal_draw(double mean, double sigma, Rng&
 __device__ __forceinline__ uint32_t base_idx(uint32_t c) { return (c >> 1) & 3u; }
 __device__ __forceinline__ uint32_t idx_base(uint32_t i) { return (0x47544341u >> (8u * i)) & 0xffu; }
 __device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// bit i of 0x80045 is set for i = 'A'-'A', 'C'-'A', 'G'-'A', 'T'-'A'
+__device__ __forceinline__ bool acgt_fast(uint32_t c) {
+    uint32_t d = c - 'A';
+    return d < 26u && ((0x80045u >> d) & 1u);
+}
+__device__ __forceinline__ uint32_t op_len(uint32_t op) { return (op >> 28) == NS_OP_LIT ? (op & 0x00ffffffu) : (op & 0x0fffffffu); }
+
+// IUPAC resolution of case_convert (:744-746): members in the reference's list order, picked uniformly.
+// r8 is a uniform byte; t3 a uniform value in {0,1,2}.
+__device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r8, uint32_t t3) {
+    uint32_t n, set;   // set: up to 4 members packed one byte each
+    switch (c) {
+    case 'Y': n = 2; set = 'C' | ('T' << 8); break;
+    case 'R': n = 2; set = 'A' | ('G' << 8); break;
+    case 'W': n = 2; set = 'A' | ('T' << 8); break;
+    case 'S': n = 2; set = 'G' | ('C' << 8); break;
+    case 'K': n = 2; set = 'T' | ('G' << 8); break;
+    case 'M': n = 2; set = 'C' | ('A' << 8); break;
+    case 'D': n = 3; set = 'A' | ('G' << 8) | ('T' << 16); break;
+    case 'V': n = 3; set = 'A' | ('C' << 8) | ('G' << 16); break;
+    case 'H': n = 3; set = 'A' | ('C' << 8) | ('T' << 16); break;
+    case 'B': n = 3; set = 'C' | ('G' << 8) | ('T' << 16); break;
+    case 'N':
+    case 'X': n = 4; set = 'A' | ('T' << 8) | ('C' << 16) | ('G' << 24); break;
+    default: return c;
+    }
+    uint32_t k = (n == 3) ? t3 : ((r8 >> 4) & (n - 1));
+    return (set >> (8 * k)) & 0xffu;
+}
+
+// case_convert of ONE reference base of one read, as a pure function of (read, piece, forward offset in the segment):
+// every kernel that looks at the same base of the same read (emit, homopolymer pass) sees the same resolution.
+__device__ __forceinline__ uint32_t converted_ref_base(uint32_t c, uint64_t seed, uint64_t rid, uint32_t piece_in_read,
+                                                       uint32_t fwd_off) {
+    if (c - 'a' < 26u) c -= 32;
+    if (acgt_fast(c)) return c;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 w = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_IUPAC, 0, piece_in_read), fwd_off >> 3), key);
+    uint32_t wd = (fwd_off & 4u) ? ((fwd_off & 2u) ? w.w : w.z) : ((fwd_off & 2u) ? w.y : w.x);
+    uint32_t h = (fwd_off & 1u) ? (wd >> 16) : (wd & 0xffffu);
+    uint32_t r8 = h & 0xffu, r3 = h >> 8;
+    return resolve_iupac(c, r8, r3 == 255u ? 0u : r3 % 3u);
+}

@@ -39,35 +39,6 @@ struct EmitArgs {
     uint32_t* counter;
 };
 
-// IUPAC resolution of case_convert (:744-746): members in the reference's list order, picked uniformly.
-// r8 is a uniform byte; t3 a uniform value in {0,1,2} derived from it.
-__device__ __forceinline__ uint32_t resolve_iupac(uint32_t c, uint32_t r8, uint32_t t3) {
-    uint32_t n, set;   // set: up to 4 members packed one byte each
-    switch (c) {
-    case 'Y': n = 2; set = 'C' | ('T' << 8); break;
-    case 'R': n = 2; set = 'A' | ('G' << 8); break;
-    case 'W': n = 2; set = 'A' | ('T' << 8); break;
-    case 'S': n = 2; set = 'G' | ('C' << 8); break;
-    case 'K': n = 2; set = 'T' | ('G' << 8); break;
-    case 'M': n = 2; set = 'C' | ('A' << 8); break;
-    case 'D': n = 3; set = 'A' | ('G' << 8) | ('T' << 16); break;
-    case 'V': n = 3; set = 'A' | ('C' << 8) | ('G' << 16); break;
-    case 'H': n = 3; set = 'A' | ('C' << 8) | ('T' << 16); break;
-    case 'B': n = 3; set = 'C' | ('G' << 8) | ('T' << 16); break;
-    case 'N':
-    case 'X': n = 4; set = 'A' | ('T' << 8) | ('C' << 16) | ('G' << 24); break;
-    default: return c;
-    }
-    uint32_t k = (n == 3) ? t3 : ((r8 >> 4) & (n - 1));
-    return (set >> (8 * k)) & 0xffu;
-}
-
-// bit i of 0x80045 is set for i = 'A'-'A', 'C'-'A', 'G'-'A', 'T'-'A'
-__device__ __forceinline__ bool acgt_fast(uint32_t c) {
-    uint32_t d = c - 'A';
-    return d < 26u && ((0x80045u >> d) & 1u);
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -121,9 +92,9 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                 uint32_t t = t_loaded + lane;
                 uint32_t op = 0;
                 if (t < n_ops) op = __ldg(&ops[rev ? n_ops - 1 - t : t]);
-                uint32_t ty = op >> 28, len = op & 0x0fffffffu;
+                uint32_t ty = op >> 28, len = op_len(op);
                 uint32_t o = (ty == NS_OP_DEL) ? 0u : len;
-                uint32_t r = (ty == NS_OP_INS || ty == NS_OP_HT) ? 0u : len;
+                uint32_t r = (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
                 uint32_t so = warp_incl_scan(o, lane), sr = warp_incl_scan(r, lane);
                 if (t < n_ops) {
                     ring_out[t % EMIT_RING] = out_loaded + so - o;
@@ -156,8 +127,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                 uint32_t op = ring_op[k % EMIT_RING];
                 uint32_t ty = op >> 28;
                 uint32_t within = plo - ring_out[k % EMIT_RING];
-                uint32_t rem = (op & 0x0fffffffu) - within;
-                uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty == NS_OP_INS || ty == NS_OP_HT) ? 0u : within);
+                uint32_t rem = op_len(op) - within;
+                uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty < 2u) ? within : 0u);
 
                 // ---- all randomness of the chunk up front, position-indexed, identical in every lane's control flow:
                 //      base i uses byte i of `bw` (substitution / inserted base / IUPAC member) and bits [24i, 24i+24)
@@ -187,7 +158,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                             ++k;
                             op = ring_op[k % EMIT_RING];
                             ty = op >> 28;
-                            rem = (ty == NS_OP_DEL) ? 0u : (op & 0x0fffffffu);
+                            rem = (ty == NS_OP_DEL) ? 0u : op_len(op);
                             rpos = ring_ref[k % EMIT_RING];
                         }
                         --rem;
@@ -203,14 +174,16 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                             uint32_t c = __ldg(&cbase[ab]);
                             ++rpos;
                             if (c - 'a' < 26u) c -= 32;
-                            if (!acgt_fast(c)) c = resolve_iupac(c, r8n, (r8n == 255u) ? 0u : r8n % 3u);
+                            if (!acgt_fast(c)) c = converted_ref_base(c, a.cfg.seed, rid, piece - rm.piece_first, f);
                             oi = base_idx(c);
                             if (ty == NS_OP_MIS) oi = (oi + 1u + t3) & 3u;     // one of the three other bases
+                        } else if (ty == NS_OP_LIT) {
+                            oi = (op >> 26) & 3u;                              // literal base of a rewritten homopolymer
                         }
                         sb[i >> 2] |= idx_base(oi ^ flip) << (8 * (i & 3));
                         if (FASTQ) {
                             // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3); gap/unaligned -> unmapped(4)
-                            const uint32_t qs = unmapped ? 4u : ((0x30102u >> (4u * ty)) & 7u);
+                            const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
                             const int bit = 24 * i;
                             const uint32_t u24 = __funnelshift_r(qw[bit >> 5], qw[(bit >> 5) + 1], bit & 31) & 0xffffffu;
                             const uint32_t e = lut[qs * QLUT_SIZE + (u24 >> QLUT_FRAC_BITS)];

@@ -1,0 +1,304 @@
+// Homopolymer pass (-hp -k K): the K-dependent half of mutate_read (/root/reference/src/simulator.py:1920-1947)
+// and mutate_homo (:618-705) with its length model (model_homopolymer_lengths.py:167-186, 204-209, 246-260),
+// as a rewrite of each aligned segment's edit script.  One LANE walks one segment:
+//
+//  1. error filter: an error event whose interval touches a homopolymer run (>= K equal bases) of the UNMUTATED,
+//     case-converted segment is dropped -- [pos, pos+n) for mis/del, (pos-0.5, pos-0.5+n) for ins, i.e. reference
+//     positions pos-1 .. pos+n-1 (:1929-1947).  Dropped events turn into copies in the EVENT script (what the reference
+//     logs in <out>_aligned_error_profile is the filtered list).
+//  2. mutate_homo: the walker streams the mutated segment base by base (copied reference bases, substituted and
+//     inserted bases -- whose values are fixed here and carried to the emit kernel as literal ops), finds runs >= K,
+//     draws the new run length round(max(0, N(mu(L), sigma(L)))) and emits the run as literals: a contraction keeps
+//     the qualities of the LAST bases of the run (:688-690), an expansion appends "ins"-state qualities (:692-695),
+//     each new base is substituted with probability hp_mis_rate and only the first substitution gets a "mis" quality
+//     (:671-682, :697-700).
+//
+// The rewritten script uses COPY / DEL (reference skip) / LIT / HT ops only; the emit kernel needs no random draws for
+// its bases.  COUNT pass: new op count and output length per piece; WRITE pass: the scripts.
+#pragma once
+#include "device_common.cuh"
+
+struct HpArgs {
+    DevRef ref;
+    DevCfg cfg;
+    uint64_t first_id;
+    const NsReadMeta* reads;
+    NsPieceMeta* pieces;
+    uint32_t n_pieces;
+    uint32_t* ops;              // event scripts (in place: dropped events) and rewritten scripts
+    uint64_t* out_n_ops;        // COUNT: per piece
+    const uint64_t* out_off;    // WRITE: per piece offsets of the rewritten scripts (already includes the base)
+    double hp[2][6];            // rows AT, CG: const, alpha1, beta1, breakpoint1, intercept, slope
+    double hp_mis_rate;
+    uint32_t* counter;
+};
+
+#define HP_MAX_SEG 12
+
+template <bool WRITE>
+struct ScriptOut {
+    uint32_t* base;
+    uint32_t n, pend, out_len;      // pend = pending op word (0xffffffff = none); same-kind ops are merged
+    __device__ __forceinline__ void begin(uint32_t* b) {
+        base = b;
+        n = 0;
+        pend = 0xffffffffu;
+        out_len = 0;
+    }
+    __device__ __forceinline__ void flush() {
+        if (pend != 0xffffffffu) {
+            if (WRITE) base[n] = pend;
+            ++n;
+        }
+        pend = 0xffffffffu;
+    }
+    // kind word: type<<28 (| base<<26 | state<<24 for LIT); len added to the pending op when the kind matches
+    __device__ __forceinline__ void add(uint32_t kind, uint32_t len) {
+        if (len == 0) return;
+        if ((kind >> 28) != NS_OP_DEL) out_len += len;
+        const uint32_t mask = (kind >> 28) == NS_OP_LIT ? 0xff000000u : 0xf0000000u;
+        if (pend != 0xffffffffu && (pend & mask) == kind) {
+            pend += len;
+            return;
+        }
+        flush();
+        pend = kind | len;
+    }
+};
+
+struct HpWalker {
+    const uint8_t* cb;
+    uint64_t clen, seed, rid;
+    uint32_t pos, piece_in_read, ref_len, K;
+    __device__ __forceinline__ uint32_t base_at(uint32_t x) const {     // case-converted reference base index at offset x
+        uint64_t ab = (uint64_t)pos + x;
+        if (ab >= clen) ab -= clen;
+        uint32_t c = converted_ref_base(__ldg(&cb[ab]), seed, rid, piece_in_read, x);
+        return acgt_fast(c) ? base_idx(c) : (4u + (c & 3u));            // non-ACGT leftovers never form ACGT runs
+    }
+    // is offset x inside a run of >= K equal bases of the unmutated segment?
+    __device__ __forceinline__ bool in_hp(int64_t x) const {
+        if (x < 0 || x >= (int64_t)ref_len) return false;
+        const uint32_t b = base_at((uint32_t)x);
+        if (b > 3u) return false;
+        uint32_t run = 1;
+        for (int64_t y = x - 1; y >= 0 && run < K && base_at((uint32_t)y) == b; --y) ++run;
+        for (int64_t y = x + 1; y < (int64_t)ref_len && run < K && base_at((uint32_t)y) == b; ++y) ++run;
+        return run >= K;
+    }
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs a) {
+    const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
+    const uint32_t K = a.cfg.kmer_bias;
+    for (;;) {
+        const uint32_t pi = atomicAdd(a.counter, 1u);
+        if (pi >= a.n_pieces) break;
+        NsPieceMeta& pm = a.pieces[pi];
+        if (pm.kind != NS_PIECE_SEGMENT) {
+            if (!WRITE) a.out_n_ops[pi] = 0;           // untouched pieces keep their script
+            continue;
+        }
+        const NsReadMeta rm = a.reads[pm.read_slot];
+        const uint64_t rid = a.first_id + pm.read_slot;
+        HpWalker w;
+        const uint64_t cstart = a.ref.chrom_off[pm.chrom];
+        w.cb = a.ref.bases + cstart;
+        w.clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
+        w.seed = a.cfg.seed;
+        w.rid = rid;
+        w.pos = pm.pos;
+        w.piece_in_read = pi - rm.piece_first;
+        w.ref_len = pm.ref_len;
+        w.K = K;
+        uint32_t* ev = a.ops + pm.ev_off;
+        const uint32_t n_ev = pm.ev_n_ops;
+        ScriptOut<WRITE> out;
+        out.begin(WRITE ? a.ops + a.out_off[pi] : nullptr);
+
+        // ---- current run of equal bases in the mutated stream
+        uint32_t run_base = 0xffu, run_len = 0, run_ref = 0, nseg = 0, n_runs = 0;
+        uint32_t seg_kind[HP_MAX_SEG], seg_cnt[HP_MAX_SEG];     // in order: 0 copy, 1 mis, 2 ins, 3 deleted reference bases
+
+        auto flush_run = [&]() {
+            if (run_len == 0) return;
+            if (run_len >= K && run_base < 4u) {
+                // new length ~ N(mu(L), sigma(L)), clipped at 0, Python round()
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_HP, 0, w.piece_in_read), n_runs), key);
+                const uint32_t cls = (run_base == 0u || run_base == 2u) ? 0u : 1u;      // A,T -> "AT" ; C,G -> "CG"
+                const double* p = a.hp[cls];
+                const double L = (double)run_len;
+                const double mu = p[0] + p[1] * L + p[2] * fmax(L - p[3], 0.0);
+                const double sigma = p[4] + p[5] * L;
+                const float z = sqrtf(-2.0f * logf(u01_open_low(r.x))) * cospif(2.0f * ((float)(r.y >> 8) * (1.0f / 16777216.0f)));
+                double x = mu + sigma * (double)z;
+                if (x < 0.0) x = 0.0;
+                const uint32_t nn = (uint32_t)rint(x);
+                // states of the new bases: last nn members (contraction) / all members + ins (expansion)
+                uint32_t skip = run_len > nn ? run_len - nn : 0u;
+                bool mis_q_used = false;
+                Rng mr;
+                if (a.hp_mis_rate > 0.0) mr.init(a.cfg.seed, rid, stream_word(ST_HP, 1, w.piece_in_read) ^ (n_runs << 4));
+                uint32_t produced = 0;
+                for (uint32_t s = 0; s <= nseg && produced < nn; ++s) {
+                    uint32_t cnt, state;
+                    if (s < nseg) {
+                        if (seg_kind[s] == 3) continue;       // deleted reference bases carry no quality
+                        cnt = seg_cnt[s];
+                        state = seg_kind[s] == 0 ? 2u : (seg_kind[s] == 1 ? 0u : 1u);
+                        if (skip >= cnt) {
+                            skip -= cnt;
+                            continue;
+                        }
+                        cnt -= skip;
+                        skip = 0;
+                    } else {
+                        cnt = nn - produced;                  // expansion: inserted-base qualities (:692-695)
+                        state = 1u;
+                    }
+                    if (cnt > nn - produced) cnt = nn - produced;
+                    if (a.hp_mis_rate > 0.0) {
+                        for (uint32_t t = 0; t < cnt; ++t) {
+                            const double pr = u01_double(mr.next64());
+                            uint32_t b = run_base, st = state;
+                            if (pr > 0.0 && pr <= a.hp_mis_rate) {
+                                b = (run_base + 1u + (mr.next() % 3u)) & 3u;
+                                if (!mis_q_used) {
+                                    st = 0u;
+                                    mis_q_used = true;
+                                }
+                            }
+                            out.add((NS_OP_LIT << 28) | (b << 26) | (st << 24), 1);
+                        }
+                    } else {
+                        out.add((NS_OP_LIT << 28) | (run_base << 26) | (state << 24), cnt);
+                    }
+                    produced += cnt;
+                }
+                out.add(NS_OP_DEL << 28, run_ref);            // the reference bases the run stood on
+                ++n_runs;
+            } else {
+                for (uint32_t s = 0; s < nseg; ++s) {
+                    if (seg_kind[s] == 0) {
+                        out.add(NS_OP_COPY << 28, seg_cnt[s]);
+                    } else if (seg_kind[s] == 3) {
+                        out.add(NS_OP_DEL << 28, seg_cnt[s]);
+                    } else {
+                        out.add((NS_OP_LIT << 28) | ((run_base & 3u) << 26) | ((seg_kind[s] == 1 ? 0u : 1u) << 24), seg_cnt[s]);
+                        if (seg_kind[s] == 1) out.add(NS_OP_DEL << 28, seg_cnt[s]);
+                    }
+                }
+            }
+            run_len = 0;
+            run_ref = 0;
+            nseg = 0;
+            run_base = 0xffu;
+        };
+        auto feed = [&](uint32_t b, uint32_t kind) {          // one base of the mutated stream
+            if (b != run_base || b > 3u) {
+                flush_run();
+                run_base = b;
+            }
+            ++run_len;
+            if (kind != 2) ++run_ref;
+            if (nseg > 0 && seg_kind[nseg - 1] == kind) {
+                ++seg_cnt[nseg - 1];
+            } else if (nseg < HP_MAX_SEG) {
+                seg_kind[nseg] = kind;
+                seg_cnt[nseg] = 1;
+                ++nseg;
+            } else {
+                ++seg_cnt[nseg - 1];                           // pathological run: lump into the last segment
+                if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
+            }
+        };
+
+        // per-event random bases: Philox-7 block per op, one byte per base
+        uint32_t rpos = 0;
+        for (uint32_t k = 0; k < n_ev; ++k) {
+            uint32_t op = ev[k];
+            uint32_t ty = op >> 28;
+            const uint32_t len = op & 0x0fffffffu;
+            if (ty == NS_OP_HT) {
+                flush_run();
+                out.add(NS_OP_HT << 28, len);
+                continue;
+            }
+            if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && len > 0) {
+                // ---- error filter (:1929-1947)
+                const int64_t lo = ty == NS_OP_INS ? (int64_t)rpos - 1 : (int64_t)rpos;
+                const int64_t hi = (int64_t)rpos + (int64_t)len - 1;
+                bool drop = false;
+                for (int64_t x = lo; x <= hi && !drop; ++x) drop = w.in_hp(x);
+                if (drop) {
+                    op = ty == NS_OP_INS ? (NS_OP_COPY << 28) : ((NS_OP_COPY << 28) | len);
+                    if (WRITE) ev[k] = op;
+                    ty = NS_OP_COPY;
+                    if ((op & 0x0fffffffu) == 0) continue;
+                }
+            }
+            if (ty == NS_OP_COPY) {
+                for (uint32_t t = 0; t < len; ++t) feed(w.base_at(rpos + t), 0);
+                rpos += len;
+            } else if (ty == NS_OP_DEL) {
+                // deleted bases vanish from the read: their neighbours become adjacent and may join one run
+                if (run_len == 0) {
+                    out.add(NS_OP_DEL << 28, len);
+                } else {
+                    run_ref += len;
+                    if (nseg > 0 && seg_kind[nseg - 1] == 3) seg_cnt[nseg - 1] += len;
+                    else if (nseg < HP_MAX_SEG) {
+                        seg_kind[nseg] = 3;
+                        seg_cnt[nseg] = len;
+                        ++nseg;
+                    } else {                                   // pathological: close the run here
+                        flush_run();
+                        out.add(NS_OP_DEL << 28, len);
+                    }
+                }
+                rpos += len;
+            } else {
+                for (uint32_t t = 0; t < len; ++t) {
+                    const uint4 r = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece_in_read), (k << 8) + (t >> 4)), key);
+                    const uint32_t wd = (t & 8u) ? ((t & 4u) ? r.w : r.z) : ((t & 4u) ? r.y : r.x);
+                    const uint32_t r8 = (wd >> (8u * (t & 3u))) & 0xffu;
+                    uint32_t b;
+                    if (ty == NS_OP_MIS) {
+                        const uint32_t orig = w.base_at(rpos + t);
+                        const uint32_t rr = r8 == 255u ? 0u : r8;
+                        b = ((orig & 3u) + 1u + rr % 3u) & 3u;
+                        feed(b, 1);
+                    } else {
+                        b = r8 & 3u;
+                        feed(b, 2);
+                    }
+                }
+                if (ty == NS_OP_MIS) rpos += len;
+            }
+        }
+        flush_run();
+        out.flush();
+        if (!WRITE) {
+            a.out_n_ops[pi] = out.n;
+            pm.out_len = out.out_len;
+        } else {
+            pm.op_off = a.out_off[pi];
+            pm.n_ops = out.n;
+        }
+    }
+}
+
+// after the COUNT pass: out_rel of every piece and the read length from the new piece lengths
+__global__ void hp_fix_reads(NsReadMeta* reads, NsPieceMeta* pieces, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NsReadMeta& r = reads[i];
+    uint32_t cur = 0;
+    for (uint32_t q = 0; q < r.n_pieces; ++q) {
+        NsPieceMeta& p = pieces[r.piece_first + q];
+        p.out_rel = cur;
+        cur += p.out_len;
+    }
+    r.seq_len = cur;
+}

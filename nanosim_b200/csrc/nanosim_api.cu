@@ -17,6 +17,7 @@
 #include "plan_kernel.cuh"
 #include "emit_kernel.cuh"
 #include "uread_kernel.cuh"
+#include "hp_kernel.cuh"
 
 namespace {
 
@@ -81,7 +82,7 @@ struct NsContext {
 
     // batch state
     DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
-        stats, sort_keys, sort_vals, sort_tmp;
+        stats, sort_keys, sort_vals, sort_tmp, hp_off;
     uint64_t* h_totals = nullptr;   // pinned
     NsBatchInfo last{};
     int last_kind = 0;
@@ -130,6 +131,17 @@ __global__ void scatter_flagged_off(NsPieceMeta* pieces, const NsReadMeta* reads
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && (reads[pieces[i].read_slot].flags & 1u)) pieces[i].op_off = base + off[i];
 }
+__global__ void copy_ev_fields(NsPieceMeta* pieces, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        pieces[i].ev_off = pieces[i].op_off;
+        pieces[i].ev_n_ops = pieces[i].n_ops;
+    }
+}
+__global__ void add_base_u64(uint64_t* v, uint32_t n, uint64_t base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += base;
+}
 __global__ void gather_read_bytes(const NsReadMeta* reads, uint32_t n, uint64_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = ((uint64_t)reads[i].seq_len + 15u) & ~(uint64_t)15u;
@@ -176,8 +188,8 @@ __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* rea
     atomicAdd(&st[1], (unsigned long long)pm.ref_len);
     uint64_t run = 0, ht = 0, n_ev = 0;
     bool first = true;
-    for (uint32_t k = 0; k < pm.n_ops; ++k) {
-        uint32_t op = ops[pm.op_off + k];
+    for (uint32_t k = 0; k < pm.ev_n_ops; ++k) {         // the event script (== op script unless -hp rewrote it)
+        uint32_t op = ops[pm.ev_off + k];
         uint32_t ty = op >> 28, len = op & 0x0fffffffu;
         if (ty == NS_OP_HT) {
             ht += len;
@@ -278,7 +290,7 @@ int ns_destroy(NsContext* ctx) {
     DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
-                      &ctx->sort_tmp};
+                      &ctx->sort_tmp, &ctx->hp_off};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
         DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf};
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
@@ -413,7 +425,9 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
         return fail(ctx, NS_EINVAL, "Please provide both mean and standard deviation of read length!");
     if (cfg->median_len != 0.0 && cfg->chimeric) return fail(ctx, NS_EINVAL, "Lognormal distributed reads cannot be chimeric!");
     if (cfg->median_len < 0.0 || cfg->sd_len < 0.0) return fail(ctx, NS_EINVAL, "ns_configure: negative -med/-sd");
-    if (cfg->kmer_bias != 0) return fail(ctx, NS_EINVAL, "ns_configure: homopolymer simulation (-hp/-k) is not implemented yet");
+    if (cfg->kmer_bias != 0 && ctx->have_model && !ctx->hmodel.has_hp)
+        return fail(ctx, NS_ESTATE, "ns_configure: -hp/-k needs _hp_lengths_model_parameters.tsv in the model");
+    if (cfg->kmer_bias == 1) return fail(ctx, NS_EINVAL, "ns_configure: -k must be >= 2 (every base is a run of length 1)");
     ctx->hcfg = *cfg;
     ctx->dcfg.circular = cfg->circular;
     ctx->dcfg.perfect = cfg->perfect;
@@ -671,8 +685,63 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(cudaGetLastError());
         launches += 2;
     }
+    copy_ev_fields<<<gp, tb, 0, st>>>(pa.pieces, n_pieces);
+    uint64_t n_ops_total = n_ops, seq_bytes_final = seq_bytes, total_bases_final = total_bases;
+    if (ctx->hcfg.kmer_bias > 0 && kind == NS_KIND_ALIGNED && !ctx->hcfg.perfect) {
+        // ---- homopolymer pass (hp_kernel.cuh): count, re-scan lengths and script offsets, write
+        if (!ctx->hmodel.has_hp) return fail(ctx, NS_ESTATE, "ns_simulate: -hp/-k needs homopolymer parameters in the model");
+        HpArgs ha;
+        ha.ref = ctx->dref;
+        ha.cfg = ctx->dcfg;
+        ha.first_id = first_read_id;
+        ha.reads = pa.reads;
+        ha.pieces = pa.pieces;
+        ha.n_pieces = n_pieces;
+        ha.ops = pa.ops;
+        ha.out_n_ops = ctx->scan_in.as<uint64_t>();
+        ha.out_off = nullptr;
+        memcpy(ha.hp, ctx->hmodel.hp, sizeof ha.hp);
+        ha.hp_mis_rate = ctx->hmodel.hp_mis_rate;
+        ha.counter = ctx->counter.as<uint32_t>();
+        const unsigned hp_blocks = std::min<unsigned>((n_pieces + 127) / 128, (unsigned)ctx->sm_count * 16u);
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        hp_kernel<false><<<hp_blocks, 128, 0, st>>>(ha);
+        CK(cudaGetLastError());
+        hp_fix_reads<<<gb, tb, 0, st>>>(pa.reads, pa.pieces, n);
+        CK(ctx->hp_off.ensure((size_t)n_pieces * sizeof(uint64_t)));
+        {
+            int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->hp_off.as<uint64_t>(), n_pieces);
+            if (rc) return rc;
+        }
+        last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->hp_off.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 6);
+        add_base_u64<<<gp, tb, 0, st>>>(ctx->hp_off.as<uint64_t>(), n_pieces, n_ops);
+        CK(cudaMemsetAsync(ctx->totals.as<uint64_t>() + 3, 0, sizeof(uint64_t), st));
+        gather_read_bytes<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_in.as<uint64_t>());
+        {
+            int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
+            if (rc) return rc;
+        }
+        scatter_read_off<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_out.as<uint64_t>());
+        last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
+        sum_bases<<<std::min<unsigned>(gb, 1024u), tb, 0, st>>>(pa.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
+        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_ops_total = n_ops + ctx->h_totals[6];
+        seq_bytes_final = ctx->h_totals[2];
+        total_bases_final = ctx->h_totals[3];
+        CK(ctx->ops.ensure_keep((size_t)(n_ops_total + 4) * sizeof(uint32_t), (size_t)n_ops * sizeof(uint32_t), st));
+        CK(ctx->seq.ensure((size_t)seq_bytes_final + 16));
+        if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes_final + 16));
+        pa.ops = ctx->ops.as<uint32_t>();
+        ha.ops = pa.ops;
+        ha.out_off = ctx->hp_off.as<uint64_t>();
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        hp_kernel<true><<<hp_blocks, 128, 0, st>>>(ha);
+        CK(cudaGetLastError());
+        launches += 14;
+    }
     CK(cudaEventRecord(ctx->ev[4], st));
-    launches += 1;    // emit
+    launches += 2;    // ev copy + emit
 
     // ---- emit
     EmitArgs ea;
@@ -710,9 +779,9 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(cudaStreamSynchronize(st));
 
     NsBatchInfo& bi = ctx->last;
-    bi.seq_bytes = seq_bytes;
-    bi.n_ops = n_ops;
-    bi.total_bases = total_bases;
+    bi.seq_bytes = seq_bytes_final;
+    bi.n_ops = n_ops_total;
+    bi.total_bases = total_bases_final;
     bi.n_reads = n;
     bi.n_pieces = n_pieces;
     bi.n_launches = launches;

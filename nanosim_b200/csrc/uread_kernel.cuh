@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                             if (ab >= clen) ab -= clen;
                             uint32_t c = __ldg(&cb[ab]);
                             if (c - 'a' < 26u) c -= 32;
-                            if (!acgt_fast(c)) c = resolve_iupac(c, w & 0xffu, ((w >> 8) & 0xffu) % 3u);
+                            if (!acgt_fast(c)) c = converted_ref_base(c, cfg.seed, rid, 0u, R + (uint32_t)roff);
                             oi = base_idx(c);
                             if (sub) oi = (oi + 1u + t3) & 3u;
                         }
@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 p.l_new = (uint32_t)l_new;
                 p.ref_req = m_ref;
                 p.read_slot = slot;
+                p.ev_off = 0;
+                p.ev_n_ops = 0;
+                p.reserved = 0;
                 a.pieces[slot] = p;
                 NsReadMeta q;
                 q.seq_off = 0;

@@ -71,7 +71,47 @@ def format_records(batch, names, fastq, n_threads=8):
     return out.tobytes()
 
 
-def error_profile_rows(batch, names, ref):
+_M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def _philox4x32(ctr, key, rounds):
+    """numpy Philox4x32 (vectorised over the first axis of ctr [n,4] uint64-held uint32 words); mirrors
+    csrc/device_common.cuh:philox4x32."""
+    c = [ctr[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(rounds):
+        p0 = np.uint64(_M0) * c[0]
+        p1 = np.uint64(_M1) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0 = (k0 + np.uint64(_W0)) & mask
+        k1 = (k1 + np.uint64(_W1)) & mask
+    return np.stack(c, axis=1)
+
+
+def event_bases_hp(seed, rid, piece_in_read, k, n, is_mis, orig_idx=None):
+    """Bases the homopolymer pass assigned to error event k of a segment (csrc/hp_kernel.cuh): one byte of Philox-7
+    block (k<<8)+(t>>4) per base.  Returns ACGT index array in the device's order A C T G = 0 1 2 3."""
+    t = np.arange(n, dtype=np.uint64)
+    stream = (6 << 28) | (piece_in_read & 0x07ffffff)            # ST_EMIT_B, kind 0
+    ctr = np.stack([np.full(n, rid & 0xFFFFFFFF, dtype=np.uint64), np.full(n, (rid >> 32) & 0xFFFFFFFF, dtype=np.uint64),
+                    np.full(n, stream, dtype=np.uint64), (np.uint64(k) << np.uint64(8)) + (t >> np.uint64(4))], axis=1)
+    blk = _philox4x32(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF), 7)
+    word = blk[np.arange(n), ((t >> np.uint64(2)) & np.uint64(3)).astype(np.int64)]
+    r8 = ((word >> (np.uint64(8) * (t & np.uint64(3)))) & np.uint64(0xFF)).astype(np.int64)
+    if not is_mis:
+        return r8 & 3
+    rr = np.where(r8 == 255, 0, r8)
+    return (orig_idx + 1 + rr % 3) & 3
+
+
+_IDX_BASE = np.frombuffer(b"ACTG", dtype=np.uint8)
+_BASE_IDX = np.zeros(256, dtype=np.int64)
+for _i, _c in enumerate(b"ACTG"):
+    _BASE_IDX[_c] = _i
+
+
+def error_profile_rows(batch, names, ref, seed=0):
     """The rows mutate_read logs for every aligned segment (needs batch.ops).  ``ref`` is the PackedReference.
     Reference bases are shown upper-cased as stored (an IUPAC code is shown as the code itself)."""
     rows = []
@@ -89,7 +129,8 @@ def error_profile_rows(batch, names, ref):
             pc = pieces[p0 + k]
             if pc["kind"] != L.NS_PIECE_SEGMENT:
                 continue
-            ops = ops_all[int(pc["op_off"]): int(pc["op_off"]) + int(pc["n_ops"])]
+            ops = ops_all[int(pc["ev_off"]): int(pc["ev_off"]) + int(pc["ev_n_ops"])]    # the error-event script
+            rewritten = int(pc["ev_off"]) != int(pc["op_off"])                        # -hp: bases fixed by the hp pass
             ty = (ops >> 28).astype(np.int64)
             ln = (ops & 0x0fffffff).astype(np.int64)
             out_adv = np.where(ty == L.NS_OP_DEL, 0, ln)
@@ -106,7 +147,14 @@ def error_profile_rows(batch, names, ref):
                 else:
                     idx = (base + rs + np.arange(n)) % clen if base + rs + n > clen else np.arange(base + rs, base + rs + n)
                     refb = ref.bases[cstart + idx].tobytes().decode().upper()
-                seqb = "-" * n if t == L.NS_OP_DEL else fwd[os_:os_ + n].tobytes().decode()
+                if t == L.NS_OP_DEL:
+                    seqb = "-" * n
+                elif rewritten:
+                    orig = _BASE_IDX[np.frombuffer(refb.encode(), dtype=np.uint8)] if t == L.NS_OP_MIS else None
+                    bi = event_bases_hp(seed, batch.first_id + i, k, int(j), n, t == L.NS_OP_MIS, orig)
+                    seqb = _IDX_BASE[bi].tobytes().decode()
+                else:
+                    seqb = fwd[os_:os_ + n].tobytes().decode()
                 seg_rows.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (names[i], rs, ("mis", "ins", "del")[t - 1], n, refb, seqb))
             rows.extend(reversed(seg_rows))
     return rows

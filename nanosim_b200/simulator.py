@@ -67,6 +67,7 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
     prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number_list[0], per)
     prof.perfect = per
     _log("Read KDF of aligned reads")
+    prof.seed = seed
     prof.engine = Engine(device=device, seed=seed)
     prof.engine.set_reference(prof.ref)
     prof.engine.set_model(prof.tables, perfect=per)
@@ -105,7 +106,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             names = read_names(b, prof.ref.names, job[1], perfect=per)
             f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
             if want_err:
-                f_err.writelines(error_profile_rows(b, names, prof.ref))
+                f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
 
         pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned)
     if not per:

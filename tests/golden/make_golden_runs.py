@@ -34,6 +34,7 @@ CONFIGS = {
     "guppy_perfect": (GUPPY, ["--perfect"], False),
     # eight independent single-threaded processes per chunk (independent numpy streams for the unaligned phase)
     "guppy_fasta_t1": (GUPPY, [], False),
+    "guppyq_fastq_t1": (GUPPY + "+q", ["--fastq"], True),
 }
 
 

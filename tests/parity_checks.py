@@ -50,24 +50,27 @@ def load_tables(model, **kw):
 
 
 def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, min_len=50, max_len=None, circular=False,
-                device=0, unaligned_scripts=False):
+                device=0, unaligned_scripts=False, kmer_bias=0):
     from nanosim_b200.engine import Engine
 
-    cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect)
+    cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect, homopolymer=bool(kmer_bias))
     eng = Engine(device=device, seed=seed)
     eng.set_reference(ref)
     eng.set_model(t, perfect=perfect)
     eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
-                  max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts)
+                  max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts,
+                  kmer_bias=kmer_bias)
     return eng, cm, t
 
 
-def _piece_layout(batch, pc):
-    ops = batch.ops[int(pc["op_off"]): int(pc["op_off"]) + int(pc["n_ops"])]
+def _piece_layout(batch, pc, events=False):
+    """events=True: the piece's error-event script (ev_off/ev_n_ops); else the script the emit kernel applied."""
+    o, n = (int(pc["ev_off"]), int(pc["ev_n_ops"])) if events else (int(pc["op_off"]), int(pc["n_ops"]))
+    ops = batch.ops[o:o + n]
     ty = (ops >> 28).astype(np.int64)
-    ln = (ops & 0x0fffffff).astype(np.int64)
+    ln = np.where(ty == 5, ops & 0x00ffffff, ops & 0x0fffffff).astype(np.int64)
     out_adv = np.where(ty == 3, 0, ln)
-    ref_adv = np.where((ty == 2) | (ty == 4), 0, ln)
+    ref_adv = np.where((ty == 2) | (ty == 4) | (ty == 5), 0, ln)
     out_start = np.concatenate([[0], np.cumsum(out_adv)[:-1]]) if len(ops) else np.zeros(0, dtype=np.int64)
     ref_start = np.concatenate([[0], np.cumsum(ref_adv)[:-1]]) if len(ops) else np.zeros(0, dtype=np.int64)
     return ty, ln, out_adv, ref_adv, out_start, ref_start
@@ -99,6 +102,13 @@ def check_edit_scripts(batch, ref, fastq, max_reads=None):
             assert int(out_adv.sum()) == int(pc["out_len"])
             assert int(ref_adv.sum()) == int(pc["ref_len"])
             assert (ln > 0).all()
+            lit = ty == 5
+            if lit.any():                               # literal bases of the homopolymer pass (A C T G = 0 1 2 3)
+                o_ops = batch.ops[int(pc["op_off"]): int(pc["op_off"]) + int(pc["n_ops"])]
+                want = np.frombuffer(b"ACTG", dtype=np.uint8)[((o_ops[lit] >> 26) & 3).astype(np.int64)]
+                lo_idx = np.repeat(out_start[lit], ln[lit]) + (np.arange(int(ln[lit].sum())) - np.repeat(np.cumsum(ln[lit]) - ln[lit], ln[lit]))
+                got = fwd[cursor:cursor + int(pc["out_len"])][lo_idx]
+                assert (got == np.repeat(want, ln[lit])).all(), "literal base mismatch (read %d piece %d)" % (i, k)
             if k == 0 and int(r["head"]) > 0:
                 assert ty[0] == 4 and ln[0] == int(r["head"])
             if k == npc - 1 and int(r["tail"]) > 0:
@@ -176,6 +186,7 @@ def batch_stats(batch, ref, fastq, s=None):
         s["len_head"][rs._bin(rs.HT_EDGES, head)] += 1
         s["len_tail"][rs._bin(rs.HT_EDGES, tail)] += 1
         comp += np.bincount(raw, minlength=256)
+        s["hp_runs"] += rs.hp_run_hist(raw)
         if fastq:
             qq = batch.qual[so:so + Lr]
             lead, trail = (tail, head) if r["reversed"] else (head, tail)
@@ -185,7 +196,8 @@ def batch_stats(batch, ref, fastq, s=None):
             continue
         fwd = _COMP[raw[::-1]] if r["reversed"] else raw
         for pc in segs:
-            ty, ln, out_adv, ref_adv, out_start, ref_start = _piece_layout(batch, pc)
+            ty, ln, out_adv, ref_adv, out_start, ref_start = _piece_layout(batch, pc, events=True)
+            rewritten = int(pc["ev_off"]) != int(pc["op_off"])      # -hp: output positions of events are not recoverable
             ev = np.nonzero((ty >= 1) & (ty <= 3))[0]
             if len(ev) == 0:
                 continue
@@ -204,6 +216,8 @@ def batch_stats(batch, ref, fastq, s=None):
                 (s["first_match"] if first else s["match_run"])[min(run, rs.RUN_CAP)] += 1
                 first = False
                 cur = rp + (n if t != 2 else 0)
+                if rewritten:
+                    continue
                 if t == 1 and n == 1:
                     a = _BIDX[_UPPER[ref.bases[cstart + (int(pc["pos"]) + rp) % clen]]]
                     b = _BIDX[fwd[int(pc["out_rel"]) + int(out_start[j])]]
@@ -326,7 +340,7 @@ def compare_stats(a, b, rate_tol, p_min, keys=None, label=""):
 # --------------------------------------------------------------------------------------
 # oracle runs
 # --------------------------------------------------------------------------------------
-def oracle_stats(cm, ref_records, n_aligned, n_unaligned, fastq, chimeric=False, seed=1234, tmpdir=None):
+def oracle_stats(cm, ref_records, n_aligned, n_unaligned, fastq, chimeric=False, seed=1234, tmpdir=None, kmer_bias=None):
     """Runs the pure-Python oracle (oracle/nanosim_oracle.py) and returns its run_stats via the same text files the
     reference would write."""
     import random
@@ -336,12 +350,12 @@ def oracle_stats(cm, ref_records, n_aligned, n_unaligned, fastq, chimeric=False,
     from conftest import oracle_model
 
     tmp = tmpdir or tempfile.mkdtemp(prefix="oracle_run_")
-    m = oracle_model(cm, tmp, fastq=fastq, chimeric=chimeric)
+    m = oracle_model(cm, tmp, fastq=fastq, chimeric=chimeric, homopolymer=bool(kmer_bias))
     oref = no.OracleReference(ref_records)
     random.seed(seed)
     np.random.seed(seed)
     sink = no.ReadSink()
-    no.simulation_aligned_genome(oref, m, sink, "linear", 50, oref.max_chrom, None, None, None, fastq, n_aligned, False, chimeric)
+    no.simulation_aligned_genome(oref, m, sink, "linear", 50, oref.max_chrom, None, None, kmer_bias, fastq, n_aligned, False, chimeric)
     ext = ".fastq" if fastq else ".fasta"
     prefix = os.path.join(tmp, "oracle")
     with open(prefix + "_aligned_reads" + ext, "w") as f:

@@ -18,6 +18,7 @@ LEN_EDGES = np.unique(np.round(np.logspace(1.0, 6.0, 151)).astype(np.int64))    
 HT_EDGES = np.concatenate([[0, 1, 2, 3, 5, 8], np.unique(np.round(np.logspace(1.0, 5.5, 46)).astype(np.int64))])
 EV_CAP = 64          # event lengths 1..63, 64+
 RUN_CAP = 512        # match runs 0..511, 512+
+HP_CAP = 48          # homopolymer run lengths 0..47, 48+
 EPR_EDGES = np.concatenate([np.arange(0, 20), np.unique(np.round(np.logspace(np.log10(20), 5, 60)).astype(np.int64))])
 
 
@@ -45,11 +46,25 @@ def empty():
         "qual_ht": np.zeros(94, dtype=np.int64),
         "qual_unaligned": np.zeros(94, dtype=np.int64),
         "base_comp_aligned": np.zeros(4, dtype=np.int64),
+        "hp_runs": np.zeros(HP_CAP + 1, dtype=np.int64),      # homopolymer run lengths (>= 3) in aligned reads
     }
+
+
+def hp_run_hist(arr):
+    """Histogram of the lengths of maximal runs of equal bytes (only runs >= 3 are counted)."""
+    if len(arr) == 0:
+        return np.zeros(HP_CAP + 1, dtype=np.int64)
+    change = np.flatnonzero(arr[1:] != arr[:-1])
+    runs = np.diff(np.concatenate([[-1], change, [len(arr) - 1]]))
+    runs = runs[runs >= 3]
+    return np.bincount(np.minimum(runs, HP_CAP), minlength=HP_CAP + 1)
 
 
 def merge(a, b):
     for k, v in b.items():
+        if k not in a:
+            a[k] = v
+            continue
         if isinstance(v, dict):
             for kk in v:
                 a[k][kk] = a[k][kk] + v[kk]
@@ -142,7 +157,9 @@ def add_reads(s, path, fastq, aligned=True):
                 s["len_middle_ref"][_bin(LEN_EDGES, m)] += 1
             s["len_head"][_bin(HT_EDGES, head)] += 1
             s["len_tail"][_bin(HT_EDGES, tail)] += 1
-            comp += np.bincount(np.frombuffer(seq.encode(), dtype=np.uint8), minlength=256)
+            arr8 = np.frombuffer(seq.encode(), dtype=np.uint8)
+            comp += np.bincount(arr8, minlength=256)
+            s["hp_runs"] += hp_run_hist(arr8)
             if q is not None:
                 qq = np.frombuffer(q.encode(), dtype=np.uint8)
                 lead, trail = (tail, head) if strand == "R" else (head, tail)

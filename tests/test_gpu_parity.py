@@ -279,11 +279,112 @@ def test_qualities_vs_unmodified_reference_guppyq(ecoli, L):
     eng.close()
     fails = pc.compare_stats(s, gold, rate_tol=3e-3, p_min=1e-6, label="guppyq",
                              keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
-    for k in ("qual_middle", "qual_ht", "qual_unaligned"):
-        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+    # unaligned qualities: with -t 8 the reference's unaligned workers share one numpy stream (simulator.py:1648-1660),
+    # i.e. identical quality draws in all eight workers; they are compared with independent -t 1 processes instead.
+    p1 = os.path.join(GOLDEN, "ref_stats_guppyq_fastq_t1.json")
+    g1 = rs.load(p1)[0] if os.path.exists(p1) else None
+    for k, g in (("qual_middle", gold), ("qual_ht", gold), ("qual_unaligned", g1)):
+        if g is None:
+            continue
+        st, dof, p = pc.chi2_two_sample(s[k], g[k])
         print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
         if p < 1e-6:
             fails.append("guppyq %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    assert not fails, "\n".join(fails)
+
+
+def _hp_reference(n_chrom=3, size=40000, seed=11):
+    """ACGT-only reference rich in homopolymer runs (4..14) so that the -hp/-k paths are exercised on every read."""
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(seed)
+    recs = []
+    for c in range(n_chrom):
+        s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size)].copy()
+        for _ in range(size // 60):
+            p = int(rng.integers(0, size - 20))
+            s[p:p + int(rng.integers(4, 15))] = b"ACGT"[int(rng.integers(0, 4))]
+        recs.append(("hp%d" % c, s))
+    return PackedReference.from_records(recs), [(n, a.tobytes().decode()) for n, a in recs]
+
+
+def _in_hp_mask(seg, k):
+    change = np.flatnonzero(seg[1:] != seg[:-1])
+    bounds = np.concatenate([[0], change + 1, [len(seg)]])
+    runs = np.diff(bounds)
+    return np.repeat(runs >= k, runs)
+
+
+def test_homopolymer_scripts_bit_exact_and_filter_invariant(L):
+    """-hp -k 6: (1) the rewritten scripts (COPY / reference skips / literals) reproduce the device's bases exactly;
+    (2) no surviving error event touches a homopolymer run of the unmutated segment (simulator.py:1929-1947)."""
+    ref, _ = _hp_reference()
+    eng, cm, t = pc.make_engine("dorado", ref, fastq=True, chimeric=True, kmer_bias=6, seed=13)
+    info = eng.simulate(L.NS_KIND_ALIGNED, 0, 1200)
+    b = eng.fetch(want_ops=True)
+    assert pc.check_edit_scripts(b, ref, True) > 0
+    assert ((b.ops[:0] >> 28) == 5).sum() == 0
+    ref_off = ref.offsets.astype(np.int64)
+    n_events = n_lit = 0
+    for pcs in b.pieces[b.pieces["kind"] == L.NS_PIECE_SEGMENT]:
+        assert int(pcs["ev_off"]) != int(pcs["op_off"])
+        seg = ref.bases[int(ref_off[pcs["chrom"]]) + int(pcs["pos"]): int(ref_off[pcs["chrom"]]) + int(pcs["pos"]) + int(pcs["ref_len"])]
+        mask = _in_hp_mask(seg, 6)
+        ty, ln, out_adv, ref_adv, out_start, ref_start = pc._piece_layout(b, pcs, events=True)
+        for j in np.nonzero((ty >= 1) & (ty <= 3))[0]:
+            lo = int(ref_start[j]) - (1 if ty[j] == 2 else 0)
+            hi = int(ref_start[j]) + int(ln[j]) - 1
+            assert not mask[max(lo, 0):min(hi, len(mask) - 1) + 1].any(), "event inside a homopolymer survived"
+            n_events += 1
+        o = b.ops[int(pcs["op_off"]): int(pcs["op_off"]) + int(pcs["n_ops"])]
+        n_lit += int(((o >> 28) == 5).sum())
+    assert n_events > 1000 and n_lit > 1000
+    eng.close()
+
+
+def test_homopolymer_statistics_vs_oracle(L, tmp_path):
+    """mutate_homo + the error filter against the pure-Python oracle on a homopolymer-rich reference."""
+    ref, recs = _hp_reference(size=60000)
+    eng, cm, t = pc.make_engine("dorado", ref, fastq=True, kmer_bias=6, seed=19)
+    s_dev = rs.empty()
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 20000)
+    pc.batch_stats(eng.fetch(want_ops=True), ref, True, s_dev)
+    eng.close()
+    s_or = pc.oracle_stats(cm, recs, 220, 0, True, tmpdir=str(tmp_path), kmer_bias=6)
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.08, p_min=1e-5, label="hp",
+                             keys=["len_aligned", "len_middle_ref", "match_run", "first_match"])
+    for k in ("hp_runs", "qual_middle"):
+        st, dof, p = pc.chi2_two_sample(s_dev[k], s_or[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-5:
+            fails.append("hp %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    # net length change of the pass: mean read length relative to the aligned region, device vs oracle
+    rd = s_dev["aligned_bases"] / s_dev["ref_bases"]
+    ro = s_or["aligned_bases"] / s_or["ref_bases"]
+    assert abs(rd / ro - 1) < 0.01, (rd, ro)
+    assert not fails, "\n".join(fails)
+
+
+def test_homopolymer_vs_unmodified_reference(ecoli, L):
+    """50k reads of `simulator.py genome --fastq --chimeric -hp -k 6` (dorado model, unmodified reference)."""
+    path = os.path.join(GOLDEN, "ref_stats_dorado_fastq_hp6_chimeric.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    if "hp_runs" not in gold:
+        pytest.skip("golden file predates the homopolymer histogram")
+    eng, cm, t = pc.make_engine("dorado", ecoli, fastq=True, chimeric=True, kmer_bias=6, seed=79)
+    s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
+    eng.close()
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("hp per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    fails = pc.compare_stats(s, gold, rate_tol=4e-3, p_min=1e-6, label="hp6",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("hp_runs", "qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("hp6 %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    assert abs(s["aligned_bases"] / s["ref_bases"] / (gold["aligned_bases"] / gold["ref_bases"]) - 1) < 2e-3
     assert not fails, "\n".join(fails)
 
 

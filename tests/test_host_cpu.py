@@ -24,7 +24,7 @@ def test_library_exports_every_header_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     # struct layouts the ctypes mirror relies on
-    assert ctypes.sizeof(_lib.NsReadMeta) == 32 and ctypes.sizeof(_lib.NsPieceMeta) == 48
+    assert ctypes.sizeof(_lib.NsReadMeta) == 32 and ctypes.sizeof(_lib.NsPieceMeta) == 64
 
 
 def test_no_cpu_fallback_without_gpu():
