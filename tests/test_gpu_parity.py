@@ -358,9 +358,10 @@ def test_homopolymer_statistics_vs_oracle(L, tmp_path):
         if p < 1e-5:
             fails.append("hp %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
     # net length change of the pass: mean read length relative to the aligned region, device vs oracle
-    rd = s_dev["aligned_bases"] / s_dev["ref_bases"]
-    ro = s_or["aligned_bases"] / s_or["ref_bases"]
-    assert abs(rd / ro - 1) < 0.01, (rd, ro)
+    rd = (s_dev["aligned_bases"] - s_dev["head_bases"] - s_dev["tail_bases"]) / s_dev["ref_bases"]
+    ro = (s_or["aligned_bases"] - s_or["head_bases"] - s_or["tail_bases"]) / s_or["ref_bases"]
+    print("middle bases per reference base: device %.5f oracle %.5f" % (rd, ro))
+    assert abs(rd / ro - 1) < 3e-3, (rd, ro)
     assert not fails, "\n".join(fails)
 
 
@@ -384,7 +385,10 @@ def test_homopolymer_vs_unmodified_reference(ecoli, L):
         print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
         if p < 1e-6:
             fails.append("hp6 %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
-    assert abs(s["aligned_bases"] / s["ref_bases"] / (gold["aligned_bases"] / gold["ref_bases"]) - 1) < 2e-3
+    md = (s["aligned_bases"] - s["head_bases"] - s["tail_bases"]) / s["ref_bases"]
+    mg = (gold["aligned_bases"] - gold["head_bases"] - gold["tail_bases"]) / gold["ref_bases"]
+    print("middle bases per reference base: device %.6f reference %.6f" % (md, mg))
+    assert abs(md / mg - 1) < 1e-3
     assert not fails, "\n".join(fails)
 
 
