@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 template <bool FASTQ>
-__global__ void __launch_bounds__(EMIT_WARPS * 32, 3) emit_kernel(const __grid_constant__ EmitArgs a) {
+__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_constant__ EmitArgs a) {
     extern __shared__ uint32_t smem[];
     uint32_t* lut = smem;                                        // FASTQ only
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -124,102 +124,80 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 3) emit_kernel(const __grid_c
                     if (ring_out[mid % EMIT_RING] <= plo) l = mid; else h = mid;
                 }
                 uint32_t k = l;
-                // ---- per-op state, refreshed only when the walk enters a new op (ops cover ~7 bases for the guppy
-                //      model, ~50 for dorado): kind flags, quality-table row, reference pointer and direction
-                uint32_t rem, mis_add, fixed_oi;
-                bool from_ref, fixed;
-                const uint32_t* lrow = lut;
-                const uint8_t* rp = cbase;
-                const uint8_t* const cend = cbase + clen;
-                const int dir = rev ? -1 : 1;
-                auto enter_op = [&](uint32_t within) {
-                    const uint32_t op = ring_op[k % EMIT_RING];
-                    const uint32_t ty = op >> 28;
-                    rem = (ty == NS_OP_DEL) ? 0u : op_len(op) - within;
-                    from_ref = ty < 2u;                                    // COPY or MIS read the reference
-                    mis_add = (ty == NS_OP_MIS) ? 1u : 0u;
-                    fixed = ty == NS_OP_LIT;                               // literal base of a rewritten homopolymer
-                    fixed_oi = (op >> 26) & 3u;
-                    if (FASTQ) {
-                        // COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3), LIT carries its state; gap/unaligned -> unmapped(4)
-                        const uint32_t qs = unmapped ? 4u : (fixed ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
-                        lrow = lut + qs * QLUT_SIZE;
-                    }
-                    if (from_ref) {
-                        const uint32_t rpos = ring_ref[k % EMIT_RING] + within;
-                        uint64_t ab = (uint64_t)pm.pos + (rev ? ref_len - 1 - rpos : rpos);
-                        if (ab >= clen) ab -= clen;                        // circular wrap (:1756-1760)
-                        rp = cbase + ab;
-                    }
-                };
-                enter_op(plo - ring_out[k % EMIT_RING]);
+                uint32_t op = ring_op[k % EMIT_RING];
+                uint32_t ty = op >> 28;
+                uint32_t within = plo - ring_out[k % EMIT_RING];
+                uint32_t rem = op_len(op) - within;
+                uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty < 2u) ? within : 0u);
 
-                // ---- randomness: position-indexed and identical in every lane's control flow.  One Philox-7 block per
-                //      four bases; word j of block o belongs to base 4o+j: its low 24 bits are the quality uniform, its
-                //      high byte picks the substituted / inserted base.
+                // ---- all randomness of the chunk up front, position-indexed, identical in every lane's control flow:
+                //      base i uses byte i of `bw` (substitution / inserted base / IUPAC member) and bits [24i, 24i+24)
+                //      of `qw` (its quality value).
                 const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
                 const uint32_t id_lo = (uint32_t)rid, id_hi = (uint32_t)(rid >> 32);
-                const uint32_t sw = stream_word(ST_EMIT_B, a.kind, chunk);
-                const uint32_t flip = rev ? 2u : 0u;
-                const bool circ = a.cfg.circular != 0;
-
-                uint32_t sb0 = 0, sb1 = 0, sb2 = 0, sb3 = 0, sq0 = 0, sq1 = 0, sq2 = 0, sq3 = 0;
-                const uint32_t i0 = lo - cs, i1 = hi - cs;
-#pragma unroll 1
-                for (uint32_t o = 0; o < 4; ++o) {
-                    if (4 * o + 4 <= i0 || 4 * o >= i1) continue;
-                    const uint4 r4 = philox4x32_7(make_uint4(id_lo, id_hi, sw, o), key);
-                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-                    uint32_t wb = 0, wq = 0;
+                const uint4 bw4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, a.kind, chunk), 0u), key);
+                const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
+                uint32_t qw[13];
+                if (FASTQ) {
+                    const uint32_t sw = stream_word(ST_EMIT_Q, a.kind, chunk);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t i = 4 * o + j;
-                        if (i >= i0 && i < i1) {
-                            while (rem == 0) {
-                                ++k;
-                                enter_op(0);
+                    for (int j = 0; j < 3; ++j) {
+                        uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
+                        qw[4 * j] = t.x; qw[4 * j + 1] = t.y; qw[4 * j + 2] = t.z; qw[4 * j + 3] = t.w;
+                    }
+                    qw[12] = 0;
+                }
+                const uint32_t flip = rev ? 2u : 0u;
+
+                uint32_t sb[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+                const uint32_t i0 = lo - cs, i1 = hi - cs;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if ((uint32_t)i >= i0 && (uint32_t)i < i1) {
+                        while (rem == 0) {
+                            ++k;
+                            op = ring_op[k % EMIT_RING];
+                            ty = op >> 28;
+                            rem = (ty == NS_OP_DEL) ? 0u : op_len(op);
+                            rpos = ring_ref[k % EMIT_RING];
+                        }
+                        --rem;
+                        const uint32_t r8 = (bw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                        const uint32_t r8n = (bw[((i + 1) & 15) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
+                        const uint32_t rr = (r8 == 255u) ? r8n : r8;           // 0..254 -> exactly uniform mod 3
+                        const uint32_t t3 = rr - 3u * ((rr * 171u) >> 9);
+                        uint32_t oi = r8 & 3u;                                 // random.choice(BASES) / np.random.choice
+                        if (ty < 2u) {                                         // COPY or MIS: reads the reference
+                            uint32_t f = rev ? ref_len - 1 - rpos : rpos;
+                            uint64_t ab = (uint64_t)pm.pos + f;
+                            if (ab >= clen) ab -= clen;                        // circular wrap (:1756-1760)
+                            uint32_t c = __ldg(&cbase[ab]);
+                            ++rpos;
+                            if (c - 'a' < 26u) c -= 32;
+                            if (!acgt_fast(c)) c = converted_ref_base(c, a.cfg.seed, rid, piece - rm.piece_first, f);
+                            oi = base_idx(c);
+                            if (ty == NS_OP_MIS) oi = (oi + 1u + t3) & 3u;     // one of the three other bases
+                        } else if (ty == NS_OP_LIT) {
+                            oi = (op >> 26) & 3u;                              // literal base of a rewritten homopolymer
+                        }
+                        sb[i >> 2] |= idx_base(oi ^ flip) << (8 * (i & 3));
+                        if (FASTQ) {
+                            // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3); gap/unaligned -> unmapped(4)
+                            const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
+                            const int bit = 24 * i;
+                            const uint32_t u24 = __funnelshift_r(qw[bit >> 5], qw[(bit >> 5) + 1], bit & 31) & 0xffffffu;
+                            const uint32_t e = lut[qs * QLUT_SIZE + (u24 >> QLUT_FRAC_BITS)];
+                            uint32_t q = e & 0xffu;
+                            if (e >> 31) {                                     // bucket spans >2 quality values: exact scan
+                                const uint32_t* cdf = a.qcdf + qs * NS_QUAL_SLOTS;
+                                while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf[q])) ++q;
+                            } else {
+                                q += ((u24 & ((1u << QLUT_FRAC_BITS) - 1u)) >= ((e >> 8) & 0x3fffu)) ? 1u : 0u;
                             }
-                            --rem;
-                            const uint32_t w = rw[j];
-                            const uint32_t r8 = w >> 24;
-                            uint32_t oi = fixed ? fixed_oi : (r8 & 3u);        // literal / random.choice(BASES)
-                            if (from_ref) {
-                                uint32_t c = __ldg(rp);
-                                if (!acgt_fast(c)) {                           // lower case or IUPAC (case_convert :743-755)
-                                    uint64_t off = (uint64_t)(rp - cbase);
-                                    off = off >= pm.pos ? off - pm.pos : off + clen - pm.pos;
-                                    c = converted_ref_base(c, a.cfg.seed, rid, piece - rm.piece_first, (uint32_t)off);
-                                }
-                                rp += dir;
-                                if (circ) {
-                                    if (rp == cend) rp = cbase;
-                                    else if (rp < cbase) rp = cend - 1;
-                                }
-                                const uint32_t rr = (r8 == 255u) ? ((w >> 16) & 0xffu) : r8;   // 0..254 -> exactly uniform mod 3
-                                const uint32_t t3 = rr - 3u * ((rr * 171u) >> 9);
-                                oi = (base_idx(c) + mis_add * (1u + t3)) & 3u; // MIS: one of the three other bases
-                            }
-                            wb |= __byte_perm(0x47544341u, 0u, oi ^ flip) << (8 * j) & (0xffu << (8 * j));
-                            if (FASTQ) {
-                                const uint32_t u24 = w & 0xffffffu;
-                                const uint32_t e = lrow[u24 >> QLUT_FRAC_BITS];
-                                uint32_t q = e & 0xffu;
-                                if (e >> 31) {                                 // bucket spans >2 quality values: exact scan
-                                    const uint32_t* cdf = a.qcdf + (uint32_t)((lrow - lut) / QLUT_SIZE) * NS_QUAL_SLOTS;
-                                    while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf[q])) ++q;
-                                } else {
-                                    q += ((u24 & ((1u << QLUT_FRAC_BITS) - 1u)) >= ((e >> 8) & 0x3fffu)) ? 1u : 0u;
-                                }
-                                wq |= (q + 33u) << (8 * j);
-                            }
+                            sq[i >> 2] |= (q + 33u) << (8 * (i & 3));
                         }
                     }
-                    if (o == 0) { sb0 = wb; sq0 = wq; }
-                    else if (o == 1) { sb1 = wb; sq1 = wq; }
-                    else if (o == 2) { sb2 = wb; sq2 = wq; }
-                    else { sb3 = wb; sq3 = wq; }
                 }
-                const uint32_t sb[4] = {sb0, sb1, sb2, sb3}, sq[4] = {sq0, sq1, sq2, sq3};
                 if (i0 == 0 && i1 == 16) {
                     *reinterpret_cast<uint4*>(seq_out + cs) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
                     if (FASTQ) *reinterpret_cast<uint4*>(qual_out + cs) = make_uint4(sq[0], sq[1], sq[2], sq[3]);
