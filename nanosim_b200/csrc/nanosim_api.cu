@@ -83,7 +83,8 @@ struct NsContext {
     // batch state
     DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
         stats, sort_keys, sort_vals, sort_tmp, hp_off;
-    uint64_t* h_totals = nullptr;   // pinned
+    uint64_t* h_totals = nullptr;   // pinned + mapped
+    uint64_t* h_totals_dev = nullptr;
     NsBatchInfo last{};
     int last_kind = 0;
     uint64_t last_first_id = 0;
@@ -141,6 +142,12 @@ __global__ void copy_ev_fields(NsPieceMeta* pieces, uint32_t n) {
 __global__ void add_base_u64(uint64_t* v, uint32_t n, uint64_t base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += base;
+}
+// The batch totals the host needs mid-pipeline are written straight into mapped pinned host memory: a cudaMemcpy
+// would queue behind another context's multi-GB device->host transfer on the copy engine and serialise the pipelines.
+__global__ void publish_totals(const uint64_t* totals, volatile uint64_t* host) {
+    if (threadIdx.x < 8) host[threadIdx.x] = totals[threadIdx.x];
+    __threadfence_system();
 }
 __global__ void gather_read_bytes(const NsReadMeta* reads, uint32_t n, uint64_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,7 +270,8 @@ int ns_create(int device, uint64_t seed, NsContext** out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_totals, 8 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_totals, 8 * sizeof(uint64_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->h_totals_dev, ctx->h_totals, 0);
     if (e == cudaSuccess && device >= 0 && device < 64 && !g_base[device]) {
         e = cudaEventCreate(&g_base[device]);
         if (e == cudaSuccess) e = cudaEventRecord(g_base[device], ctx->stream);
@@ -514,7 +522,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         scatter_read_off<<<gbu, tbu, 0, st>>>(ua.reads, n, ctx->scan_out.as<uint64_t>());
         last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
         sum_bases<<<std::min<unsigned>(gbu, 1024u), tbu, 0, st>>>(ua.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
-        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
         CK(cudaStreamSynchronize(st));
         const uint64_t seq_bytes_u = ctx->h_totals[2], total_bases_u = ctx->h_totals[3];
         CK(ctx->ops.ensure(64));
@@ -585,7 +593,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         narrow_u64<<<gb, tb, 0, st>>>(ctx->scan_out.as<uint64_t>(), n, ctx->piece_first.as<uint32_t>());
         last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 0);
         launches += 6;
-        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
         CK(cudaStreamSynchronize(st));
         n_pieces = (uint32_t)ctx->h_totals[0];
         d_nseg = ctx->nseg.as<uint32_t>();
@@ -620,7 +628,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(ctx->sort_tmp.ensure(tmp));
         CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, st));
     }
-    CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
     CK(cudaStreamSynchronize(st));
     const uint64_t primary_ops = ctx->h_totals[4];
     CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
@@ -666,7 +674,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         if (rc) return rc;
     }
     last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 1);
-    CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
     CK(cudaStreamSynchronize(st));
     const uint64_t overflow_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
     const uint32_t n_flagged = (uint32_t)(ctx->h_totals[5] & 0xffffffffull);
@@ -724,7 +732,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         scatter_read_off<<<gb, tb, 0, st>>>(pa.reads, n, ctx->scan_out.as<uint64_t>());
         last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
         sum_bases<<<std::min<unsigned>(gb, 1024u), tb, 0, st>>>(pa.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
-        CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
         CK(cudaStreamSynchronize(st));
         n_ops_total = n_ops + ctx->h_totals[6];
         seq_bytes_final = ctx->h_totals[2];

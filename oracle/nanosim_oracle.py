@@ -775,3 +775,308 @@ def format_records(records, fastq):
         if fastq:
             out.append("+\n" + "".join(chr(q + 33) for q in quals) + "\n")
     return "".join(out)
+
+
+# --------------------------------------------------------------------------------------
+# metagenome mode
+# --------------------------------------------------------------------------------------
+class OracleMetaReference:
+    """seq_dict[species][chrom] / seq_len / dict_dna_type / max_chrom for metagenome mode (simulator.py:284-339)."""
+
+    def __init__(self, genomes, dna_types=None):
+        """genomes: ordered {species: [(chrom_key, sequence), ...]}; dna_types: {species: {chrom_key: type}}."""
+        self.seq_dict, self.seq_len, self.dict_dna_type, self.max_chrom = {}, {}, {}, {}
+        for sp, recs in genomes.items():
+            self.seq_dict[sp], self.seq_len[sp], self.dict_dna_type[sp] = {}, {}, {}
+            self.max_chrom[sp] = 0
+            for key, seq in recs:
+                self.seq_dict[sp][key] = seq
+                self.seq_len[sp][key] = len(seq)
+                self.dict_dna_type[sp][key] = "circular"          # local files default to circular (:323)
+                self.max_chrom[sp] = max(self.max_chrom[sp], len(seq))
+        for sp, d in (dna_types or {}).items():
+            for key, ty in d.items():
+                self.dict_dna_type[sp][key] = ty
+
+    @staticmethod
+    def from_genome_list(genome_list, dna_type_list=None):
+        """genome list: species<TAB>fasta path (:259-266); dna type list: species<TAB>chrom header<TAB>type (:327-339)."""
+        genomes = {}
+        with open(genome_list) as f:
+            for line in f.readlines():
+                fields = line.split("\t")
+                sp = "_".join(fields[0].split())
+                genomes[sp] = read_fasta(fields[1].strip("\n"))
+        types = {}
+        if dna_type_list:
+            with open(dna_type_list) as f:
+                for line in f.readlines():
+                    fields = line.split("\t")
+                    sp = "_".join(fields[0].split())
+                    key = "-".join(re.split(r"[_\s]\s*", fields[1].partition(" ")[0])).split(".")[0]
+                    types.setdefault(sp, {})[key] = fields[2].strip("\n")
+        return OracleMetaReference(genomes, types)
+
+
+def read_abundance(path):
+    """simulator.py:360-380 -> (number_list, {sampleN: {species: abundance}})."""
+    with open(path) as f:
+        header = f.readline()
+        numbers = [int(x) for x in header.strip().split("\t")[1:]]
+        samples = ["sample" + str(i) for i in range(len(numbers))]
+        multi = {s: {} for s in samples}
+        for line in f.readlines():
+            fields = line.split("\t")
+            sp = "_".join(fields[0].split())
+            vals = [float(x) for x in fields[1:]]
+            for i, s in enumerate(samples):
+                multi[s][sp] = vals[i]
+    return numbers, multi
+
+
+def inflate_abun(dict_abun, species, abun_inflation):
+    """simulator.py:2018-2022."""
+    return 1 - (1 - dict_abun[species]) * abun_inflation
+
+
+def extract_read_meta(ref, length, s=None):
+    """simulator.py:1704-1749 (metagenome branch of extract_read)."""
+    if not s:
+        s = random.choice(list(ref.seq_len.keys()))
+    key = random.choice(list(ref.seq_len[s].keys()))
+    klen = ref.seq_len[s][key]
+    if length > klen:
+        longer, longer_target = [], []
+        for ts in ref.seq_len:
+            for tk in ref.seq_len[ts]:
+                if length < ref.seq_len[ts][tk]:
+                    (longer_target if ts == s else longer).append((ts, tk))
+        assert len(longer) > 0 or len(longer_target) > 0
+        s, key = random.choice(longer_target) if longer_target else random.choice(longer)
+        klen = ref.seq_len[s][key]
+    seq = ref.seq_dict[s][key]
+    if ref.dict_dna_type[s][key] == "circular":
+        pos = random.randint(0, klen)
+        if length + pos > klen:
+            out = seq[pos:] + seq[0: length - klen + pos]
+        else:
+            out = seq[pos: pos + length]
+    else:
+        pos = random.randint(0, klen - length)
+        out = seq[pos: pos + length]
+    return out, s + "-" + key + "_" + str(pos)
+
+
+def assign_species(length_list, seg_list, current, dict_abun, dict_abun_inflated):
+    """simulator.py:758-811."""
+    seg_sorted = sorted(seg_list, reverse=True)
+    segs_chimera = sum([x for x in seg_list if x > 1])
+    lengths = length_list[:segs_chimera] + sorted(length_list[segs_chimera:], reverse=True)
+    species_list = [""] * len(length_list)
+    total_bases = sum(length_list) + sum(current.values())
+    total_abun = sum(dict_abun.values())
+    quota = {sp: total_bases * ab / total_abun - current[sp] for sp, ab in dict_abun.items()}
+    ptr = 0
+    pre = ""
+    n = len(lengths)
+    for seg in seg_sorted:
+        if ptr + seg > n:
+            break
+        for e in range(seg):
+            if e == 0:
+                avail = [s for s, q in quota.items() if q - lengths[ptr] > 0]
+                if len(avail) == 0:
+                    avail = [s for s, q in quota.items() if q > 0]
+                sp = random.choice(avail)
+            else:
+                avail = [s for s, q in quota.items() if q - lengths[ptr] > 0 and s != pre]
+                p = random.uniform(0, 100)
+                if p <= dict_abun_inflated[pre] and quota[pre] > 0:
+                    sp = pre
+                elif p > dict_abun_inflated[pre] and len(avail) > 0:
+                    sp = random.choice(avail)
+                else:
+                    avail = [s for s, q in quota.items() if q - lengths[ptr] > 0]
+                    if len(avail) == 0:
+                        avail = [s for s, q in quota.items() if q > 0]
+                    sp = random.choice(avail)
+            species_list[ptr] = sp
+            quota[sp] -= lengths[ptr]
+            ptr += 1
+            pre = sp
+    return species_list[:ptr], lengths[:ptr], np.array(seg_sorted[:ptr])
+
+
+def simulation_gap_meta(ref, model, length, fastq):
+    """simulation_gap (:1552-1568) with dna_type == "metagenome"."""
+    if length == 0:
+        return "", []
+    _, middle_ref, e_dict, e_count = unaligned_error_list(length, model)
+    gap, gap_name = extract_read_meta(ref, middle_ref)
+    gap = case_convert(gap)
+    mutated, _ = mutate_read(gap, gap_name, None, e_dict, e_count, False, False, model)
+    quals = base_qualities(model.base_qual["unmapped"], len(mutated)) if fastq else []
+    return mutated, quals
+
+
+def simulation_aligned_metagenome(ref, model, sink, dict_abun, dict_abun_inflated, min_l, max_l, kmer_bias, fastq,
+                                  num_simulate, per=False, chimeric=False):
+    """simulator.py:814-1040 (KDE lengths only; -med/-sd not restated)."""
+    remaining = num_simulate
+    if chimeric:
+        num_segment = np.random.geometric(1 / model.segment_mean, num_simulate)
+    else:
+        num_segment = np.ones(num_simulate, dtype=int)
+    rem_segments = num_segment
+    rem_gaps = rem_segments - 1
+    passed = 0
+    current = {sp: 0 for sp in dict_abun.keys()}
+    while remaining > 0:
+        if per:
+            ref_lengths = [x for x in kde_lengths(model.kde_aligned, sum(rem_segments)) if min_l <= x <= max_l]
+            if len(ref_lengths) == 0:
+                continue
+        else:
+            rem_lengths = [x for x in kde_lengths(model.kde_ht, int(remaining * 1.3), True) if x >= 0]
+            ratio_list = [x for x in kde_lengths(model.kde_ht_ratio, int(remaining * 1.5)) if 0 <= x <= 1]
+            ref_lengths = [x for x in kde_lengths(model.kde_aligned, sum(rem_segments)) if 0 < x <= max_l]
+            if len(ref_lengths) == 0:
+                continue
+        gap_lengths = kde_lengths(model.kde_gap, sum(rem_gaps), True) if sum(rem_gaps) > 0 else []
+        gap_lengths = [max(0, int(x)) for x in gap_lengths]
+        species_pool, ref_lengths, rem_segments = assign_species(ref_lengths, rem_segments, current, dict_abun,
+                                                                 dict_abun_inflated)
+        is_reversed = random.random() > model.strandness_rate
+        seg_ptr = gap_ptr = sp_ptr = 0
+        for each in range(len(rem_segments)):
+            segments = rem_segments[each]
+            if (not per and each >= min(len(ratio_list), len(rem_lengths))) or seg_ptr + segments > len(ref_lengths):
+                break
+            ref_len_list = [int(round(ref_lengths[seg_ptr + x])) for x in range(segments)]
+            gap_len_list = [int(round(gap_lengths[gap_ptr + x])) for x in range(segments - 1)]
+            species_list = [species_pool[sp_ptr + x] for x in range(segments)]
+            if per:
+                seg_ptr += 1
+                gap_ptr += 1
+                sp_ptr += 1
+                index = sink.take_index()
+                new_read, name, quals = "", "", []
+                for s in range(len(ref_len_list)):
+                    seg, seg_name = extract_read_meta(ref, ref_len_list[s], species_list[s])
+                    new_read += seg
+                    name += seg_name
+                    if fastq:
+                        quals.extend(base_qualities(model.base_qual["match"], ref_len_list[s]))
+                name = name + "_perfect_" + str(index)
+                mutated = case_convert(new_read)
+                if len(mutated) < min_l or len(mutated) > max_l:
+                    continue
+                head = tail = 0
+                name += "_R" if is_reversed else "_F"
+                name += "_0_" + str(sum(ref_len_list)) + "_0"
+            else:
+                gaps, gap_quals, seg_lens, seg_dicts, seg_counts = [], [], [], [], []
+                remainder = int(round(rem_lengths[each]))
+                ratio = ratio_list[each]
+                total = remainder
+                restart = False
+                for each_ref in ref_len_list:
+                    middle, middle_ref, e_dict, e_count = error_list(each_ref, model, fastq)
+                    if total + middle_ref > max_l:
+                        restart = True
+                        break
+                    total += middle_ref
+                    seg_lens.append(middle_ref)
+                    seg_dicts.append(e_dict)
+                    seg_counts.append(e_count)
+                if restart:
+                    continue
+                for g in gap_len_list:
+                    mg, gq = simulation_gap_meta(ref, model, g, fastq)
+                    gaps.append(mg)
+                    gap_quals.append(gq)
+                    if total + len(mg) > max_l:
+                        restart = True
+                        break
+                    total += len(mg)
+                if restart or total < min_l or total > max_l:
+                    continue
+                seg_ptr += segments
+                gap_ptr += segments - 1
+                sp_ptr += segments
+                index = sink.take_index()
+                if remainder == 0:
+                    head = tail = 0
+                else:
+                    head = int(round(remainder * ratio))
+                    tail = remainder - head
+                n_seg = len(seg_lens)
+                segs = [None] * n_seg
+                comps = []
+                for s in range(n_seg):
+                    segs[s], seg_name = extract_read_meta(ref, seg_lens[s], species_list[s])
+                    comps.append(seg_name)
+                    if s < len(gaps):
+                        comps.append("gap_" + str(len(gaps[s])))
+                name = ";".join(comps) + "_aligned_" + str(index)
+                if n_seg > 1:
+                    name += "_chimeric"
+                name += "_R" if is_reversed else "_F"
+                name += "_" + str(head) + "_" + ";".join(str(x) for x in seg_lens) + "_" + str(tail)
+                mutated, quals = "", []
+                for s in range(n_seg):
+                    seg = case_convert(segs[s])
+                    sm, sq = mutate_read(seg, name, sink.error_rows, seg_dicts[s], seg_counts[s], fastq, kmer_bias, model)
+                    if kmer_bias:
+                        sm, sq = mutate_homo(sm, sq, kmer_bias, model)
+                    mutated += sm
+                    quals.extend(sq)
+                    if s < len(gaps):
+                        mutated += gaps[s]
+                        quals.extend(gap_quals[s])
+                    current[species_list[s]] += len(seg)
+                if fastq:
+                    ht = base_qualities(model.base_qual["ht"], head + tail)
+                    quals = ht[:head] + quals + ht[head:]
+            mutated = "".join(np.random.choice(ACGT_ORDER, head)) + mutated + "".join(np.random.choice(ACGT_ORDER, tail))
+            if len(mutated) < min_l or len(mutated) > max_l:
+                continue
+            if is_reversed:
+                mutated = reverse_complement(mutated)
+                quals.reverse()
+            sink.records.append((name, mutated, quals if fastq else None))
+            passed += 1
+        remaining = num_simulate - passed
+        rem_segments = num_segment[passed:]
+        rem_gaps = rem_segments - 1
+
+
+def simulation_unaligned_meta(ref, model, sink, min_l, max_l, fastq, num_simulate):
+    """simulation_unaligned (:1482-1549) with dna_type == "metagenome" (random species, :1705-1706)."""
+    remaining = num_simulate
+    passed = 0
+    while remaining > 0:
+        ref_l = kde_lengths(model.kde_unaligned, remaining)
+        for j in range(len(ref_l)):
+            m_ref = int(ref_l[j])
+            _, middle_ref, e_dict, e_count = unaligned_error_list(m_ref, model)
+            if middle_ref < min_l or middle_ref > max_l:
+                continue
+            index = sink.take_index()
+            read, name = extract_read_meta(ref, middle_ref)
+            name = name + "_unaligned_" + str(index)
+            read = case_convert(read)
+            mutated, _ = mutate_read(read, name, None, e_dict, e_count, False, False, model)
+            if len(mutated) < min_l or len(mutated) > max_l:
+                continue
+            quals = base_qualities(model.base_qual["unmapped"], len(mutated)) if fastq else []
+            p = random.random()
+            if p > model.strandness_rate:
+                mutated = reverse_complement(mutated)
+                name += "_R"
+                quals.reverse()
+            else:
+                name += "_F"
+            sink.records.append((name + "_0_" + str(middle_ref) + "_0", mutated, quals if fastq else None))
+            passed += 1
+        remaining = num_simulate - passed
