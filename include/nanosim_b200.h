@@ -45,6 +45,11 @@ typedef struct {
     uint64_t n_bases;
     const uint64_t* chrom_off;   /* n_chrom + 1 offsets into bases, file order */
     uint32_t n_chrom;
+    /* metagenome mode (seq_dict[species][chrom], dict_dna_type, :284-339); NULL / 0 in genome mode.  The chromosomes of
+     * one species must be contiguous, species in genome-list order. */
+    uint32_t n_species;
+    const uint32_t* chrom_species;   /* species index of every chromosome */
+    const uint8_t* chrom_circular;   /* 1 = "circular" (the default for local files, :323), 0 = "linear" */
 } NsReference;
 
 /* One joblib KernelDensity pickle (kde_aligned, kde_ht, ... :545-577): gaussian kernel, training samples + bandwidth.
@@ -87,7 +92,7 @@ typedef struct {
 
 /* The scalar arguments of simulation()/simulation_aligned_genome()/simulation_unaligned(). */
 typedef struct {
-    uint32_t mode;            /* 0 genome */
+    uint32_t mode;            /* 0 genome, 1 metagenome */
     uint32_t circular;        /* dna_type == "circular" (single chromosome) */
     uint32_t perfect;
     uint32_t fastq;
@@ -185,6 +190,9 @@ int ns_clone(NsContext* parent, NsContext** out);
 int ns_set_reference(NsContext* ctx, const NsReference* ref);
 int ns_set_model(NsContext* ctx, const NsModel* model);
 int ns_configure(NsContext* ctx, const NsRunConfig* cfg);
+/* metagenome: dict_abun / dict_abun_inflated of the current sample (main() :2497-2514), one value per species in
+ * genome-list order; resets the running per-species base counts that assign_species (:758-811) keeps per worker. */
+int ns_set_abundance(NsContext* ctx, const double* abun, const double* abun_inflated, uint32_t n_species);
 
 /* --- simulation_aligned_genome / simulation_unaligned worker bodies (:1266-1454, :1482-1549) ---------------- */
 /* Simulates reads [first_read_id, first_read_id + n_reads) of `kind`; results stay in HBM until the next call. */

@@ -16,12 +16,13 @@ NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT, NS_OP_LIT = 0, 1, 2, 3, 4
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
-EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_reference", "ns_set_model", "ns_configure",
+EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_reference", "ns_set_model", "ns_configure",
            "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records"]
 
 
 class NsReference(C.Structure):
-    _fields_ = [("bases", C.c_void_p), ("n_bases", C.c_uint64), ("chrom_off", C.c_void_p), ("n_chrom", C.c_uint32)]
+    _fields_ = [("bases", C.c_void_p), ("n_bases", C.c_uint64), ("chrom_off", C.c_void_p), ("n_chrom", C.c_uint32),
+                ("n_species", C.c_uint32), ("chrom_species", C.c_void_p), ("chrom_circular", C.c_void_p)]
 
 
 class NsKde(C.Structure):
@@ -110,6 +111,8 @@ def lib():
     L.ns_set_reference.restype = C.c_int
     L.ns_set_model.argtypes = [P, C.POINTER(NsModel)]
     L.ns_set_model.restype = C.c_int
+    L.ns_set_abundance.argtypes = [P, P, P, C.c_uint32]
+    L.ns_set_abundance.restype = C.c_int
     L.ns_configure.argtypes = [P, C.POINTER(NsRunConfig)]
     L.ns_configure.restype = C.c_int
     L.ns_simulate.argtypes = [P, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(NsBatchInfo)]

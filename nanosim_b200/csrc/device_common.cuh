@@ -32,10 +32,15 @@ struct DevRef {
     const uint64_t* chrom_off;          // n_chrom + 1
     uint64_t genome_len;
     uint32_t n_chrom;
+    // metagenome
+    uint32_t n_species;
+    const uint32_t* chrom_species;      // per chromosome
+    const uint8_t* chrom_circular;      // per chromosome
+    const uint32_t* species_chrom_off;  // n_species + 1: chromosomes of species s are [off[s], off[s+1])
 };
 
 struct DevCfg {
-    uint32_t circular, perfect, fastq, chimeric, kmer_bias;
+    uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome;
     uint32_t min_len, max_len;
     uint64_t seed;
     double median_len, sd_len;          // -med / -sd (0 = lengths from the KDEs)

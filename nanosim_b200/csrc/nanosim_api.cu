@@ -74,7 +74,10 @@ struct NsContext {
     DevRef dref{};
     std::vector<uint64_t> h_chrom_off;
 
-    DevBuf kde[5], alias, qlut, qcdf;
+    DevBuf kde[5], alias, qlut, qcdf, ref_species, ref_circular, ref_sp_off;
+    std::vector<uint32_t> h_sp_off;
+    std::vector<double> abun, abun_inflated, species_bases;     // metagenome: dict_abun, dict_abun_inflated, running totals
+    DevBuf sp_bases_dev;
     DevModel dmodel{};
     NsModel hmodel{};
     NsRunConfig hcfg{};
@@ -298,9 +301,10 @@ int ns_destroy(NsContext* ctx) {
     DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
-                      &ctx->sort_tmp, &ctx->hp_off};
+                      &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
-        DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf};
+        DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->ref_species,
+                            &ctx->ref_circular, &ctx->ref_sp_off};
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
         for (auto& k : ctx->kde) { k.p = nullptr; k.cap = 0; }
     }
@@ -330,6 +334,13 @@ int ns_clone(NsContext* parent, NsContext** out) {
     c->alias = parent->alias;
     c->qlut = parent->qlut;
     c->qcdf = parent->qcdf;
+    c->ref_species = parent->ref_species;
+    c->ref_circular = parent->ref_circular;
+    c->ref_sp_off = parent->ref_sp_off;
+    c->h_sp_off = parent->h_sp_off;
+    c->abun = parent->abun;
+    c->abun_inflated = parent->abun_inflated;
+    c->species_bases.assign(parent->abun.size(), 0.0);      // every clone is its own worker (own running totals)
     for (int i = 0; i < 5; ++i) c->kde[i] = parent->kde[i];
     c->dref = parent->dref;
     c->h_chrom_off = parent->h_chrom_off;
@@ -362,6 +373,36 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     ctx->dref.chrom_off = ctx->ref_off.as<uint64_t>();
     ctx->dref.genome_len = ref->n_bases;
     ctx->dref.n_chrom = ref->n_chrom;
+    ctx->dref.n_species = 0;
+    ctx->dref.chrom_species = nullptr;
+    ctx->dref.chrom_circular = nullptr;
+    ctx->dref.species_chrom_off = nullptr;
+    if (ref->n_species > 0) {
+        if (!ref->chrom_species || !ref->chrom_circular)
+            return fail(ctx, NS_EINVAL, "ns_set_reference: n_species > 0 needs chrom_species and chrom_circular");
+        std::vector<uint32_t> sp(ref->n_chrom);
+        std::vector<uint8_t> circ(ref->n_chrom);
+        CK(cudaMemcpy(sp.data(), ref->chrom_species, sp.size() * 4, cudaMemcpyDefault));
+        CK(cudaMemcpy(circ.data(), ref->chrom_circular, circ.size(), cudaMemcpyDefault));
+        ctx->h_sp_off.assign(ref->n_species + 1, 0);
+        for (uint32_t i = 0; i < ref->n_chrom; ++i) {
+            if (sp[i] >= ref->n_species || (i > 0 && sp[i] < sp[i - 1]))
+                return fail(ctx, NS_EINVAL, "ns_set_reference: chromosomes must be grouped by species in species order");
+            ctx->h_sp_off[sp[i] + 1] = i + 1;
+        }
+        for (uint32_t k = 1; k <= ref->n_species; ++k) {
+            if (ctx->h_sp_off[k] == 0) ctx->h_sp_off[k] = ctx->h_sp_off[k - 1];
+            if (ctx->h_sp_off[k] == ctx->h_sp_off[k - 1]) return fail(ctx, NS_EINVAL, "ns_set_reference: species %u has no chromosome", k - 1);
+        }
+        CK(upload(ctx->ref_species, sp.data(), sp.size() * 4, ctx->stream));
+        CK(upload(ctx->ref_circular, circ.data(), circ.size(), ctx->stream));
+        CK(upload(ctx->ref_sp_off, ctx->h_sp_off.data(), ctx->h_sp_off.size() * 4, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->dref.n_species = ref->n_species;
+        ctx->dref.chrom_species = ctx->ref_species.as<uint32_t>();
+        ctx->dref.chrom_circular = ctx->ref_circular.as<uint8_t>();
+        ctx->dref.species_chrom_off = ctx->ref_sp_off.as<uint32_t>();
+    }
     ctx->have_ref = true;
     ctx->have_batch = false;
     return NS_OK;
@@ -426,7 +467,10 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
 
 int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     if (!ctx || !cfg) return fail(ctx, NS_EINVAL, "ns_configure: null argument");
-    if (cfg->mode != 0) return fail(ctx, NS_EINVAL, "ns_configure: only genome mode (0) is implemented");
+    if (cfg->mode > 1) return fail(ctx, NS_EINVAL, "ns_configure: mode must be 0 (genome) or 1 (metagenome)");
+    if (cfg->mode == 1 && ctx->have_ref && ctx->dref.n_species == 0)
+        return fail(ctx, NS_ESTATE, "ns_configure: metagenome mode needs a reference with species information");
+    if (cfg->mode == 1 && cfg->kmer_bias != 0) return fail(ctx, NS_EINVAL, "ns_configure: -hp/-k is not offered in metagenome mode");
     if (cfg->max_len < cfg->min_len) return fail(ctx, NS_EINVAL, "Maximum read length must be longer than Minimum read length!");
     if (cfg->perfect && cfg->chimeric) return fail(ctx, NS_EINVAL, "Perfect reads cannot be chimeric");
     if ((cfg->median_len != 0.0) != (cfg->sd_len != 0.0))
@@ -442,6 +486,7 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.fastq = cfg->fastq;
     ctx->dcfg.chimeric = cfg->chimeric;
     ctx->dcfg.kmer_bias = cfg->kmer_bias;
+    ctx->dcfg.metagenome = cfg->mode == 1 ? 1u : 0u;
     ctx->dcfg.min_len = cfg->min_len;
     ctx->dcfg.max_len = cfg->max_len;
     ctx->dcfg.seed = ctx->seed;
@@ -451,6 +496,101 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->have_batch = false;
     return NS_OK;
 }
+
+int ns_set_abundance(NsContext* ctx, const double* abun, const double* abun_inflated, uint32_t n_species) {
+    if (!ctx || !abun || n_species == 0) return fail(ctx, NS_EINVAL, "ns_set_abundance: null argument");
+    if (!ctx->have_ref || ctx->dref.n_species != n_species)
+        return fail(ctx, NS_ESTATE, "ns_set_abundance: the reference has %u species, got %u", ctx ? ctx->dref.n_species : 0, n_species);
+    ctx->abun.assign(abun, abun + n_species);
+    if (abun_inflated) ctx->abun_inflated.assign(abun_inflated, abun_inflated + n_species);
+    else ctx->abun_inflated.assign(n_species, 0.0);
+    ctx->species_bases.assign(n_species, 0.0);
+    return NS_OK;
+}
+
+// ---- assign_species (:758-811) on the host: a sequential greedy pass over the batch's segments.
+namespace {
+struct HostRng {       // splitmix64 stream keyed by (seed, batch id); only drives the species choices
+    uint64_t s;
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    uint32_t below(uint32_t n) { return (uint32_t)(((unsigned __int128)next() * n) >> 64); }
+};
+
+// reads: order = reads with the most segments first (stable), then single-segment reads by decreasing length;
+// quota[s] = total_bases * abun[s] / sum(abun) - current[s]; every segment takes a uniformly random species whose quota
+// still fits it (else any species with quota left); later segments of a chimeric read stay in the previous species with
+// probability abun_inflated[prev] % (:793-797).
+void assign_species_host(const std::vector<uint32_t>& n_seg, const std::vector<uint32_t>& piece_first,
+                         std::vector<NsPieceMeta>& pieces, const std::vector<double>& abun, const std::vector<double>& inflated,
+                         const std::vector<double>& current, HostRng& rng) {
+    const uint32_t n = (uint32_t)n_seg.size(), S = (uint32_t)abun.size();
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (n_seg[a] != n_seg[b]) return n_seg[a] > n_seg[b];
+        if (n_seg[a] > 1) return false;
+        return pieces[piece_first[a]].ref_req > pieces[piece_first[b]].ref_req;
+    });
+    double to_add = 0, cur = 0, tot_abun = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t q = 0; q < n_seg[i]; ++q) to_add += pieces[piece_first[i] + 2 * q].ref_req;
+    for (uint32_t s = 0; s < S; ++s) {
+        cur += current[s];
+        tot_abun += abun[s];
+    }
+    std::vector<double> quota(S);
+    for (uint32_t s = 0; s < S; ++s) quota[s] = (to_add + cur) * abun[s] / tot_abun - current[s];
+    std::vector<uint32_t> avail;
+    avail.reserve(S);
+    auto pick = [&](double len, int exclude) -> uint32_t {
+        avail.clear();
+        for (uint32_t s = 0; s < S; ++s)
+            if (quota[s] - len > 0 && (int)s != exclude) avail.push_back(s);
+        if (avail.empty() && exclude < 0)
+            for (uint32_t s = 0; s < S; ++s)
+                if (quota[s] > 0) avail.push_back(s);
+        if (avail.empty()) return 0xffffffffu;
+        return avail[rng.below((uint32_t)avail.size())];
+    };
+    for (uint32_t oi = 0; oi < n; ++oi) {
+        const uint32_t i = order[oi];
+        int pre = -1;
+        for (uint32_t q = 0; q < n_seg[i]; ++q) {
+            NsPieceMeta& pm = pieces[piece_first[i] + 2 * q];
+            const double len = pm.ref_req;
+            uint32_t sp;
+            if (q == 0) {
+                sp = pick(len, -1);
+            } else {
+                const double p = rng.uniform() * 100.0;
+                uint32_t other = pick(len, pre);
+                if (p <= inflated[pre] && quota[pre] > 0) sp = (uint32_t)pre;
+                else if (p > inflated[pre] && other != 0xffffffffu) sp = other;
+                else sp = pick(len, -1);
+            }
+            if (sp == 0xffffffffu) {                      // cannot happen while sum(quota) >= len; keep it total anyway
+                sp = 0;
+                for (uint32_t s = 1; s < S; ++s)
+                    if (quota[s] > quota[sp]) sp = s;
+            }
+            pm.chrom = sp;                                // species id travels in `chrom` until the position is drawn
+            quota[sp] -= len;
+            pre = (int)sp;
+        }
+    }
+}
+
+__global__ void species_bases_kernel(const NsPieceMeta* pieces, uint32_t n, const uint32_t* chrom_species, double* acc) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && pieces[i].kind == NS_PIECE_SEGMENT) atomicAdd(&acc[chrom_species[pieces[i].chrom]], (double)pieces[i].ref_len);
+}
+}  // namespace
 
 static int exclusive_scan_u64(NsContext* ctx, const uint64_t* in, uint64_t* out, uint32_t n) {
     size_t tmp = 0;
@@ -632,6 +772,26 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(cudaStreamSynchronize(st));
     const uint64_t primary_ops = ctx->h_totals[4];
     CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
+    uint32_t batch_reversed = 0;
+    if (ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) {
+        // ---- assign_species (:758-811): sequential greedy quota fill over this batch's segments, on the host
+        if (ctx->abun.size() != ctx->dref.n_species) return fail(ctx, NS_ESTATE, "ns_simulate: call ns_set_abundance first");
+        std::vector<NsPieceMeta> hp((size_t)n_pieces);
+        std::vector<uint32_t> hseg(n, 1u), hfirst(n);
+        CK(cudaMemcpyAsync(hp.data(), ctx->pieces.p, (size_t)n_pieces * sizeof(NsPieceMeta), cudaMemcpyDeviceToHost, st));
+        if (chim) {
+            CK(cudaMemcpyAsync(hseg.data(), ctx->nseg.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hfirst.data(), ctx->piece_first.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        if (!chim)
+            for (uint32_t i = 0; i < n; ++i) hfirst[i] = i;
+        HostRng hr{ctx->seed * 0x9E3779B97F4A7C15ull ^ (first_read_id + 0x1234567ull)};
+        batch_reversed = hr.uniform() > (double)ctx->dmodel.strandness ? 1u : 0u;      // once per batch (:860)
+        assign_species_host(hseg, hfirst, hp, ctx->abun, ctx->abun_inflated, ctx->species_bases, hr);
+        CK(cudaMemcpyAsync(ctx->pieces.p, hp.data(), (size_t)n_pieces * sizeof(NsPieceMeta), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
     CK(cudaEventRecord(ctx->ev[1], st));
     launches += 10;
 
@@ -651,6 +811,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     pa.order = vals_out;
     pa.counter = ctx->counter.as<uint32_t>();
     pa.n_flagged = (uint32_t*)(ctx->totals.as<uint64_t>() + 5);
+    pa.batch_reversed = batch_reversed;
     const unsigned plan_tb = 128;
     unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * 16u);
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
@@ -784,6 +945,17 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[5], st));
+    if (ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) {
+        // current_species_bases[species] += len(new_seg) (:1004) for the next batch's quotas
+        const uint32_t S = ctx->dref.n_species;
+        CK(ctx->sp_bases_dev.ensure((size_t)S * sizeof(double)));
+        CK(cudaMemsetAsync(ctx->sp_bases_dev.p, 0, (size_t)S * sizeof(double), st));
+        species_bases_kernel<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, ctx->dref.chrom_species, ctx->sp_bases_dev.as<double>());
+        std::vector<double> add(S);
+        CK(cudaMemcpyAsync(add.data(), ctx->sp_bases_dev.p, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t k = 0; k < S; ++k) ctx->species_bases[k] += add[k];
+    }
     CK(cudaStreamSynchronize(st));
 
     NsBatchInfo& bi = ctx->last;

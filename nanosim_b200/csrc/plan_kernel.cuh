@@ -34,6 +34,7 @@ struct PlanArgs {
     const uint32_t* order;      // read slots by decreasing drawn length (nullptr => identity)
     uint32_t* counter;          // work-fetch counter (zeroed before launch)
     uint32_t* n_flagged;        // REPLAY=false: number of reads whose script overflowed its slot
+    uint32_t batch_reversed;    // metagenome: is_reversed is drawn once per batch (:860)
 };
 
 #define NS_MAX_SAME_LEN_RETRIES 64
@@ -135,6 +136,50 @@ __device__ __forceinline__ void draw_position(const DevRef& ref, const DevCfg& c
     pos = 0;
 }
 
+// extract_read, metagenome branch (:1704-1749): uniform chromosome of the species (species < 0: uniform species
+// first, :1705-1706); a chromosome shorter than the segment is replaced by a uniformly chosen longer one, same species
+// first; circular chromosomes start anywhere in [0, len] and wrap, linear ones in [0, len - length].
+__device__ __forceinline__ void draw_position_meta(const DevRef& ref, Rng& rng, int species, uint32_t length, uint32_t& chrom,
+                                                   uint32_t& pos) {
+    uint32_t sp = species >= 0 ? (uint32_t)species : (uint32_t)__umul64hi(rng.next64(), (uint64_t)ref.n_species);
+    const uint32_t c0 = __ldg(&ref.species_chrom_off[sp]), c1 = __ldg(&ref.species_chrom_off[sp + 1]);
+    uint32_t c = c0 + (uint32_t)__umul64hi(rng.next64(), (uint64_t)(c1 - c0));
+    uint64_t clen = __ldg(&ref.chrom_off[c + 1]) - __ldg(&ref.chrom_off[c]);
+    if ((uint64_t)length > clen) {
+        uint32_t n_same = 0, n_all = 0;
+        for (uint32_t q = 0; q < ref.n_chrom; ++q) {
+            const uint64_t l = __ldg(&ref.chrom_off[q + 1]) - __ldg(&ref.chrom_off[q]);
+            if ((uint64_t)length < l) {
+                ++n_all;
+                if (q >= c0 && q < c1) ++n_same;
+            }
+        }
+        const bool same = n_same > 0;
+        const uint32_t n_pick = same ? n_same : n_all - n_same;   // the reference's `longer_chroms` excludes the species
+        if (n_pick > 0) {
+            uint32_t r = (uint32_t)__umul64hi(rng.next64(), (uint64_t)n_pick);
+            for (uint32_t q = 0; q < ref.n_chrom; ++q) {
+                const uint64_t l = __ldg(&ref.chrom_off[q + 1]) - __ldg(&ref.chrom_off[q]);
+                const bool in_sp = q >= c0 && q < c1;
+                if ((uint64_t)length < l && in_sp == same) {
+                    if (r == 0) {
+                        c = q;
+                        break;
+                    }
+                    --r;
+                }
+            }
+            clen = __ldg(&ref.chrom_off[c + 1]) - __ldg(&ref.chrom_off[c]);
+        }
+    }
+    chrom = c;
+    if (__ldg(&ref.chrom_circular[c])) {
+        pos = (uint32_t)__umul64hi(rng.next64(), clen + 1);
+    } else {
+        pos = clen >= length ? (uint32_t)__umul64hi(rng.next64(), clen - length + 1) : 0u;
+    }
+}
+
 // ref_lengths / gap_lengths of generation `gen` for one aligned read (:1285-1299, :1309-1310) -> pieces[].ref_req
 __device__ __forceinline__ void draw_lengths(const DevModel& m, const DevCfg& cfg, uint32_t kind, uint64_t rid, uint32_t gen,
                                              uint32_t n_seg, NsPieceMeta* pieces) {
@@ -162,6 +207,13 @@ __device__ __forceinline__ void draw_lengths(const DevModel& m, const DevCfg& cf
             }
             bool ok = cfg.perfect ? (x >= (double)cfg.min_len && x <= (double)cfg.max_len)
                                   : (x > 0.0 && x <= (double)cfg.max_len);
+            if (cfg.metagenome) {                        // int(round(x)) (:871); a zero-length segment is legal there
+                if (ok) {
+                    len = (uint32_t)rint(x);
+                    break;
+                }
+                continue;
+            }
             // int(x) == 0 makes the reference's extract_read spin forever (:1767-1780); redraw instead
             if (ok && (uint32_t)x > 0) {
                 len = (uint32_t)x;
@@ -289,14 +341,16 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 head = tail = 0;
                 remainder = 0;
                 reversed = u01_double(rng.next64()) > (double)m.strandness;
+                if (cfg.metagenome) reversed = a.batch_reversed;
             } else {
                 // remainder = 10^x - 1 >= 0, ratio in [0,1] (:1456-1479), strand (:1312)
                 double rem = -1.0;
                 for (int it = 0; it < 100000 && rem < 0.0; ++it) rem = pow(10.0, kde_draw(m.ht, rng)) - 1.0;
                 double ratio = -1.0;
                 for (int it = 0; it < 100000 && (ratio < 0.0 || ratio > 1.0); ++it) ratio = kde_draw(m.ratio, rng);
-                remainder = (uint32_t)rem;
+                remainder = cfg.metagenome ? (uint32_t)rint(rem) : (uint32_t)rem;       // int(round()) (:916) vs int() (:1351)
                 reversed = u01_double(rng.next64()) > (double)m.strandness;
+                if (cfg.metagenome) reversed = a.batch_reversed;
                 if (remainder == 0) {
                     head = tail = 0;
                 } else {
@@ -438,7 +492,12 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 pm.l_new = (uint32_t)(l_new < 0 ? 0 : l_new);
             }
             actual += sink.out_len;
-            if (!is_gap) total += (uint64_t)(l_new < 0 ? 0 : l_new);      // `total += middle` (:1362): segments only
+            if (cfg.metagenome && !unal_kind) {
+                // metagenome: total = remainder + middle_ref of the segments + mutated gap lengths (:924-943)
+                total += is_gap ? (uint64_t)sink.out_len : (uint64_t)middle_ref;
+            } else if (!is_gap) {
+                total += (uint64_t)(l_new < 0 ? 0 : l_new);               // `total += middle` (:1362): segments only
+            }
             ++p;
             phase = (p < n_pieces) ? PH_PIECE : PH_CHECK;
             break;
@@ -498,7 +557,14 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             for (uint32_t q = 0; q < n_pieces; ++q) {
                 NsPieceMeta& pm = a.pieces[piece_first + q];
                 uint32_t chrom = 0, ppos = 0;
-                if (pm.ref_len > 0) draw_position(a.ref, cfg, pr, pm.ref_len, chrom, ppos);
+                if (cfg.metagenome) {
+                    // segments carry the species assign_species gave them (in `chrom`); gaps and unaligned reads take a
+                    // uniformly random species (:1705-1706)
+                    const bool seg = !unal_kind && !(q & 1u);
+                    draw_position_meta(a.ref, pr, seg ? (int)pm.chrom : -1, pm.ref_len, chrom, ppos);
+                } else if (pm.ref_len > 0) {
+                    draw_position(a.ref, cfg, pr, pm.ref_len, chrom, ppos);
+                }
                 pm.chrom = chrom;
                 pm.pos = ppos;
             }

@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             Rng pr;
             pr.init(cfg.seed, rid, stream_word(ST_POS, NS_KIND_UNALIGNED, attempt));
             uint32_t chrom = 0, ppos = 0;
-            draw_position(a.ref, cfg, pr, middle_ref, chrom, ppos);
+            if (cfg.metagenome) draw_position_meta(a.ref, pr, -1, middle_ref, chrom, ppos);
+            else draw_position(a.ref, cfg, pr, middle_ref, chrom, ppos);
             if (lane == 0) {
                 NsPieceMeta p;
                 p.op_off = 0;

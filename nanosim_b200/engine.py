@@ -77,12 +77,25 @@ class Engine:
     def set_reference(self, ref):
         """ref: PackedReference (host) -- or pass device pointers via set_reference_ptr."""
         self.ref = ref
-        r = L.NsReference(_ptr(ref.bases), ref.genome_len, _ptr(ref.offsets), len(ref.names))
+        sp = getattr(ref, "chrom_species", None)
+        if sp is not None:
+            sp = np.ascontiguousarray(sp, dtype=np.uint32)
+            circ = np.ascontiguousarray(ref.chrom_circular, dtype=np.uint8)
+            r = L.NsReference(_ptr(ref.bases), ref.genome_len, _ptr(ref.offsets), len(ref.names), len(ref.species),
+                              _ptr(sp), _ptr(circ))
+        else:
+            r = L.NsReference(_ptr(ref.bases), ref.genome_len, _ptr(ref.offsets), len(ref.names), 0, None, None)
         self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
+
+    def set_abundance(self, abun, inflated=None):
+        """dict_abun / dict_abun_inflated of one sample, per species in genome-list order (metagenome mode)."""
+        a = np.ascontiguousarray(abun, dtype=np.float64)
+        i = np.ascontiguousarray(inflated, dtype=np.float64) if inflated is not None else None
+        self._check(self._lib.ns_set_abundance(self._ctx, _ptr(a), _ptr(i), len(a)))
 
     def set_reference_ptr(self, bases_ptr, n_bases, offsets):
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1)
+        r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1, 0, None, None)
         self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
 
     def set_model(self, t: DeviceTables, perfect=False):
@@ -130,10 +143,10 @@ class Engine:
         self.tables = t
 
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
-                  max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False):
+                  max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
-        cfg = L.NsRunConfig(0, int(circular), int(perfect), int(fastq), int(chimeric), int(kmer_bias or 0),
+        cfg = L.NsRunConfig(1 if metagenome else 0, int(circular), int(perfect), int(fastq), int(chimeric), int(kmer_bias or 0),
                             int(min_len), int(min(max_len, 0x0fffffff)), float(median_len or 0.0), float(sd_len or 0.0),
                             L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0, 0)
         self._check(self._lib.ns_configure(self._ctx, C.byref(cfg)))

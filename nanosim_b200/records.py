@@ -19,7 +19,7 @@ for _a, _b in (("A", "T"), ("C", "G")):
     _COMP[ord(_a)], _COMP[ord(_b)] = ord(_b), ord(_a)
 
 
-def read_names(batch, ref_names, index_base, perfect=False):
+def read_names(batch, ref_names, index_base, perfect=False, metagenome=False):
     """index_base: value of the reference's shared ``total_simulated`` counter for the batch's first read."""
     reads, pieces = batch.reads, batch.pieces
     names = []
@@ -38,7 +38,14 @@ def read_names(batch, ref_names, index_base, perfect=False):
             loc = "".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
             names.append("%s_perfect_%d_%s_0_%d_0" % (loc, idx, strand, sum(int(s["ref_len"]) for s in segs)))
             continue
-        loc = ";".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
+        if metagenome:          # gap lengths are part of the name in metagenome mode (:965-969)
+            comps = []
+            for k in range(npc):
+                pc = pieces[p0 + k]
+                comps.append("gap_%d" % pc["out_len"] if k & 1 else "%s_%d" % (ref_names[pc["chrom"]], pc["pos"]))
+            loc = ";".join(comps)
+        else:
+            loc = ";".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
         nm = "%s_aligned_%d" % (loc, idx)
         if len(segs) > 1:
             nm += "_chimeric"

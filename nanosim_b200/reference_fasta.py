@@ -78,3 +78,93 @@ class PackedReference:
             body = blob[nl + 1:e].replace(b"\n", b"").replace(b"\r", b"")
             recs.append((header, body))
         return PackedReference.from_records(recs)
+
+
+class MetaReference(PackedReference):
+    """Metagenome reference (simulator.py:256-266, 284-339): species in genome-list order, the chromosomes of a species
+    contiguous; chromosome names are ``{species}-{chrom}`` as in read names (:1747); per-chromosome circular/linear."""
+
+    def __init__(self, names, bases, offsets, species, chrom_species, chrom_circular, chrom_keys):
+        super().__init__(names, bases, offsets)
+        self.species = list(species)
+        self.chrom_species = np.ascontiguousarray(chrom_species, dtype=np.uint32)
+        self.chrom_circular = np.ascontiguousarray(chrom_circular, dtype=np.uint8)
+        self.chrom_keys = list(chrom_keys)
+
+    @property
+    def max_chrom_per_species(self):
+        L = self.lengths
+        return {sp: int(L[self.chrom_species == i].max()) for i, sp in enumerate(self.species)}
+
+    @staticmethod
+    def species_key(name):
+        return "_".join(name.split())
+
+    @staticmethod
+    def from_genomes(genomes, dna_types=None):
+        """genomes: ordered [(species, [(fasta header, sequence bytes/str/array), ...])]; dna_types: {species: {chrom: type}}."""
+        names, parts, offs, sp_idx, circ, keys, species = [], [], [0], [], [], [], []
+        for si, (sp, recs) in enumerate(genomes):
+            sp = MetaReference.species_key(sp)
+            species.append(sp)
+            one = PackedReference.from_records(recs)
+            for ci, key in enumerate(one.names):
+                a, b = int(one.offsets[ci]), int(one.offsets[ci + 1])
+                names.append(sp + "-" + key)
+                keys.append(key)
+                parts.append(one.bases[a:b])
+                offs.append(offs[-1] + (b - a))
+                sp_idx.append(si)
+                ty = (dna_types or {}).get(sp, {}).get(key, "circular")      # local files default to circular (:323)
+                circ.append(1 if ty == "circular" else 0)
+        bases = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+        return MetaReference(names, bases, np.asarray(offs, dtype=np.uint64), species, sp_idx, circ, keys)
+
+    @staticmethod
+    def from_genome_list(genome_list, dna_type_list=None):
+        genomes = []
+        with open(genome_list) as f:
+            for line in f.readlines():
+                if not line.strip():
+                    continue
+                fields = line.split("\t")
+                path = fields[1].strip("\n")
+                if path.startswith(("ftp", "http")):
+                    raise ValueError("streaming reference genomes from RefSeq (simulator.py:295-315) is not supported")
+                one = PackedReference.from_fasta(path)
+                recs = [(k, one.bases[int(one.offsets[i]):int(one.offsets[i + 1])]) for i, k in enumerate(one.names)]
+                genomes.append((fields[0], recs))
+        types = {}
+        known = {MetaReference.species_key(g[0]) for g in genomes}
+        if dna_type_list:
+            with open(dna_type_list) as f:
+                for line in f.readlines():
+                    if not line.strip():
+                        continue
+                    fields = line.split("\t")
+                    sp = MetaReference.species_key(fields[0])
+                    if sp not in known:
+                        raise KeyError("You didn't provide a reference genome for " + sp)
+                    types.setdefault(sp, {})[normalise_name(fields[1])] = fields[2].strip("\n")
+        return MetaReference.from_genomes(genomes, types)
+
+
+def read_abundance(path, species):
+    """Abundance table (simulator.py:360-380): header ``Size<TAB>n1<TAB>n2...``, one row per species.  Returns
+    (number_list, [per-sample abundance vector in ``species`` order])."""
+    with open(path) as f:
+        header = f.readline()
+        numbers = [int(x) for x in header.strip().split("\t")[1:]]
+        table = {}
+        for line in f.readlines():
+            if not line.strip():
+                continue
+            fields = line.split("\t")
+            if len(numbers) != len(fields) - 1:
+                raise ValueError("Abundance file is incorrectly formatted. Check that each row has the same number of columns")
+            sp = MetaReference.species_key(fields[0])
+            if sp not in species:
+                raise KeyError("You didn't provide a reference genome for " + sp)
+            table[sp] = [float(x) for x in fields[1:]]
+    samples = [[table[sp][i] for sp in species] for i in range(len(numbers))]
+    return numbers, samples

@@ -24,7 +24,7 @@ from .engine import Engine
 from .model import DeviceTables, load_model
 from .pipeline import BatchPipeline
 from .records import error_profile_rows, format_records, read_names
-from .reference_fasta import PackedReference
+from .reference_fasta import MetaReference, PackedReference, read_abundance
 
 VERSION = "3.2.2-b200"
 
@@ -50,14 +50,27 @@ class Profile:
 def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
                  polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
                  device=0, seed=0):
-    if mode != "genome":
-        sys.stderr.write("nanosim_b200: only genome mode is implemented in this build\n")
+    if mode not in ("genome", "metagenome"):
+        sys.stderr.write("nanosim_b200: transcriptome mode is not implemented in this build\n")
         sys.exit(1)
     prof = Profile()
     _log("Read in reference ")
-    prof.ref = PackedReference.from_fasta(ref_g)
+    if mode == "metagenome":
+        try:
+            prof.ref = MetaReference.from_genome_list(ref_g, dna_type)       # ref_g = genome list, dna_type = dna type list
+            _log("Read in abundance profile")
+            number_list, prof.samples = read_abundance(abun, prof.ref.species)
+        except KeyError as e:
+            sys.stderr.write(str(e).strip("'\"") + "\n")
+            sys.exit(1)
+        except ValueError as e:
+            sys.stderr.write(str(e) + "\n")
+            sys.exit(1)
+        prof.number_list = number_list
+    else:
+        prof.ref = PackedReference.from_fasta(ref_g)
     prof.max_chrom = prof.ref.max_chrom
-    if len(prof.ref.names) > 1 and dna_type == "circular":
+    if mode == "genome" and len(prof.ref.names) > 1 and dna_type == "circular":
         sys.stderr.write("Do not choose circular if there is more than one chromosome in the genome!\n")
         sys.exit(1)
     _log("Read error profile")
@@ -65,6 +78,7 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
     prof.tables = DeviceTables(cm, fastq=fastq, homopolymer=homopolymer, chimeric=chimeric, perfect=per,
                                strandness=strandness, mode=mode)
     prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number_list[0], per)
+    prof.counts = [prof.tables.split_counts(n, per) for n in number_list]
     prof.perfect = per
     _log("Read KDF of aligned reads")
     prof.seed = seed
@@ -85,8 +99,10 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                median_l=None, sd_l=None, model_ir=False, uracil=False, polya=None, chimeric=False,
                batch_reads=65536, error_profile=True, rank=0, world=1):
     eng = prof.engine
+    meta = mode == "metagenome"
     eng.configure(circular=(dna_type == "circular"), perfect=per, fastq=fastq, chimeric=chimeric,
-                  kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0)
+                  kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0,
+                  metagenome=meta)
     ext = ".fastq" if fastq else ".fasta"
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
@@ -103,7 +119,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             f_err.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
 
         def sink_aligned(info, b, job):
-            names = read_names(b, prof.ref.names, job[1], perfect=per)
+            names = read_names(b, prof.ref.names, job[1], perfect=per, metagenome=meta)
             f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
             if want_err:
                 f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
@@ -188,9 +204,118 @@ def build_parser():
     g.add_argument('--batch_reads', help='Reads simulated per GPU batch (Default = 65536)', type=int, default=65536)
     g.add_argument('--no_error_profile', help='Skip writing <out>_aligned_error_profile', action='store_true', default=False)
     g.add_argument('--device', help='CUDA device index (Default = LOCAL_RANK or 0)', type=int, default=None)
-    for name in ("transcriptome", "metagenome"):
-        sub.add_parser(name, help="Not implemented in this build", add_help=False)
-    return parser, g
+    mg = sub.add_parser('metagenome', help="Run the simulator on metagenome mode")
+    mg.add_argument('-gl', '--genome_list', help="Reference metagenome list, tsv file, the first column is species/strain "
+                    "name, the second column is the reference genome fasta/fastq file directory", required=True)
+    mg.add_argument('-a', '--abun', help="Abundance list, tsv file with header, the abundance of all species in each sample "
+                    "need to sum up to 100", required=True)
+    mg.add_argument('-dl', '--dna_type_list', help="DNA type list, tsv file, the first column is species/strain, the second "
+                    "column is the chromosome name, the third column is the DNA type: circular OR linear")
+    mg.add_argument('-c', '--model_prefix', help='Location and prefix of error profiles generated from characterization '
+                    'step (Default = training)', default="training")
+    mg.add_argument('-o', '--output', help='Output location and prefix for simulated reads (Default = simulated)',
+                    default="simulated")
+    mg.add_argument('-max', '--max_len', help='The maximum length for simulated reads (Default = Infinity)', type=int,
+                    default=float("inf"))
+    mg.add_argument('-min', '--min_len', help='The minimum length for simulated reads (Default = 50)', type=int, default=50)
+    mg.add_argument('-med', '--median_len', help='The median read length (Default = None)', type=int, default=None)
+    mg.add_argument('-sd', '--sd_len', help='The standard deviation of read length in log scale (Default = None)',
+                    type=float, default=None)
+    mg.add_argument('--seed', help='Manually seeds the pseudo-random number generator', type=int, default=None)
+    mg.add_argument('-hp', '--homopolymer', help=argparse.SUPPRESS, action='store_true', default=False)
+    mg.add_argument('-k', '--KmerBias', help=argparse.SUPPRESS, type=int, default=None)
+    mg.add_argument('-s', '--strandness', help='Percentage of antisense sequences. Overrides the value profiled in '
+                    'characterization stage. Should be between 0 and 1', type=float, default=None)
+    mg.add_argument('--perfect', help='Ignore error profiles and simulate perfect reads', action='store_true', default=False)
+    mg.add_argument('--abun_var', help='Simulate random variation in abundance values, takes in two values, format: '
+                    'relative_var_low, relative_var_high, Example: -0.5 0.5)', nargs='+', type=float, default=None)
+    mg.add_argument('--fastq', help='Output fastq files instead of fasta files', action='store_true', default=False)
+    mg.add_argument('--chimeric', help='Simulate chimeric reads', action='store_true', default=False)
+    mg.add_argument('-t', '--num_threads', help='Number of host threads used for record formatting (Default = 1)', type=int,
+                    default=1)
+    mg.add_argument('--batch_reads', help='Reads simulated per GPU batch (Default = 65536)', type=int, default=65536)
+    mg.add_argument('--no_error_profile', help='Skip writing <out>_aligned_error_profile', action='store_true', default=False)
+    mg.add_argument('--device', help='CUDA device index (Default = LOCAL_RANK or 0)', type=int, default=None)
+    sub.add_parser("transcriptome", help="Not implemented in this build", add_help=False)
+    return parser, g, mg
+
+
+def add_abundance_var(expected, total_len, var_low, var_high, rnd):
+    """add_abundance_var (:594-615): largest |variation| to the species with the largest genome, renormalised to 100."""
+    n = len(expected)
+    var = sorted((rnd.uniform(var_low, var_high) for _ in range(n)), key=abs)
+    by_size = sorted(range(n), key=lambda k: total_len[k])
+    per_species = [0.0] * n
+    for v, k in zip(var, by_size):
+        per_species[k] = v
+    with_var = [e + e * per_species[k] for k, e in enumerate(expected)]
+    tot = sum(with_var)
+    return [a * 100 / tot for a in with_var]
+
+
+def main_metagenome(args, parser_mg):
+    """main(), metagenome branch (:2416-2527)."""
+    import random
+
+    max_len, min_len = args.max_len, args.min_len
+    if args.homopolymer and (args.KmerBias is None or args.KmerBias < 0):
+        print("\nPlease input proper kmer bias value >= 0 to simulate homopolymer contraction and expansion events from\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    if args.strandness and (args.strandness < 0 or args.strandness > 1):
+        print("\nPlease input proper strandness value between 0 and 1\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    if (args.median_len and not args.sd_len) or (args.sd_len and not args.median_len):
+        sys.stderr.write("\nPlease provide both mean and standard deviation of read length!\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    if args.median_len and args.sd_len and args.chimeric:
+        sys.stderr.write("\nLognormal distributed reads cannot be chimeric!\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    if max_len < min_len:
+        sys.stderr.write("\nMaximum read length must be longer than Minimum read length!\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    if args.perfect and args.chimeric:
+        print("\nPerfect reads cannot be chimeric\n")
+        parser_mg.print_help(sys.stderr)
+        sys.exit(1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    _log(' '.join(sys.argv))
+    dir_name = os.path.dirname(args.output)
+    if dir_name != '':
+        os.makedirs(dir_name, exist_ok=True)
+    prof = read_profile(args.genome_list, [], args.model_prefix, args.perfect, "metagenome", args.strandness,
+                        dna_type=args.dna_type_list, abun=args.abun, chimeric=args.chimeric, homopolymer=args.homopolymer,
+                        fastq=args.fastq, device=device, seed=args.seed or 0)
+    rnd = random.Random(args.seed)
+    L_ = prof.ref.lengths
+    total_len = [int(L_[prof.ref.chrom_species == i].sum()) for i in range(len(prof.ref.species))]
+    max_len = min(max_len, max(prof.ref.max_chrom_per_species.values()))          # :2525
+    for s_idx, expected in enumerate(prof.samples):
+        abun = add_abundance_var(expected, total_len, float(args.abun_var[0]), float(args.abun_var[1]), rnd) \
+            if args.abun_var else list(expected)
+        beta = prof.tables.abun_inflation
+        inflated = [1 - (1 - a) * beta for a in abun] if args.chimeric else None           # inflate_abun (:2018-2022)
+        prof.engine.set_abundance(abun, inflated)
+        _log("Simulating sample sample%d" % s_idx)
+        prof.number_aligned, prof.number_unaligned = prof.counts[s_idx]
+        simulation(prof, "metagenome", args.output + "_sample%d" % s_idx, "metagenome", args.perfect, None, None, max_len,
+                   min_len, max(args.num_threads, 1), args.fastq, args.median_len, args.sd_len, chimeric=args.chimeric,
+                   batch_reads=args.batch_reads, error_profile=not args.no_error_profile, rank=rank, world=world)
+        if world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("gloo")
+            dist.barrier()
+            if rank == 0:
+                merge_rank_files(args.output + "_sample%d" % s_idx, args.fastq, args.perfect, world)
+            dist.barrier()
+    _log("Finished!")
 
 
 def coverage_to_reads(prof, cm, coverage):
@@ -205,13 +330,15 @@ def coverage_to_reads(prof, cm, coverage):
 
 
 def main(argv=None):
-    parser, parser_g = build_parser()
+    parser, parser_g, parser_mg = build_parser()
     args = parser.parse_args(argv)
     if args.mode is None:
         parser.print_help(sys.stderr)
         sys.exit(1)
+    if args.mode == "metagenome":
+        return main_metagenome(args, parser_mg)
     if args.mode != "genome":
-        sys.stderr.write("nanosim_b200: %s mode is not implemented in this build (genome only)\n" % args.mode)
+        sys.stderr.write("nanosim_b200: %s mode is not implemented in this build\n" % args.mode)
         sys.exit(1)
     number = [args.number]
     max_len, min_len = args.max_len, args.min_len

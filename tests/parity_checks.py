@@ -20,7 +20,7 @@ for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
 import run_stats as rs  # noqa: E402
 
 DATA = os.path.join(ROOT, "nanosim_b200", "data")
-MODELS = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz"}
+MODELS = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz", "even": "even_err3152364_v3.2.2.npz"}
 
 _COMP = np.arange(256, dtype=np.uint8)
 for _a, _b in (("A", "T"), ("C", "G")):
@@ -60,6 +60,21 @@ def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, m
     eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
                   max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts,
                   kmer_bias=kmer_bias)
+    return eng, cm, t
+
+
+def make_meta_engine(ref, abun, fastq=True, chimeric=True, perfect=False, seed=1, min_len=50, max_len=None, model="even"):
+    """Metagenome-mode engine on a MetaReference with one sample's abundance vector (percent, species order)."""
+    from nanosim_b200.engine import Engine
+
+    cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect, mode="metagenome")
+    eng = Engine(device=0, seed=seed)
+    eng.set_reference(ref)
+    eng.set_model(t, perfect=perfect)
+    inflated = [1 - (1 - a) * t.abun_inflation for a in abun] if chimeric else None
+    eng.set_abundance(abun, inflated)
+    eng.configure(perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
+                  max_len=min(max_len or ref.max_chrom, ref.max_chrom), metagenome=True)
     return eng, cm, t
 
 
@@ -115,7 +130,9 @@ def check_edit_scripts(batch, ref, fastq, max_reads=None):
                 assert ty[-1] == 4 and ln[-1] == int(r["tail"])
             cstart, clen = int(ref_off[pc["chrom"]]), int(ref_off[pc["chrom"] + 1] - ref_off[pc["chrom"]])
             if int(pc["ref_len"]) > 0:
-                assert int(pc["pos"]) + int(pc["ref_len"]) <= clen or clen == ref.genome_len, "segment leaves its chromosome"
+                circ = getattr(ref, "chrom_circular", None)
+                wraps_ok = clen == ref.genome_len if circ is None else bool(circ[pc["chrom"]])
+                assert int(pc["pos"]) + int(pc["ref_len"]) <= clen or wraps_ok, "segment leaves its chromosome"
             seg = fwd[cursor:cursor + int(pc["out_len"])]
             use = (ty == 0) | (ty == 1)
             if use.any():

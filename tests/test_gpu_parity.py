@@ -392,6 +392,123 @@ def test_homopolymer_vs_unmodified_reference(ecoli, L):
     assert not fails, "\n".join(fails)
 
 
+@pytest.fixture(scope="module")
+def meta_ref():
+    from conftest import meta_fixture
+    from nanosim_b200.reference_fasta import MetaReference, read_abundance
+    meta_fixture()                                   # writes genome_list_local.tsv with this checkout's paths
+    meta = os.path.join(GOLDEN, "meta")
+    ref = MetaReference.from_genome_list(os.path.join(meta, "genome_list_local.tsv"), os.path.join(meta, "dna_type.tsv"))
+    numbers, samples = read_abundance(os.path.join(meta, "abundance.tsv"), ref.species)
+    return ref, numbers, samples
+
+
+def _species_base_fractions(b, ref, L):
+    seg = b.pieces[b.pieces["kind"] == L.NS_PIECE_SEGMENT]
+    sp = ref.chrom_species[seg["chrom"]]
+    tot = np.bincount(sp, weights=seg["ref_len"].astype(np.float64), minlength=len(ref.species))
+    return tot / tot.sum()
+
+
+def test_metagenome_scripts_strand_and_quota(meta_ref, L):
+    """Metagenome mode on four species (linear + circular chromosomes): bit-exact scripts, one strand per batch
+    (simulator.py:860), per-chromosome circular wrap, species base composition follows the abundance quotas (:772-775)."""
+    ref, numbers, samples = meta_ref
+    eng, cm, t = pc.make_meta_engine(ref, samples[0], fastq=True, chimeric=True, seed=23)
+    fr_all = np.zeros(len(ref.species))
+    strands = set()
+    for k in range(3):
+        eng.simulate(L.NS_KIND_ALIGNED, k * 4000, 4000)
+        b = eng.fetch(want_ops=True)
+        assert pc.check_edit_scripts(b, ref, True, max_reads=1500) > 0
+        assert len(set(b.reads["reversed"].tolist())) == 1          # is_reversed is drawn once per batch
+        strands.add(int(b.reads["reversed"][0]))
+        fr_all += _species_base_fractions(b, ref, L)
+        seg = b.pieces[b.pieces["kind"] == L.NS_PIECE_SEGMENT]
+        lin = ref.chrom_circular[seg["chrom"]] == 0
+        assert ((seg["pos"].astype(np.int64) + seg["ref_len"])[lin] <= ref.lengths[seg["chrom"]][lin]).all()
+    want = np.asarray(samples[0]) / np.sum(samples[0])
+    print("species base fractions", fr_all / 3, "abundance", want)
+    assert np.abs(fr_all / 3 - want).max() < 0.01
+    assert (b.reads["n_pieces"] > 1).any()
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 6000)
+    bu = eng.fetch()
+    cnt = np.bincount(ref.chrom_species[bu.pieces["chrom"]], minlength=len(ref.species)) / len(bu.pieces)
+    print("unaligned species fractions", cnt)          # uniform species choice (:1705-1706), then rejection by length
+    assert cnt.min() > 0.1
+    eng.close()
+
+
+def test_metagenome_statistics_vs_oracle(meta_ref, L, tmp_path):
+    """simulation_aligned_metagenome of the pinned oracle (a few hundred reads) vs the device."""
+    import nanosim_oracle as no
+    from conftest import meta_fixture, oracle_model
+    ref, numbers, samples = meta_ref
+    eng, cm, t = pc.make_meta_engine(ref, samples[0], fastq=True, chimeric=True, seed=29)
+    s_dev = rs.empty()
+    fr = np.zeros(len(ref.species))
+    for k in range(4):
+        eng.simulate(L.NS_KIND_ALIGNED, k * 5000, 5000)
+        b = eng.fetch(want_ops=True)
+        pc.batch_stats(b, ref, True, s_dev)
+        fr += _species_base_fractions(b, ref, L) / 4
+    eng.close()
+    oref, onum, omulti = meta_fixture()
+    m = oracle_model(cm, tmp_path, fastq=True, chimeric=True, mode="metagenome")
+    abun = omulti["sample0"]
+    infl = {sp: no.inflate_abun(abun, sp, m.abun_inflation) for sp in abun}
+    import random
+    random.seed(77)
+    np.random.seed(77)
+    sink = no.ReadSink()
+    no.simulation_aligned_metagenome(oref, m, sink, abun, infl, 50, max(oref.max_chrom.values()), None, True, 450, False, True)
+    prefix = os.path.join(str(tmp_path), "ometa")
+    with open(prefix + "_aligned_reads.fastq", "w") as f:
+        f.write(no.format_records(sink.records, True))
+    with open(prefix + "_aligned_error_profile", "w") as f:
+        f.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+        f.writelines(r + "\n" for r in sink.error_rows)
+    s_or = rs.stats_from_prefix(prefix, True)
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.05, p_min=1e-5, label="meta",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s_dev[k], s_or[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-5:
+            fails.append("meta %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    fc_d, fc_o = s_dev["n_chimeric"] / s_dev["n_aligned"], s_or["n_chimeric"] / s_or["n_aligned"]
+    assert abs(fc_d - fc_o) < 0.035, (fc_d, fc_o)
+    # species composition of the oracle run from its read names ({species}-{chrom}_{pos};...)
+    tot = {sp: 0 for sp in abun}
+    for name, seq, q in sink.records:
+        parts = name.rsplit("_", 4)
+        lens = [int(x) for x in parts[3].split(";")]
+        locs = [c for c in parts[0].split("_aligned_")[0].split(";") if not c.startswith("gap_")]
+        for loc, n in zip(locs, lens):
+            tot[[sp for sp in abun if loc.startswith(sp + "-")][0]] += n
+    fo = np.asarray([tot[sp] for sp in ref.species], dtype=np.float64)
+    fo /= fo.sum()
+    print("species base fractions device", fr, "oracle", fo)
+    assert np.abs(fr - fo).max() < 0.03
+    assert not fails, "\n".join(fails)
+
+
+def test_cli_metagenome_end_to_end(meta_ref, tmp_path, L):
+    from nanosim_b200 import simulator
+    meta = os.path.join(GOLDEN, "meta")
+    out = os.path.join(str(tmp_path), "mg")
+    simulator.main(["metagenome", "-gl", os.path.join(meta, "genome_list_local.tsv"), "-a", os.path.join(meta, "abundance.tsv"),
+                    "-dl", os.path.join(meta, "dna_type.tsv"), "-c", os.path.join(pc.DATA, pc.MODELS["even"]), "-o", out,
+                    "--fastq", "--chimeric", "--seed", "3"])
+    for i, n in enumerate((300, 200)):
+        s = rs.stats_from_prefix(out + "_sample%d" % i, True)
+        assert s["n_aligned"] + s["n_unaligned"] == n
+        first = open(out + "_sample%d_aligned_reads.fastq" % i).readline()
+        assert first.startswith("@") and "-" in first and "_aligned_" in first
+    chim = [l for l in open(out + "_sample0_aligned_reads.fastq") if l.startswith("@") and "_chimeric_" in l]
+    assert all(";gap_" in l for l in chim)
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
