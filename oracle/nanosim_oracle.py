@@ -1080,3 +1080,191 @@ def simulation_unaligned_meta(ref, model, sink, min_l, max_l, fastq, num_simulat
             sink.records.append((name + "_0_" + str(middle_ref) + "_0", mutated, quals if fastq else None))
             passed += 1
         remaining = num_simulate - passed
+
+
+# --------------------------------------------------------------------------------------
+# transcriptome mode (without intron retention: --no_model_ir)
+# --------------------------------------------------------------------------------------
+class OracleTrxReference:
+    """seq_dict / seq_len for the reference transcriptome (simulator.py:341-349) + expression profile (:383-401)."""
+
+    def __init__(self, seqs, dict_exp, polya_ids=None):
+        self.seq_dict = dict(seqs)
+        self.seq_len = {k: len(v) for k, v in self.seq_dict.items()}
+        self.max_chrom = max(self.seq_len.values()) if self.seq_len else 0
+        self.dict_exp = dict(dict_exp)
+        self.ecdf_length_list, self.ecdf_weight_list = make_cdf(self.dict_exp, self.seq_len)
+        self.trx_with_polya = {t: 0 for t in (polya_ids or [])}
+
+    @staticmethod
+    def from_files(fasta, exp_path, polya_path=None):
+        dict_exp = {}
+        with open(exp_path) as f:
+            f.readline()
+            for line in f:
+                parts = line.split("\t")
+                tid = parts[0].split(".")[0]
+                tpm = float(parts[2])
+                if tpm > 0:
+                    dict_exp[tid] = tpm
+        polya = None
+        if polya_path:
+            with open(polya_path) as f:
+                polya = [line.strip().split(".")[0] for line in f.readlines()]
+        return OracleTrxReference(read_fasta(fasta), dict_exp, polya)
+
+
+def make_cdf(dict_exp, dict_len):
+    """simulator.py:69-97."""
+    total = 0
+    vals = []
+    for item in dict_exp:
+        if item in dict_len:
+            total += dict_exp[item]
+    for item in dict_exp:
+        if item in dict_len:
+            vals.append((item, dict_exp[item] / float(total)))
+    vals_sorted = sorted(vals, key=lambda x: x[1])
+    cdf = np.cumsum([x[1] for x in vals_sorted])
+    bounds = [0] + list(cdf)
+    weights, lengths = [], []
+    for i, t in enumerate(vals_sorted):
+        weights.append(abs(bounds[i + 1] - bounds[i]))
+        lengths.append((t[0], dict_len[t[0]]))
+    return lengths, weights
+
+
+def select_nearest_kde2d(sampled, ref_len_total):
+    """simulator.py:108-111."""
+    idx = np.abs(sampled[:, 0] - ref_len_total).argmin()
+    return int(sampled[idx][1])
+
+
+def extract_read_trx(ref, key, length, trx_has_polya, buffer=10):
+    """simulator.py:1683-1691."""
+    pos = random.randint(0, ref.seq_len[key] - length)
+    seq = ref.seq_dict[key][pos: pos + length]
+    retain = bool(trx_has_polya and pos + length + buffer >= ref.seq_len[key])
+    return seq, pos, retain
+
+
+def extract_read_transcriptome(ref, length):
+    """simulator.py:1695-1703 (extract_read with dna_type == "transcriptome", used by unaligned reads)."""
+    while True:
+        key = random.choice(list(ref.seq_len.keys()))
+        if length < ref.seq_len[key]:
+            pos = random.randint(0, ref.seq_len[key] - length)
+            return ref.seq_dict[key][pos: pos + length], key + "_" + str(pos)
+
+
+def simulation_aligned_transcriptome(ref, model, sink, kmer_bias, basecaller, num_simulate, polya, fastq, per=False,
+                                     uracil=False):
+    """simulator.py:1043-1263 with model_ir == False."""
+    import scipy.stats
+
+    scale = 2.409858743694814 if basecaller == "albacore" else 4.168299657168961
+
+    def polya_len_draw():
+        return int(scipy.stats.expon.rvs(loc=2.0, scale=scale))
+
+    remainder_l = kde_lengths(model.kde_ht, num_simulate, True)
+    ratio_tmp = kde_lengths(model.kde_ht_ratio, num_simulate)
+    ratio_l = [1 if x > 1 else x for x in ratio_tmp]
+    ratio_l = [0 if x < 0 else x for x in ratio_l]
+    simulated = 0
+    sampled = kde_lengths(model.kde_aligned_2d, num_simulate, False, False)
+    trx_sampled = set()
+    while simulated < num_simulate:
+        while True:
+            ref_trx, ref_trx_len = random.choices(ref.ecdf_length_list, weights=ref.ecdf_weight_list, k=1)[0]
+            if ref_trx in trx_sampled:
+                sampled = kde_lengths(model.kde_aligned_2d, num_simulate, False, False)
+                trx_sampled = set()
+            ref_len_aligned = select_nearest_kde2d(sampled, ref_trx_len)
+            if ref_len_aligned < ref_trx_len:
+                break
+        trx_sampled.add(ref_trx)
+        has_polya = polya and ref_trx in ref.trx_with_polya
+        is_reversed = random.random() > model.strandness_rate
+        if per:
+            index = sink.take_index()
+            new_read, pos, retain = extract_read_trx(ref, ref_trx, ref_len_aligned, has_polya)
+            name = ref_trx + "_" + str(pos) + "_perfect_" + str(index)
+            mutated = case_convert(new_read)
+            quals = base_qualities(model.base_qual["match"], ref_len_aligned) if fastq else []
+            head = tail = 0
+            name += "_R" if is_reversed else "_F"
+            if retain:
+                polya_len = polya_len_draw()
+                if polya_len > 0:
+                    mutated += "A" * polya_len
+            else:
+                polya_len = 0
+            name += "_0_" + str(ref_len_aligned) + "_" + str(polya_len)
+        else:
+            middle, middle_ref, e_dict, e_count = error_list(ref_len_aligned, model, fastq)
+            if middle_ref > ref_trx_len:
+                continue
+            index = sink.take_index()
+            new_read, pos, retain = extract_read_trx(ref, ref_trx, middle_ref, has_polya)
+            name = str(ref_trx) + "_" + str(pos) + "_aligned_" + str(index)
+            name += "_R" if is_reversed else "_F"
+            remainder = int(remainder_l[simulated])
+            ratio = ratio_l[simulated]
+            if remainder == 0:
+                head = tail = 0
+            else:
+                head = int(round(remainder * ratio))
+                tail = remainder - head
+            polya_len = polya_len_draw() if retain else 0
+            name += "_" + str(head) + "_" + str(middle_ref) + "_" + str(tail + polya_len)
+            new_read = case_convert(new_read)
+            mutated, quals = mutate_read(new_read, name, sink.error_rows, e_dict, e_count, fastq, kmer_bias, model)
+            if kmer_bias:
+                mutated, quals = mutate_homo(mutated, quals, kmer_bias, model)
+            if polya_len > 0:
+                mutated += "A" * polya_len
+        if fastq:
+            ht = base_qualities(model.base_qual["ht"], head + tail + polya_len)
+            for _ in range(polya_len):
+                quals.append(ht.pop())
+            quals = ht[:head] + quals + ht[head:]
+        mutated = "".join(np.random.choice(ACGT_ORDER, head)) + mutated + "".join(np.random.choice(ACGT_ORDER, tail))
+        if is_reversed:
+            mutated = reverse_complement(mutated)
+            quals.reverse()
+        if uracil:
+            mutated = mutated.translate(str.maketrans("T", "U"))
+        sink.records.append((name, mutated, quals if fastq else None))
+        simulated += 1
+
+
+def simulation_unaligned_transcriptome(ref, model, sink, min_l, max_l, fastq, num_simulate):
+    """simulation_unaligned (:1482-1549) with dna_type == "transcriptome"."""
+    remaining = num_simulate
+    passed = 0
+    while remaining > 0:
+        ref_l = kde_lengths(model.kde_unaligned, remaining)
+        for j in range(len(ref_l)):
+            m_ref = int(ref_l[j])
+            _, middle_ref, e_dict, e_count = unaligned_error_list(m_ref, model)
+            if middle_ref < min_l or middle_ref > max_l:
+                continue
+            index = sink.take_index()
+            read, name = extract_read_transcriptome(ref, middle_ref)
+            name = name + "_unaligned_" + str(index)
+            read = case_convert(read)
+            mutated, _ = mutate_read(read, name, None, e_dict, e_count, False, False, model)
+            if len(mutated) < min_l or len(mutated) > max_l:
+                continue
+            quals = base_qualities(model.base_qual["unmapped"], len(mutated)) if fastq else []
+            p = random.random()
+            if p > model.strandness_rate:
+                mutated = reverse_complement(mutated)
+                name += "_R"
+                quals.reverse()
+            else:
+                name += "_F"
+            sink.records.append((name + "_0_" + str(middle_ref) + "_0", mutated, quals if fastq else None))
+            passed += 1
+        remaining = num_simulate - passed

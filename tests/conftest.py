@@ -13,7 +13,7 @@ if ORACLE_DIR not in sys.path:
 DATA = os.path.join(ROOT, "nanosim_b200", "data")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MODEL_FILES = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz",
-               "even": "even_err3152364_v3.2.2.npz"}
+               "even": "even_err3152364_v3.2.2.npz", "drna": "drna_bham1_guppy_plusq.npz"}
 
 
 def pytest_configure(config):
@@ -61,4 +61,5 @@ def oracle_model(cm, tmpdir, fastq=True, homopolymer=False, chimeric=False, perf
     m.kde_unaligned = kde("unaligned_length")
     m.kde_gap = kde("gap_length")
     m.kde_aligned = kde("aligned_reads") if perfect else kde("aligned_region")
+    m.kde_aligned_2d = kde("aligned_region_2d")
     return m
