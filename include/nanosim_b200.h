@@ -52,6 +52,17 @@ typedef struct {
     const uint8_t* chrom_circular;   /* 1 = "circular" (the default for local files, :323), 0 = "linear" */
 } NsReference;
 
+/* transcriptome mode: dict_exp / ecdf_length_list / ecdf_weight_list (make_cdf :69-97) and trx_with_polya (:455-463).
+ * The n_expressed transcripts present in both the expression profile and the reference, as a Walker alias table over
+ * their TPM shares; expr_chrom[i] = index of transcript i among the reference's records. */
+typedef struct {
+    const uint32_t* alias_prob;
+    const uint32_t* alias_idx;
+    const uint32_t* expr_chrom;
+    uint32_t n_expressed;
+    const uint8_t* chrom_has_polya;  /* per reference record; NULL = no --polya list */
+} NsExpression;
+
 /* One joblib KernelDensity pickle (kde_aligned, kde_ht, ... :545-577): gaussian kernel, training samples + bandwidth.
  * A draw is data[floor(u*n)] + N(0, bandwidth)  (sklearn KernelDensity.sample; call site :235). */
 typedef struct {
@@ -71,6 +82,12 @@ typedef struct {
     NsKde kde_ht_ratio;       /* _ht_ratio.pkl */
     NsKde kde_unaligned;      /* _unaligned_length.pkl (n = 0 if absent) */
     NsKde kde_gap;            /* _gap_length.pkl, log10(x+1) domain (n = 0 if absent) */
+    /* _aligned_region_2d.pkl (transcriptome): training rows (transcript length, aligned length) sorted by transcript
+     * length; n_kde2d = 0 if absent.  select_nearest_kde2d (:108-111) is sampled exactly from them, see plan_kernel.cuh */
+    const float* kde2d_x;
+    const float* kde2d_y;
+    uint32_t n_kde2d;
+    float kde2d_bandwidth;
     const uint32_t* alias_prob;
     const uint32_t* alias_idx;
     const uint32_t* alias_desc;
@@ -92,7 +109,7 @@ typedef struct {
 
 /* The scalar arguments of simulation()/simulation_aligned_genome()/simulation_unaligned(). */
 typedef struct {
-    uint32_t mode;            /* 0 genome, 1 metagenome */
+    uint32_t mode;            /* 0 genome, 1 metagenome, 2 transcriptome (--no_model_ir) */
     uint32_t circular;        /* dna_type == "circular" (single chromosome) */
     uint32_t perfect;
     uint32_t fastq;
@@ -103,13 +120,16 @@ typedef struct {
     double median_len;        /* 0 = off (-med / -sd) */
     double sd_len;
     uint32_t flags;           /* NS_FLAG_* */
-    uint32_t reserved;
+    uint32_t kde2d_sample;    /* transcriptome: size N of the 2-D KDE sample select_nearest_kde2d searches (:1072, :1090):
+                                 the reference uses the number of aligned reads of the worker */
+    double polya_scale;       /* transcriptome --polya: scale of expon(loc=2, scale) (:1046-1053); 0 = no polyA tails */
 } NsRunConfig;
 
 /* Unaligned reads normally take the warp-per-read fast path, which writes bases directly and keeps no edit scripts.
  * With this flag they go through the same plan/script/emit pipeline as aligned reads (identical lengths, strands and
  * positions; used by the tests to check the fast path against re-applied edit scripts). */
 #define NS_FLAG_UNALIGNED_SCRIPTS 1u
+#define NS_FLAG_URACIL 2u            /* --uracil: T -> U in the emitted reads (:1247-1248) */
 
 #define NS_KIND_ALIGNED 0
 #define NS_KIND_UNALIGNED 1
@@ -145,7 +165,7 @@ typedef struct {
     uint32_t read_slot;       /* index of the owning read inside the batch */
     uint64_t ev_off;          /* the piece's ERROR-EVENT script (what mutate_read logs, :2006-2008): equal to op_off/n_ops */
     uint32_t ev_n_ops;        /* unless -hp/-k rewrote the emitted script (mutate_homo); then this is the script before it */
-    uint32_t reserved;
+    uint32_t polya_len;       /* transcriptome: length of the simulated polyA tail (0 otherwise) */
 } NsPieceMeta;
 
 /* Edit script element: (type << 28) | length.  The op list of a piece, applied left to right to the reference
@@ -156,7 +176,7 @@ typedef struct {
 #define NS_OP_DEL 3u     /* skip n reference bases                              */
 #define NS_OP_HT 4u      /* n random head/tail bases        (ht quality)        */
 #define NS_OP_LIT 5u     /* n copies of a literal base: bits [27:26] base (A C T G = 0 1 2 3), [25:24] quality state
-                            (0 mis, 1 ins, 2 match), [23:0] n.  Only in scripts rewritten by the homopolymer pass. */
+                            (0 mis, 1 ins, 2 match, 3 ht), [23:0] n.  Scripts rewritten by the homopolymer pass; polyA tails. */
 #define NS_OP_TYPE(op) ((op) >> 28)
 #define NS_OP_LEN(op) (NS_OP_TYPE(op) == NS_OP_LIT ? ((op) & 0x00ffffffu) : ((op) & 0x0fffffffu))
 
@@ -193,6 +213,8 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg);
 /* metagenome: dict_abun / dict_abun_inflated of the current sample (main() :2497-2514), one value per species in
  * genome-list order; resets the running per-species base counts that assign_species (:758-811) keeps per worker. */
 int ns_set_abundance(NsContext* ctx, const double* abun, const double* abun_inflated, uint32_t n_species);
+/* transcriptome: expression profile + polyA list (read_profile :383-463). */
+int ns_set_expression(NsContext* ctx, const NsExpression* expr);
 
 /* --- simulation_aligned_genome / simulation_unaligned worker bodies (:1266-1454, :1482-1549) ---------------- */
 /* Simulates reads [first_read_id, first_read_id + n_reads) of `kind`; results stay in HBM until the next call. */

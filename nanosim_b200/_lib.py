@@ -16,7 +16,7 @@ NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT, NS_OP_LIT = 0, 1, 2, 3, 4
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
-EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_reference", "ns_set_model", "ns_configure",
+EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
            "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records"]
 
 
@@ -32,6 +32,7 @@ class NsKde(C.Structure):
 class NsModel(C.Structure):
     _fields_ = [
         ("kde_aligned", NsKde), ("kde_ht", NsKde), ("kde_ht_ratio", NsKde), ("kde_unaligned", NsKde), ("kde_gap", NsKde),
+        ("kde2d_x", C.c_void_p), ("kde2d_y", C.c_void_p), ("n_kde2d", C.c_uint32), ("kde2d_bandwidth", C.c_float),
         ("alias_prob", C.c_void_p), ("alias_idx", C.c_void_p), ("alias_desc", C.c_void_p),
         ("n_tables", C.c_uint32), ("alias_len", C.c_uint32),
         ("match_bin_lo", C.c_void_p), ("match_bin_hi", C.c_void_p),
@@ -47,10 +48,17 @@ class NsModel(C.Structure):
 class NsRunConfig(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("circular", C.c_uint32), ("perfect", C.c_uint32), ("fastq", C.c_uint32),
                 ("chimeric", C.c_uint32), ("kmer_bias", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32),
-                ("median_len", C.c_double), ("sd_len", C.c_double), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("median_len", C.c_double), ("sd_len", C.c_double), ("flags", C.c_uint32), ("kde2d_sample", C.c_uint32),
+                ("polya_scale", C.c_double)]
+
+
+class NsExpression(C.Structure):
+    _fields_ = [("alias_prob", C.c_void_p), ("alias_idx", C.c_void_p), ("expr_chrom", C.c_void_p),
+                ("n_expressed", C.c_uint32), ("chrom_has_polya", C.c_void_p)]
 
 
 NS_FLAG_UNALIGNED_SCRIPTS = 1
+NS_FLAG_URACIL = 2
 
 
 class NsReadMeta(C.Structure):
@@ -63,7 +71,7 @@ class NsPieceMeta(C.Structure):
     _fields_ = [("op_off", C.c_uint64), ("n_ops", C.c_uint32), ("kind", C.c_uint32), ("chrom", C.c_uint32),
                 ("pos", C.c_uint32), ("ref_len", C.c_uint32), ("out_len", C.c_uint32), ("out_rel", C.c_uint32),
                 ("l_new", C.c_uint32), ("ref_req", C.c_uint32), ("read_slot", C.c_uint32),
-                ("ev_off", C.c_uint64), ("ev_n_ops", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ev_off", C.c_uint64), ("ev_n_ops", C.c_uint32), ("polya_len", C.c_uint32)]
 
 
 class NsBatchInfo(C.Structure):
@@ -82,7 +90,7 @@ READ_DTYPE = np.dtype([("seq_off", "<u8"), ("seq_len", "<u4"), ("head", "<u4"), 
 PIECE_DTYPE = np.dtype([("op_off", "<u8"), ("n_ops", "<u4"), ("kind", "<u4"), ("chrom", "<u4"), ("pos", "<u4"),
                         ("ref_len", "<u4"), ("out_len", "<u4"), ("out_rel", "<u4"), ("l_new", "<u4"),
                         ("ref_req", "<u4"), ("read_slot", "<u4"), ("ev_off", "<u8"), ("ev_n_ops", "<u4"),
-                        ("reserved", "<u4")], align=True)
+                        ("polya_len", "<u4")], align=True)
 assert READ_DTYPE.itemsize == C.sizeof(NsReadMeta) == 32
 assert PIECE_DTYPE.itemsize == C.sizeof(NsPieceMeta) == 64
 
@@ -113,6 +121,8 @@ def lib():
     L.ns_set_model.restype = C.c_int
     L.ns_set_abundance.argtypes = [P, P, P, C.c_uint32]
     L.ns_set_abundance.restype = C.c_int
+    L.ns_set_expression.argtypes = [P, C.POINTER(NsExpression)]
+    L.ns_set_expression.restype = C.c_int
     L.ns_configure.argtypes = [P, C.POINTER(NsRunConfig)]
     L.ns_configure.restype = C.c_int
     L.ns_simulate.argtypes = [P, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(NsBatchInfo)]

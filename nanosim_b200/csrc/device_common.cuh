@@ -16,6 +16,10 @@ struct DevKde {
 
 struct DevModel {
     DevKde aligned, ht, ratio, unaligned, gap;
+    const float* kde2d_x;               // transcriptome: (transcript length, aligned length) rows sorted by x
+    const float* kde2d_y;
+    uint32_t n_kde2d;
+    float kde2d_bw;
     const uint2* alias;                 // interleaved (accept threshold, alias index)
     uint32_t tab_off[NS_MAX_TABLES];
     uint32_t tab_n[NS_MAX_TABLES];
@@ -37,10 +41,16 @@ struct DevRef {
     const uint32_t* chrom_species;      // per chromosome
     const uint8_t* chrom_circular;      // per chromosome
     const uint32_t* species_chrom_off;  // n_species + 1: chromosomes of species s are [off[s], off[s+1])
+    // transcriptome
+    const uint2* expr_alias;            // Walker alias over the expressed transcripts (TPM shares)
+    const uint32_t* expr_chrom;         // expressed transcript -> reference record
+    uint32_t n_expressed;
+    const uint8_t* chrom_has_polya;     // per reference record (nullptr: no polyA list)
 };
 
 struct DevCfg {
-    uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome;
+    uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome, transcriptome, uracil, kde2d_n;
+    double polya_scale;
     uint32_t min_len, max_len;
     uint64_t seed;
     double median_len, sd_len;          // -med / -sd (0 = lengths from the KDEs)
@@ -149,6 +159,10 @@ __device__ __forceinline__ double lognormal_draw(double mean, double sigma, Rng&
 // base <-> index helpers: A C G T -> 0 1 3 2 via (c >> 1) & 3 ; complement = idx ^ 2
 __device__ __forceinline__ uint32_t base_idx(uint32_t c) { return (c >> 1) & 3u; }
 __device__ __forceinline__ uint32_t idx_base(uint32_t i) { return (0x47544341u >> (8u * i)) & 0xffu; }
+// emitted character of a base index; --uracil writes U for T (:1247-1248)
+__device__ __forceinline__ uint32_t emit_char(uint32_t i, uint32_t uracil) {
+    return ((uracil ? 0x47554341u : 0x47544341u) >> (8u * i)) & 0xffu;
+}
 __device__ __forceinline__ bool is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 // bit i of 0x80045 is set for i = 'A'-'A', 'C'-'A', 'G'-'A', 'T'-'A'
 __device__ __forceinline__ bool acgt_fast(uint32_t c) {

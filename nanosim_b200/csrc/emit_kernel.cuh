@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
                         } else if (ty == NS_OP_LIT) {
                             oi = (op >> 26) & 3u;                              // literal base of a rewritten homopolymer
                         }
-                        sb[i >> 2] |= idx_base(oi ^ flip) << (8 * (i & 3));
+                        sb[i >> 2] |= emit_char(oi ^ flip, a.cfg.uracil) << (8 * (i & 3));
                         if (FASTQ) {
                             // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3); gap/unaligned -> unmapped(4)
                             const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));

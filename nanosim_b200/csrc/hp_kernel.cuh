@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 out.add(NS_OP_HT << 28, len);
                 continue;
             }
+            if (ty == NS_OP_LIT) {                         // polyA tail (appended after mutate_homo, :1229-1230)
+                flush_run();
+                out.add(op & 0xff000000u, op & 0x00ffffffu);
+                continue;
+            }
             if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && len > 0) {
                 // ---- error filter (:1929-1947)
                 const int64_t lo = ty == NS_OP_INS ? (int64_t)rpos - 1 : (int64_t)rpos;

@@ -74,7 +74,8 @@ struct NsContext {
     DevRef dref{};
     std::vector<uint64_t> h_chrom_off;
 
-    DevBuf kde[5], alias, qlut, qcdf, ref_species, ref_circular, ref_sp_off;
+    DevBuf kde[5], alias, qlut, qcdf, ref_species, ref_circular, ref_sp_off, kde2d_x, kde2d_y, expr_alias, expr_chrom, chrom_polya;
+    bool have_expr = false;
     std::vector<uint32_t> h_sp_off;
     std::vector<double> abun, abun_inflated, species_bases;     // metagenome: dict_abun, dict_abun_inflated, running totals
     DevBuf sp_bases_dev;
@@ -301,10 +302,12 @@ int ns_destroy(NsContext* ctx) {
     DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
-                      &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev};
+                      &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev, &ctx->kde2d_x, &ctx->kde2d_y,
+                      &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
         DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->ref_species,
-                            &ctx->ref_circular, &ctx->ref_sp_off};
+                            &ctx->ref_circular, &ctx->ref_sp_off, &ctx->kde2d_x, &ctx->kde2d_y, &ctx->expr_alias,
+                            &ctx->expr_chrom, &ctx->chrom_polya};
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
         for (auto& k : ctx->kde) { k.p = nullptr; k.cap = 0; }
     }
@@ -337,6 +340,12 @@ int ns_clone(NsContext* parent, NsContext** out) {
     c->ref_species = parent->ref_species;
     c->ref_circular = parent->ref_circular;
     c->ref_sp_off = parent->ref_sp_off;
+    c->kde2d_x = parent->kde2d_x;
+    c->kde2d_y = parent->kde2d_y;
+    c->expr_alias = parent->expr_alias;
+    c->expr_chrom = parent->expr_chrom;
+    c->chrom_polya = parent->chrom_polya;
+    c->have_expr = parent->have_expr;
     c->h_sp_off = parent->h_sp_off;
     c->abun = parent->abun;
     c->abun_inflated = parent->abun_inflated;
@@ -377,6 +386,11 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     ctx->dref.chrom_species = nullptr;
     ctx->dref.chrom_circular = nullptr;
     ctx->dref.species_chrom_off = nullptr;
+    ctx->dref.expr_alias = nullptr;
+    ctx->dref.expr_chrom = nullptr;
+    ctx->dref.n_expressed = 0;
+    ctx->dref.chrom_has_polya = nullptr;
+    ctx->have_expr = false;
     if (ref->n_species > 0) {
         if (!ref->chrom_species || !ref->chrom_circular)
             return fail(ctx, NS_EINVAL, "ns_set_reference: n_species > 0 needs chrom_species and chrom_circular");
@@ -427,8 +441,24 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
         dst[i]->n = src[i]->n;
         dst[i]->bw = src[i]->bandwidth;
     }
-    if (m->kde_aligned.n == 0 || m->kde_ht.n == 0 || m->kde_ht_ratio.n == 0)
-        return fail(ctx, NS_EINVAL, "ns_set_model: aligned / ht / ht_ratio KDEs are required");
+    if ((m->kde_aligned.n == 0 && m->n_kde2d == 0) || m->kde_ht.n == 0 || m->kde_ht_ratio.n == 0)
+        return fail(ctx, NS_EINVAL, "ns_set_model: aligned (or 2-D aligned) / ht / ht_ratio KDEs are required");
+    d.kde2d_x = d.kde2d_y = nullptr;
+    d.n_kde2d = 0;
+    d.kde2d_bw = 0.f;
+    if (m->n_kde2d > 0) {
+        if (!m->kde2d_x || !m->kde2d_y) return fail(ctx, NS_EINVAL, "ns_set_model: n_kde2d > 0 needs kde2d_x / kde2d_y");
+        std::vector<float> hx(m->n_kde2d);
+        CK(cudaMemcpy(hx.data(), m->kde2d_x, hx.size() * sizeof(float), cudaMemcpyDefault));
+        for (uint32_t i = 1; i < m->n_kde2d; ++i)
+            if (hx[i] < hx[i - 1]) return fail(ctx, NS_EINVAL, "ns_set_model: kde2d_x must be sorted ascending");
+        CK(upload(ctx->kde2d_x, m->kde2d_x, (size_t)m->n_kde2d * sizeof(float), ctx->stream));
+        CK(upload(ctx->kde2d_y, m->kde2d_y, (size_t)m->n_kde2d * sizeof(float), ctx->stream));
+        d.kde2d_x = ctx->kde2d_x.as<float>();
+        d.kde2d_y = ctx->kde2d_y.as<float>();
+        d.n_kde2d = m->n_kde2d;
+        d.kde2d_bw = m->kde2d_bandwidth;
+    }
     // interleave (prob, alias) so that one 8-byte load serves a draw
     std::vector<uint32_t> hp(m->alias_len), hi(m->alias_len), desc(2 * m->n_tables);
     CK(cudaMemcpy(hp.data(), m->alias_prob, hp.size() * 4, cudaMemcpyDefault));
@@ -467,7 +497,10 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
 
 int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     if (!ctx || !cfg) return fail(ctx, NS_EINVAL, "ns_configure: null argument");
-    if (cfg->mode > 1) return fail(ctx, NS_EINVAL, "ns_configure: mode must be 0 (genome) or 1 (metagenome)");
+    if (cfg->mode > 2) return fail(ctx, NS_EINVAL, "ns_configure: mode must be 0 (genome), 1 (metagenome) or 2 (transcriptome)");
+    if (cfg->mode == 2 && cfg->chimeric) return fail(ctx, NS_EINVAL, "ns_configure: transcriptome reads are not chimeric");
+    if (cfg->mode == 2 && ctx->have_model && ctx->dmodel.n_kde2d == 0)
+        return fail(ctx, NS_ESTATE, "ns_configure: transcriptome mode needs _aligned_region_2d.pkl in the model");
     if (cfg->mode == 1 && ctx->have_ref && ctx->dref.n_species == 0)
         return fail(ctx, NS_ESTATE, "ns_configure: metagenome mode needs a reference with species information");
     if (cfg->mode == 1 && cfg->kmer_bias != 0) return fail(ctx, NS_EINVAL, "ns_configure: -hp/-k is not offered in metagenome mode");
@@ -487,6 +520,10 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.chimeric = cfg->chimeric;
     ctx->dcfg.kmer_bias = cfg->kmer_bias;
     ctx->dcfg.metagenome = cfg->mode == 1 ? 1u : 0u;
+    ctx->dcfg.transcriptome = cfg->mode == 2 ? 1u : 0u;
+    ctx->dcfg.uracil = (cfg->flags & NS_FLAG_URACIL) ? 1u : 0u;
+    ctx->dcfg.kde2d_n = cfg->kde2d_sample ? cfg->kde2d_sample : 1u;
+    ctx->dcfg.polya_scale = cfg->polya_scale;
     ctx->dcfg.min_len = cfg->min_len;
     ctx->dcfg.max_len = cfg->max_len;
     ctx->dcfg.seed = ctx->seed;
@@ -505,6 +542,38 @@ int ns_set_abundance(NsContext* ctx, const double* abun, const double* abun_infl
     if (abun_inflated) ctx->abun_inflated.assign(abun_inflated, abun_inflated + n_species);
     else ctx->abun_inflated.assign(n_species, 0.0);
     ctx->species_bases.assign(n_species, 0.0);
+    return NS_OK;
+}
+
+int ns_set_expression(NsContext* ctx, const NsExpression* ex) {
+    if (!ctx || !ex || !ex->alias_prob || !ex->alias_idx || !ex->expr_chrom || ex->n_expressed == 0)
+        return fail(ctx, NS_EINVAL, "ns_set_expression: null argument or no expressed transcript");
+    if (!ctx->have_ref) return fail(ctx, NS_ESTATE, "ns_set_expression: set the reference transcriptome first");
+    if (ctx->borrowed) return fail(ctx, NS_ESTATE, "ns_set_expression: a cloned context shares its parent's tables");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = ex->n_expressed;
+    std::vector<uint32_t> hp(n), hi(n), hc(n);
+    CK(cudaMemcpy(hp.data(), ex->alias_prob, n * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(hi.data(), ex->alias_idx, n * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(hc.data(), ex->expr_chrom, n * 4, cudaMemcpyDefault));
+    std::vector<uint2> inter(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (hi[i] >= n || hc[i] >= ctx->dref.n_chrom) return fail(ctx, NS_EINVAL, "ns_set_expression: index out of range at %u", i);
+        inter[i] = make_uint2(hp[i], hi[i]);
+    }
+    CK(upload(ctx->expr_alias, inter.data(), inter.size() * sizeof(uint2), ctx->stream));
+    CK(upload(ctx->expr_chrom, hc.data(), hc.size() * 4, ctx->stream));
+    ctx->dref.expr_alias = ctx->expr_alias.as<uint2>();
+    ctx->dref.expr_chrom = ctx->expr_chrom.as<uint32_t>();
+    ctx->dref.n_expressed = n;
+    ctx->dref.chrom_has_polya = nullptr;
+    if (ex->chrom_has_polya) {
+        CK(upload(ctx->chrom_polya, ex->chrom_has_polya, ctx->dref.n_chrom, ctx->stream));
+        ctx->dref.chrom_has_polya = ctx->chrom_polya.as<uint8_t>();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_expr = true;
+    ctx->have_batch = false;
     return NS_OK;
 }
 
@@ -609,6 +678,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         return fail(ctx, NS_ESTATE, "ns_simulate: model has no unaligned-length KDE");
     if (kind == NS_KIND_ALIGNED && ctx->hcfg.chimeric && ctx->dmodel.gap.n == 0)
         return fail(ctx, NS_ESTATE, "ns_simulate: chimeric simulation needs the gap-length KDE");
+    if (ctx->dcfg.transcriptome && kind == NS_KIND_ALIGNED && !ctx->have_expr)
+        return fail(ctx, NS_ESTATE, "ns_simulate: transcriptome mode needs ns_set_expression");
     if (ctx->hcfg.fastq && !ctx->hmodel.has_qual)
         return fail(ctx, NS_ESTATE, "ns_simulate: --fastq needs base-quality parameters in the model");
     if (ctx->hcfg.max_len > 0x0fffffffu) ctx->dcfg.max_len = 0x0fffffffu;

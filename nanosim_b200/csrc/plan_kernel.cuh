@@ -180,6 +180,67 @@ __device__ __forceinline__ void draw_position_meta(const DevRef& ref, Rng& rng, 
     }
 }
 
+// extract_read, transcriptome branch (:1695-1703, unaligned reads): uniform transcript until it is longer than the
+// read, uniform start.
+__device__ __forceinline__ void draw_position_trx(const DevRef& ref, Rng& rng, uint32_t length, uint32_t& chrom, uint32_t& pos) {
+    for (int it = 0; it < 1000000; ++it) {
+        const uint32_t c = (uint32_t)__umul64hi(rng.next64(), (uint64_t)ref.n_chrom);
+        const uint64_t clen = __ldg(&ref.chrom_off[c + 1]) - __ldg(&ref.chrom_off[c]);
+        if ((uint64_t)length < clen) {
+            chrom = c;
+            pos = (uint32_t)__umul64hi(rng.next64(), clen - length + 1);
+            return;
+        }
+    }
+    chrom = 0;
+    pos = 0;
+}
+
+// select_nearest_kde2d (:108-111) on a size-N sample of the 2-D KDE (:1072, :1090), sampled EXACTLY without drawing the
+// N points: the KDE adds N(0, bw ~ 0.1) to integer training rows (x_i, y_i), so the sample point nearest to the
+// transcript length L is a training row at some integer distance d; with p(d) = #{|x_i - L| <= d} / M,
+// P(min distance <= d) = 1 - (1 - p(d))^N.  Inverting with one uniform gives d* = min{d: p(d) >= 1 - (1-u)^(1/N)};
+// by symmetry the nearest point is uniform over the rows at distance exactly d*, and its aligned length is
+// int(y_i + N(0, bw)).  O(log^2 M) instead of the reference's O(N) argmin per read.
+__device__ __forceinline__ uint32_t lower_bound_f(const float* x, uint32_t n, float v) {     // first i with x[i] >= v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&x[mid]) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t nearest_aligned_length(const DevModel& m, uint32_t n_sample, uint32_t L, Rng& rng) {
+    const uint32_t M = m.n_kde2d;
+    const double u = u01_double(rng.next64());
+    const double q = -expm1(log1p(-u) / (double)(n_sample > 0 ? n_sample : 1));     // 1 - (1-u)^(1/N)
+    const double need = q * (double)M;
+    const float fl = (float)L;
+    const float xmin = __ldg(&m.kde2d_x[0]), xmax = __ldg(&m.kde2d_x[M - 1]);
+    uint32_t dlo = 0, dhi = (uint32_t)fmaxf(fabsf(fl - xmin), fabsf(xmax - fl)) + 1;    // count(dhi) == M
+    while (dlo < dhi) {                                                                // smallest d with count(d) >= need
+        const uint32_t d = (dlo + dhi) >> 1;
+        const uint32_t a = lower_bound_f(m.kde2d_x, M, fl - (float)d);
+        const uint32_t b = lower_bound_f(m.kde2d_x, M, fl + (float)d + 0.5f);
+        if ((double)(b - a) >= need && b > a) dhi = d; else dlo = d + 1;
+    }
+    const uint32_t d = dlo;
+    // rows at distance exactly d: x == L - d and (d > 0) x == L + d
+    const uint32_t a0 = lower_bound_f(m.kde2d_x, M, fl - (float)d), a1 = lower_bound_f(m.kde2d_x, M, fl - (float)d + 0.5f);
+    uint32_t b0 = 0, b1 = 0;
+    if (d > 0) {
+        b0 = lower_bound_f(m.kde2d_x, M, fl + (float)d);
+        b1 = lower_bound_f(m.kde2d_x, M, fl + (float)d + 0.5f);
+    }
+    const uint32_t cnt = (a1 - a0) + (b1 - b0);
+    uint32_t r = (uint32_t)__umul64hi(rng.next64(), (uint64_t)(cnt > 0 ? cnt : 1));
+    const uint32_t row = cnt == 0 ? (a0 < M ? a0 : M - 1) : (r < a1 - a0 ? a0 + r : b0 + (r - (a1 - a0)));
+    const uint32_t r1 = rng.next(), r2 = rng.next();
+    const float z = sqrtf(-2.0f * logf(u01_open_low(r1))) * cospif(2.0f * ((float)(r2 >> 8) * (1.0f / 16777216.0f)));
+    const double y = (double)__ldg(&m.kde2d_y[row]) + (double)m.kde2d_bw * (double)z;
+    return y > 0.0 ? (uint32_t)y : 0u;
+}
+
 // ref_lengths / gap_lengths of generation `gen` for one aligned read (:1285-1299, :1309-1310) -> pieces[].ref_req
 __device__ __forceinline__ void draw_lengths(const DevModel& m, const DevCfg& cfg, uint32_t kind, uint64_t rid, uint32_t gen,
                                              uint32_t n_seg, NsPieceMeta* pieces) {
@@ -239,7 +300,9 @@ __global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t f
     const uint32_t ns = n_seg ? n_seg[i] : 1u;
     const uint32_t pf = piece_first ? piece_first[i] : i;
     uint64_t total = 0;
-    if (kind == NS_KIND_ALIGNED) {
+    if (kind == NS_KIND_ALIGNED && cfg.transcriptome) {
+        caps[pf] = 0;                   // the aligned length depends on the transcript drawn inside the attempt: exact pass
+    } else if (kind == NS_KIND_ALIGNED) {
         draw_lengths(m, cfg, kind, first_id + i, 0, ns, pieces + pf);
         for (uint32_t q = 0; q < 2 * ns - 1; ++q) {
             const uint32_t len = pieces[pf + q].ref_req;
@@ -336,6 +399,41 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 if (r <= 0 && !REPLAY) {
                     ++attempt;                      // rejected: middle_ref < min_l
                     break;
+                }
+            } else if (cfg.transcriptome) {
+                // transcript by TPM (random.choices over make_cdf, :1084), aligned length from the 2-D KDE nearest the
+                // transcript length, redrawn until it is shorter than the transcript (:1085-1109)
+                uint32_t trx = 0, tlen = 0, alen = 0;
+                for (int it = 0; it < 1000000; ++it) {
+                    const uint32_t r = rng.next();
+                    const uint64_t pp = (uint64_t)r * a.ref.n_expressed;
+                    const uint32_t j = (uint32_t)(pp >> 32);
+                    const uint2 e = __ldg(&a.ref.expr_alias[j]);
+                    const uint32_t k = ((uint32_t)pp < e.x || e.x == 0xffffffffu) ? j : e.y;
+                    trx = __ldg(&a.ref.expr_chrom[k]);
+                    tlen = (uint32_t)(__ldg(&a.ref.chrom_off[trx + 1]) - __ldg(&a.ref.chrom_off[trx]));
+                    alen = nearest_aligned_length(m, cfg.kde2d_n, tlen, rng);
+                    if (alen < tlen) break;
+                }
+                NsPieceMeta& pm0 = a.pieces[piece_first];
+                pm0.ref_req = alen;
+                pm0.chrom = trx;                                           // the transcript travels in `chrom`
+                reversed = u01_double(rng.next64()) > (double)m.strandness;
+                head = tail = 0;
+                remainder = 0;
+                if (!cfg.perfect) {
+                    // remainder_l[simulated], head_vs_ht_ratio_l[simulated] (:1066-1070): one draw per ACCEPTED read, no
+                    // filtering (a negative 10^x-1 truncates to 0, the ratio is clamped to [0,1])
+                    Rng hr;
+                    hr.init(cfg.seed, rid, stream_word(ST_LEN, a.kind, 0));
+                    const double rem = pow(10.0, kde_draw(m.ht, hr)) - 1.0;
+                    double ratio = kde_draw(m.ratio, hr);
+                    ratio = ratio > 1.0 ? 1.0 : (ratio < 0.0 ? 0.0 : ratio);
+                    remainder = rem > 0.0 ? (uint32_t)rem : 0u;
+                    if (remainder > 0) {
+                        head = (uint32_t)rint((double)remainder * ratio);
+                        tail = remainder - head;
+                    }
                 }
             } else if (cfg.perfect) {
                 head = tail = 0;
@@ -480,7 +578,16 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
             NsPieceMeta& pm = a.pieces[piece_first + p];
             bool is_gap = unal_kind || (p & 1u);
             sink.flush();
-            if (!unal_kind && p + 1 == n_pieces && tail > 0) sink.put(NS_OP_HT, tail);
+            if (cfg.transcriptome && !unal_kind) {
+                // the polyA tail sits between the mutated transcript piece and the tail (:1229-1241); its length is only
+                // known after the position draw, so the first pass appends it in PH_CHECK and the replay reads it back
+                if (REPLAY) {
+                    sink.put((NS_OP_LIT << 28) | (0u << 26) | (3u << 24), pm.polya_len);
+                    sink.put(NS_OP_HT, tail);
+                }
+            } else if (!unal_kind && p + 1 == n_pieces && tail > 0) {
+                sink.put(NS_OP_HT, tail);
+            }
             if (!REPLAY) {
                 if (sink.n > sink.cap) overflow = true;
                 pm.n_ops = sink.n;
@@ -508,6 +615,49 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 break;
             }
             bool ok1, ok2;
+            if (cfg.transcriptome && !unal_kind) {
+                NsPieceMeta& pm = a.pieces[piece_first];
+                const uint32_t trx = pm.chrom;
+                const uint32_t tlen = (uint32_t)(__ldg(&a.ref.chrom_off[trx + 1]) - __ldg(&a.ref.chrom_off[trx]));
+                if (!cfg.perfect && pm.ref_len > tlen) {                  // `if middle_ref > ref_trx_len: continue` (:1148)
+                    ++attempt;
+                    phase = PH_ATT;
+                    break;
+                }
+                // extract_read_trx (:1683-1691): uniform start; the read keeps a polyA tail when it ends within 10 bases
+                // of the transcript's 3' end and the transcript is in the --polya list
+                Rng pr;
+                pr.init(cfg.seed, rid, stream_word(ST_POS, a.kind, attempt));
+                const uint32_t ppos = (uint32_t)__umul64hi(pr.next64(), (uint64_t)(tlen - pm.ref_len) + 1);
+                uint32_t polya_len = 0;
+                const bool has = a.ref.chrom_has_polya && cfg.polya_scale > 0.0 && __ldg(&a.ref.chrom_has_polya[trx]);
+                if (has && (uint64_t)ppos + pm.ref_len + 10 >= tlen) {
+                    const double uu = 1.0 - u01_double(pr.next64());     // (0,1]
+                    polya_len = (uint32_t)(2.0 - cfg.polya_scale * log(uu));   // int(expon(loc=2, scale).rvs()) (:1053)
+                }
+                sink.put((NS_OP_LIT << 28) | (0u << 26) | (3u << 24), polya_len);
+                sink.put(NS_OP_HT, tail);
+                if (sink.n > sink.cap) overflow = true;
+                pm.pos = ppos;
+                pm.polya_len = polya_len;
+                pm.n_ops = sink.n;
+                pm.out_len = sink.out_len;
+                actual = sink.out_len;
+                NsReadMeta rm;
+                rm.seq_off = 0;
+                rm.seq_len = (uint32_t)actual;
+                rm.head = head;
+                rm.tail = tail;
+                rm.piece_first = piece_first;
+                rm.n_pieces = 1;
+                rm.reversed = (uint8_t)reversed;
+                rm.flags = (uint8_t)(overflow ? 1 : 0);
+                rm.attempts = attempt;
+                if (overflow) atomicAdd(a.n_flagged, 1u);
+                a.reads[slot] = rm;
+                phase = PH_FETCH;
+                break;
+            }
             if (unal_kind) {
                 // :1503 middle_ref in range, :1517 len(read_mutated) in range
                 ok1 = middle_ref >= cfg.min_len && middle_ref <= cfg.max_len;
@@ -562,6 +712,8 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                     // uniformly random species (:1705-1706)
                     const bool seg = !unal_kind && !(q & 1u);
                     draw_position_meta(a.ref, pr, seg ? (int)pm.chrom : -1, pm.ref_len, chrom, ppos);
+                } else if (cfg.transcriptome) {
+                    draw_position_trx(a.ref, pr, pm.ref_len, chrom, ppos);
                 } else if (pm.ref_len > 0) {
                     draw_position(a.ref, cfg, pr, pm.ref_len, chrom, ppos);
                 }

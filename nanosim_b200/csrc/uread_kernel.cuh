@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                             if (sub) oi = (oi + 1u + t3) & 3u;
                         }
                         const uint32_t dst = rev ? rm.seq_len - 1 - o : o;
-                        sq[dst] = (uint8_t)idx_base(rev ? oi ^ 2u : oi);
+                        sq[dst] = (uint8_t)emit_char(rev ? oi ^ 2u : oi, cfg.uracil);
                         if (FASTQ) {
                             const uint32_t u24 = w & 0xffffffu;
                             const uint32_t e = lut[u24 >> QLUT_FRAC_BITS];
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             pr.init(cfg.seed, rid, stream_word(ST_POS, NS_KIND_UNALIGNED, attempt));
             uint32_t chrom = 0, ppos = 0;
             if (cfg.metagenome) draw_position_meta(a.ref, pr, -1, middle_ref, chrom, ppos);
+            else if (cfg.transcriptome) draw_position_trx(a.ref, pr, middle_ref, chrom, ppos);
             else draw_position(a.ref, cfg, pr, middle_ref, chrom, ppos);
             if (lane == 0) {
                 NsPieceMeta p;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 p.read_slot = slot;
                 p.ev_off = 0;
                 p.ev_n_ops = 0;
-                p.reserved = 0;
+                p.polya_len = 0;
                 a.pieces[slot] = p;
                 NsReadMeta q;
                 q.seq_off = 0;

@@ -115,6 +115,10 @@ class Engine:
         m.kde_ht_ratio = kde("ht_ratio")
         m.kde_unaligned = kde("unaligned_length")
         m.kde_gap = kde("gap_length")
+        if getattr(t, "kde2d", None) is not None:
+            keep.append(t.kde2d)
+            m.kde2d_x, m.kde2d_y = _ptr(t.kde2d[0]), _ptr(t.kde2d[1])
+            m.n_kde2d, m.kde2d_bandwidth = len(t.kde2d[0]), float(t.kde2d[2])
         arrays = dict(prob=np.ascontiguousarray(t.alias_prob, dtype=np.uint32),
                       idx=np.ascontiguousarray(t.alias_idx, dtype=np.uint32),
                       desc=np.ascontiguousarray(t.alias_desc.reshape(-1), dtype=np.uint32),
@@ -142,13 +146,24 @@ class Engine:
         self._check(self._lib.ns_set_model(self._ctx, C.byref(m)))
         self.tables = t
 
+    def set_expression(self, alias_prob, alias_idx, expr_chrom, chrom_has_polya=None):
+        """Transcriptome mode: alias table over the expressed transcripts, their reference record indices, polyA flags."""
+        a = np.ascontiguousarray(alias_prob, dtype=np.uint32)
+        b = np.ascontiguousarray(alias_idx, dtype=np.uint32)
+        c = np.ascontiguousarray(expr_chrom, dtype=np.uint32)
+        d = np.ascontiguousarray(chrom_has_polya, dtype=np.uint8) if chrom_has_polya is not None else None
+        ex = L.NsExpression(_ptr(a), _ptr(b), _ptr(c), len(a), _ptr(d))
+        self._check(self._lib.ns_set_expression(self._ctx, C.byref(ex)))
+
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
-                  max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False):
+                  max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False,
+                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
-        cfg = L.NsRunConfig(1 if metagenome else 0, int(circular), int(perfect), int(fastq), int(chimeric), int(kmer_bias or 0),
-                            int(min_len), int(min(max_len, 0x0fffffff)), float(median_len or 0.0), float(sd_len or 0.0),
-                            L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0, 0)
+        flags = (L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0) | (L.NS_FLAG_URACIL if uracil else 0)
+        cfg = L.NsRunConfig(2 if transcriptome else (1 if metagenome else 0), int(circular), int(perfect), int(fastq),
+                            int(chimeric), int(kmer_bias or 0), int(min_len), int(min(max_len, 0x0fffffff)),
+                            float(median_len or 0.0), float(sd_len or 0.0), flags, int(kde2d_sample), float(polya_scale or 0.0))
         self._check(self._lib.ns_configure(self._ctx, C.byref(cfg)))
         self.fastq = bool(fastq)
 

@@ -407,6 +407,13 @@ class DeviceTables:
         self.kde = {}
         for k, (data, bw) in cm.kde.items():
             self.kde[k] = (np.ascontiguousarray(data.astype(np.float32)), np.float32(bw))
+        # ---- 2-D KDE of (transcript length, aligned length), transcriptome mode: rows sorted by transcript length
+        self.kde2d = None
+        if "aligned_region_2d" in cm.kde:
+            d2, bw2 = cm.kde["aligned_region_2d"]
+            order = np.argsort(d2[:, 0], kind="stable")
+            self.kde2d = (np.ascontiguousarray(d2[order, 0].astype(np.float32)),
+                          np.ascontiguousarray(d2[order, 1].astype(np.float32)), np.float32(bw2))
         # ---- base qualities
         self.has_qual = "base_qualities_model_parameters.tsv" in t
         self.qual_cdf = np.zeros((5, Q_MAX + 1), dtype=np.uint32)

@@ -19,7 +19,7 @@ for _a, _b in (("A", "T"), ("C", "G")):
     _COMP[ord(_a)], _COMP[ord(_b)] = ord(_b), ord(_a)
 
 
-def read_names(batch, ref_names, index_base, perfect=False, metagenome=False):
+def read_names(batch, ref_names, index_base, perfect=False, metagenome=False, transcriptome=False):
     """index_base: value of the reference's shared ``total_simulated`` counter for the batch's first read."""
     reads, pieces = batch.reads, batch.pieces
     names = []
@@ -34,6 +34,11 @@ def read_names(batch, ref_names, index_base, perfect=False, metagenome=False):
             names.append("%s_%d_unaligned_%d_%s_0_%d_0" % (ref_names[pc["chrom"]], pc["pos"], idx, strand, pc["ref_len"]))
             continue
         segs = [pieces[p0 + k] for k in range(0, npc, 2)]
+        if transcriptome:       # {trx}_{pos}_aligned|perfect_{idx}_{F|R}_{head}_{middle_ref}_{tail+polyA} (:1188-1219)
+            pc = segs[0]
+            names.append("%s_%d_%s_%d_%s_%d_%d_%d" % (ref_names[pc["chrom"]], pc["pos"], "perfect" if perfect else "aligned", idx,
+                                                      strand, r["head"], pc["ref_len"], int(r["tail"]) + int(pc["polya_len"])))
+            continue
         if perfect:
             loc = "".join("%s_%d" % (ref_names[s["chrom"]], s["pos"]) for s in segs)
             names.append("%s_perfect_%d_%s_0_%d_0" % (loc, idx, strand, sum(int(s["ref_len"]) for s in segs)))

@@ -168,3 +168,47 @@ def read_abundance(path, species):
             table[sp] = [float(x) for x in fields[1:]]
     samples = [[table[sp][i] for sp in species] for i in range(len(numbers))]
     return numbers, samples
+
+
+POLYA_SCALE = {"albacore": 2.409858743694814, "guppy": 4.168299657168961}      # simulator.py:1046-1049
+
+
+def read_expression(path, ref):
+    """Expression profile (simulator.py:385-401 + make_cdf :69-97): ``target_id est_counts tpm`` with a header; IDs are cut
+    at the first '.'; transcripts with tpm > 0 that exist in the reference, with their TPM shares.
+    Returns (expr_chrom uint32[n], weights float64[n])."""
+    dict_exp = {}
+    with open(path) as f:
+        f.readline()
+        for line in f:
+            parts = line.split("\t")
+            if len(parts) < 3:
+                raise ValueError("Expression profile must contain 3 columns: ID, count, TPM ")
+            tpm = float(parts[2])
+            if tpm > 0:
+                dict_exp[parts[0].split(".")[0]] = tpm
+    if len(dict_exp) == 0:
+        raise ValueError("Expression profile contains no TPM values > 0")
+    index = {k: i for i, k in enumerate(ref.names)}
+    chrom, w = [], []
+    for tid, tpm in dict_exp.items():
+        if tid in index:
+            chrom.append(index[tid])
+            w.append(tpm)
+    if not chrom:
+        raise ValueError("Please make sure transcript IDs in the expression profile match with those in reference "
+                         "transcriptome (example: both Ensembl IDs)")
+    w = np.asarray(w, dtype=np.float64)
+    return np.asarray(chrom, dtype=np.uint32), w / w.sum()
+
+
+def read_polya_list(path, ref):
+    """--polya list (simulator.py:455-463): one transcript ID per line -> uint8 flag per reference record."""
+    flags = np.zeros(len(ref.names), dtype=np.uint8)
+    index = {k: i for i, k in enumerate(ref.names)}
+    with open(path) as f:
+        for line in f.readlines():
+            i = index.get(line.strip().split(".")[0])
+            if i is not None:
+                flags[i] = 1
+    return flags

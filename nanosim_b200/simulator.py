@@ -24,7 +24,9 @@ from .engine import Engine
 from .model import DeviceTables, load_model
 from .pipeline import BatchPipeline
 from .records import error_profile_rows, format_records, read_names
-from .reference_fasta import MetaReference, PackedReference, read_abundance
+from .reference_fasta import (POLYA_SCALE, MetaReference, PackedReference, read_abundance, read_expression,
+                              read_polya_list)
+from .model import build_alias
 
 VERSION = "3.2.2-b200"
 
@@ -50,8 +52,8 @@ class Profile:
 def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
                  polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
                  device=0, seed=0):
-    if mode not in ("genome", "metagenome"):
-        sys.stderr.write("nanosim_b200: transcriptome mode is not implemented in this build\n")
+    if mode == "transcriptome" and model_ir:
+        sys.stderr.write("nanosim_b200: intron retention simulation is not implemented; run with --no_model_ir\n")
         sys.exit(1)
     prof = Profile()
     _log("Read in reference ")
@@ -67,6 +69,18 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
             sys.stderr.write(str(e) + "\n")
             sys.exit(1)
         prof.number_list = number_list
+    elif mode == "transcriptome":
+        prof.ref = PackedReference.from_fasta(ref_t)
+        _log("Read in expression profile")
+        try:
+            prof.expr_chrom, prof.expr_weights = read_expression(exp, prof.ref)
+        except ValueError as e:
+            sys.stderr.write(str(e) + "\n")
+            sys.exit(1)
+        prof.polya_flags = None
+        if polya:
+            _log("Read in list of transcripts with polyA tails")
+            prof.polya_flags = read_polya_list(polya, prof.ref)
     else:
         prof.ref = PackedReference.from_fasta(ref_g)
     prof.max_chrom = prof.ref.max_chrom
@@ -85,6 +99,9 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
     prof.engine = Engine(device=device, seed=seed)
     prof.engine.set_reference(prof.ref)
     prof.engine.set_model(prof.tables, perfect=per)
+    if mode == "transcriptome":
+        pr, al = build_alias(prof.expr_weights)
+        prof.engine.set_expression(pr, al, prof.expr_chrom, prof.polya_flags)
     return prof
 
 
@@ -100,9 +117,13 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                batch_reads=65536, error_profile=True, rank=0, world=1):
     eng = prof.engine
     meta = mode == "metagenome"
+    trx = mode == "transcriptome"
+    lo_a, hi_a = _shard(prof.number_aligned, rank, world)
     eng.configure(circular=(dna_type == "circular"), perfect=per, fastq=fastq, chimeric=chimeric,
                   kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0,
-                  metagenome=meta)
+                  metagenome=meta, transcriptome=trx, uracil=bool(uracil),
+                  polya_scale=POLYA_SCALE.get(basecaller, POLYA_SCALE["guppy"]) if (trx and polya) else 0.0,
+                  kde2d_sample=max(1, hi_a - lo_a))        # the reference's 2-D KDE sample has one row per read of the worker
     ext = ".fastq" if fastq else ".fasta"
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
@@ -119,7 +140,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             f_err.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
 
         def sink_aligned(info, b, job):
-            names = read_names(b, prof.ref.names, job[1], perfect=per, metagenome=meta)
+            names = read_names(b, prof.ref.names, job[1], perfect=per, metagenome=meta, transcriptome=trx)
             f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
             if want_err:
                 f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
@@ -236,8 +257,42 @@ def build_parser():
     mg.add_argument('--batch_reads', help='Reads simulated per GPU batch (Default = 65536)', type=int, default=65536)
     mg.add_argument('--no_error_profile', help='Skip writing <out>_aligned_error_profile', action='store_true', default=False)
     mg.add_argument('--device', help='CUDA device index (Default = LOCAL_RANK or 0)', type=int, default=None)
-    sub.add_parser("transcriptome", help="Not implemented in this build", add_help=False)
-    return parser, g, mg
+    t = sub.add_parser('transcriptome', help="Run the simulator on transcriptome mode")
+    t.add_argument('-rt', '--ref_t', help='Input reference transcriptome', required=True)
+    t.add_argument('-rg', '--ref_g', help='Input reference genome, required if intron retention simulation is on', default='')
+    t.add_argument('-e', '--exp', help='Expression profile in the specified format as described in README', required=True)
+    t.add_argument('-c', '--model_prefix', help='Location and prefix of error profiles generated from characterization '
+                   'step (Default = training)', default="training")
+    t.add_argument('-o', '--output', help='Output location and prefix for simulated reads (Default = simulated)',
+                   default="simulated")
+    t.add_argument('-n', '--number', help='Number of reads to be simulated (Default = 20000)', type=int, default=20000)
+    t.add_argument('-x', '--coverage', help='Coverage of the simulated reads, overrides the number of reads', type=float,
+                   default=None)
+    t.add_argument('-max', '--max_len', help='The maximum length for simulated unaligned reads (Default = Infinity)',
+                   type=int, default=float("inf"))
+    t.add_argument('-min', '--min_len', help='The minimum length for simulated unaligned reads (Default = 50)', type=int,
+                   default=50)
+    t.add_argument('--seed', help='Manually seeds the pseudo-random number generator', type=int, default=None)
+    t.add_argument('-hp', '--homopolymer', help='Simulate homopolymer lengths (Default = False)', action='store_true',
+                   default=False)
+    t.add_argument('-k', '--KmerBias', help='Minimum homopolymer length to simulate homopolymer contraction and expansion '
+                   'events in, a typical k is 6', type=int, default=None)
+    t.add_argument('-b', '--basecaller', help='Simulate polyA tails with respect to chosen basecaller: albacore or guppy',
+                   choices=["albacore", "guppy"], default=None)
+    t.add_argument('-s', '--strandness', help='Proportion of sense sequences. Overrides the value profiled in '
+                   'characterization stage. Should be between 0 and 1', type=float, default=None)
+    t.add_argument('--no_model_ir', help='Ignore simulating intron retention events', action='store_false', default=True)
+    t.add_argument('--perfect', help='Ignore profiles and simulate perfect reads', action='store_true', default=False)
+    t.add_argument('--polya', help='Simulate polyA tails for given list of transcripts', default=None)
+    t.add_argument('--fastq', help='Output fastq files instead of fasta files', action='store_true', default=False)
+    t.add_argument('-t', '--num_threads', help='Number of host threads used for record formatting (Default = 1)', type=int,
+                   default=1)
+    t.add_argument('--uracil', help='Converts the thymine (T) bases to uracil (U) in the output fasta format',
+                   action='store_true', default=False)
+    t.add_argument('--batch_reads', help='Reads simulated per GPU batch (Default = 65536)', type=int, default=65536)
+    t.add_argument('--no_error_profile', help='Skip writing <out>_aligned_error_profile', action='store_true', default=False)
+    t.add_argument('--device', help='CUDA device index (Default = LOCAL_RANK or 0)', type=int, default=None)
+    return parser, g, mg, t
 
 
 def add_abundance_var(expected, total_len, var_low, var_high, rnd):
@@ -251,6 +306,59 @@ def add_abundance_var(expected, total_len, var_low, var_high, rnd):
     with_var = [e + e * per_species[k] for k, e in enumerate(expected)]
     tot = sum(with_var)
     return [a * 100 / tot for a in with_var]
+
+
+def main_transcriptome(args, parser_t):
+    """main(), transcriptome branch (:2322-2414)."""
+    max_len, min_len = args.max_len, args.min_len
+    model_ir = args.no_model_ir
+    if args.homopolymer and (args.KmerBias is None or args.KmerBias < 0):
+        print("\nPlease input proper kmer bias value >= 0 to simulate homopolymer contraction and expansion events from\n")
+        parser_t.print_help(sys.stderr)
+        sys.exit(1)
+    if args.strandness and (args.strandness < 0 or args.strandness > 1):
+        print("\nPlease input proper strandness value between 0 and 1\n")
+        parser_t.print_help(sys.stderr)
+        sys.exit(1)
+    if max_len < min_len:
+        sys.stderr.write("\nMaximum read length must be longer than Minimum read length!\n")
+        parser_t.print_help(sys.stderr)
+        sys.exit(1)
+    if model_ir and args.ref_g == '':
+        sys.stderr.write("\nPlease provide a reference genome to simulate intron retention events!\n")
+        parser_t.print_help(sys.stderr)
+        sys.exit(1)
+    if args.polya and args.basecaller is None:
+        print("\nPlease input basecaller to simulate polyA tails from.\n")
+        parser_t.print_help(sys.stderr)
+        sys.exit(1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = args.device if args.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    _log(' '.join(sys.argv))
+    dir_name = os.path.dirname(args.output)
+    if dir_name != '':
+        os.makedirs(dir_name, exist_ok=True)
+    number = [args.number]
+    prof = read_profile(args.ref_g, number, args.model_prefix, args.perfect, "transcriptome", args.strandness,
+                        ref_t=args.ref_t, dna_type="linear", model_ir=model_ir, polya=args.polya, exp=args.exp,
+                        homopolymer=args.homopolymer, fastq=args.fastq, device=device, seed=args.seed or 0)
+    if args.coverage is not None:
+        number[0] = coverage_to_reads(prof, prof.tables.cm, args.coverage)
+        prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number[0], args.perfect)
+    max_len = min(max_len, prof.max_chrom)
+    simulation(prof, "transcriptome", args.output, "transcriptome", args.perfect, args.KmerBias if args.homopolymer else None,
+               args.basecaller, max_len, min_len, max(args.num_threads, 1), args.fastq, None, None, model_ir, args.uracil,
+               args.polya, batch_reads=args.batch_reads, error_profile=not args.no_error_profile, rank=rank, world=world)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        dist.barrier()
+        if rank == 0:
+            merge_rank_files(args.output, args.fastq, args.perfect, world)
+        dist.barrier()
+    _log("Finished!")
 
 
 def main_metagenome(args, parser_mg):
@@ -330,16 +438,15 @@ def coverage_to_reads(prof, cm, coverage):
 
 
 def main(argv=None):
-    parser, parser_g, parser_mg = build_parser()
+    parser, parser_g, parser_mg, parser_t = build_parser()
     args = parser.parse_args(argv)
     if args.mode is None:
         parser.print_help(sys.stderr)
         sys.exit(1)
     if args.mode == "metagenome":
         return main_metagenome(args, parser_mg)
-    if args.mode != "genome":
-        sys.stderr.write("nanosim_b200: %s mode is not implemented in this build\n" % args.mode)
-        sys.exit(1)
+    if args.mode == "transcriptome":
+        return main_transcriptome(args, parser_t)
     number = [args.number]
     max_len, min_len = args.max_len, args.min_len
     if args.homopolymer and (args.KmerBias is None or args.KmerBias < 0):

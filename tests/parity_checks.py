@@ -20,7 +20,8 @@ for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
 import run_stats as rs  # noqa: E402
 
 DATA = os.path.join(ROOT, "nanosim_b200", "data")
-MODELS = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz", "even": "even_err3152364_v3.2.2.npz"}
+MODELS = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.2.1.npz", "even": "even_err3152364_v3.2.2.npz",
+          "drna": "drna_bham1_guppy_plusq.npz"}
 
 _COMP = np.arange(256, dtype=np.uint8)
 for _a, _b in (("A", "T"), ("C", "G")):
@@ -75,6 +76,23 @@ def make_meta_engine(ref, abun, fastq=True, chimeric=True, perfect=False, seed=1
     eng.set_abundance(abun, inflated)
     eng.configure(perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
                   max_len=min(max_len or ref.max_chrom, ref.max_chrom), metagenome=True)
+    return eng, cm, t
+
+
+def make_trx_engine(ref, expr_chrom, expr_weights, polya_flags=None, fastq=True, perfect=False, seed=1, polya_scale=0.0,
+                    uracil=False, kde2d_sample=400, min_len=50, model="drna", unaligned_scripts=False):
+    """Transcriptome-mode engine (no intron retention)."""
+    from nanosim_b200.engine import Engine
+    from nanosim_b200.model import build_alias
+
+    cm, t = load_tables(model, fastq=fastq, perfect=perfect)
+    eng = Engine(device=0, seed=seed)
+    eng.set_reference(ref)
+    eng.set_model(t, perfect=perfect)
+    pr, al = build_alias(expr_weights)
+    eng.set_expression(pr, al, expr_chrom, polya_flags)
+    eng.configure(perfect=perfect, fastq=fastq, min_len=min_len, max_len=ref.max_chrom, transcriptome=True, uracil=uracil,
+                  polya_scale=polya_scale, kde2d_sample=kde2d_sample, unaligned_scripts=unaligned_scripts)
     return eng, cm, t
 
 

@@ -509,6 +509,121 @@ def test_cli_metagenome_end_to_end(meta_ref, tmp_path, L):
     assert all(";gap_" in l for l in chim)
 
 
+@pytest.fixture(scope="module")
+def trx_ref():
+    from nanosim_b200.reference_fasta import PackedReference, read_expression, read_polya_list
+    T = os.path.join(GOLDEN, "trx")
+    ref = PackedReference.from_fasta(os.path.join(T, "transcripts.fa"))
+    chrom, w = read_expression(os.path.join(T, "expression.tsv"), ref)
+    return ref, chrom, w, read_polya_list(os.path.join(T, "polya.txt"), ref)
+
+
+def test_transcriptome_scripts_polya_uracil(trx_ref, L):
+    """Transcriptome mode (--no_model_ir): bit-exact scripts, reads inside their transcript, polyA rule
+    (simulator.py:1689), T->U, expressed transcripts only."""
+    from nanosim_b200.reference_fasta import POLYA_SCALE
+    ref, chrom, w, polya = trx_ref
+    eng, cm, t = pc.make_trx_engine(ref, chrom, w, polya, fastq=True, seed=41, polya_scale=POLYA_SCALE["guppy"])
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 6000)
+    b = eng.fetch(want_ops=True)
+    assert pc.check_edit_scripts(b, ref, True) > 0
+    pcs = b.pieces
+    tlen = ref.lengths[pcs["chrom"]]
+    assert set(np.unique(pcs["chrom"]).tolist()) <= set(chrom.tolist())
+    assert (pcs["pos"].astype(np.int64) + pcs["ref_len"] <= tlen).all()
+    near_end = pcs["pos"].astype(np.int64) + pcs["ref_len"] + 10 >= tlen
+    flagged = polya[pcs["chrom"]] == 1
+    assert ((pcs["polya_len"] > 0) <= (near_end & flagged)).all()          # a tail only where the rule allows one
+    assert (pcs["polya_len"][near_end & flagged] >= 2).all()               # int(expon(loc=2)) >= 2
+    mean_tail = pcs["polya_len"][near_end & flagged].mean()
+    assert abs(mean_tail - (2 + POLYA_SCALE["guppy"] - 0.5)) < 0.4, mean_tail
+    fr = b.reads["reversed"].mean()
+    assert fr < 0.03                                                        # dRNA strandness 0.994
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 1500)
+    bu = eng.fetch()
+    assert (bu.pieces["pos"].astype(np.int64) + bu.pieces["ref_len"] <= ref.lengths[bu.pieces["chrom"]]).all()
+    assert (bu.pieces["ref_len"] < ref.lengths[bu.pieces["chrom"]]).all()  # `if length < seq_len[key]` (:1698)
+    eng.close()
+    eng, _, _ = pc.make_trx_engine(ref, chrom, w, None, fastq=False, seed=41, uracil=True)
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 500)
+    bq = eng.fetch()
+    used = np.concatenate([bq.seq[int(r["seq_off"]):int(r["seq_off"]) + int(r["seq_len"])] for r in bq.reads])
+    assert (used != ord("T")).all() and (used == ord("U")).any()
+    assert (bq.pieces["polya_len"] == 0).all()
+    eng.close()
+
+
+def test_transcriptome_statistics_vs_oracle(trx_ref, L, tmp_path):
+    """simulation_aligned_transcriptome of the pinned oracle (600 reads, 2-D KDE sample of 600 rows) vs the device with the
+    same sample size: the aligned-length-given-transcript law (select_nearest_kde2d), transcript usage, error rates."""
+    import random
+    import nanosim_oracle as no
+    from conftest import oracle_model
+    from nanosim_b200.reference_fasta import POLYA_SCALE
+    ref, chrom, w, polya = trx_ref
+    N = 600
+    eng, cm, t = pc.make_trx_engine(ref, chrom, w, polya, fastq=True, seed=43, polya_scale=POLYA_SCALE["guppy"], kde2d_sample=N)
+    s_dev = rs.empty()
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 40000)
+    b = eng.fetch(want_ops=True)
+    pc.batch_stats(b, ref, True, s_dev)
+    use_dev = np.bincount(b.pieces["chrom"], minlength=len(ref.names)).astype(np.float64)
+    frac_dev = (b.pieces["ref_len"] / ref.lengths[b.pieces["chrom"]])
+    eng.close()
+    T = os.path.join(GOLDEN, "trx")
+    oref = no.OracleTrxReference.from_files(os.path.join(T, "transcripts.fa"), os.path.join(T, "expression.tsv"),
+                                            os.path.join(T, "polya.txt"))
+    m = oracle_model(cm, tmp_path, fastq=True)
+    s_or = rs.empty()
+    use_or = np.zeros(len(ref.names))
+    frac_or = []
+    for rep in range(3):                                    # three independent workers of N reads each
+        random.seed(500 + rep)
+        np.random.seed(500 + rep)
+        sink = no.ReadSink()
+        no.simulation_aligned_transcriptome(oref, m, sink, None, "guppy", N, True, True, False, False)
+        prefix = os.path.join(str(tmp_path), "otrx%d" % rep)
+        with open(prefix + "_aligned_reads.fastq", "w") as f:
+            f.write(no.format_records(sink.records, True))
+        with open(prefix + "_aligned_error_profile", "w") as f:
+            f.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+            f.writelines(r + "\n" for r in sink.error_rows)
+        rs.merge(s_or, rs.stats_from_prefix(prefix, True))
+        for name, seq, q in sink.records:
+            trx = name.split("_")[0]
+            i = ref.names.index(trx)
+            use_or[i] += 1
+            frac_or.append(int(name.rsplit("_", 4)[3]) / ref.lengths[i])
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.06, p_min=1e-5, label="trx",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    st, dof, p = pc.chi2_two_sample(use_dev, use_or)
+    print("transcript usage chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    if p < 1e-5:
+        fails.append("transcript usage chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    edges = np.linspace(0, 1.0001, 21)
+    st, dof, p = pc.chi2_two_sample(np.histogram(frac_dev, edges)[0], np.histogram(frac_or, edges)[0])
+    print("aligned fraction of transcript chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    if p < 1e-5:
+        fails.append("aligned/transcript length ratio chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    assert not fails, "\n".join(fails)
+
+
+def test_cli_transcriptome_end_to_end(trx_ref, tmp_path, L):
+    from nanosim_b200 import simulator
+    T = os.path.join(GOLDEN, "trx")
+    out = os.path.join(str(tmp_path), "tx")
+    simulator.main(["transcriptome", "-rt", os.path.join(T, "transcripts.fa"), "-e", os.path.join(T, "expression.tsv"),
+                    "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", "800", "-o", out, "--no_model_ir", "--fastq",
+                    "--polya", os.path.join(T, "polya.txt"), "-b", "guppy", "--seed", "5"])
+    s = rs.stats_from_prefix(out, True)
+    assert s["n_aligned"] + s["n_unaligned"] == 800 and s["n_aligned"] == int(round(800 * 1.6565173181434516 / 2.6565173181434516))
+    first = open(out + "_aligned_reads.fastq").readline()
+    assert first.startswith("@ENST") and "_aligned_0_" in first
+    with pytest.raises(SystemExit):
+        simulator.main(["transcriptome", "-rt", os.path.join(T, "transcripts.fa"), "-e", os.path.join(T, "expression.tsv"),
+                        "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", "10", "-o", out, "--polya", os.path.join(T, "polya.txt")])
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
