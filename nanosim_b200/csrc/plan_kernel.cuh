@@ -84,6 +84,13 @@ struct OpSink {
         if (WRITE && n < cap) base[n] = (type << 28) | len;
         ++n;
     }
+    // literal run (polyA): `len` copies of base index `base` with quality state `state`
+    __device__ __forceinline__ void put_lit(uint32_t base_idx, uint32_t state, uint32_t len) {
+        if (len == 0) return;
+        out_len += len;
+        if (WRITE && n < cap) base[n] = (NS_OP_LIT << 28) | (base_idx << 26) | (state << 24) | len;
+        ++n;
+    }
     // the reference's e_dict[pos - 0.5] overwrite: a second insertion at the same position replaces the first (:1882)
     __device__ __forceinline__ void replace_last_ins(uint32_t old_len, uint32_t len) {
         out_len = out_len - old_len + len;
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                 // the polyA tail sits between the mutated transcript piece and the tail (:1229-1241); its length is only
                 // known after the position draw, so the first pass appends it in PH_CHECK and the replay reads it back
                 if (REPLAY) {
-                    sink.put((NS_OP_LIT << 28) | (0u << 26) | (3u << 24), pm.polya_len);
+                    sink.put_lit(0u, 3u, pm.polya_len);
                     sink.put(NS_OP_HT, tail);
                 }
             } else if (!unal_kind && p + 1 == n_pieces && tail > 0) {
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanA
                     const double uu = 1.0 - u01_double(pr.next64());     // (0,1]
                     polya_len = (uint32_t)(2.0 - cfg.polya_scale * log(uu));   // int(expon(loc=2, scale).rvs()) (:1053)
                 }
-                sink.put((NS_OP_LIT << 28) | (0u << 26) | (3u << 24), polya_len);
+                sink.put_lit(0u, 3u, polya_len);
                 sink.put(NS_OP_HT, tail);
                 if (sink.n > sink.cap) overflow = true;
                 pm.pos = ppos;
