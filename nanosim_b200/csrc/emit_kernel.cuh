@@ -5,23 +5,26 @@
 // (:1433-1435, :1675-1680) and the per-state quality draws (model_base_qualities.py:120-130) in ONE pass:
 //
 //   * a warp owns one piece (an aligned segment with its head/tail, a chimeric gap, or an unaligned read) and
-//     streams its ops 32 at a time; a warp-wide scan turns op lengths into (output start, reference start) pairs
-//     kept in a shared-memory ring;
-//   * every lane produces one 16-byte output chunk per step: it binary-searches the ring for the op covering its
-//     first base, then walks ops/reference bytes sequentially, so global stores are 16-byte vectors, 512 B per
-//     warp and fully coalesced for both the base and the quality stream;
+//     streams its ops 32 at a time; a warp-wide scan turns them into ring entries {output start, absolute reference
+//     offset, length, per-op constants} in shared memory (deletions only advance the reference offset and get no
+//     entry; a pad entry aligns the piece to its first 16-byte chunk, a sentinel closes it);
+//   * every lane produces one 16-byte output chunk per step: it binary-searches the ring for the entry covering its
+//     first base, then runs a BRANCH-FREE, fully unrolled 16-base loop: a predicated ring advance, a predicated
+//     reference byte load, one table lookup for case/IUPAC classification, one for the quality bucket.  Lanes of a
+//     warp sit in different ops, so anything branchy would be executed by everybody anyway; the rare cases (IUPAC
+//     codes, quality buckets that hold more than two values) only raise a flag and are patched afterwards;
 //   * reverse-strand reads are produced directly in output order by walking the edit script and the reference
-//     backwards and complementing (no second pass over the read);
-//   * all randomness is Philox keyed by (seed, read id, chunk index), so the bytes do not depend on the batch,
-//     the launch geometry or the GPU count.
+//     backwards with a complemented character table (no second pass over the read);
+//   * all randomness is Philox keyed by (seed, read id, chunk index): one 32-bit word per base (8 bits base choice,
+//     24 bits quality uniform), so the bytes do not depend on the batch, the launch geometry or the GPU count.
 #pragma once
 #include "device_common.cuh"
 
 #define EMIT_WARPS 8
 #define EMIT_RING 256
-#define QLUT_BITS 11
-#define QLUT_SIZE (1 << QLUT_BITS)
-#define QLUT_FRAC_BITS (24 - QLUT_BITS)     // quality uniforms are 24-bit
+
+#define EMIT_F_REF 4u        // info bit: the base is read from the reference (COPY, MIS)
+#define EMIT_F_MIS 8u        // info bit: ... and substituted by one of the three other bases
 
 struct EmitArgs {
     DevRef ref;
@@ -48,19 +51,81 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+// Per-op constants of a ring entry: [1:0] 3 when the base is random (INS, HT, pad), [2] EMIT_F_REF, [3] EMIT_F_MIS,
+// [15:8] the character classified when the reference is not read ('A' -> index 0, or the literal base of a LIT op),
+// [31:16] byte offset of the quality state's bucket table.
+__device__ __forceinline__ uint32_t emit_op_info(uint32_t op, bool unmapped) {
+    const uint32_t ty = op >> 28;
+    // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3) LIT->its own; gap/unaligned -> unmapped(4)
+    const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
+    uint32_t info = (qs * QLUT_SIZE * 4u) << 16;
+    if (ty < 2u) info |= EMIT_F_REF | (ty == NS_OP_MIS ? EMIT_F_MIS : 0u) | ((uint32_t)'A' << 8);
+    else if (ty == NS_OP_LIT) info |= idx_base((op >> 26) & 3u) << 8;
+    else info |= 3u | ((uint32_t)'A' << 8);
+    return info;
+}
+
+struct EmitPiece {
+    const uint8_t* cbase;    // first base of the chromosome
+    uint32_t pos, clen;      // piece start within the chromosome, chromosome length
+    uint32_t rev;
+    uint32_t tbl;            // output characters of base indices 0..3 (complemented for reverse reads)
+    uint32_t piece_in_read;
+    uint64_t rid;
+};
+
+// Exact slow path for ONE base (IUPAC reference codes, quality buckets with more than two values): locates the ring
+// entry of padded piece coordinate x again and redoes the base with the same random word.  Returns char | qchar << 8.
 template <bool FASTQ>
-__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_constant__ EmitArgs a) {
-    extern __shared__ uint32_t smem[];
-    uint32_t* lut = smem;                                        // FASTQ only
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* ring = smem + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0) + warp * (3 * EMIT_RING);
-    uint32_t* ring_out = ring;
-    uint32_t* ring_ref = ring + EMIT_RING;
-    uint32_t* ring_op = ring + 2 * EMIT_RING;
-    if (FASTQ) {
-        for (int i = threadIdx.x; i < NS_N_QUAL_STATES * QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[i];
-        __syncthreads();
+__device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiece& pc, const uint4* ring, uint32_t w_ret,
+                                               uint32_t w_loaded, uint32_t x, uint32_t w, uint32_t p) {
+    uint32_t l = w_ret, h = w_loaded;
+    while (h - l > 1) {
+        uint32_t mid = (l + h) >> 1;
+        if (ring[mid & (EMIT_RING - 1)].x <= x) l = mid; else h = mid;
     }
+    const uint4 e = ring[l & (EMIT_RING - 1)];
+    const uint32_t within = x - e.x, info = e.w;
+    uint32_t oi;
+    if (info & EMIT_F_REF) {
+        uint32_t rabs = pc.rev ? e.y - within : e.y + within;
+        if (rabs >= pc.clen) rabs += pc.rev ? pc.clen : 0u - pc.clen;
+        uint32_t c = __ldg(pc.cbase + rabs);
+        if (c - 'a' < 26u) c -= 32;
+        if (!acgt_fast(c)) {
+            const uint32_t f = rabs >= pc.pos ? rabs - pc.pos : rabs + pc.clen - pc.pos;
+            c = converted_ref_base(c, a.cfg.seed, pc.rid, pc.piece_in_read, f);
+        }
+        oi = base_idx(c);
+        if (info & EMIT_F_MIS) oi = (oi + 1u + __umulhi(p, 3u)) & 3u;
+    } else {
+        oi = (info & 3u) ? (w & 3u) : base_idx((info >> 8) & 0xffu);
+    }
+    uint32_t out = (pc.tbl >> (8u * oi)) & 0xffu;
+    if (FASTQ) {
+        const uint32_t* cdf = a.qcdf + ((info >> 16) / (QLUT_SIZE * 4u)) * NS_QUAL_SLOTS;
+        out |= qual_char_exact(cdf, w) << 8;
+    }
+    return out;
+}
+
+template <bool FASTQ>
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_constant__ EmitArgs a) {
+    extern __shared__ uint4 smem4[];
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem4);                          // FASTQ only
+    uint8_t* cvt = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* ring = reinterpret_cast<uint4*>(cvt + 256) + warp * EMIT_RING;
+    if (FASTQ)
+        for (int i = threadIdx.x; i < NS_N_QUAL_STATES * QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[i];
+    {   // case_convert classification: base index 0..3 (A C T G), 4 = needs the IUPAC path
+        uint32_t c = threadIdx.x;
+        uint32_t u = (c - 'a' < 26u) ? c - 32u : c;
+        cvt[c] = (uint8_t)(acgt_fast(u) ? base_idx(u) : 4u);
+    }
+    __syncthreads();
+    const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
+    const uint32_t lane_lt = (1u << lane) - 1u;
 
     for (;;) {
         uint32_t piece = 0;
@@ -70,156 +135,189 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(const __grid_cons
         const NsPieceMeta pm = a.pieces[piece];
         if (pm.out_len == 0) continue;
         const NsReadMeta rm = a.reads[pm.read_slot];
-        const uint64_t rid = a.first_id + pm.read_slot;
         const bool rev = rm.reversed != 0;
-        const uint32_t out_len = pm.out_len, n_ops = pm.n_ops, ref_len = pm.ref_len;
-        const uint32_t A = rev ? rm.seq_len - pm.out_rel - out_len : pm.out_rel;   // piece start in read coordinates
+        const uint32_t n_ops = pm.n_ops, ref_len = pm.ref_len;
+        const uint32_t A = rev ? rm.seq_len - pm.out_rel - pm.out_len : pm.out_rel;    // piece start in read coordinates
+        const uint32_t pad = A & 15u, P0 = A - pad;          // x = read coordinate - P0: chunks are x/16
+        const uint32_t x_end = pad + pm.out_len;
         const uint64_t cstart = a.ref.chrom_off[pm.chrom];
-        const uint64_t clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
-        const uint8_t* __restrict__ cbase = a.ref.bases + cstart;
+        EmitPiece pc;
+        pc.cbase = a.ref.bases + cstart;
+        pc.pos = pm.pos;
+        pc.clen = (uint32_t)(a.ref.chrom_off[pm.chrom + 1] - cstart);
+        pc.rev = rev;
+        {
+            const uint32_t t = a.cfg.uracil ? 0x47554341u : 0x47544341u;             // "ACTG" / "ACUG"
+            pc.tbl = rev ? __byte_perm(t, 0, 0x1032) : t;                            // complement: A<->T, C<->G
+        }
+        pc.piece_in_read = piece - rm.piece_first;
+        pc.rid = a.first_id + pm.read_slot;
+        const uint8_t* __restrict__ cbase = pc.cbase;
+        const uint32_t clen = pc.clen, tbl = pc.tbl;
+        const bool wraps = (uint64_t)pm.pos + ref_len > clen;                        // circular wrap (:1756-1760)
+        const uint32_t dir = rev ? 0xffffffffu : 1u, wrap_fix = rev ? clen : 0u - clen;
         const uint32_t* __restrict__ ops = a.ops + pm.op_off;
-        uint8_t* seq_out = a.seq + rm.seq_off;
-        uint8_t* qual_out = FASTQ ? a.qual + rm.seq_off : nullptr;
+        uint8_t* seq_out = a.seq + rm.seq_off + P0;
+        uint8_t* qual_out = FASTQ ? a.qual + rm.seq_off + P0 : nullptr;
         const bool unmapped = pm.kind != NS_PIECE_SEGMENT;
+        const uint32_t id_lo = (uint32_t)pc.rid, id_hi = (uint32_t)(pc.rid >> 32);
+        const uint32_t info_pad = emit_op_info(NS_OP_HT << 28, unmapped);
 
-        uint32_t t_loaded = 0, t_ret = 0, out_loaded = 0, ref_loaded = 0, prog = 0;
-        while (prog < out_len) {
+        uint32_t t_loaded = 0, w_loaded = 0, w_ret = 0, out_loaded = pad, ref_loaded = 0, prog = 0;
+        bool closed = false;
+        if (pad) {
+            if (lane == 0) ring[0] = make_uint4(0u, 0u, pad, info_pad);
+            w_loaded = 1;
+        }
+        while (prog < x_end) {
             // ---- 1. stream ops into the ring until the next 32 chunks are covered or the ring is full
-            const uint32_t first_chunk = (A + prog) >> 4;
-            uint32_t target = (first_chunk + 32) * 16 - A;
-            if (target > out_len) target = out_len;
-            while (out_loaded < target && t_loaded < n_ops && (t_loaded - t_ret) + 32 <= EMIT_RING) {
-                uint32_t t = t_loaded + lane;
+            uint32_t target = prog + 512u < x_end ? prog + 512u : x_end;
+            while (out_loaded < target && t_loaded < n_ops && (w_loaded - w_ret) + 33u <= EMIT_RING) {
+                const uint32_t t = t_loaded + lane;
                 uint32_t op = 0;
                 if (t < n_ops) op = __ldg(&ops[rev ? n_ops - 1 - t : t]);
-                uint32_t ty = op >> 28, len = op_len(op);
-                uint32_t o = (ty == NS_OP_DEL) ? 0u : len;
-                uint32_t r = (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
-                uint32_t so = warp_incl_scan(o, lane), sr = warp_incl_scan(r, lane);
-                if (t < n_ops) {
-                    ring_out[t % EMIT_RING] = out_loaded + so - o;
-                    ring_ref[t % EMIT_RING] = ref_loaded + sr - r;
-                    ring_op[t % EMIT_RING] = op;
+                const uint32_t ty = op >> 28, len = op_len(op);
+                const uint32_t o = (ty == NS_OP_DEL) ? 0u : len;
+                const uint32_t r = (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
+                const uint32_t so = warp_incl_scan(o, lane), sr = warp_incl_scan(r, lane);
+                const bool keep = o != 0u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const uint32_t rstart = ref_loaded + sr - r;                      // reference bases consumed before this op
+                    uint32_t ab = pm.pos + (rev ? ref_len - 1u - rstart : rstart);    // first base in walking order
+                    if (wraps && ab >= clen) ab -= clen;
+                    ring[(w_loaded + __popc(bal & lane_lt)) & (EMIT_RING - 1)] =
+                        make_uint4(out_loaded + so - o, ab, len, emit_op_info(op, unmapped));
                 }
                 out_loaded += __shfl_sync(0xffffffffu, so, 31);
                 ref_loaded += __shfl_sync(0xffffffffu, sr, 31);
+                w_loaded += __popc(bal);
                 t_loaded += (n_ops - t_loaded < 32u) ? n_ops - t_loaded : 32u;
+            }
+            if (!closed && (t_loaded == n_ops || out_loaded >= x_end)) {
+                // sentinel: walking past the end of the piece stays inside the ring (ops left over are deletions)
+                if (lane == 0) ring[w_loaded & (EMIT_RING - 1)] = make_uint4(out_loaded, 0u, 0x7fffffffu, info_pad);
+                ++w_loaded;
+                closed = true;
             }
             __syncwarp();
             // ---- 2. what can be produced now: whole chunks up to the loaded frontier (or the piece end)
             uint32_t lim = out_loaded < target ? out_loaded : target;
-            if (lim < out_len) lim = ((A + lim) & ~15u) > A + prog ? ((A + lim) & ~15u) - A : prog;
-            // (ring holds >= 64 ops beyond t_ret, i.e. >= 1 whole chunk, so lim > prog whenever ops remain)
+            if (lim < x_end) lim &= ~15u;
+            // (the ring holds >= 200 entries of >= 1 base beyond w_ret, so lim > prog whenever ops remain)
             // ---- 3. one 16-byte chunk per lane
-            const uint32_t chunk = first_chunk + lane;
-            uint32_t cs = chunk * 16;                                  // chunk start, read coordinates
-            uint32_t lo = cs > A + prog ? cs : A + prog;
-            uint32_t hi = cs + 16 < A + lim ? cs + 16 : A + lim;
-            if (lo < hi) {
-                const uint32_t plo = lo - A;                           // piece coordinates
-                // upper_bound over ring_out in [t_ret, t_loaded): last op whose output start <= plo
-                uint32_t l = t_ret, h = t_loaded;
+            const uint32_t cs = prog + 16u * lane;
+            if (cs < lim) {
+                uint32_t l = w_ret, h = w_loaded;     // last entry whose output start <= cs
                 while (h - l > 1) {
                     uint32_t mid = (l + h) >> 1;
-                    if (ring_out[mid % EMIT_RING] <= plo) l = mid; else h = mid;
+                    if (ring[mid & (EMIT_RING - 1)].x <= cs) l = mid; else h = mid;
                 }
                 uint32_t k = l;
-                uint32_t op = ring_op[k % EMIT_RING];
-                uint32_t ty = op >> 28;
-                uint32_t within = plo - ring_out[k % EMIT_RING];
-                uint32_t rem = op_len(op) - within;
-                uint32_t rpos = ring_ref[k % EMIT_RING] + ((ty < 2u) ? within : 0u);
-
-                // ---- all randomness of the chunk up front, position-indexed, identical in every lane's control flow:
-                //      base i uses byte i of `bw` (substitution / inserted base / IUPAC member) and bits [24i, 24i+24)
-                //      of `qw` (its quality value).
-                const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
-                const uint32_t id_lo = (uint32_t)rid, id_hi = (uint32_t)(rid >> 32);
-                const uint4 bw4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, a.kind, chunk), 0u), key);
-                const uint32_t bw[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
-                uint32_t qw[13];
+                uint32_t rem, rabs, info;
+                {
+                    const uint4 e = ring[k & (EMIT_RING - 1)];
+                    const uint32_t within = cs - e.x;
+                    rem = e.z - within;
+                    info = e.w;
+                    rabs = rev ? e.y - within : e.y + within;
+                    if (wraps && rabs >= clen) rabs += wrap_fix;
+                }
+                // ---- all randomness of the chunk up front, position-indexed: base i owns one 32-bit word (FASTQ: low
+                //      byte = base choice, high 24 bits = quality uniform) or one byte (FASTA)
+                const uint32_t chunk = (P0 + cs) >> 4;
+                uint32_t W[FASTQ ? 16 : 4];
                 if (FASTQ) {
                     const uint32_t sw = stream_word(ST_EMIT_Q, a.kind, chunk);
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
-                        qw[4 * j] = t.x; qw[4 * j + 1] = t.y; qw[4 * j + 2] = t.z; qw[4 * j + 3] = t.w;
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
+                        W[4 * j] = t.x; W[4 * j + 1] = t.y; W[4 * j + 2] = t.z; W[4 * j + 3] = t.w;
                     }
-                    qw[12] = 0;
+                } else {
+                    const uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, a.kind, chunk), 0u), key);
+                    W[0] = t.x; W[1] = t.y; W[2] = t.z; W[3] = t.w;
                 }
-                const uint32_t flip = rev ? 2u : 0u;
-
-                uint32_t sb[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-                const uint32_t i0 = lo - cs, i1 = hi - cs;
+                uint32_t sb[4], sq[4] = {0, 0, 0, 0};
+                uint32_t bad = 0, slow = 0, sel = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if ((uint32_t)i >= i0 && (uint32_t)i < i1) {
-                        while (rem == 0) {
-                            ++k;
-                            op = ring_op[k % EMIT_RING];
-                            ty = op >> 28;
-                            rem = (ty == NS_OP_DEL) ? 0u : op_len(op);
-                            rpos = ring_ref[k % EMIT_RING];
-                        }
-                        --rem;
-                        const uint32_t r8 = (bw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                        const uint32_t r8n = (bw[((i + 1) & 15) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
-                        const uint32_t rr = (r8 == 255u) ? r8n : r8;           // 0..254 -> exactly uniform mod 3
-                        const uint32_t t3 = rr - 3u * ((rr * 171u) >> 9);
-                        uint32_t oi = r8 & 3u;                                 // random.choice(BASES) / np.random.choice
-                        if (ty < 2u) {                                         // COPY or MIS: reads the reference
-                            uint32_t f = rev ? ref_len - 1 - rpos : rpos;
-                            uint64_t ab = (uint64_t)pm.pos + f;
-                            if (ab >= clen) ab -= clen;                        // circular wrap (:1756-1760)
-                            uint32_t c = __ldg(&cbase[ab]);
-                            ++rpos;
-                            if (c - 'a' < 26u) c -= 32;
-                            if (!acgt_fast(c)) c = converted_ref_base(c, a.cfg.seed, rid, piece - rm.piece_first, f);
-                            oi = base_idx(c);
-                            if (ty == NS_OP_MIS) oi = (oi + 1u + t3) & 3u;     // one of the three other bases
-                        } else if (ty == NS_OP_LIT) {
-                            oi = (op >> 26) & 3u;                              // literal base of a rewritten homopolymer
-                        }
-                        sb[i >> 2] |= emit_char(oi ^ flip, a.cfg.uracil) << (8 * (i & 3));
-                        if (FASTQ) {
-                            // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3); gap/unaligned -> unmapped(4)
-                            const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
-                            const int bit = 24 * i;
-                            const uint32_t u24 = __funnelshift_r(qw[bit >> 5], qw[(bit >> 5) + 1], bit & 31) & 0xffffffu;
-                            const uint32_t e = lut[qs * QLUT_SIZE + (u24 >> QLUT_FRAC_BITS)];
-                            uint32_t q = e & 0xffu;
-                            if (e >> 31) {                                     // bucket spans >2 quality values: exact scan
-                                const uint32_t* cdf = a.qcdf + qs * NS_QUAL_SLOTS;
-                                while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf[q])) ++q;
-                            } else {
-                                q += ((u24 & ((1u << QLUT_FRAC_BITS) - 1u)) >= ((e >> 8) & 0x3fffu)) ? 1u : 0u;
-                            }
-                            sq[i >> 2] |= (q + 33u) << (8 * (i & 3));
+                    if (rem == 0) {                                    // next entry (never empty, never a deletion)
+                        ++k;
+                        const uint4 e = ring[k & (EMIT_RING - 1)];
+                        rem = e.z;
+                        rabs = e.y;
+                        info = e.w;
+                    }
+                    --rem;
+                    // base i's random bits: rb low 2 bits = random.choice(BASES); rp = 16+ uniform bits, MSB-aligned, whose
+                    // product with 3 picks one of the three other bases (bias 2^-16)
+                    const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
+                    const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
+                                              : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2],
+                                                            ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
+                    uint32_t c = (info >> 8) & 0xffu;
+                    if (info & EMIT_F_REF) {
+                        c = __ldg(cbase + rabs);
+                        rabs += dir;
+                        if (wraps && rabs >= clen) rabs += wrap_fix;
+                    }
+                    const uint32_t code = cvt[c];
+                    bad |= code;
+                    uint32_t v = code | (rb & info & 3u);
+                    if (info & EMIT_F_MIS) v += 1u + __umulhi(rp, 3u);
+                    sel += v << (4 * (i & 3));
+                    if (FASTQ) {
+                        const uint32_t w = W[i];
+                        const uint32_t e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + (info >> 16) +
+                                                                              ((w >> 19) & 0x1ffcu));
+                        slow |= e;
+                        sq[i >> 2] |= qual_char_fast(e, w) << (8 * (i & 3));
+                    }
+                    if ((i & 3) == 3) {
+                        sb[i >> 2] = __byte_perm(tbl, 0, sel & 0x3333u);
+                        sel = 0;
+                    }
+                }
+                // ---- rare exact paths, one base at a time
+                if ((bad & 4u) || (FASTQ && (slow & 0x80u))) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool need = (bad & 4u) || (FASTQ && ((sq[i >> 2] >> (8 * (i & 3))) & 0x80u));
+                        if (need) {
+                            const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
+                            const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
+                                                      : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2],
+                                                                    ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
+                            const uint32_t f = emit_fix_base<FASTQ>(a, pc, ring, w_ret, w_loaded, cs + i, rb, rp);
+                            const uint32_t m = 0xffu << (8 * (i & 3));
+                            sb[i >> 2] = (sb[i >> 2] & ~m) | ((f & 0xffu) << (8 * (i & 3)));
+                            if (FASTQ) sq[i >> 2] = (sq[i >> 2] & ~m) | ((f >> 8) << (8 * (i & 3)));
                         }
                     }
                 }
-                if (i0 == 0 && i1 == 16) {
+                if (cs >= pad && cs + 16u <= x_end) {
                     *reinterpret_cast<uint4*>(seq_out + cs) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
                     if (FASTQ) *reinterpret_cast<uint4*>(qual_out + cs) = make_uint4(sq[0], sq[1], sq[2], sq[3]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if ((uint32_t)i >= i0 && (uint32_t)i < i1) {
+                        if (cs + i >= pad && cs + i < x_end) {
                             seq_out[cs + i] = (uint8_t)(sb[i >> 2] >> (8 * (i & 3)));
                             if (FASTQ) qual_out[cs + i] = (uint8_t)(sq[i >> 2] >> (8 * (i & 3)));
                         }
                     }
                 }
             }
-            // ---- 4. retire ops that end before the new frontier
+            // ---- 4. retire entries that end before the new frontier
             prog = lim;
             {
-                uint32_t l = t_ret, h = t_loaded;
+                uint32_t l = w_ret, h = w_loaded;
                 while (h - l > 1) {
                     uint32_t mid = (l + h) >> 1;
-                    if (ring_out[mid % EMIT_RING] <= prog) l = mid; else h = mid;
+                    if (ring[mid & (EMIT_RING - 1)].x <= prog) l = mid; else h = mid;
                 }
-                t_ret = l;
+                w_ret = l;
             }
             __syncwarp();
         }

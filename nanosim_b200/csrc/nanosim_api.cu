@@ -230,7 +230,7 @@ cudaError_t upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, s);
 }
 
-// Bucket table over 24-bit quality uniforms: entry = q_lo | threshold << 8 | multi << 31.
+// Bucket table over 24-bit quality uniforms; entry layout in device_common.cuh (qual_char_fast).
 // A draw u24 falls into bucket u24 >> QLUT_FRAC_BITS; when the bucket holds at most one cdf boundary the quality is
 // q_lo + (frac >= threshold); buckets with two or more boundaries (rare tail qualities) are flagged for an exact scan.
 void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut, std::vector<uint32_t>& cdf24) {
@@ -253,9 +253,9 @@ void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vect
             uint32_t lo = b << shift, hi = lo + ((1u << shift) - 1u);
             uint32_t qlo = qof(lo), qhi = qof(hi);
             uint32_t e;
-            if (qhi == qlo) e = qlo | ((1u << shift) << 8);
-            else if (qhi == qlo + 1) e = qlo | ((c[qlo] - lo) << 8);
-            else e = qlo | 0x80000000u;
+            if (qhi == qlo) e = (qlo + 32u);                                   // threshold 0: always +1 (qlo >= 1)
+            else if (qhi == qlo + 1) e = (qlo + 33u) | ((c[qlo] - lo) << 19);   // 1 <= c[qlo] - lo < 2^13
+            else e = 0x80u;
             lut[(size_t)s * QLUT_SIZE + b] = e;
         }
     }
@@ -999,7 +999,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ea.qcdf = ctx->qcdf.as<uint32_t>();
     ea.counter = ctx->counter.as<uint32_t>();
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-    const size_t ring_bytes = (size_t)EMIT_WARPS * 3 * EMIT_RING * 4;
+    const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 256;
     if (ctx->hcfg.fastq) {
         size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
         CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -148,10 +148,9 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                         // one 32-bit word per base: Philox-7 block o>>2, word o&3 of the read's unaligned base stream
                         const uint4 w4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, NS_KIND_UNALIGNED, 0), o >> 2), key);
                         const uint32_t w = (o & 2u) ? ((o & 1u) ? w4.w : w4.z) : ((o & 1u) ? w4.y : w4.x);
-                        const uint32_t r8 = w >> 24;
-                        uint32_t rr = r8 == 255u ? (w & 0xffu) : r8;
-                        rr = rr == 255u ? 0u : rr;
-                        const uint32_t t3 = rr % 3u;
+                        const uint32_t wn = (o & 2u) ? ((o & 1u) ? w4.x : w4.w) : ((o & 1u) ? w4.z : w4.y);   // next word of the block
+                        const uint32_t r8 = w & 0xffu;                       // low byte: base choice; high 24 bits: quality
+                        const uint32_t t3 = __umulhi(__byte_perm(w, wn, 0x0444), 3u);
                         uint32_t oi = r8 & 3u;
                         int roff = -1;
                         bool sub = false;
@@ -178,16 +177,10 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                         const uint32_t dst = rev ? rm.seq_len - 1 - o : o;
                         sq[dst] = (uint8_t)emit_char(rev ? oi ^ 2u : oi, cfg.uracil);
                         if (FASTQ) {
-                            const uint32_t u24 = w & 0xffffffu;
-                            const uint32_t e = lut[u24 >> QLUT_FRAC_BITS];
-                            uint32_t q = e & 0xffu;
-                            if (e >> 31) {
-                                const uint32_t* cdf = a.qcdf + 4 * NS_QUAL_SLOTS;
-                                while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf[q])) ++q;
-                            } else {
-                                q += ((u24 & ((1u << QLUT_FRAC_BITS) - 1u)) >= ((e >> 8) & 0x3fffu)) ? 1u : 0u;
-                            }
-                            qq[dst] = (uint8_t)(q + 33u);
+                            const uint32_t e = lut[w >> (32 - QLUT_BITS)];
+                            uint32_t q = qual_char_fast(e, w);
+                            if (q & 0x80u) q = qual_char_exact(a.qcdf + 4 * NS_QUAL_SLOTS, w);
+                            qq[dst] = (uint8_t)q;
                         }
                     }
                     __syncwarp();
