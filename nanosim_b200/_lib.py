@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnanosim_b200.so")
+LIB_PATH = os.environ.get("NANOSIM_B200_LIB") or os.path.join(_HERE, "libnanosim_b200.so")     # env: A/B builds of the kernels
 
 NS_MAX_SEGMENTS = 16
 NS_N_ERR_STATES = 7

@@ -172,16 +172,18 @@ __device__ __forceinline__ bool acgt_fast(uint32_t c) {
 // Base-quality bucket table over 24-bit uniforms (built on the host, nanosim_api.cu:build_qlut).  A random word w carries
 // the uniform in its high 24 bits; bucket = w >> 21.  Entry: [7:0] ASCII character of the bucket's lower value (minus one
 // when the bucket holds a single value), [31:19] 13-bit threshold on the fraction: char += (fraction >= threshold).
-// A bucket with more than two values has entry 0x80 (an impossible character) and is resolved by qual_char_exact.
+// A bucket with more than two values has entry 0x80 | lowest value << 8 (an impossible character) and is resolved by
+// qual_char_exact.
 #define QLUT_BITS 11
 #define QLUT_SIZE (1 << QLUT_BITS)
 #define QLUT_FRAC_BITS (24 - QLUT_BITS)
 __device__ __forceinline__ uint32_t qual_char_fast(uint32_t e, uint32_t w) {
     return (e & 0xffu) + (((w << QLUT_BITS) >= (e & 0xfff80000u)) ? 1u : 0u);
 }
-__device__ __forceinline__ uint32_t qual_char_exact(const uint32_t* cdf24, uint32_t w) {
+// exact scan for a flagged bucket; bits [14:8] of its entry hold the bucket's lowest quality value
+__device__ __forceinline__ uint32_t qual_char_exact(const uint32_t* cdf24, uint32_t w, uint32_t e) {
     const uint32_t u24 = w >> 8;
-    uint32_t q = 0;
+    uint32_t q = (e >> 8) & 0x7fu;
     while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf24[q])) ++q;
     return q + 33u;
 }

@@ -22,6 +22,9 @@
 
 #define EMIT_WARPS 8
 #define EMIT_RING 256
+#ifndef EMIT_MIN_BLOCKS
+#define EMIT_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims for
+#endif
 
 #define EMIT_F_REF 4u        // info bit: the base is read from the reference (COPY, MIS)
 #define EMIT_F_MIS 8u        // info bit: ... and substituted by one of the three other bases
@@ -40,6 +43,7 @@ struct EmitArgs {
     const uint32_t* qlut;        // [5][QLUT_SIZE] packed bucket table (built on the host from qual_cdf)
     const uint32_t* qcdf;        // [5][94], 24-bit fixed point
     uint32_t* counter;
+    const uint32_t* order;       // piece processing order (longest first) or null
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -103,14 +107,64 @@ __device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiec
     }
     uint32_t out = (pc.tbl >> (8u * oi)) & 0xffu;
     if (FASTQ) {
-        const uint32_t* cdf = a.qcdf + ((info >> 16) / (QLUT_SIZE * 4u)) * NS_QUAL_SLOTS;
-        out |= qual_char_exact(cdf, w) << 8;
+        const uint32_t qs = (info >> 16) / (QLUT_SIZE * 4u);
+        const uint32_t qe = __ldg(&a.qlut[qs * QLUT_SIZE + (w >> (32 - QLUT_BITS))]);
+        out |= ((qe & 0x80u) ? qual_char_exact(a.qcdf + qs * NS_QUAL_SLOTS, w, qe) : qual_char_fast(qe, w)) << 8;
     }
     return out;
 }
 
+// The branch-free 16-base walk of one chunk (see the header comment).  WRAPS: the piece crosses the origin of a circular
+// chromosome (:1756-1760).
+template <bool FASTQ, bool WRAPS>
+__device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* lut, const uint8_t* cvt,
+                                             const uint8_t* __restrict__ cbase, const uint32_t (&W)[FASTQ ? 16 : 4], uint32_t& k,
+                                             uint32_t& rem, uint32_t& rabs, uint32_t& info, uint32_t dir, uint32_t clen,
+                                             uint32_t wrap_fix, uint32_t tbl, uint32_t (&sb)[4], uint32_t (&sq)[4], uint32_t& bad,
+                                             uint32_t& slow) {
+    uint32_t sel = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (rem == 0) {                                    // next entry (never empty, never a deletion)
+            ++k;
+            const uint4 e = ring[k & (EMIT_RING - 1)];
+            rem = e.z;
+            rabs = e.y;
+            info = e.w;
+        }
+        --rem;
+        // base i's random bits: rb low 2 bits = random.choice(BASES); rp = 16+ uniform bits, MSB-aligned, whose
+        // product with 3 picks one of the three other bases (bias 2^-16)
+        const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
+        const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
+                                  : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2], ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
+        uint32_t c = (info >> 8) & 0xffu;
+        if (info & EMIT_F_REF) {
+            c = __ldg(cbase + rabs);
+            rabs += dir;
+            if (WRAPS && rabs >= clen) rabs += wrap_fix;
+        }
+        const uint32_t code = cvt[c];
+        bad |= code;
+        uint32_t v = code | (rb & info & 3u);
+        if (info & EMIT_F_MIS) v += 1u + __umulhi(rp, 3u);
+        sel += v << (4 * (i & 3));
+        if (FASTQ) {
+            const uint32_t w = W[i];
+            const uint32_t e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + (info >> 16) +
+                                                                  ((w >> 19) & 0x1ffcu));
+            slow |= e;
+            sq[i >> 2] |= qual_char_fast(e, w) << (8 * (i & 3));
+        }
+        if ((i & 3) == 3) {
+            sb[i >> 2] = __byte_perm(tbl, 0, sel & 0x3333u);
+            sel = 0;
+        }
+    }
+}
+
 template <bool FASTQ>
-__global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_constant__ EmitArgs a) {
+__global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ EmitArgs a) {
     extern __shared__ uint4 smem4[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem4);                          // FASTQ only
     uint8_t* cvt = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));
@@ -132,6 +186,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_c
         if (lane == 0) piece = atomicAdd(a.counter, 1u);
         piece = __shfl_sync(0xffffffffu, piece, 0);
         if (piece >= a.n_pieces) break;
+        if (a.order) piece = __ldg(&a.order[piece]);
         const NsPieceMeta pm = a.pieces[piece];
         if (pm.out_len == 0) continue;
         const NsReadMeta rm = a.reads[pm.read_slot];
@@ -207,13 +262,14 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_c
             // (the ring holds >= 200 entries of >= 1 base beyond w_ret, so lim > prog whenever ops remain)
             // ---- 3. one 16-byte chunk per lane
             const uint32_t cs = prog + 16u * lane;
+            uint32_t k = w_ret;
             if (cs < lim) {
                 uint32_t l = w_ret, h = w_loaded;     // last entry whose output start <= cs
                 while (h - l > 1) {
                     uint32_t mid = (l + h) >> 1;
                     if (ring[mid & (EMIT_RING - 1)].x <= cs) l = mid; else h = mid;
                 }
-                uint32_t k = l;
+                k = l;
                 uint32_t rem, rabs, info;
                 {
                     const uint4 e = ring[k & (EMIT_RING - 1)];
@@ -239,46 +295,9 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_c
                     W[0] = t.x; W[1] = t.y; W[2] = t.z; W[3] = t.w;
                 }
                 uint32_t sb[4], sq[4] = {0, 0, 0, 0};
-                uint32_t bad = 0, slow = 0, sel = 0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (rem == 0) {                                    // next entry (never empty, never a deletion)
-                        ++k;
-                        const uint4 e = ring[k & (EMIT_RING - 1)];
-                        rem = e.z;
-                        rabs = e.y;
-                        info = e.w;
-                    }
-                    --rem;
-                    // base i's random bits: rb low 2 bits = random.choice(BASES); rp = 16+ uniform bits, MSB-aligned, whose
-                    // product with 3 picks one of the three other bases (bias 2^-16)
-                    const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
-                    const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
-                                              : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2],
-                                                            ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
-                    uint32_t c = (info >> 8) & 0xffu;
-                    if (info & EMIT_F_REF) {
-                        c = __ldg(cbase + rabs);
-                        rabs += dir;
-                        if (wraps && rabs >= clen) rabs += wrap_fix;
-                    }
-                    const uint32_t code = cvt[c];
-                    bad |= code;
-                    uint32_t v = code | (rb & info & 3u);
-                    if (info & EMIT_F_MIS) v += 1u + __umulhi(rp, 3u);
-                    sel += v << (4 * (i & 3));
-                    if (FASTQ) {
-                        const uint32_t w = W[i];
-                        const uint32_t e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + (info >> 16) +
-                                                                              ((w >> 19) & 0x1ffcu));
-                        slow |= e;
-                        sq[i >> 2] |= qual_char_fast(e, w) << (8 * (i & 3));
-                    }
-                    if ((i & 3) == 3) {
-                        sb[i >> 2] = __byte_perm(tbl, 0, sel & 0x3333u);
-                        sel = 0;
-                    }
-                }
+                uint32_t bad = 0, slow = 0;
+                if (wraps) emit_chunk16<FASTQ, true>(ring, lut, cvt, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
+                else emit_chunk16<FASTQ, false>(ring, lut, cvt, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
                 // ---- rare exact paths, one base at a time
                 if ((bad & 4u) || (FASTQ && (slow & 0x80u))) {
 #pragma unroll
@@ -309,16 +328,13 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 2) emit_kernel(const __grid_c
                     }
                 }
             }
-            // ---- 4. retire entries that end before the new frontier
-            prog = lim;
+            // ---- 4. retire: the entry the last active lane stopped in starts before the new frontier
             {
-                uint32_t l = w_ret, h = w_loaded;
-                while (h - l > 1) {
-                    uint32_t mid = (l + h) >> 1;
-                    if (ring[mid & (EMIT_RING - 1)].x <= prog) l = mid; else h = mid;
-                }
-                w_ret = l;
+                const uint32_t n_act = (lim - prog + 15u) >> 4;
+                const uint32_t k_last = __shfl_sync(0xffffffffu, k, n_act ? n_act - 1u : 0u);
+                if (n_act) w_ret = k_last;
             }
+            prog = lim;
             __syncwarp();
         }
     }

@@ -255,7 +255,7 @@ void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vect
             uint32_t e;
             if (qhi == qlo) e = (qlo + 32u);                                   // threshold 0: always +1 (qlo >= 1)
             else if (qhi == qlo + 1) e = (qlo + 33u) | ((c[qlo] - lo) << 19);   // 1 <= c[qlo] - lo < 2^13
-            else e = 0x80u;
+            else e = 0x80u | (qlo << 8);
             lut[(size_t)s * QLUT_SIZE + b] = e;
         }
     }
@@ -695,89 +695,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     }
     const uint32_t n = n_reads;
     uint32_t launches = 0;
-    if (kind == NS_KIND_UNALIGNED && !(ctx->hcfg.flags & NS_FLAG_UNALIGNED_SCRIPTS)) {
-        // ---- warp-per-read fast path (uread_kernel.cuh): count pass, scan, write pass; no edit scripts
-        const unsigned tbu = 256, gbu = (n + tbu - 1) / tbu;
-        CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
-        CK(ctx->pieces.ensure((size_t)n * sizeof(NsPieceMeta)));
-        CK(ctx->counter.ensure(64));
-        CK(ctx->totals.ensure(8 * sizeof(uint64_t)));
-        CK(ctx->scan_in.ensure((size_t)n * sizeof(uint64_t)));
-        CK(ctx->scan_out.ensure((size_t)n * sizeof(uint64_t)));
-        CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * sizeof(uint64_t), st));
-        CK(cudaEventRecord(ctx->ev[0], st));
-        UreadArgs ua;
-        ua.m = ctx->dmodel;
-        ua.ref = ctx->dref;
-        ua.cfg = ctx->dcfg;
-        ua.first_id = first_read_id;
-        ua.n_reads = n;
-        ua.reads = ctx->reads.as<NsReadMeta>();
-        ua.pieces = ctx->pieces.as<NsPieceMeta>();
-        ua.seq = nullptr;
-        ua.qual = nullptr;
-        ua.qlut = ctx->qlut.as<uint32_t>();
-        ua.qcdf = ctx->qcdf.as<uint32_t>();
-        ua.counter = ctx->counter.as<uint32_t>();
-        const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
-        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-        CK(cudaEventRecord(ctx->ev[1], st));
-        uread_kernel<false, false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[2], st));
-        gather_read_bytes<<<gbu, tbu, 0, st>>>(ua.reads, n, ctx->scan_in.as<uint64_t>());
-        {
-            int rc = exclusive_scan_u64(ctx, ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n);
-            if (rc) return rc;
-        }
-        scatter_read_off<<<gbu, tbu, 0, st>>>(ua.reads, n, ctx->scan_out.as<uint64_t>());
-        last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n, ctx->totals.as<uint64_t>(), 2);
-        sum_bases<<<std::min<unsigned>(gbu, 1024u), tbu, 0, st>>>(ua.reads, n, (unsigned long long*)(ctx->totals.as<uint64_t>() + 3));
-        publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
-        CK(cudaStreamSynchronize(st));
-        const uint64_t seq_bytes_u = ctx->h_totals[2], total_bases_u = ctx->h_totals[3];
-        CK(ctx->ops.ensure(64));
-        CK(ctx->seq.ensure((size_t)seq_bytes_u + 16));
-        if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes_u + 16));
-        CK(cudaEventRecord(ctx->ev[3], st));
-        CK(cudaEventRecord(ctx->ev[4], st));
-        ua.seq = ctx->seq.as<uint8_t>();
-        ua.qual = ctx->qual.as<uint8_t>();
-        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-        if (ctx->hcfg.fastq) uread_kernel<true, true><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
-        else uread_kernel<true, false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[5], st));
-        CK(cudaStreamSynchronize(st));
-        NsBatchInfo& bu = ctx->last;
-        bu.seq_bytes = seq_bytes_u;
-        bu.n_ops = 0;
-        bu.total_bases = total_bases_u;
-        bu.n_reads = n;
-        bu.n_pieces = n;
-        bu.n_launches = 2 + 6;
-        float msu = 0;
-        cudaEventElapsedTime(&msu, ctx->ev[0], ctx->ev[1]);
-        bu.ms_setup = msu;
-        cudaEventElapsedTime(&msu, ctx->ev[1], ctx->ev[2]);
-        bu.ms_plan = msu;
-        cudaEventElapsedTime(&msu, ctx->ev[2], ctx->ev[3]);
-        bu.ms_scan = msu;
-        bu.ms_script = 0.f;
-        cudaEventElapsedTime(&msu, ctx->ev[4], ctx->ev[5]);
-        bu.ms_emit = msu;
-        cudaEventElapsedTime(&msu, ctx->ev[0], ctx->ev[5]);
-        bu.ms_total = msu;
-        cudaEventElapsedTime(&msu, g_base[ctx->device], ctx->ev[0]);
-        bu.t_begin_ms = msu;
-        cudaEventElapsedTime(&msu, g_base[ctx->device], ctx->ev[5]);
-        bu.t_end_ms = msu;
-        ctx->last_kind = kind;
-        ctx->last_first_id = first_read_id;
-        ctx->have_batch = true;
-        if (info) *info = bu;
-        return NS_OK;
-    }
+    const bool fast_unaligned = kind == NS_KIND_UNALIGNED && !(ctx->hcfg.flags & NS_FLAG_UNALIGNED_SCRIPTS);
     const unsigned tb = 256, gb = (n + tb - 1) / tb;
     CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
     CK(ctx->counter.ensure(64));
@@ -821,7 +739,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     uint32_t* keys_out = keys_in + n;
     uint32_t* vals_in = ctx->sort_vals.as<uint32_t>();
     uint32_t* vals_out = vals_in + n;
-    const bool exact_only = (kind == NS_KIND_UNALIGNED);
+    const bool exact_only = (kind == NS_KIND_UNALIGNED) && !fast_unaligned;
     lengths_kernel<<<gb, tb, 0, st>>>(ctx->dmodel, ctx->dcfg, (uint32_t)kind, first_read_id, n, d_nseg, d_pfirst,
                                       ctx->pieces.as<NsPieceMeta>(), 1.0f / std::max(1.0f, ctx->hmodel.mean_ref_per_event),
                                       exact_only ? 1u : 0u, ctx->scan_in.as<uint64_t>(), keys_in, vals_in);
@@ -841,7 +759,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     }
     publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
     CK(cudaStreamSynchronize(st));
-    const uint64_t primary_ops = ctx->h_totals[4];
+    // primary script area = the capped slots (+ a bump pool for re-drawn unaligned reads, uread_kernel.cuh)
+    const uint64_t slot_ops = ctx->h_totals[4];
+    const uint64_t pool_ops = fast_unaligned ? slot_ops / 16 + (1u << 20) : 0;
+    const uint64_t primary_ops = slot_ops + pool_ops;
     CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
     uint32_t batch_reversed = 0;
     if (ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) {
@@ -885,8 +806,26 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     pa.batch_reversed = batch_reversed;
     const unsigned plan_tb = 128;
     unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * 16u);
+    // unaligned reads without NS_FLAG_UNALIGNED_SCRIPTS: warp-per-read evaluation (uread_kernel.cuh), same outputs
+    UreadArgs ua;
+    ua.m = ctx->dmodel;
+    ua.ref = ctx->dref;
+    ua.cfg = ctx->dcfg;
+    ua.first_id = first_read_id;
+    ua.n_reads = n;
+    ua.reads = pa.reads;
+    ua.pieces = pa.pieces;
+    ua.ops = pa.ops;
+    ua.order = vals_out;
+    ua.counter = pa.counter;
+    ua.n_flagged = pa.n_flagged;
+    ua.pool_cursor = (unsigned long long*)(ctx->totals.as<uint64_t>() + 7);
+    ua.pool_base = slot_ops;
+    ua.pool_size = pool_ops;
+    const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-    plan_kernel<false><<<plan_blocks, plan_tb, 0, st>>>(pa);
+    if (fast_unaligned) uread_kernel<false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
+    else plan_kernel<false><<<plan_blocks, plan_tb, 0, st>>>(pa);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], st));
     launches += 1;
@@ -921,7 +860,9 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         pa.ops = ctx->ops.as<uint32_t>();
         scatter_flagged_off<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_out.as<uint64_t>(), primary_ops);
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-        plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
+        ua.ops = pa.ops;
+        if (fast_unaligned) uread_kernel<true><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
+        else plan_kernel<true><<<plan_blocks, plan_tb, 0, st>>>(pa);
         CK(cudaGetLastError());
         launches += 2;
     }
@@ -998,6 +939,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ea.qlut = ctx->qlut.as<uint32_t>();
     ea.qcdf = ctx->qcdf.as<uint32_t>();
     ea.counter = ctx->counter.as<uint32_t>();
+    ea.order = chim ? nullptr : vals_out;        // one piece per read: the plan's longest-first order serves the emit too
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
     const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 256;
     if (ctx->hcfg.fastq) {

@@ -323,8 +323,17 @@ __global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t f
             }
             caps[pf + q] = exact_only ? 0 : cap;
         }
-    } else {
+    } else if (exact_only) {
         caps[pf] = 0;                                                    // scripted unaligned reads: exact pass only
+    } else {
+        // unaligned fast path (uread_kernel.cuh): slot from the attempt-0 length (block 0 of the attempt stream); an
+        // unmerged unaligned script has at most 4 ops per reference base, in practice ~0.7
+        Rng r0;
+        r0.init(cfg.seed, first_id + i, stream_word(ST_ATT, NS_KIND_UNALIGNED, 0));
+        const double x = cfg.median_len > 0.0 ? lognormal_draw(log(cfg.median_len), cfg.sd_len, r0) : kde_draw(m.unaligned, r0);
+        const uint64_t len = x >= 1.0 ? (x < 268435455.0 ? (uint64_t)x : 268435455ull) : 0ull;
+        caps[pf] = len + (len >> 1) + 64;
+        total = len;
     }
     keys[i] = total > 0xffffffffull ? 0xffffffffu : (uint32_t)total;
     vals[i] = i;

@@ -6,17 +6,21 @@
 // position, the first non-insertion draw that reaches m_ref ends the read exactly where the sequential loop would,
 // and consecutive insertions are folded into the following step with a ballot/shuffle.  Draw k uses Philox block
 // k+1 of the attempt's stream, i.e. exactly the words the sequential state machine in plan_kernel.cuh consumes for
-// its k-th loop iteration, so both paths produce the same read lengths, rejections, strands and positions
+// its k-th loop iteration, so both paths produce the same read lengths, rejections, strands, positions and bytes
 // (tests/test_gpu_parity.py::test_unaligned_fast_path_equals_scripted_path).
 //
-// The WRITE pass lets each lane write the bases (and "unmapped"-state qualities, :1521) its own draw produces:
-// with mutate_read's right-to-left string edits (:1957-1995) a step of length s at `pos` preceded by `a` inserted
-// bases (key ceil(pos + 0.1) = pos + 1) becomes
-//     match : ref[pos]                 + a random
-//     mis   : sub(ref[pos])            + a random + sub(ref[pos+1 .. +rest]) + ref[.. covered]
-//     del   :                            (a - covered) random               + ref[.. covered]
-// with covered = min(a, s - 1) and rest = s - 1 - covered (the substitution / deletion also hits the inserted
-// bases that sit inside its span; re-randomised random bases stay uniform).
+// Every lane writes the ops of its own draw into the read's edit script; emit_kernel turns the script into bases and
+// "unmapped"-state qualities (:1521).  With mutate_read's right-to-left string edits (:1957-1995) a step of length s at
+// `pos` preceded by `a` inserted bases (key ceil(pos + 0.1) = pos + 1) becomes
+//     match : COPY 1, INS a
+//     mis   : MIS 1,  INS a,           MIS rest, COPY covered
+//     del   : DEL 1,  INS a - covered, DEL rest, COPY covered
+// with covered = min(a, s - 1) and rest = s - 1 - covered (the substitution / deletion also hits the inserted bases
+// that sit inside its span; re-randomised random bases stay uniform).  Empty ops are dropped, equal neighbours inside
+// a draw are merged, and a run of plain matches becomes one COPY.
+//
+// Like plan_kernel, the first pass writes into a slot sized from the attempt-0 length (lengths_kernel) and flags the
+// read when the script does not fit (or a later attempt was longer); flagged reads are replayed into exact slots.
 #pragma once
 #include "device_common.cuh"
 #include "emit_kernel.cuh"
@@ -29,45 +33,40 @@ struct UreadArgs {
     uint64_t first_id;
     uint32_t n_reads;
     NsReadMeta* reads;
-    NsPieceMeta* pieces;
-    uint8_t* seq;            // WRITE only
-    uint8_t* qual;
-    const uint32_t* qlut;    // [5][QLUT_SIZE]
-    const uint32_t* qcdf;
+    NsPieceMeta* pieces;     // [n_reads + 1]: op_off of piece i+1 bounds the slot of piece i (first pass)
+    uint32_t* ops;
+    const uint32_t* order;   // processing order (longest first), may be null
     uint32_t* counter;
+    uint32_t* n_flagged;
+    // slots for re-drawn reads (a rejected attempt draws a new length, :1503): bump-allocated behind the primary area
+    unsigned long long* pool_cursor;
+    uint64_t pool_base, pool_size;
 };
 
 #define UREAD_WARPS 8
 
-template <bool WRITE, bool FASTQ>
+template <bool REPLAY>
 __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_constant__ UreadArgs a) {
-    __shared__ uint32_t lut[(WRITE && FASTQ) ? QLUT_SIZE : 1];
-    __shared__ uint32_t dsc_all[WRITE ? UREAD_WARPS : 1][5][32];
-    uint32_t (*dsc)[32] = dsc_all[WRITE ? (threadIdx.x >> 5) : 0];
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const int lane = threadIdx.x & 31;
     const uint32_t lane_lt = (1u << lane) - 1u;
-    if (WRITE && FASTQ) {
-        for (int i = threadIdx.x; i < QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[4 * QLUT_SIZE + i];   // "unmapped"
-        __syncthreads();
-    }
     const uint2 key = make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
 
     for (;;) {
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(a.counter, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= a.n_reads) break;
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(a.counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= a.n_reads) break;
+        const uint32_t slot = a.order ? a.order[idx] : idx;
+        if (REPLAY && !(a.reads[slot].flags & 1u)) continue;
         const uint64_t rid = a.first_id + slot;
         const uint32_t id_lo = (uint32_t)rid, id_hi = (uint32_t)(rid >> 32);
-        uint32_t attempt = WRITE ? a.reads[slot].attempts : 0u;
-        NsReadMeta rm;
-        NsPieceMeta pm;
-        if (WRITE) {
-            rm = a.reads[slot];
-            pm = a.pieces[slot];
-        }
+        uint32_t attempt = REPLAY ? a.reads[slot].attempts : 0u;
+        uint64_t op_off = a.pieces[slot].op_off;
+        uint32_t* ops = a.ops + op_off;
+        // first pass: the slot ends where the next piece's begins; replay: exact slot
+        uint32_t cap = REPLAY ? 0xffffffffu : (uint32_t)(a.pieces[slot + 1].op_off - op_off);
         for (;;) {   // rejection loop (:1503, :1517); every lane runs it redundantly on warp-uniform values
             const uint32_t sw = stream_word(ST_ATT, NS_KIND_UNALIGNED, attempt);
             Rng r0;
@@ -81,7 +80,20 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 continue;
             }
             const uint32_t m_ref = (uint32_t)mr;
-            uint32_t base = 0, pos_base = 0, carry_a = 0, out_base = 0, middle_ref = m_ref, n_draws = 0;
+            if (!REPLAY && attempt > 0) {                        // the slot was sized for attempt 0: take a new one
+                const uint32_t need = m_ref + (m_ref >> 1) + 64u;
+                unsigned long long off = 0;
+                if (lane == 0) off = atomicAdd(a.pool_cursor, (unsigned long long)need);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (off + need <= a.pool_size) {
+                    op_off = a.pool_base + off;
+                    cap = need;
+                } else {
+                    cap = 0;                                     // pool exhausted: count only, replay later
+                }
+                ops = a.ops + op_off;
+            }
+            uint32_t base = 0, pos_base = 0, carry_a = 0, middle_ref = m_ref, n_draws = 0, n_ops = 0;
             int64_t l_new = (int64_t)m_ref;
             bool done = false;
             while (!done) {
@@ -97,94 +109,57 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 const int jstop = stop_mask ? __ffs(stop_mask) - 1 : 32;
                 const bool valid = lane <= jstop;
                 const uint32_t nonins_mask = __ballot_sync(0xffffffffu, nonins);
+                // inserted bases pending in front of a non-insertion draw = I - I(previous non-insertion draw)
                 const uint32_t below = nonins_mask & lane_lt;
                 const int pn = below ? 31 - __clz(below) : -1;
                 const uint32_t I_pn = __shfl_sync(0xffffffffu, I, pn < 0 ? 0 : pn);
                 const uint32_t a_ins = nonins ? (pn >= 0 ? I - I_pn : I + carry_a) : 0u;
-                // bases this draw produces / signed length change
-                uint32_t covered = 0, rest = 0, outn = 0;
-                if (nonins && valid) {
-                    if (kind == 0) {
-                        outn = 1 + a_ins;
-                    } else {
-                        covered = a_ins < s - 1 ? a_ins : s - 1;
-                        rest = s - 1 - covered;
-                        outn = kind == 1 ? s + a_ins : a_ins;
-                    }
-                }
-                const uint32_t O = out_base + warp_incl_scan(outn, lane) - outn;
                 int32_t delta = 0;
                 if (valid) delta = kind == 2 ? (int32_t)s : (kind == 3 ? -(int32_t)s : 0);
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
                 l_new += delta;
 
-                if (WRITE) {
-                    // ---- emission: publish the draws' descriptors, then the warp writes the block's output bases
-                    //      cooperatively (output index -> owning draw by binary search over the output offsets)
-                    const uint32_t tot = __shfl_sync(0xffffffffu, O + outn, 31) - out_base;
-                    dsc[0][lane] = O - out_base;
-                    dsc[1][lane] = P - s;                                   // reference offset of the step
-                    dsc[2][lane] = kind;
-                    dsc[3][lane] = kind == 3 ? a_ins - covered : a_ins;     // surviving inserted bases
-                    dsc[4][lane] = rest;
-                    __syncwarp();
-                    const uint64_t cstart = a.ref.chrom_off[pm.chrom];
-                    const uint64_t clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
-                    const uint8_t* __restrict__ cb = a.ref.bases + cstart;
-                    const bool rev = rm.reversed != 0;
-                    uint8_t* sq = a.seq + rm.seq_off;
-                    uint8_t* qq = FASTQ ? a.qual + rm.seq_off : nullptr;
-                    for (uint32_t i = lane; i < tot; i += 32) {
-                        uint32_t l = 0, h = 32;                              // last draw whose output offset <= i
-                        while (h - l > 1) {
-                            uint32_t mid = (l + h) >> 1;
-                            if (dsc[0][mid] <= i) l = mid; else h = mid;
-                        }
-                        const uint32_t t = i - dsc[0][l], R = dsc[1][l], kd = dsc[2][l], n_ins = dsc[3][l], rst = dsc[4][l];
-                        const uint32_t n_first = kd == 3 ? 0u : 1u;          // ref[pos] itself (copied or substituted)
-                        const uint32_t n_mid = kd == 1 ? rst : 0u;           // further substituted reference bases
-                        const uint32_t o = out_base + i;
-                        // one 32-bit word per base: Philox-7 block o>>2, word o&3 of the read's unaligned base stream
-                        const uint4 w4 = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, NS_KIND_UNALIGNED, 0), o >> 2), key);
-                        const uint32_t w = (o & 2u) ? ((o & 1u) ? w4.w : w4.z) : ((o & 1u) ? w4.y : w4.x);
-                        const uint32_t wn = (o & 2u) ? ((o & 1u) ? w4.x : w4.w) : ((o & 1u) ? w4.z : w4.y);   // next word of the block
-                        const uint32_t r8 = w & 0xffu;                       // low byte: base choice; high 24 bits: quality
-                        const uint32_t t3 = __umulhi(__byte_perm(w, wn, 0x0444), 3u);
-                        uint32_t oi = r8 & 3u;
-                        int roff = -1;
-                        bool sub = false;
-                        if (t < n_first) {
-                            roff = 0;
-                            sub = kd == 1;
-                        } else if (t < n_first + n_ins) {
-                            roff = -1;
-                        } else if (t < n_first + n_ins + n_mid) {
-                            roff = 1 + (int)(t - n_first - n_ins);
-                            sub = true;
+                // ---- this draw's ops (at most four), empty ones dropped and equal neighbours merged
+                uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;          // an empty op is the zero word (COPY of length 0)
+                const bool emits = valid && nonins;
+                // a run of plain matches (no pending insertion) is written once, by its first lane
+                const uint32_t plain_mask = __ballot_sync(0xffffffffu, emits && kind == 0 && a_ins == 0);
+                if (emits) {
+                    if (kind == 0) {
+                        if (a_ins == 0) {
+                            if (!(lane > 0 && ((plain_mask >> (lane - 1)) & 1u))) {
+                                const uint32_t run = __ffs(~(plain_mask >> lane)) - 1;       // consecutive set bits from `lane`
+                                o0 = (NS_OP_COPY << 28) | (run == 0xffffffffu ? 32u - lane : run);
+                            }
                         } else {
-                            roff = 1 + (int)rst + (int)(t - n_first - n_ins - n_mid);
+                            o0 = (NS_OP_COPY << 28) | 1u;
+                            o1 = (NS_OP_INS << 28) | a_ins;
                         }
-                        if (roff >= 0) {
-                            uint64_t ab = (uint64_t)pm.pos + R + (uint32_t)roff;
-                            if (ab >= clen) ab -= clen;
-                            uint32_t c = __ldg(&cb[ab]);
-                            if (c - 'a' < 26u) c -= 32;
-                            if (!acgt_fast(c)) c = converted_ref_base(c, cfg.seed, rid, 0u, R + (uint32_t)roff);
-                            oi = base_idx(c);
-                            if (sub) oi = (oi + 1u + t3) & 3u;
+                    } else {
+                        const uint32_t covered = a_ins < s - 1 ? a_ins : s - 1;
+                        const uint32_t rest = s - 1 - covered;
+                        const uint32_t T = kind == 1 ? NS_OP_MIS : NS_OP_DEL;
+                        const uint32_t n_ins = kind == 1 ? a_ins : a_ins - covered;
+                        if (n_ins == 0) {
+                            o0 = (T << 28) | (1u + rest);
+                        } else {
+                            o0 = (T << 28) | 1u;
+                            o1 = (NS_OP_INS << 28) | n_ins;
+                            if (rest) o2 = (T << 28) | rest;
                         }
-                        const uint32_t dst = rev ? rm.seq_len - 1 - o : o;
-                        sq[dst] = (uint8_t)emit_char(rev ? oi ^ 2u : oi, cfg.uracil);
-                        if (FASTQ) {
-                            const uint32_t e = lut[w >> (32 - QLUT_BITS)];
-                            uint32_t q = qual_char_fast(e, w);
-                            if (q & 0x80u) q = qual_char_exact(a.qcdf + 4 * NS_QUAL_SLOTS, w);
-                            qq[dst] = (uint8_t)q;
-                        }
+                        if (covered) o3 = (NS_OP_COPY << 28) | covered;
                     }
-                    __syncwarp();
                 }
+                const uint32_t p1 = o0 ? 1u : 0u, p2 = p1 + (o1 ? 1u : 0u), p3 = p2 + (o2 ? 1u : 0u);
+                const uint32_t cnt = p3 + (o3 ? 1u : 0u);
+                const uint32_t incl = warp_incl_scan(cnt, lane);
+                const uint32_t at = n_ops + incl - cnt;
+                if (o0 && at < cap) ops[at] = o0;
+                if (o1 && at + p1 < cap) ops[at + p1] = o1;
+                if (o2 && at + p2 < cap) ops[at + p2] = o2;
+                if (o3 && at + p3 < cap) ops[at + p3] = o3;
+                n_ops += __shfl_sync(0xffffffffu, incl, 31);
 
                 if (jstop < 32) {
                     const uint32_t Pstop = __shfl_sync(0xffffffffu, P, jstop);
@@ -203,11 +178,10 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                     } else {
                         carry_a += I31;
                     }
-                    out_base = __shfl_sync(0xffffffffu, O + outn, 31);     // O already includes the old out_base
                     base += 32;
                 }
             }
-            if (WRITE) break;
+            if (REPLAY) break;
             const bool ok = middle_ref >= cfg.min_len && middle_ref <= cfg.max_len && l_new >= (int64_t)cfg.min_len &&
                             l_new <= (int64_t)cfg.max_len;
             if (!ok) {
@@ -224,9 +198,10 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             else if (cfg.transcriptome) draw_position_trx(a.ref, pr, middle_ref, chrom, ppos);
             else draw_position(a.ref, cfg, pr, middle_ref, chrom, ppos);
             if (lane == 0) {
+                const bool overflow = n_ops > cap;
                 NsPieceMeta p;
-                p.op_off = 0;
-                p.n_ops = 0;
+                p.op_off = op_off;
+                p.n_ops = n_ops;
                 p.kind = NS_PIECE_UNALIGNED;
                 p.chrom = chrom;
                 p.pos = ppos;
@@ -236,8 +211,8 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 p.l_new = (uint32_t)l_new;
                 p.ref_req = m_ref;
                 p.read_slot = slot;
-                p.ev_off = 0;
-                p.ev_n_ops = 0;
+                p.ev_off = op_off;
+                p.ev_n_ops = n_ops;
                 p.polya_len = 0;
                 a.pieces[slot] = p;
                 NsReadMeta q;
@@ -248,9 +223,10 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 q.piece_first = slot;
                 q.n_pieces = 1;
                 q.reversed = (uint8_t)reversed;
-                q.flags = 0;
+                q.flags = overflow ? 1 : 0;
                 q.attempts = attempt;
                 a.reads[slot] = q;
+                if (overflow) atomicAdd(a.n_flagged, 1u);
             }
             break;
         }

@@ -177,8 +177,15 @@ def check_fast_unaligned(fast, scripted, ref, fastq):
         assert np.array_equal(fast.reads[k], scripted.reads[k]), "unaligned fast path differs in reads.%s" % k
     for k in ("chrom", "pos", "ref_len", "out_len", "ref_req", "l_new"):
         assert np.array_equal(fast.pieces[k], scripted.pieces[k]), "unaligned fast path differs in pieces.%s" % k
+    # both paths feed the same emit kernel with position-indexed randomness: identical bytes
+    assert np.array_equal(fast.seq, scripted.seq), "unaligned fast path: bases differ from the scripted path"
+    if fastq:
+        assert np.array_equal(fast.qual, scripted.qual), "unaligned fast path: qualities differ from the scripted path"
     hybrid = Batch(fast.info, fast.seq, fast.qual, scripted.reads, scripted.pieces, scripted.ops, fast.kind, fast.first_id)
-    return check_edit_scripts(hybrid, ref, fastq)
+    nb = check_edit_scripts(hybrid, ref, fastq)
+    if fast.ops is not None:            # the fast path's own (less merged) scripts describe the same bases
+        nb += check_edit_scripts(fast, ref, fastq)
+    return nb
 
 
 def batch_stats(batch, ref, fastq, s=None):

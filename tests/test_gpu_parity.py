@@ -66,7 +66,7 @@ def test_edit_scripts_bit_exact_mini_ref(model, kw, mini_ref, L):
 def test_unaligned_fast_path_equals_scripted_path(model, fastq, mini_ref, L):
     """The warp-per-read unaligned kernel evaluates unaligned_error_list 32 draws at a time; the scripted path runs
     it sequentially and keeps edit scripts.  Same seed => same lengths, rejections, strands and positions, and the
-    fast path's bases must satisfy the scripted path's edit scripts bit-exactly."""
+    fast path's bytes must equal the scripted path's and satisfy both paths' edit scripts bit-exactly."""
     a, _, _ = pc.make_engine(model, mini_ref, fastq=fastq, seed=21, unaligned_scripts=True)
     a.simulate(L.NS_KIND_UNALIGNED, 100, 1500)
     bs = a.fetch(want_ops=True)
@@ -74,9 +74,9 @@ def test_unaligned_fast_path_equals_scripted_path(model, fastq, mini_ref, L):
     a.close()
     b, _, _ = pc.make_engine(model, mini_ref, fastq=fastq, seed=21)
     info = b.simulate(L.NS_KIND_UNALIGNED, 100, 1500)
-    bf = b.fetch()
+    bf = b.fetch(want_ops=True)
     b.close()
-    assert info.n_ops == 0 and bf.reads["seq_len"].min() >= 50
+    assert info.n_ops > 0 and bf.reads["seq_len"].min() >= 50
     assert pc.check_fast_unaligned(bf, bs, mini_ref, fastq) > 0
     assert bf.reads["attempts"].max() > 0
 

@@ -18,4 +18,7 @@ for rep in range(2):
           "flagged", int((b.reads["flags"] & 1).sum()), "ops used", int(b.pieces["n_ops"].sum()), "of", info.n_ops)
     if nu:
         info = eng.simulate(L.NS_KIND_UNALIGNED, 0, nu)
-        print("unaligned", info.total_bases, info.ms_plan, info.ms_script, info.ms_emit)
+        bu = eng.fetch()
+        print("unaligned", info.total_bases, "plan %.2f scan %.2f script %.2f emit %.2f total %.2f" % (info.ms_plan, info.ms_scan, info.ms_script, info.ms_emit, info.ms_total),
+              "flagged", int((bu.reads["flags"] & 1).sum()), "attempts>0", int((bu.reads["attempts"] > 0).sum()), "max len", int(bu.reads["seq_len"].max()),
+              "ops/base %.3f" % (bu.pieces["n_ops"].sum() / max(1, bu.pieces["ref_len"].sum())))
