@@ -115,6 +115,7 @@ def _shard(n, rank, world):
 def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min_l, num_threads, fastq,
                median_l=None, sd_l=None, model_ir=False, uracil=False, polya=None, chimeric=False,
                batch_reads=65536, error_profile=True, rank=0, world=1):
+    fmt_threads = max(1, min(num_threads, os.cpu_count() or 1))     # host threads of the record formatter
     eng = prof.engine
     meta = mode == "metagenome"
     trx = mode == "transcriptome"
@@ -123,7 +124,8 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                   kmer_bias=kmer_bias or 0, min_len=min_l, max_len=max_l, median_len=median_l or 0.0, sd_len=sd_l or 0.0,
                   metagenome=meta, transcriptome=trx, uracil=bool(uracil),
                   polya_scale=POLYA_SCALE.get(basecaller, POLYA_SCALE["guppy"]) if (trx and polya) else 0.0,
-                  kde2d_sample=max(1, hi_a - lo_a))        # the reference's 2-D KDE sample has one row per read of the worker
+                  # the reference's 2-D KDE sample has one row per read of a WORKER (:1072): -t sets its size as it does there
+                  kde2d_sample=max(1, (hi_a - lo_a) // max(1, num_threads)))
     ext = ".fastq" if fastq else ".fasta"
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
@@ -141,7 +143,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
 
         def sink_aligned(info, b, job):
             names = read_names(b, prof.ref.names, job[1], perfect=per, metagenome=meta, transcriptome=trx)
-            f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
+            f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads))
             if want_err:
                 f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
 
@@ -154,7 +156,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             def sink_unaligned(info, b, job):
                 # the reference's read index keeps counting after the aligned reads (shared total_simulated, :1574)
                 names = read_names(b, prof.ref.names, prof.number_aligned + job[1])
-                f_reads.write(format_records(b, names, fastq, n_threads=max(1, num_threads)))
+                f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads))
 
             pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned)
     pipe.close()

@@ -7,6 +7,7 @@
    per-base mis/ins/del counts within +-0.1 % (north_star), length / event histograms by chi-square.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -622,6 +623,100 @@ def test_cli_transcriptome_end_to_end(trx_ref, tmp_path, L):
     with pytest.raises(SystemExit):
         simulator.main(["transcriptome", "-rt", os.path.join(T, "transcripts.fa"), "-e", os.path.join(T, "expression.tsv"),
                         "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", "10", "-o", out, "--polya", os.path.join(T, "polya.txt")])
+
+
+def _by_chrom(path, fastq):
+    sys.path.insert(0, GOLDEN)
+    from make_golden_runs_modes import by_chrom
+    return by_chrom(path, fastq)
+
+
+def _share_diff(a, b):
+    keys = sorted(set(a) | set(b))
+    va = np.array([a.get(k, 0) for k in keys], dtype=np.float64)
+    vb = np.array([b.get(k, 0) for k in keys], dtype=np.float64)
+    return keys, va, vb, np.abs(va / va.sum() - vb / vb.sum()).max()
+
+
+def test_transcriptome_vs_unmodified_reference(trx_ref, tmp_path, L):
+    """400k reads of the unmodified `simulator.py transcriptome --no_model_ir -b guppy --polya ... -n 8000 -t 8` (50 runs,
+    tests/golden/make_golden_runs_modes.py) against this CLI: same files, same parser.  -t is chosen so that the 2-D
+    length-KDE sample has the reference's 623 rows per worker."""
+    from nanosim_b200 import simulator
+    path = os.path.join(GOLDEN, "ref_stats_trx_drna_fasta.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    T = os.path.join(GOLDEN, "trx")
+    out = os.path.join(str(tmp_path), "tx")
+    n = 200000
+    simulator.main(["transcriptome", "-rt", os.path.join(T, "transcripts.fa"), "-e", os.path.join(T, "expression.tsv"),
+                    "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", str(n), "-o", out, "--no_model_ir",
+                    "--polya", os.path.join(T, "polya.txt"), "-b", "guppy", "--seed", "17", "-t", str(n // 8000 * 8)])
+    s = rs.stats_from_prefix(out, False)
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("trx per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    fails = pc.compare_stats(s, gold, rate_tol=3e-3, p_min=1e-6, label="trx",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match",
+                                   "len_unaligned", "events_per_read"])
+    reads, bases = _by_chrom(out + "_aligned_reads.fasta", False)
+    keys, va, vb, _ = _share_diff(reads, gold["by_chrom_reads"])
+    st, dof, p = pc.chi2_two_sample(va, vb)
+    print("reads per transcript: chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    if p < 1e-6:
+        fails.append("trx reads per transcript chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    _, _, _, d = _share_diff(bases, gold["by_chrom_bases"])
+    print("max |share| difference of bases per transcript %.4g" % d)
+    if d > 3e-3:
+        fails.append("trx bases per transcript: share differs by %.4g" % d)
+    fr = s["strand_R_aligned"] / s["n_aligned"], gold["strand_R_aligned"] / gold["n_aligned"]
+    assert abs(fr[0] - fr[1]) < 2e-3, fr
+    assert not fails, "\n".join(fails)
+
+
+def test_metagenome_vs_unmodified_reference(meta_ref, tmp_path, L):
+    """200k reads of the unmodified `simulator.py metagenome --fastq --chimeric` (Even model, 10 runs of 20000, -t 8)
+    against this CLI on the same 4-species fixture: histograms, rates, qualities, species and chromosome shares."""
+    from nanosim_b200 import simulator
+    path = os.path.join(GOLDEN, "ref_stats_meta_even_fastq_chimeric.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    meta = os.path.join(GOLDEN, "meta")
+    ab = os.path.join(str(tmp_path), "abun.tsv")
+    with open(os.path.join(meta, "abundance.tsv")) as f, open(ab, "w") as o:
+        f.readline()
+        o.write("Size\t40000\n")
+        for line in f:
+            pp = line.rstrip("\n").split("\t")
+            o.write("%s\t%s\n" % (pp[0], pp[1]))
+    out = os.path.join(str(tmp_path), "mg")
+    simulator.main(["metagenome", "-gl", os.path.join(meta, "genome_list_local.tsv"), "-a", ab, "-dl", os.path.join(meta, "dna_type.tsv"),
+                    "-c", os.path.join(pc.DATA, pc.MODELS["even"]), "-o", out, "--fastq", "--chimeric", "--seed", "23",
+                    "--batch_reads", "20000"])
+    s = rs.stats_from_prefix(out + "_sample0", True)
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("meta per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    fails = pc.compare_stats(s, gold, rate_tol=3e-3, p_min=1e-6, label="meta",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match", "events_per_read"])
+    for k in ("qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+        print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("meta %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    reads, bases = _by_chrom(out + "_sample0_aligned_reads.fastq", True)
+    sp = lambda d: {k2: sum(v for k, v in d.items() if k.split("-")[0] == k2) for k2 in {k.split("-")[0] for k in d}}
+    _, va, vb, d_sp = _share_diff(sp(bases), sp(gold["by_chrom_bases"]))
+    _, _, _, d_ch = _share_diff(reads, gold["by_chrom_reads"])
+    print("species base shares device", va / va.sum(), "reference", vb / vb.sum(), "max diff %.4g; chromosome read shares max diff %.4g" % (d_sp, d_ch))
+    if d_sp > 0.01:
+        fails.append("meta species base shares differ by %.4g" % d_sp)
+    if d_ch > 0.01:
+        fails.append("meta chromosome read shares differ by %.4g" % d_ch)
+    fc = s["n_chimeric"] / s["n_aligned"], gold["n_chimeric"] / gold["n_aligned"]
+    if abs(fc[0] / fc[1] - 1) > 0.06:
+        fails.append("meta chimeric fraction %.4f vs %.4f" % fc)
+    assert not fails, "\n".join(fails)
 
 
 def test_lognormal_lengths_med_sd(ecoli, L):
