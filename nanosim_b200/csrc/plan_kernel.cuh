@@ -339,8 +339,11 @@ __global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t f
     vals[i] = i;
 }
 
+#ifndef PLAN_MIN_BLOCKS
+#define PLAN_MIN_BLOCKS 4     // resident 128-thread blocks per SM the register allocation aims for
+#endif
 template <bool REPLAY>
-__global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ PlanArgs a) {
+__global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid_constant__ PlanArgs a) {
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const bool unal_kind = (a.kind == NS_KIND_UNALIGNED);
