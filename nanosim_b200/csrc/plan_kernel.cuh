@@ -510,6 +510,10 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
         }
         case PH_EVENT: {   // one pass of the while-loop body of error_list (:1858-1914)
             uint4 r = rng.next4();
+            // the next match length only depends on the previous one (:1891-1903): its table lookup is issued first so
+            // that it overlaps the error-length lookup below
+            const uint32_t b = match_bin(m, bin_lut, prev_match);
+            uint32_t mt = alias_draw(m, 4 + b, r.z);
             // error type from the Markov chain keyed by prev_error[+"0"] (:1860-1864)
             uint32_t e;
             if (r.x < m.trans[err_state][0]) e = 1;
@@ -532,9 +536,6 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                     middle_ref = pos;
                 }
             }
-            // next match length given the previous one (:1891-1903)
-            uint32_t b = match_bin(m, bin_lut, prev_match);
-            uint32_t mt = alias_draw(m, 4 + b, r.z);
             if (mt == m.tab_n[4 + b] - 1) mt = step;  // ECDF miss: `step` keeps the error length (:1895-1898)
             if (prev_match == 0 && mt == 0) mt = 1;
             prev_match = mt;

@@ -2,15 +2,15 @@
 
 ``depth`` contexts (``ns_clone``: one copy of the reference and model in HBM, separate streams and batch buffers) are
 driven by ``depth`` host threads (ctypes releases the GIL during library calls), so that while one batch is being copied
-device->host into its pinned buffers the next batch's plan/emit kernels already run.  Results are handed to the consumer
-strictly in submission order, which keeps output files identical to a sequential run.
+device->host into its pinned buffers the next batch's plan/emit kernels already run.  A context that finishes pulls the
+next job at once (batches differ a lot in duration: unaligned batches are short and latency-bound), simulates it, and only
+then waits for its pinned buffers to be released.  Results are handed to the consumer strictly in submission order,
+which keeps output files identical to a sequential run.
 
 This replaces the reference's ``for i in range(num_threads): mp.Process(...)`` fan-out
 (/root/reference/src/simulator.py:1590-1622): same role (keep the machine busy), one GPU instead of N forks.
 """
 import threading
-from collections import deque
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -54,21 +54,19 @@ class BatchPipeline:
         self.depth = len(self.engines)
         self.fetch, self.want_ops, self.want_pieces = fetch, want_ops, want_pieces
         self.bufs = [_HostBuffers(engine.fastq) for _ in self.engines]
-        self.pool = ThreadPoolExecutor(max_workers=self.depth)
-        self.locks = [threading.Lock() for _ in self.engines]
         self.hint = {"seq": 0, "reads": 0, "pieces": 0, "ops": 0}     # largest batch seen by any slot (pinned allocs are slow)
 
     def close(self):
-        self.pool.shutdown(wait=True)
         for e in self.engines[1:]:
             e.close()
 
-    def _work(self, slot, job):
+    def _simulate(self, slot, job):
+        kind, first, n = job
+        return self.engines[slot].simulate(kind, first, n)
+
+    def _fetch(self, slot, job, info):
         kind, first, n = job
         eng, hb = self.engines[slot], self.bufs[slot]
-        info = eng.simulate(kind, first, n)
-        if not self.fetch:
-            return info, None
         fastq = eng.fastq
         nb = {"seq": int(info.seq_bytes), "reads": int(info.n_reads) * L.READ_DTYPE.itemsize,
               "pieces": int(info.n_pieces) * L.PIECE_DTYPE.itemsize, "ops": int(info.n_ops) * 4}
@@ -85,30 +83,92 @@ class BatchPipeline:
             ops = hb.ensure("ops", nb["ops"], self.hint["ops"])[:nb["ops"]]
         eng.fetch_into(hb.ptr("seq"), hb.ptr("qual") if fastq else None, hb.ptr("reads"),
                        hb.ptr("pieces") if pieces is not None else None, hb.ptr("ops") if ops is not None else None)
-        b = Batch(info, seq, qual, reads.view(L.READ_DTYPE), pieces.view(L.PIECE_DTYPE) if pieces is not None else None,
-                  ops.view(np.uint32) if ops is not None else np.zeros(0, dtype=np.uint32) if self.want_ops else None, kind, first)
-        return info, b
+        return Batch(info, seq, qual, reads.view(L.READ_DTYPE), pieces.view(L.PIECE_DTYPE) if pieces is not None else None,
+                     ops.view(np.uint32) if ops is not None else np.zeros(0, dtype=np.uint32) if self.want_ops else None, kind, first)
 
-    def run(self, jobs, consume=None):
+    def warm(self, jobs):
+        """Runs every job once on EVERY context (results discarded) so that device and pinned buffers reach their
+        working size before anything is timed: growing a device buffer is a cudaFree + cudaMalloc, which synchronises
+        the whole device and stalls the other contexts."""
+        jobs = list(jobs)
+
+        def one(slot):
+            for job in jobs:
+                info = self._simulate(slot, job)
+                if self.fetch:
+                    self._fetch(slot, job, info)
+
+        threads = [threading.Thread(target=one, args=(s,), daemon=True) for s in range(self.depth)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+
+    def run(self, jobs, consume=None, static_assign=False):
         """jobs: iterable of (kind, first_read_id, n_reads).  consume(info, batch, job) runs on the calling thread in
-        submission order; the batch's buffers are reused as soon as consume returns.  Returns the list of infos."""
+        submission order; the batch's buffers are reused as soon as consume returns.  Returns the list of infos.
+        static_assign: job j always runs on context j % depth (needed when a context carries state from batch to batch,
+        i.e. the metagenome species quotas) instead of on whichever context is free."""
+        jobs = list(jobs)
+        n = len(jobs)
+        results = [None] * n
+        done = [threading.Event() for _ in range(n)]
+        released = [threading.Event() for _ in range(self.depth)]     # the slot's pinned buffers may be overwritten
+        for ev in released:
+            ev.set()
+        cursor = [0]
+        lock = threading.Lock()
+        errors = []
+
+        def worker(slot):
+            j = slot
+            try:
+                while True:
+                    if static_assign:
+                        if j >= n or errors:
+                            return
+                    else:
+                        with lock:
+                            j = cursor[0]
+                            if j >= n or errors:
+                                return
+                            cursor[0] += 1
+                    info = self._simulate(slot, jobs[j])
+                    b = None
+                    if self.fetch:
+                        released[slot].wait()
+                        released[slot].clear()
+                        b = self._fetch(slot, jobs[j], info)
+                    results[j] = (info, b, slot)
+                    done[j].set()
+                    if static_assign:
+                        j += self.depth
+            except BaseException as e:          # noqa: BLE001 -- re-raised on the calling thread
+                errors.append(e)
+                for ev in done:
+                    ev.set()
+
+        threads = [threading.Thread(target=worker, args=(s,), daemon=True) for s in range(min(self.depth, max(n, 1)))]
+        for t in threads:
+            t.start()
         infos = []
-        pending = deque()
-        jobs = iter(jobs)
-        i = 0
-
-        def drain_one():
-            fut, job = pending.popleft()
-            info, b = fut.result()
-            if consume is not None:
-                consume(info, b, job)
-            infos.append(info)
-
-        for job in jobs:
-            if len(pending) == self.depth:
-                drain_one()
-            pending.append((self.pool.submit(self._work, i % self.depth, job), job))
-            i += 1
-        while pending:
-            drain_one()
+        try:
+            for j in range(n):
+                done[j].wait()
+                if errors:
+                    raise errors[0]
+                info, b, slot = results[j]
+                results[j] = None
+                if consume is not None:
+                    consume(info, b, jobs[j])
+                infos.append(info)
+                if self.fetch:
+                    released[slot].set()
+        finally:
+            if len(infos) < n:
+                errors.append(RuntimeError("pipeline aborted"))
+                for ev in released:
+                    ev.set()
+            for t in threads:
+                t.join()
         return infos

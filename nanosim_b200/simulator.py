@@ -147,7 +147,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             if want_err:
                 f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
 
-        pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned)
+        pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned, static_assign=meta)
     if not per:
         _log("Start simulation of random reads")
         lo, hi = _shard(prof.number_unaligned, rank, world)
@@ -158,7 +158,7 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                 names = read_names(b, prof.ref.names, prof.number_aligned + job[1])
                 f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads))
 
-            pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned)
+            pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned, static_assign=meta)
     pipe.close()
 
 
