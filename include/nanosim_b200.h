@@ -241,6 +241,27 @@ int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadM
                           const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
                           int n_threads);
 
+/* Host-side rows of <out>_aligned_error_profile (mutate_read's log, :2006-2008; the caller writes the header line
+ * :1634): for every aligned segment of every read, its error events right to left --
+ * "name<TAB>position in the segment's reference<TAB>mis|ins|del<TAB>length<TAB>reference bases<TAB>read bases".
+ * Needs the fetched ops (event scripts), the host copy of the reference (bases + chrom_off as passed to
+ * ns_set_reference), the seed of the context and the id of the batch's first read.  Same two-call protocol and name
+ * layout as ns_format_records; multi-threaded. */
+int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces, const uint32_t* ops,
+                                uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
+                                const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
+                                int n_threads);
+
+/* Host-side read names of a fetched batch in the reference's formats (genome :1390-1402, metagenome :965-969,
+ * transcriptome :1188-1219, perfect :1332-1343, unaligned :1511/:1529-1534), written as NUL-terminated strings back to
+ * back (name_off[i] = start of read i's name): the layout the two formatters above take.  flags: bit 0 perfect,
+ * bit 1 metagenome, bit 2 transcriptome.  index_base = the reference's shared total_simulated counter at the batch's
+ * first read.  chrom_names uses the same layout (one name per reference record).  Two-call protocol: out == NULL
+ * returns the bytes needed. */
+int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint32_t n_reads, int kind, uint32_t flags,
+                        uint64_t index_base, const char* chrom_names, const uint64_t* chrom_name_off, char* out,
+                        uint64_t out_cap, uint64_t* name_off);
+
 #ifdef __cplusplus
 }
 #endif

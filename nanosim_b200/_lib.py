@@ -17,7 +17,7 @@ NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
 EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
-           "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records"]
+           "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names"]
 
 
 class NsReference(C.Structure):
@@ -135,5 +135,9 @@ def lib():
     L.ns_op_stats.restype = C.c_int
     L.ns_format_records.argtypes = [P, P, P, C.c_uint32, P, P, C.c_int, P, C.c_uint64, C.c_int]
     L.ns_format_records.restype = C.c_int64
+    L.ns_format_error_profile.argtypes = [P, P, P, P, C.c_uint32, P, P, P, P, C.c_uint64, C.c_uint64, P, C.c_uint64, C.c_int]
+    L.ns_format_error_profile.restype = C.c_int64
+    L.ns_format_names.argtypes = [P, P, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, P, P, P, C.c_uint64, P]
+    L.ns_format_names.restype = C.c_int64
     _lib = L
     return L

@@ -60,7 +60,7 @@ struct DevCfg {
 // Philox4x32-10 (Salmon et al., SC'11).  Counter = (read id lo, read id hi, stream word, block index); key = seed.
 // ------------------------------------------------------------------------------------------------------------
 template <int ROUNDS>
-__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+__host__ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
@@ -76,12 +76,12 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
 // 7 rounds -- the smallest round count that passes BigCrush in Salmon et al. (SC'11, table 2) -- for the bulk
 // per-base streams of the emit kernel (quality values, substituted / inserted bases).
-__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
+__host__ __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
 
 // stream word layout: [31:28] purpose, [27] kind, [26:0] attempt / generation
 enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6, ST_IUPAC = 7, ST_HP = 8 };
 
-__device__ __forceinline__ uint32_t stream_word(uint32_t purpose, uint32_t kind, uint32_t sub) {
+__host__ __device__ __forceinline__ uint32_t stream_word(uint32_t purpose, uint32_t kind, uint32_t sub) {
     return (purpose << 28) | ((kind & 1u) << 27) | (sub & 0x07ffffffu);
 }
 

@@ -1109,4 +1109,272 @@ int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadM
     return (int64_t)off[n_reads];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// host-side <out>_aligned_error_profile rows (mutate_read's log, simulator.py:2006-2008; header written by the caller):
+// for every aligned segment, its error events right to left: name, position in the segment's reference, type, length,
+// reference bases, read bases.  Events come from the segment's EVENT script (after the -k filter); when the
+// homopolymer pass rewrote the emitted script, the bases of an event are the ones that pass fixed (hp_kernel.cuh:
+// byte t of Philox-7 block (event index << 8) + (t >> 4) of stream ST_EMIT_B), otherwise they are read back from the
+// sequence.  Two-call protocol like ns_format_records.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+inline int dec_len(uint64_t v) {
+    int n = 1;
+    while (v >= 10) {
+        v /= 10;
+        ++n;
+    }
+    return n;
+}
+inline char* put_dec(char* p, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+struct EvRow {
+    uint32_t type, len, ref_start, out_start, index;
+};
+}  // namespace
+
+int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces, const uint32_t* ops,
+                                uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
+                                const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
+                                int n_threads) {
+    if (!seq || !reads || !pieces || !ops || !ref_bases || !chrom_off || !names || !name_off) return NS_EINVAL;
+    static const char kTypes[3][4] = {"mis", "ins", "del"};
+    uint8_t comp[256];
+    for (int c = 0; c < 256; ++c) comp[c] = (uint8_t)c;
+    comp['A'] = 'T'; comp['T'] = 'A'; comp['C'] = 'G'; comp['G'] = 'C';
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    // one read: returns the bytes its rows take; writes them when p != nullptr
+    auto do_read = [&](uint32_t i, char* p) -> uint64_t {
+        const NsReadMeta& r = reads[i];
+        const char* nm = names + name_off[i];
+        const size_t nl = strlen(nm);
+        const uint64_t rid = first_id + i;
+        const uint32_t L = r.seq_len;
+        const uint8_t* rs = seq + r.seq_off;
+        const bool rev = r.reversed != 0;
+        uint64_t bytes = 0;
+        std::vector<EvRow> ev;
+        for (uint32_t k = 0; k < r.n_pieces; k += 2) {
+            const NsPieceMeta& pc = pieces[r.piece_first + k];
+            if (pc.kind != NS_PIECE_SEGMENT) continue;
+            const uint32_t* sc = ops + pc.ev_off;
+            const bool rewritten = pc.ev_off != pc.op_off;
+            const uint64_t cstart = chrom_off[pc.chrom], clen = chrom_off[pc.chrom + 1] - cstart;
+            ev.clear();
+            uint32_t o = pc.out_rel, rf = 0;
+            for (uint32_t j = 0; j < pc.ev_n_ops; ++j) {
+                const uint32_t op = sc[j], ty = NS_OP_TYPE(op), ln = NS_OP_LEN(op);
+                if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && ln) ev.push_back(EvRow{ty, ln, rf, o, j});
+                if (ty != NS_OP_DEL) o += ln;
+                if (ty == NS_OP_COPY || ty == NS_OP_MIS || ty == NS_OP_DEL) rf += ln;
+            }
+            for (size_t e = ev.size(); e-- > 0;) {
+                const EvRow& w = ev[e];
+                const uint64_t row = nl + 1 + dec_len(w.ref_start) + 1 + 3 + 1 + dec_len(w.len) + 1 + (uint64_t)w.len + 1 + w.len + 1;
+                bytes += row;
+                if (!p) continue;
+                memcpy(p, nm, nl);
+                p += nl;
+                *p++ = '\t';
+                p = put_dec(p, w.ref_start);
+                *p++ = '\t';
+                memcpy(p, kTypes[w.type - 1], 3);
+                p += 3;
+                *p++ = '\t';
+                p = put_dec(p, w.len);
+                *p++ = '\t';
+                char* refp = p;
+                if (w.type == NS_OP_INS) {
+                    memset(p, '-', w.len);
+                } else {
+                    for (uint32_t t = 0; t < w.len; ++t) {
+                        uint64_t ab = (uint64_t)pc.pos + w.ref_start + t;
+                        if (ab >= clen) ab -= clen;
+                        uint8_t c = ref_bases[cstart + ab];
+                        if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+                        p[t] = (char)c;
+                    }
+                }
+                p += w.len;
+                *p++ = '\t';
+                if (w.type == NS_OP_DEL) {
+                    memset(p, '-', w.len);
+                } else if (rewritten) {
+                    for (uint32_t t = 0; t < w.len; ++t) {
+                        const uint4 blk = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, k),
+                                                                  (w.index << 8) + (t >> 4)), key);
+                        const uint32_t word = ((t >> 2) & 3u) == 0 ? blk.x : (((t >> 2) & 3u) == 1 ? blk.y : (((t >> 2) & 3u) == 2 ? blk.z : blk.w));
+                        const uint32_t r8 = (word >> (8u * (t & 3u))) & 0xffu;
+                        uint32_t bi;
+                        if (w.type == NS_OP_INS) {
+                            bi = r8 & 3u;
+                        } else {
+                            const char rc = refp[t];
+                            const uint32_t orig = rc == 'C' ? 1u : (rc == 'T' ? 2u : (rc == 'G' ? 3u : 0u));
+                            const uint32_t rr = r8 == 255u ? 0u : r8;
+                            bi = (orig + 1u + rr % 3u) & 3u;
+                        }
+                        p[t] = "ACTG"[bi];
+                    }
+                } else {
+                    for (uint32_t t = 0; t < w.len; ++t) {
+                        const uint32_t x = w.out_start + t;
+                        p[t] = (char)(rev ? comp[rs[L - 1 - x]] : rs[x]);
+                    }
+                }
+                p += w.len;
+                *p++ = '\n';
+            }
+        }
+        return bytes;
+    };
+    int nt = std::max(1, std::min(n_threads, 64));
+    std::vector<uint64_t> off((size_t)n_reads + 1, 0);
+    {
+        auto count = [&](uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; ++i) off[i + 1] = do_read(i, nullptr);
+        };
+        if (nt == 1 || n_reads < 64) {
+            count(0, n_reads);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) {
+                uint32_t lo = (uint32_t)((uint64_t)n_reads * t / nt), hi = (uint32_t)((uint64_t)n_reads * (t + 1) / nt);
+                if (hi > lo) th.emplace_back(count, lo, hi);
+            }
+            for (auto& x : th) x.join();
+        }
+        for (uint32_t i = 0; i < n_reads; ++i) off[i + 1] += off[i];
+    }
+    if (!out) return (int64_t)off[n_reads];
+    if (off[n_reads] > out_cap) return NS_ENOMEM;
+    auto fill = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) do_read(i, out + off[i]);
+    };
+    if (nt == 1 || n_reads < 64) {
+        fill(0, n_reads);
+    } else {
+        std::vector<std::thread> th;
+        uint32_t lo = 0;
+        for (int t = 0; t < nt; ++t) {
+            uint64_t goal = off[n_reads] * (uint64_t)(t + 1) / nt;
+            uint32_t hi = (uint32_t)(std::upper_bound(off.begin(), off.end(), goal) - off.begin());
+            hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_reads);
+            if (t == nt - 1) hi = n_reads;
+            if (hi > lo) th.emplace_back(fill, lo, hi);
+            lo = hi;
+        }
+        for (auto& x : th) x.join();
+    }
+    return (int64_t)off[n_reads];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side read names (simulator.py:1390-1402 genome, :965-969 metagenome, :1188-1219 transcriptome, :1332-1343 perfect,
+// :1511/:1529-1534 unaligned), written as NUL-terminated strings back to back -- the layout ns_format_records and
+// ns_format_error_profile take.  flags: bit 0 perfect, bit 1 metagenome (gap lengths in the name), bit 2 transcriptome.
+// ---------------------------------------------------------------------------------------------------------
+int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint32_t n_reads, int kind, uint32_t flags,
+                        uint64_t index_base, const char* chrom_names, const uint64_t* chrom_name_off, char* out,
+                        uint64_t out_cap, uint64_t* name_off) {
+    if (!reads || !pieces || !chrom_names || !chrom_name_off) return NS_EINVAL;
+    const bool perfect = flags & 1u, meta = flags & 2u, trx = flags & 4u;
+    std::string nm;
+    uint64_t total = 0;
+    char num[32];
+    auto add_num = [&](uint64_t v) {
+        char* e = put_dec(num, v);
+        nm.append(num, (size_t)(e - num));
+    };
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        const NsReadMeta& r = reads[i];
+        const NsPieceMeta* pc = pieces + r.piece_first;
+        const char strand = r.reversed ? 'R' : 'F';
+        nm.clear();
+        if (kind == NS_KIND_UNALIGNED) {
+            nm += chrom_names + chrom_name_off[pc[0].chrom];
+            nm += '_';
+            add_num(pc[0].pos);
+            nm += "_unaligned_";
+            add_num(index_base + i);
+            nm += '_';
+            nm += strand;
+            nm += "_0_";
+            add_num(pc[0].ref_len);
+            nm += "_0";
+        } else if (trx) {
+            nm += chrom_names + chrom_name_off[pc[0].chrom];
+            nm += '_';
+            add_num(pc[0].pos);
+            nm += perfect ? "_perfect_" : "_aligned_";
+            add_num(index_base + i);
+            nm += '_';
+            nm += strand;
+            nm += '_';
+            add_num(r.head);
+            nm += '_';
+            add_num(pc[0].ref_len);
+            nm += '_';
+            add_num((uint64_t)r.tail + pc[0].polya_len);
+        } else if (perfect) {
+            uint64_t sum = 0;
+            for (uint32_t k = 0; k < r.n_pieces; k += 2) {
+                nm += chrom_names + chrom_name_off[pc[k].chrom];
+                nm += '_';
+                add_num(pc[k].pos);
+                sum += pc[k].ref_len;
+            }
+            nm += "_perfect_";
+            add_num(index_base + i);
+            nm += '_';
+            nm += strand;
+            nm += "_0_";
+            add_num(sum);
+            nm += "_0";
+        } else {
+            for (uint32_t k = 0; k < r.n_pieces; ++k) {
+                if (k & 1u) {
+                    if (!meta) continue;
+                    nm += ";gap_";
+                    add_num(pc[k].out_len);
+                    continue;
+                }
+                if (k) nm += ';';
+                nm += chrom_names + chrom_name_off[pc[k].chrom];
+                nm += '_';
+                add_num(pc[k].pos);
+            }
+            nm += "_aligned_";
+            add_num(index_base + i);
+            if (r.n_pieces > 1) nm += "_chimeric";
+            nm += '_';
+            nm += strand;
+            nm += '_';
+            add_num(r.head);
+            nm += '_';
+            for (uint32_t k = 0; k < r.n_pieces; k += 2) {
+                if (k) nm += ';';
+                add_num(pc[k].ref_len);
+            }
+            nm += '_';
+            add_num(r.tail);
+        }
+        if (out) {
+            if (total + nm.size() + 1 > out_cap) return NS_ENOMEM;
+            memcpy(out + total, nm.c_str(), nm.size() + 1);
+            if (name_off) name_off[i] = total;
+        }
+        total += nm.size() + 1;
+    }
+    return (int64_t)total;
+}
+
 }  // extern "C"

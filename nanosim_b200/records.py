@@ -59,15 +59,10 @@ def read_names(batch, ref_names, index_base, perfect=False, metagenome=False, tr
     return names
 
 
-def format_records(batch, names, fastq, n_threads=8):
-    """FASTA/FASTQ text of the batch via the library's multi-threaded formatter -> bytes."""
+def format_records(batch, names, fastq, n_threads=8, as_array=False):
+    """FASTA/FASTQ text of the batch via the library's multi-threaded formatter -> bytes (or the uint8 array itself)."""
     lib = L.lib()
-    blob = ("\0".join(names) + "\0").encode()
-    offs = np.zeros(len(names), dtype=np.uint64)
-    pos = 0
-    for i, nm in enumerate(names):
-        offs[i] = pos
-        pos += len(nm.encode()) + 1
+    blob, offs = _name_blob(names)
     reads = np.ascontiguousarray(batch.reads)
     qual_ptr = batch.qual.ctypes.data_as(C.c_void_p) if fastq else None
     need = lib.ns_format_records(batch.seq.ctypes.data_as(C.c_void_p), qual_ptr, reads.ctypes.data_as(C.c_void_p),
@@ -80,7 +75,96 @@ def format_records(batch, names, fastq, n_threads=8):
                                 out.ctypes.data_as(C.c_void_p), int(need), n_threads)
     if got != need:
         raise RuntimeError("ns_format_records failed: %d" % got)
-    return out.tobytes()
+    return out if as_array else out.tobytes()
+
+
+class NameTable:
+    """Read names as the formatters take them: NUL-terminated strings back to back + the offset of each."""
+
+    def __init__(self, blob, offs):
+        self.blob, self.offs = blob, offs
+
+    def __len__(self):
+        return len(self.offs)
+
+    def __getitem__(self, i):
+        a = int(self.offs[i])
+        return bytes(self.blob[a:self.blob.index(b"\0", a)]).decode()
+
+    def tolist(self):
+        return [x.decode() for x in bytes(self.blob).split(b"\0")[:-1]]
+
+
+_CHROM_CACHE = {}
+
+
+def name_table(batch, ref_names, index_base, perfect=False, metagenome=False, transcriptome=False):
+    """read_names() through the library (ns_format_names): same strings, no per-read Python."""
+    lib = L.lib()
+    key = id(ref_names)
+    if key not in _CHROM_CACHE or _CHROM_CACHE[key][0] is not ref_names:
+        _CHROM_CACHE.clear()
+        _CHROM_CACHE[key] = (ref_names,) + _name_blob(ref_names)
+    _, cblob, coffs = _CHROM_CACHE[key]
+    reads = np.ascontiguousarray(batch.reads)
+    pieces = np.ascontiguousarray(batch.pieces)
+    flags = (1 if perfect else 0) | (2 if metagenome else 0) | (4 if transcriptome else 0)
+    n = len(reads)
+
+    def call(out_ptr, cap, off_ptr):
+        return lib.ns_format_names(reads.ctypes.data_as(C.c_void_p), pieces.ctypes.data_as(C.c_void_p), n, int(batch.kind), flags,
+                                   C.c_uint64(int(index_base)), cblob, coffs.ctypes.data_as(C.c_void_p), out_ptr, cap, off_ptr)
+
+    need = call(None, 0, None)
+    if need < 0:
+        raise RuntimeError("ns_format_names failed: %d" % need)
+    out = np.empty(int(need), dtype=np.uint8)
+    offs = np.zeros(n, dtype=np.uint64)
+    got = call(out.ctypes.data_as(C.c_void_p), int(need), offs.ctypes.data_as(C.c_void_p))
+    if got != need:
+        raise RuntimeError("ns_format_names failed: %d" % got)
+    return NameTable(out.tobytes(), offs)
+
+
+def _name_blob(names):
+    if isinstance(names, NameTable):
+        return names.blob, names.offs
+    blob = ("\0".join(names) + "\0").encode()
+    offs = np.zeros(len(names), dtype=np.uint64)
+    pos = 0
+    for i, nm in enumerate(names):
+        offs[i] = pos
+        pos += len(nm.encode()) + 1
+    return blob, offs
+
+
+def format_error_profile(batch, names, ref, seed=0, n_threads=8, as_array=False):
+    """The rows of ``<out>_aligned_error_profile`` for a fetched batch (needs batch.ops) via the library's multi-threaded
+    formatter -> bytes.  Same text as ``"".join(error_profile_rows(...))``, which stays as the readable reference
+    implementation the tests compare against."""
+    lib = L.lib()
+    blob, offs = _name_blob(names)
+    reads = np.ascontiguousarray(batch.reads)
+    pieces = np.ascontiguousarray(batch.pieces)
+    ops = np.ascontiguousarray(batch.ops, dtype=np.uint32)
+    bases = np.ascontiguousarray(ref.bases)
+    coff = np.ascontiguousarray(ref.offsets, dtype=np.uint64)
+
+    def call(out_ptr, cap):
+        return lib.ns_format_error_profile(batch.seq.ctypes.data_as(C.c_void_p), reads.ctypes.data_as(C.c_void_p),
+                                           pieces.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p), len(names),
+                                           bases.ctypes.data_as(C.c_void_p), coff.ctypes.data_as(C.c_void_p), blob,
+                                           offs.ctypes.data_as(C.c_void_p), C.c_uint64(int(seed)), C.c_uint64(int(batch.first_id)),
+                                           out_ptr, cap, n_threads)
+
+    need = call(None, 0)
+    if need < 0:
+        raise RuntimeError("ns_format_error_profile failed: %d" % need)
+    out = np.empty(int(need), dtype=np.uint8)
+    got = call(out.ctypes.data_as(C.c_void_p), int(need))
+    if got != need:
+        raise RuntimeError("ns_format_error_profile failed: %d" % got)
+    return out if as_array else out.tobytes()
 
 
 _M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85

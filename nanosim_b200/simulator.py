@@ -23,7 +23,7 @@ from . import _lib as L
 from .engine import Engine
 from .model import DeviceTables, load_model
 from .pipeline import BatchPipeline
-from .records import error_profile_rows, format_records, read_names
+from .records import format_error_profile, format_records, name_table
 from .reference_fasta import (POLYA_SCALE, MetaReference, PackedReference, read_abundance, read_expression,
                               read_polya_list)
 from .model import build_alias
@@ -137,26 +137,27 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
     _log("Start simulation of aligned reads")
     lo, hi = _shard(prof.number_aligned, rank, world)
     with open(out + "_aligned_reads" + suffix + ext, "wb") as f_reads, \
-            open(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix), "w") as f_err:
+            open(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix), "wb") as f_err:
         if world == 1:
-            f_err.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+            f_err.write(b"Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
 
         def sink_aligned(info, b, job):
-            names = read_names(b, prof.ref.names, job[1], perfect=per, metagenome=meta, transcriptome=trx)
-            f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads))
+            names = name_table(b, prof.ref.names, job[1], perfect=per, metagenome=meta, transcriptome=trx)
+            f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads, as_array=True))
             if want_err:
-                f_err.writelines(error_profile_rows(b, names, prof.ref, seed=prof.seed))
+                f_err.write(format_error_profile(b, names, prof.ref, seed=prof.seed, n_threads=fmt_threads, as_array=True))
 
         pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned, static_assign=meta)
     if not per:
         _log("Start simulation of random reads")
         lo, hi = _shard(prof.number_unaligned, rank, world)
+        pipe.want_ops = False                              # unaligned reads are not logged (:1482-1549)
         with open(out + "_unaligned_reads" + suffix + ext, "wb") as f_reads:
 
             def sink_unaligned(info, b, job):
                 # the reference's read index keeps counting after the aligned reads (shared total_simulated, :1574)
-                names = read_names(b, prof.ref.names, prof.number_aligned + job[1])
-                f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads))
+                names = name_table(b, prof.ref.names, prof.number_aligned + job[1])
+                f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads, as_array=True))
 
             pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned, static_assign=meta)
     pipe.close()

@@ -727,6 +727,22 @@ def test_metagenome_vs_unmodified_reference(meta_ref, tmp_path, L):
     assert not fails, "\n".join(fails)
 
 
+def test_host_formatters_match_python_on_device_batches(mini_ref, L):
+    """ns_format_names / ns_format_error_profile (what the CLI writes) against the readable Python implementations on real
+    batches: chimeric dorado reads with the homopolymer pass (event bases fixed by the device), guppy reads."""
+    from nanosim_b200.records import error_profile_rows, format_error_profile, name_table, read_names
+    for model, kw in (("dorado", {"chimeric": True, "kmer_bias": 6}), ("guppy", {})):
+        eng, cm, t = pc.make_engine(model, mini_ref, fastq=True, seed=61, **kw)
+        eng.simulate(L.NS_KIND_ALIGNED, 40, 400)
+        b = eng.fetch(want_ops=True)
+        eng.close()
+        names = read_names(b, mini_ref.names, 40)
+        tab = name_table(b, mini_ref.names, 40)
+        assert tab.tolist() == names
+        want = "".join(error_profile_rows(b, names, mini_ref, seed=61)).encode()
+        assert format_error_profile(b, tab, mini_ref, seed=61, n_threads=4) == want and len(want) > 10000
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)

@@ -114,3 +114,113 @@ def test_two_rank_gloo_merge(tmp_path):
     assert open(out + "_aligned_error_profile").read().startswith("Seq_name\t")
     assert open(out + "_unaligned_reads.fasta").read() == ">u0\nAC\n>u1\nAC\n"
     assert not os.path.exists(out + "_aligned_reads0.fasta")
+
+
+def _synthetic_batch(rng, ref, n_reads, rewritten):
+    """A hand-built fetched batch (no GPU): random edit scripts applied to `ref` in Python."""
+    from nanosim_b200 import _lib as L
+    from nanosim_b200.engine import Batch
+    comp = {65: 84, 84: 65, 67: 71, 71: 67}
+    reads = np.zeros(n_reads, dtype=L.READ_DTYPE)
+    pieces, ops_all, seq_parts = [], [], []
+    seq_off = 0
+    clen = int(ref.lengths[0])
+    for i in range(n_reads):
+        n_seg = int(rng.integers(1, 3))
+        fwd = []
+        reads[i]["piece_first"] = len(pieces)
+        reads[i]["n_pieces"] = 2 * n_seg - 1
+        for k in range(2 * n_seg - 1):
+            pc = np.zeros((), dtype=L.PIECE_DTYPE)
+            pc["read_slot"] = i
+            pc["out_rel"] = len(fwd)
+            pc["chrom"] = 0
+            if k & 1:                                    # a gap piece: not logged
+                pc["kind"] = L.NS_PIECE_GAP
+                fwd += list(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 7))
+                pieces.append(pc)
+                continue
+            pc["kind"] = L.NS_PIECE_SEGMENT
+            pos = int(rng.integers(0, clen))
+            pc["pos"] = pos
+            script, out, rf = [], [], 0
+            if k == 0:
+                h = int(rng.integers(0, 4))
+                if h:
+                    script.append((L.NS_OP_HT << 28) | h)
+                    out += list(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), h))
+            for _ in range(int(rng.integers(3, 30))):
+                ty = int(rng.choice([L.NS_OP_COPY, L.NS_OP_MIS, L.NS_OP_INS, L.NS_OP_DEL]))
+                ln = int(rng.integers(1, 6 if ty else 40))
+                script.append((ty << 28) | ln)
+                if ty == L.NS_OP_INS:
+                    out += list(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), ln))
+                    continue
+                rb = [int(ref.bases[(pos + rf + t) % clen]) for t in range(ln)]         # circular wrap
+                rf += ln
+                if ty == L.NS_OP_COPY:
+                    out += [(b & 0xDF) if (b & 0xDF) in b"ACGT" else 65 for b in rb]        # IUPAC codes are resolved on the device
+                elif ty == L.NS_OP_MIS:
+                    out += [int(rng.choice([c for c in b"ACGT" if c != (b & 0xDF)])) for b in rb]
+            pc["ref_len"] = rf
+            pc["ev_off"] = len(ops_all)
+            pc["ev_n_ops"] = len(script)
+            ops_all += script
+            if rewritten and i % 2:
+                pc["op_off"] = len(ops_all)              # a separate emitted script: bases come from the hp stream
+                pc["n_ops"] = 1
+                ops_all.append((L.NS_OP_HT << 28) | len(out))
+            else:
+                pc["op_off"], pc["n_ops"] = pc["ev_off"], pc["ev_n_ops"]
+            pc["out_len"] = len(out)
+            fwd += out
+            pieces.append(pc)
+        rev = bool(rng.integers(0, 2))
+        raw = [comp[b] for b in reversed(fwd)] if rev else fwd
+        reads[i]["reversed"] = rev
+        reads[i]["seq_len"] = len(raw)
+        reads[i]["seq_off"] = seq_off
+        pad = (-len(raw)) % 16
+        seq_parts.append(np.asarray(raw + [0] * pad, dtype=np.uint8))
+        seq_off += len(raw) + pad
+    info = type("I", (), {"n_reads": n_reads})()
+    return Batch(info, np.concatenate(seq_parts), None, reads, np.asarray(pieces, dtype=L.PIECE_DTYPE),
+                 np.asarray(ops_all, dtype=np.uint32), L.NS_KIND_ALIGNED, 1000)
+
+
+@pytest.mark.parametrize("rewritten", [False, True])
+def test_error_profile_formatter_matches_python_rows(rewritten):
+    """ns_format_error_profile (host C++, threads) writes exactly the rows of records.error_profile_rows, including reverse
+    reads, circular wrap, lower-case reference bases, gap pieces, and events whose bases the homopolymer pass fixed."""
+    from nanosim_b200.records import error_profile_rows, format_error_profile
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(5)
+    body = "".join(rng.choice(list("ACGTacgtN"), 3000))
+    ref = PackedReference.from_records([("chrT test", body)])
+    b = _synthetic_batch(rng, ref, 300, rewritten)
+    names = ["chrT_%d_aligned_%d_F_0_1_0" % (i * 7, i) for i in range(300)]
+    want = "".join(error_profile_rows(b, names, ref, seed=77)).encode()
+    for nt in (1, 5):
+        got = format_error_profile(b, names, ref, seed=77, n_threads=nt)
+        assert got == want
+    assert want.count(b"\n") > 1000
+
+
+def test_name_formatter_matches_python_names():
+    """ns_format_names writes the strings of records.read_names in every mode (chimeric genome, metagenome with gap
+    lengths, perfect, transcriptome with polyA, unaligned)."""
+    from nanosim_b200 import _lib as L
+    from nanosim_b200.records import name_table, read_names
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(9)
+    ref = PackedReference.from_records([("chrT test", "".join(rng.choice(list("ACGT"), 3000))), ("sp-two", "ACGT" * 50)])
+    b = _synthetic_batch(rng, ref, 200, False)
+    b.pieces["chrom"] = rng.integers(0, 2, len(b.pieces))
+    b.pieces["polya_len"] = rng.integers(0, 9, len(b.pieces))
+    b.reads["head"] = rng.integers(0, 500, len(b.reads))
+    b.reads["tail"] = rng.integers(0, 500, len(b.reads))
+    for kw in ({}, {"metagenome": True}, {"perfect": True}, {"transcriptome": True}, {"transcriptome": True, "perfect": True}):
+        assert name_table(b, ref.names, 12345, **kw).tolist() == read_names(b, ref.names, 12345, **kw), kw
+    b.kind = L.NS_KIND_UNALIGNED
+    t = name_table(b, ref.names, 7)
+    assert t.tolist() == read_names(b, ref.names, 7) and t[3] == read_names(b, ref.names, 7)[3] and len(t) == 200
