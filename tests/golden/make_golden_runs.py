@@ -32,6 +32,7 @@ CONFIGS = {
     "dorado_fastq_chimeric": (DORADO, ["--fastq", "--chimeric"], True),
     "dorado_fastq_hp6_chimeric": (DORADO, ["--fastq", "--chimeric", "-hp", "-k", "6"], True),
     "guppy_perfect": (GUPPY, ["--perfect"], False),
+    "guppy_medsd": (GUPPY, ["-med", "5000", "-sd", "1.05"], False),
     # eight independent single-threaded processes per chunk (independent numpy streams for the unaligned phase)
     "guppy_fasta_t1": (GUPPY, [], False),
     "guppyq_fastq_t1": (GUPPY + "+q", ["--fastq"], True),

@@ -743,6 +743,23 @@ def test_host_formatters_match_python_on_device_batches(mini_ref, L):
         assert format_error_profile(b, tab, mini_ref, seed=61, n_threads=4) == want and len(want) > 10000
 
 
+def test_cli_output_is_independent_of_batching(ecoli, tmp_path, L):
+    """Many small batches through the overlapped pipeline (contexts pull jobs as they free up, results are consumed in
+    submission order) write byte-identical files to one big batch."""
+    from nanosim_b200 import simulator
+    ref = os.path.join(str(tmp_path), "ecoli5m.fa")
+    synth.ecoli5m(ref)
+    outs = []
+    for tag, batch in (("a", "100000"), ("b", "173")):
+        out = os.path.join(str(tmp_path), tag)
+        simulator.main(["genome", "-rg", ref, "-c", os.path.join(pc.DATA, pc.MODELS["guppy"]), "-n", "3000", "-o", out, "--fastq",
+                        "--seed", "12", "--batch_reads", batch, "-t", "3"])
+        outs.append(out)
+    for suffix in ("_aligned_reads.fastq", "_unaligned_reads.fastq", "_aligned_error_profile"):
+        a, b = open(outs[0] + suffix, "rb").read(), open(outs[1] + suffix, "rb").read()
+        assert a == b and len(a) > 1000, suffix
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
