@@ -760,6 +760,51 @@ def test_cli_output_is_independent_of_batching(ecoli, tmp_path, L):
         assert a == b and len(a) > 1000, suffix
 
 
+def test_perfect_reads_vs_unmodified_reference(ecoli, L):
+    """100k reads of `simulator.py genome --perfect` (unmodified reference): length law (kde_aligned_reads within
+    [min_l, max_l], :1285-1299), strand, no errors, no head/tail."""
+    path = os.path.join(GOLDEN, "ref_stats_guppy_perfect.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, perfect=True, seed=91)
+    s = _device_run_stats(eng, ecoli, L, int(gold["n_aligned"]), 0, 50000, False)
+    eng.close()
+    assert s["head_bases"] == 0 and s["tail_bases"] == 0 and sum(s["events"].values()) == 0
+    assert s["aligned_bases"] == s["ref_bases"]
+    fails = []
+    for k in ("len_aligned", "len_middle_ref"):
+        st, dof, p = pc.chi2_two_sample(s[k], gold[k])
+        print("perfect", k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-6:
+            fails.append("perfect %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    assert abs(s["aligned_bases"] / s["n_aligned"] / (gold["aligned_bases"] / gold["n_aligned"]) - 1) < 1e-2
+    assert abs(s["strand_R_aligned"] / s["n_aligned"] - gold["strand_R_aligned"] / gold["n_aligned"]) < 8e-3
+    assert not fails, "\n".join(fails)
+
+
+def test_med_sd_vs_unmodified_reference(ecoli, L):
+    """100k reads of `simulator.py genome -med 5000 -sd 1.05` (unmodified reference).  The reference subtracts a head/tail
+    remainder from a log-normal total and then filters the list, which breaks the pairing with the remainder a read
+    later gets (:1285-1296); the device subtracts an independent remainder.  Read-level laws must agree."""
+    path = os.path.join(GOLDEN, "ref_stats_guppy_medsd.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=93)
+    eng.configure(fastq=False, min_len=50, max_len=ecoli.max_chrom, median_len=5000, sd_len=1.05)
+    s = _device_run_stats(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 50000, False)
+    eng.close()
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("med/sd per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    fails = pc.compare_stats(s, gold, rate_tol=4e-3, p_min=1e-6, label="medsd",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    st, dof, p = pc.chi2_two_sample(s["len_unaligned"], gold["len_unaligned"])
+    print("med/sd len_unaligned chi2 %.1f dof %d p %.3g (the reference's -t 8 unaligned workers share one numpy stream)" % (st, dof, p))
+    assert abs(s["aligned_bases"] / s["n_aligned"] / (gold["aligned_bases"] / gold["n_aligned"]) - 1) < 1.5e-2
+    assert not fails, "\n".join(fails)
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
