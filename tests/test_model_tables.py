@@ -5,7 +5,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import oracle_model
+from conftest import DATA, oracle_model
 
 import nanosim_oracle as no
 from nanosim_b200 import model as M
@@ -120,3 +120,30 @@ def test_compiled_model_roundtrip(tmp_path, compiled_models):
     assert cm2.text == cm.text
     for k in cm.kde:
         assert np.array_equal(cm.kde[k][0], cm2.kde[k][0]) and cm.kde[k][1] == cm2.kde[k][1]
+
+
+REF_MODELS = "/root/reference/pre-trained_models"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="the reference's pre-trained models are only present in the build container")
+@pytest.mark.parametrize("tarball,prefix,shipped", [
+    ("human_NA12878_DNA_FAB49712_guppy.tar.gz", "human_NA12878_DNA_FAB49712_guppy/training", "guppy_fab49712_plusq.npz"),
+    ("human_NA12878_DNA_FAB49712_guppy_flipflop.tar.gz", "human_NA12878_DNA_FAB49712_guppy_flipflop/training", None),
+    ("human_giab_hg002_sub1M_kitv14_dorado.tar.gz", "human_giab_hg002_sub1M_kitv14_dorado/hg002_nanosim_sub1M", None),
+])
+def test_reference_model_directories_load_and_tabulate(tmp_path, tarball, prefix, shipped):
+    """`-c <model_dir>/<prefix>` on the reference's own model archives: text tables + sklearn KDE pickles -> device tables;
+    the shipped .npz is a lossless copy of the directory it was compiled from (plus the quality table of config 2)."""
+    import tarfile
+    from nanosim_b200.model import CompiledModel, DeviceTables, load_model
+    with tarfile.open(os.path.join(REF_MODELS, tarball)) as tf:
+        tf.extractall(str(tmp_path), filter="data")
+    cm = load_model(os.path.join(str(tmp_path), prefix))
+    t = DeviceTables(cm, fastq=False, chimeric="chimeric_info" in cm.text)
+    assert len(t.alias_prob) > 1000 and len(cm.kde) >= 5
+    if shipped:
+        ours = CompiledModel.load(os.path.join(DATA, shipped))
+        for k, v in cm.text.items():
+            assert ours.text[k] == v, k
+        for k, (data, bw) in cm.kde.items():
+            assert np.array_equal(ours.kde[k][0], data) and ours.kde[k][1] == bw, k
