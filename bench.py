@@ -257,8 +257,8 @@ def main():
         return (info.total_bases, info.seq_bytes, info.n_reads, info.n_pieces, info.n_launches, info.ms_total,
                 info.ms_plan, info.ms_scan, info.ms_script, info.ms_emit, info.ms_setup, info.t_begin_ms, info.t_end_ms)
 
-    # ---- kernel-only arm: outputs stay in HBM.  Two contexts (ns_clone) share the reference; the plan kernels of
-    #      one batch (latency-bound, few warps) overlap the emit kernel of the other.  Every step simulates new read ids;
+    # ---- kernel-only arm: outputs stay in HBM.  `depth` contexts (ns_clone) share the reference; the latency-bound tails
+    #      of one batch's plan / unaligned kernels overlap the emit kernel of another.  Every step simulates new read ids;
     #      a batch's working set (>2 GB written + a 3 GB reference sampled at random) is far larger than the 126 MB L2.
     pipe = BatchPipeline(eng, depth=args.depth, fetch=False)
     pipe.warm(jobs_for(range(1)))                   # every context sizes its buffers once (untimed)
@@ -358,7 +358,7 @@ def main():
         "phase_ms_per_step": {"plan": sum(r[6] for r in rows) / args.steps, "scan": sum(r[7] for r in rows) / args.steps,
                               "script": sum(r[8] for r in rows) / args.steps, "emit": emit_ms / args.steps,
                               "setup": sum(r[10] for r in rows) / args.steps,
-                              "note": "sums of per-batch CUDA-event durations; batches of the two contexts overlap"},
+                              "note": "sums of per-batch CUDA-event durations; batches of the overlapped contexts share the GPU, so these add up to more than ms_per_step"},
         "wall_ms_per_step": 1e3 * wall / max(args.steps, 1),
         "roofline": {"bound": "hbm", "kernel": "emit_kernel<FASTQ>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,

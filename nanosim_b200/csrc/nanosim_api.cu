@@ -116,10 +116,6 @@ int fail(NsContext* c, int code, const char* fmt, ...) {
             return fail(ctx, NS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-__global__ void gather_piece_ops(const NsPieceMeta* pieces, uint32_t n, uint64_t* out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = pieces[i].n_ops;
-}
 __global__ void scatter_piece_off(NsPieceMeta* pieces, uint32_t n, const uint64_t* off) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pieces[i].op_off = off[i];
