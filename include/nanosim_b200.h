@@ -221,7 +221,9 @@ int ns_set_expression(NsContext* ctx, const NsExpression* expr);
 int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_reads, NsBatchInfo* info);
 
 /* Device->host copy of the last batch into caller buffers (pinned memory recommended).  qual / pieces / ops may be
- * NULL.  seq and qual need info.seq_bytes bytes, reads n_reads entries, pieces n_pieces, ops n_ops uint32. */
+ * NULL.  seq and qual need info.seq_bytes bytes, reads n_reads entries, pieces n_pieces, ops n_ops uint32.
+ * seq arrives as ASCII as always; on the wire large batches travel as 2 bits per base (packed by a kernel, expanded by
+ * host threads inside this call: NANOSIM_B200_UNPACK_THREADS, default min(16, cores/4); 0 copies plain ASCII). */
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
 
 /* Device pointers of the last batch (for consumers that stay on the GPU, e.g. torch tensors / NCCL gathers). */

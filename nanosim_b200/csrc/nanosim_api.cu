@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -89,6 +90,11 @@ struct NsContext {
         stats, sort_keys, sort_vals, sort_tmp, hp_off;
     uint64_t* h_totals = nullptr;   // pinned + mapped
     uint64_t* h_totals_dev = nullptr;
+    // ns_fetch sends bases over PCIe as 2 bits each: device pack buffer, pinned staging, event after its copy
+    DevBuf pack_dev;
+    uint8_t* pack_host = nullptr;
+    size_t pack_host_cap = 0;
+    cudaEvent_t ev_pack = nullptr;
     NsBatchInfo last{};
     int last_kind = 0;
     uint64_t last_first_id = 0;
@@ -142,6 +148,19 @@ __global__ void copy_ev_fields(NsPieceMeta* pieces, uint32_t n) {
 __global__ void add_base_u64(uint64_t* v, uint32_t n, uint64_t base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += base;
+}
+// Bases leave the device as 2 bits each (the emit kernel only writes A C G T/U): 16 ASCII bytes -> one 32-bit word,
+// base j of a byte quadruple in bits [2j, 2j+1], code = (c >> 1) & 3 (A 0, C 1, T/U 2, G 3).  ns_fetch expands them again
+// on the host, so callers see the same ASCII buffers while the PCIe transfer of a FASTQ batch shrinks from 2 to 1.25 B/base.
+__global__ void pack_bases_kernel(const uint4* __restrict__ seq, uint32_t* __restrict__ out, uint64_t n16) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 v = seq[i];
+    auto pk = [](uint32_t w) {
+        const uint32_t t = (w >> 1) & 0x03030303u;
+        return (t | (t >> 6) | (t >> 12) | (t >> 18)) & 0xffu;
+    };
+    out[i] = pk(v.x) | (pk(v.y) << 8) | (pk(v.z) << 16) | (pk(v.w) << 24);
 }
 // The batch totals the host needs mid-pipeline are written straight into mapped pinned host memory: a cudaMemcpy
 // would queue behind another context's multi-GB device->host transfer on the copy engine and serialise the pipelines.
@@ -310,6 +329,9 @@ int ns_destroy(NsContext* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (auto& k : ctx->kde) k.release();
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->pack_host) cudaFreeHost(ctx->pack_host);
+    ctx->pack_dev.release();
+    if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -998,6 +1020,57 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     return NS_OK;
 }
 
+namespace {
+// expands 2-bit bases (pack_bases_kernel) into ASCII with `nt` host threads
+void unpack_bases(const uint8_t* packed, uint8_t* seq, uint64_t seq_bytes, bool uracil, int nt) {
+    // two packed bytes -> eight characters per table lookup (512 KB table per alphabet, built once)
+    static std::vector<uint64_t> tables[2];
+    static std::once_flag once[2];
+    const char* abc = uracil ? "ACUG" : "ACTG";
+    std::call_once(once[uracil ? 1 : 0], [&] {
+        std::vector<uint64_t>& t = tables[uracil ? 1 : 0];
+        t.resize(65536);
+        for (uint32_t b = 0; b < 65536; ++b) {
+            uint64_t w = 0;
+            for (int j = 0; j < 8; ++j) w |= (uint64_t)(uint8_t)abc[(b >> (2 * j)) & 3u] << (8 * j);
+            t[b] = w;
+        }
+    });
+    const uint64_t* lut = tables[uracil ? 1 : 0].data();
+    const uint64_t whole = seq_bytes / 8;             // 16-bit groups that expand to 8 in-range characters
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            uint16_t b;
+            memcpy(&b, packed + 2 * i, 2);
+            const uint64_t w = lut[b];
+            memcpy(seq + 8 * i, &w, 8);
+        }
+    };
+    nt = std::max(1, std::min(nt, 64));
+    if (nt == 1 || whole < (1u << 16)) {
+        work(0, whole);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) {
+            const uint64_t lo = whole * t / nt, hi = whole * (t + 1) / nt;
+            if (hi > lo) th.emplace_back(work, lo, hi);
+        }
+        for (auto& x : th) x.join();
+    }
+    for (uint64_t k = whole * 8; k < seq_bytes; ++k) seq[k] = (uint8_t)abc[(packed[k >> 2] >> (2 * (k & 3))) & 3u];
+}
+
+int unpack_threads() {
+    static const int n = [] {
+        const char* e = getenv("NANOSIM_B200_UNPACK_THREADS");     // 0: copy the bases as ASCII (no packing)
+        if (e && *e) return std::max(0, atoi(e));
+        const unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(16u, hc ? hc / 4 : 4u));
+    }();
+    return n;
+}
+}  // namespace
+
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops) {
     if (!ctx) return NS_EINVAL;
     if (!ctx->have_batch) return fail(ctx, NS_ESTATE, "ns_fetch: no simulated batch");
@@ -1005,14 +1078,37 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
     const NsBatchInfo& bi = ctx->last;
     cudaStream_t st = ctx->stream;
     if (bi.n_reads == 0) return NS_OK;
-    if (seq) CK(cudaMemcpyAsync(seq, ctx->seq.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
-    if (qual) {
-        if (!ctx->hcfg.fastq) return fail(ctx, NS_ESTATE, "ns_fetch: qualities requested but the run is not --fastq");
-        CK(cudaMemcpyAsync(qual, ctx->qual.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
+    if (qual && !ctx->hcfg.fastq) return fail(ctx, NS_ESTATE, "ns_fetch: qualities requested but the run is not --fastq");
+    const int nt = unpack_threads();
+    const bool packed = seq && nt > 0 && bi.seq_bytes >= (1u << 20);
+    if (packed) {
+        // bases: pack on the device, copy a quarter of the bytes, expand on the host while the other copies run
+        const uint64_t n16 = (bi.seq_bytes + 15) / 16;            // the seq buffer has 16 bytes of slack
+        CK(ctx->pack_dev.ensure((size_t)n16 * 4));
+        if ((size_t)n16 * 4 > ctx->pack_host_cap) {
+            if (ctx->pack_host) cudaFreeHost(ctx->pack_host);
+            ctx->pack_host = nullptr;
+            ctx->pack_host_cap = 0;
+            const size_t want = (size_t)n16 * 4 + (size_t)n16 / 2 + 4096;
+            CK(cudaHostAlloc((void**)&ctx->pack_host, want, cudaHostAllocDefault));
+            ctx->pack_host_cap = want;
+        }
+        if (!ctx->ev_pack) CK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+        pack_bases_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(ctx->seq.as<uint4>(), ctx->pack_dev.as<uint32_t>(), n16);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->pack_host, ctx->pack_dev.p, (size_t)n16 * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_pack, st));
+    } else if (seq) {
+        CK(cudaMemcpyAsync(seq, ctx->seq.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
     }
+    if (qual) CK(cudaMemcpyAsync(qual, ctx->qual.p, bi.seq_bytes, cudaMemcpyDeviceToHost, st));
     if (reads) CK(cudaMemcpyAsync(reads, ctx->reads.p, (size_t)bi.n_reads * sizeof(NsReadMeta), cudaMemcpyDeviceToHost, st));
     if (pieces) CK(cudaMemcpyAsync(pieces, ctx->pieces.p, (size_t)bi.n_pieces * sizeof(NsPieceMeta), cudaMemcpyDeviceToHost, st));
     if (ops) CK(cudaMemcpyAsync(ops, ctx->ops.p, (size_t)bi.n_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (packed) {
+        CK(cudaEventSynchronize(ctx->ev_pack));
+        unpack_bases(ctx->pack_host, seq, bi.seq_bytes, ctx->dcfg.uracil != 0, nt);
+    }
     CK(cudaStreamSynchronize(st));
     return NS_OK;
 }
