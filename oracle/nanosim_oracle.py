@@ -1113,6 +1113,67 @@ class OracleTrxReference:
                 polya = [line.strip().split(".")[0] for line in f.readlines()]
         return OracleTrxReference(read_fasta(fasta), dict_exp, polya)
 
+    def load_ir(self, genome_fasta, gff3_path, ir_markov_path):
+        """The model_ir part of read_profile (simulator.py:404-453): genome sequences (pysam.Fastafile: record name = header
+        up to the first blank), the IR Markov model (two half-open intervals per state) and the exon/intron structure of
+        every transcript from the GFF3 (HTSeq.GFF_Reader(end_included=True): start - 1, end; "chr" stripped)."""
+        self.genome = {}
+        name, parts = None, []
+        with open(genome_fasta) as f:
+            for line in f:
+                if line.startswith(">"):
+                    if name is not None:
+                        self.genome[name] = "".join(parts)
+                    name, parts = line[1:].split()[0], []
+                else:
+                    parts.append(line.strip())
+        if name is not None:
+            self.genome[name] = "".join(parts)
+        self.genome_names = list(self.genome)
+        self.ir_model = {}
+        with open(ir_markov_path) as f:
+            f.readline()
+            for line in f:
+                info = line.strip().split()
+                if not info:
+                    continue
+                self.ir_model[info[0]] = [((0, float(info[1])), "no_IR"), ((float(info[1]), float(info[1]) + float(info[2])), "IR")]
+        self.structure = {}
+        with open(gff3_path) as f:
+            for line in f:
+                if line.startswith("#") or not line.strip():
+                    continue
+                c = line.rstrip("\n").split("\t", 8)
+                if c[2] not in ("exon", "intron"):
+                    continue
+                attr, first = {}, None
+                for tok in c[8].rstrip(";").split(";"):
+                    tok = tok.strip()
+                    if not tok:
+                        continue
+                    k, v = tok.split("=", 1) if "=" in tok else tok.split(None, 1)
+                    v = v.strip().strip('"')
+                    attr[k.strip()] = v
+                    if first is None:
+                        first = v
+                if "transcript_id" in attr:
+                    fid = attr["transcript_id"]
+                elif "Parent" in attr:
+                    info = first.split(":")
+                    if len(info) == 1:
+                        fid = info[0]
+                    elif info[0] == "transcript":
+                        fid = info[1]
+                    else:
+                        continue
+                else:
+                    continue
+                fid = fid.split(".")[0]
+                chrom = c[0].strip("chr") if "chr" in c[0] else c[0]
+                start, end = int(c[3]) - 1, int(c[4])
+                self.structure.setdefault(fid, []).append((c[2], chrom, start, end, end - start, c[6]))
+        return self
+
 
 def make_cdf(dict_exp, dict_len):
     """simulator.py:69-97."""
@@ -1140,6 +1201,58 @@ def select_nearest_kde2d(sampled, ref_len_total):
     return int(sampled[idx][1])
 
 
+def update_structure(structure, ir_model):
+    """simulator.py:114-146: one IR / no_IR state per intron from the two-state Markov chain."""
+    count = sum(1 for item in structure if item[0] == "intron")
+    states, flag_ir, prev = [], False, "start"
+    for _ in range(count):
+        p = random.random()
+        for (lo, hi), flag in ir_model[prev]:
+            if lo <= p < hi:
+                if flag == "IR":
+                    flag_ir = True
+                states.append(flag)
+                prev = flag
+                break
+    if not flag_ir:
+        return False, structure
+    out, j = list(structure), -1
+    for i in range(len(out)):
+        if out[i][0] == "intron":
+            j += 1
+            if states[j] == "IR":
+                out[i] = ("retained_intron",) + out[i][1:]
+    return True, out
+
+
+def extract_read_pos(length, ref_len, structure, polya, buffer=10):
+    """simulator.py:149-191 -> ([(chrom, start, end, strand)], retain_polya, [(start, end) of the retained introns hit])."""
+    len_before = 0
+    for item in structure:
+        if item[0] == "exon":
+            len_before += item[4]
+        elif item[0] == "retained_intron":
+            break
+    start_pos = random.randint(0, min(ref_len - length, len_before))
+    ivs, ir_list, end = [], [], None
+    for item in structure:
+        if length == 0:
+            break
+        if item[0] in ("exon", "retained_intron"):
+            if start_pos < item[4]:
+                start = start_pos + item[2]
+                end = start + length if start + length <= item[3] else item[3]
+                length -= end - start
+                start_pos = 0
+                ivs.append((item[1], start, end, item[5]))
+                if item[0] == "retained_intron":
+                    ir_list.append((start, end))
+            else:
+                start_pos -= item[4]
+    retain = bool(polya and end + buffer >= structure[-1][3])
+    return ivs, retain, ir_list
+
+
 def extract_read_trx(ref, key, length, trx_has_polya, buffer=10):
     """simulator.py:1683-1691."""
     pos = random.randint(0, ref.seq_len[key] - length)
@@ -1158,8 +1271,9 @@ def extract_read_transcriptome(ref, length):
 
 
 def simulation_aligned_transcriptome(ref, model, sink, kmer_bias, basecaller, num_simulate, polya, fastq, per=False,
-                                     uracil=False):
-    """simulator.py:1043-1263 with model_ir == False."""
+                                     uracil=False, model_ir=False):
+    """simulator.py:1043-1263; model_ir needs ref.load_ir(...)."""
+    flag_chrom = model_ir and any("chr" in item for item in ref.genome_names)
     import scipy.stats
 
     scale = 2.409858743694814 if basecaller == "albacore" else 4.168299657168961
@@ -1206,8 +1320,32 @@ def simulation_aligned_transcriptome(ref, model, sink, kmer_bias, basecaller, nu
             if middle_ref > ref_trx_len:
                 continue
             index = sink.take_index()
-            new_read, pos, retain = extract_read_trx(ref, ref_trx, middle_ref, has_polya)
+            ir_list = []
+            ir_flag = False
+            if model_ir:
+                ir_flag, structure_new = update_structure(ref.structure[ref_trx], ref.ir_model)
+            if ir_flag:
+                ivs, retain, ir_list = extract_read_pos(middle_ref, ref_trx_len, structure_new, has_polya)
+                new_read, missing = "", False
+                for chrom, start, end, strand in ivs:
+                    if flag_chrom:
+                        chrom = "chr" + chrom
+                    if chrom not in ref.genome:
+                        missing = True
+                        break
+                    new_read += ref.genome[chrom][start:end]
+                if missing:
+                    continue
+                pos = ivs[0][1]
+                if strand == "-":                   # keep the read in the direction of the reference transcript
+                    new_read = reverse_complement(new_read)
+            else:
+                new_read, pos, retain = extract_read_trx(ref, ref_trx, middle_ref, has_polya)
             name = str(ref_trx) + "_" + str(pos) + "_aligned_" + str(index)
+            if len(ir_list) > 0:
+                name += "_RetainedIntron_"
+                for ir_tuple in ir_list:
+                    name += "-".join(str(x) for x in ir_tuple) + ";"
             name += "_R" if is_reversed else "_F"
             remainder = int(remainder_l[simulated])
             ratio = ratio_l[simulated]
