@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch_reads", type=int, default=262144)
     ap.add_argument("--ref_scale", type=float, default=1.0, help="scale the 3.09 Gb reference (tests only)")
-    ap.add_argument("--depth", type=int, default=3, help="overlapped contexts per GPU")
+    ap.add_argument("--depth", type=int, default=4, help="overlapped contexts per GPU")
     ap.add_argument("--timeline", default=None, help="write the per-batch phase intervals of the timed steps to this file")
     ap.add_argument("--cpu_reads", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no_cpu_baseline", action="store_true")

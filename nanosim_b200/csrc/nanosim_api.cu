@@ -5,6 +5,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1039,12 +1043,22 @@ void unpack_bases(const uint8_t* packed, uint8_t* seq, uint64_t seq_bytes, bool 
     const uint64_t* lut = tables[uracil ? 1 : 0].data();
     const uint64_t whole = seq_bytes / 8;             // 16-bit groups that expand to 8 in-range characters
     auto work = [&](uint64_t lo, uint64_t hi) {
+        const bool aligned8 = (reinterpret_cast<uintptr_t>(seq) & 7u) == 0;
         for (uint64_t i = lo; i < hi; ++i) {
             uint16_t b;
             memcpy(&b, packed + 2 * i, 2);
             const uint64_t w = lut[b];
+#if defined(__x86_64__)
+            // streaming store: the destination is written once and read much later (no read-for-ownership traffic)
+            if (aligned8) _mm_stream_si64(reinterpret_cast<long long*>(seq + 8 * i), (long long)w);
+            else memcpy(seq + 8 * i, &w, 8);
+#else
             memcpy(seq + 8 * i, &w, 8);
+#endif
         }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
     };
     nt = std::max(1, std::min(nt, 64));
     if (nt == 1 || whole < (1u << 16)) {
@@ -1105,11 +1119,20 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
     if (reads) CK(cudaMemcpyAsync(reads, ctx->reads.p, (size_t)bi.n_reads * sizeof(NsReadMeta), cudaMemcpyDeviceToHost, st));
     if (pieces) CK(cudaMemcpyAsync(pieces, ctx->pieces.p, (size_t)bi.n_pieces * sizeof(NsPieceMeta), cudaMemcpyDeviceToHost, st));
     if (ops) CK(cudaMemcpyAsync(ops, ctx->ops.p, (size_t)bi.n_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    static const bool trace = getenv("NANOSIM_B200_TRACE_FETCH") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_packed = 0, t_unpacked = 0;
     if (packed) {
         CK(cudaEventSynchronize(ctx->ev_pack));
+        t_packed = ms_since();
         unpack_bases(ctx->pack_host, seq, bi.seq_bytes, ctx->dcfg.uracil != 0, nt);
+        t_unpacked = ms_since();
     }
     CK(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "ns_fetch: %.2f GB bases; packed copy done after %.1f ms, expansion %.1f ms (%d threads), everything after %.1f ms\n",
+                bi.seq_bytes / 1e9, t_packed, t_unpacked - t_packed, nt, ms_since());
     return NS_OK;
 }
 

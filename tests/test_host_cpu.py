@@ -224,3 +224,59 @@ def test_name_formatter_matches_python_names():
     b.kind = L.NS_KIND_UNALIGNED
     t = name_table(b, ref.names, 7)
     assert t.tolist() == read_names(b, ref.names, 7) and t[3] == read_names(b, ref.names, 7)[3] and len(t) == 200
+
+
+def test_intron_retention_host_logic_matches_oracle(monkeypatch):
+    """nanosim_b200.intron_retention (GFF3 structures, vectorised IR Markov chain, extract_read_pos, script cutting) against
+    the pinned oracle functions fed the same uniforms."""
+    import random
+    from nanosim_b200 import _lib as L
+    from nanosim_b200 import intron_retention as ir
+    from nanosim_b200.reference_fasta import PackedReference
+    D = os.path.join(GOLDEN, "ir")
+    trx = PackedReference.from_fasta(os.path.join(D, "transcripts.fa"))
+    oref = no.OracleTrxReference.from_files(os.path.join(D, "transcripts.fa"), os.path.join(D, "expression.tsv"), os.path.join(D, "polya.txt"))
+    oref.load_ir(os.path.join(D, "genome.fa"), os.path.join(D, "annotation.gff3"), os.path.join(D, "IR_markov_model"))
+    st = ir.TranscriptStructures.from_gff3(os.path.join(D, "annotation.gff3"), trx.names, oref.genome_names)
+    p_no_ir = ir.read_ir_markov_model(os.path.join(D, "IR_markov_model"))
+    assert p_no_ir.tolist() == [0.6, 0.7, 0.5]
+    rng = np.random.default_rng(3)
+    checked = 0
+    for t, key in enumerate(trx.names):
+        feats_o = oref.structure.get(key, [])
+        a, b = int(st.first[t]), int(st.first[t + 1])
+        assert b - a == len(feats_o) and int(st.n_introns[t]) == sum(1 for x in feats_o if x[0] == "intron")
+        for j, f in enumerate(feats_o):                       # same features, genome record instead of the chromosome name
+            g = int(st.chrom[a + j])
+            assert (("exon", "intron")[st.ftype[a + j]], int(st.start[a + j]), int(st.end[a + j]), "-" if st.minus[a + j] else "+") == (f[0], f[2], f[3], f[5])
+            assert g == (oref.genome_names.index("chr" + f[1]) if "chr" + f[1] in oref.genome_names else -1)
+        for rep in range(40):
+            n_int = int(st.n_introns[t])
+            u = rng.random(n_int + 1)
+            feed = iter(u[:n_int].tolist())
+            monkeypatch.setattr(random, "random", lambda: next(feed))
+            flag, st_new = no.update_structure(feats_o, oref.ir_model)
+            ret = ir.draw_ir_states(p_no_ir, np.asarray([n_int]), u[None, :n_int]) if n_int else np.zeros((1, 0), dtype=bool)
+            assert bool(flag) == bool(ret.any())
+            assert [x[0] == "retained_intron" for x in st_new if x[0] != "exon"] == ret[0].tolist()
+            if not flag:
+                continue
+            ref_len = int(trx.lengths[t])
+            length = int(rng.integers(1, ref_len))
+            monkeypatch.setattr(random, "randint", lambda lo, hi: min(int(u[n_int] * (hi + 1)), hi) if hi > 0 else 0)
+            ivs_o, _, ir_o = no.extract_read_pos(length, ref_len, st_new, False)
+            feats = list(zip(st.ftype[a:b].tolist(), st.chrom[a:b].tolist(), st.start[a:b].tolist(), st.end[a:b].tolist(), st.minus[a:b].tolist()))
+            ivs = ir.extract_read_pos(length, ref_len, feats, ret[0].tolist(), float(u[n_int]))
+            assert [(s, e) for _, s, e, _, _ in ivs] == [(s, e) for _, s, e, _ in ivs_o]
+            assert [(s, e) for _, s, e, _, r in ivs if r] == [tuple(x) for x in ir_o]
+            checked += 1
+    assert checked > 100
+    # script cutting: the pieces' ops concatenate to an equivalent script and consume exactly their intervals
+    ops = np.asarray([(L.NS_OP_HT << 28) | 5, (L.NS_OP_COPY << 28) | 30, (L.NS_OP_INS << 28) | 2, (L.NS_OP_MIS << 28) | 3,
+                      (L.NS_OP_COPY << 28) | 17, (L.NS_OP_DEL << 28) | 4, (L.NS_OP_COPY << 28) | 6, (L.NS_OP_LIT << 28) | (3 << 24) | 9,
+                      (L.NS_OP_HT << 28) | 7], dtype=np.uint32)
+    parts = ir.split_script(ops, [30, 41, 60])
+    ref_used = [int(sum((o & 0x0fffffff) for o in p.tolist() if (o >> 28) in (0, 1, 3))) for p in parts]
+    assert ref_used == [30, 11, 19]
+    assert sum(ir._out_len(p) for p in parts) == ir._out_len(ops)
+    assert parts[0][0] == ops[0] and parts[-1][-1] == ops[-1] and (parts[0][2] >> 28) == L.NS_OP_INS
