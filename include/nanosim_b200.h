@@ -109,7 +109,7 @@ typedef struct {
 
 /* The scalar arguments of simulation()/simulation_aligned_genome()/simulation_unaligned(). */
 typedef struct {
-    uint32_t mode;            /* 0 genome, 1 metagenome, 2 transcriptome (--no_model_ir) */
+    uint32_t mode;            /* 0 genome, 1 metagenome, 2 transcriptome */
     uint32_t circular;        /* dna_type == "circular" (single chromosome) */
     uint32_t perfect;
     uint32_t fastq;
@@ -123,6 +123,9 @@ typedef struct {
     uint32_t kde2d_sample;    /* transcriptome: size N of the 2-D KDE sample select_nearest_kde2d searches (:1072, :1090):
                                  the reference uses the number of aligned reads of the worker */
     double polya_scale;       /* transcriptome --polya: scale of expon(loc=2, scale) (:1046-1053); 0 = no polyA tails */
+    uint32_t trx_records;     /* transcriptome with intron retention: the first trx_records reference records are the
+                                 transcripts, the rest the genome ns_reemit reads introns from; 0 = every record is a transcript */
+    uint32_t reserved;
 } NsRunConfig;
 
 /* Unaligned reads normally take the warp-per-read fast path, which writes bases directly and keeps no edit scripts.
@@ -137,6 +140,12 @@ typedef struct {
 #define NS_PIECE_SEGMENT 0    /* aligned segment (error_list + mutate_read)                  */
 #define NS_PIECE_GAP 1        /* chimeric gap (simulation_gap :1552-1568)                    */
 #define NS_PIECE_UNALIGNED 2  /* unaligned read body (simulation_unaligned :1482-1549)       */
+/* NsPieceMeta.kind: the low 16 bits hold the kind above; intron-retention reads (ns_reemit) use three flags */
+#define NS_PIECE_KIND(k) ((k) & 0xffffu)
+#define NS_PIECE_REF_REV 0x80000000u  /* the piece reads its reference backwards and complemented (minus-strand transcript) */
+#define NS_PIECE_CONT 0x40000000u     /* continues the previous segment of the read: error positions keep counting (:2006) */
+#define NS_PIECE_RETAINED 0x20000000u /* the piece lies in a retained intron (read name, :1189-1192) */
+#define NS_PIECE_GENOME 0x10000000u   /* every piece of a read laid out on the genome; ref_req = its transcript's record */
 
 /* What the reference encodes in the read name and FASTQ record (:1390-1402, :1437-1443). */
 typedef struct {
@@ -225,6 +234,17 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
  * seq arrives as ASCII as always; on the wire large batches travel as 2 bits per base (packed by a kernel, expanded by
  * host threads inside this call: NANOSIM_B200_UNPACK_THREADS, default min(16, cores/4); 0 copies plain ASCII). */
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
+
+/* Intron retention (simulator.py:1156-1183), second half: replaces the piece lists of `n_slots` reads of the last batch and
+ * emits those reads again.  The host decides which reads retain introns (nanosim_b200/intron_retention.py) and lays each of
+ * them out as pieces on the GENOME records of the reference, one per exon / retained-intron interval (NS_PIECE_REF_REV,
+ * NS_PIECE_CONT, NS_PIECE_RETAINED), with the read's edit script cut at the interval boundaries.  new_reads[k] replaces
+ * read read_slots[k] (same seq_len: the bytes are overwritten in place); new_pieces / new_ops are appended behind the
+ * batch's pieces / ops, and piece_first / op_off / ev_off in the new metadata are absolute indices into the grown arrays.
+ * All emit randomness is indexed by the position in the read, so inserted, head/tail and polyA bases and every quality
+ * value come out as before; only bases taken from the reference change. */
+int ns_reemit(NsContext* ctx, const uint32_t* read_slots, const NsReadMeta* new_reads, uint32_t n_slots,
+              const NsPieceMeta* new_pieces, uint32_t n_new_pieces, const uint32_t* new_ops, uint64_t n_new_ops);
 
 /* Device pointers of the last batch (for consumers that stay on the GPU, e.g. torch tensors / NCCL gathers). */
 int ns_device_buffers(NsContext* ctx, const uint8_t** seq, const uint8_t** qual, const NsReadMeta** reads,

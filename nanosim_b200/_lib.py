@@ -12,12 +12,13 @@ NS_N_QUAL_STATES = 5
 NS_QUAL_SLOTS = 94
 NS_KIND_ALIGNED, NS_KIND_UNALIGNED = 0, 1
 NS_PIECE_SEGMENT, NS_PIECE_GAP, NS_PIECE_UNALIGNED = 0, 1, 2
+NS_PIECE_REF_REV, NS_PIECE_CONT, NS_PIECE_RETAINED, NS_PIECE_GENOME, NS_PIECE_KIND_MASK = 0x80000000, 0x40000000, 0x20000000, 0x10000000, 0xffff
 NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT, NS_OP_LIT = 0, 1, 2, 3, 4, 5
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
 NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
 
 EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
-           "ns_simulate", "ns_fetch", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names"]
+           "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names"]
 
 
 class NsReference(C.Structure):
@@ -49,7 +50,7 @@ class NsRunConfig(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("circular", C.c_uint32), ("perfect", C.c_uint32), ("fastq", C.c_uint32),
                 ("chimeric", C.c_uint32), ("kmer_bias", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32),
                 ("median_len", C.c_double), ("sd_len", C.c_double), ("flags", C.c_uint32), ("kde2d_sample", C.c_uint32),
-                ("polya_scale", C.c_double)]
+                ("polya_scale", C.c_double), ("trx_records", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class NsExpression(C.Structure):
@@ -139,5 +140,7 @@ def lib():
     L.ns_format_error_profile.restype = C.c_int64
     L.ns_format_names.argtypes = [P, P, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, P, P, P, C.c_uint64, P]
     L.ns_format_names.restype = C.c_int64
+    L.ns_reemit.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, C.c_uint64]
+    L.ns_reemit.restype = C.c_int
     _lib = L
     return L

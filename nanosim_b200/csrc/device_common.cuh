@@ -49,7 +49,7 @@ struct DevRef {
 };
 
 struct DevCfg {
-    uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome, transcriptome, uracil, kde2d_n;
+    uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome, transcriptome, uracil, kde2d_n, trx_records;
     double polya_scale;
     uint32_t min_len, max_len;
     uint64_t seed;

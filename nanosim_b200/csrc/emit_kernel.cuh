@@ -58,21 +58,25 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // Per-op constants of a ring entry: [1:0] 3 when the base is random (INS, HT, pad), [2] EMIT_F_REF, [3] EMIT_F_MIS,
 // [15:8] the character classified when the reference is not read ('A' -> index 0, or the literal base of a LIT op),
 // [31:16] byte offset of the quality state's bucket table.
-__device__ __forceinline__ uint32_t emit_op_info(uint32_t op, bool unmapped) {
+// ref_comp: the piece classifies reference bytes with the COMPLEMENTING table (NS_PIECE_REF_REV); the characters stored for
+// ops that do not read the reference are then pre-complemented so that they classify to the intended base.
+__device__ __forceinline__ uint32_t emit_op_info(uint32_t op, bool unmapped, bool ref_comp = false) {
     const uint32_t ty = op >> 28;
     // quality state: COPY->match(2) MIS->mis(0) INS->ins(1) HT->ht(3) LIT->its own; gap/unaligned -> unmapped(4)
     const uint32_t qs = unmapped ? 4u : (ty == NS_OP_LIT ? ((op >> 24) & 3u) : ((0x30102u >> (4u * ty)) & 7u));
     uint32_t info = (qs * QLUT_SIZE * 4u) << 16;
-    if (ty < 2u) info |= EMIT_F_REF | (ty == NS_OP_MIS ? EMIT_F_MIS : 0u) | ((uint32_t)'A' << 8);
-    else if (ty == NS_OP_LIT) info |= idx_base((op >> 26) & 3u) << 8;
-    else info |= 3u | ((uint32_t)'A' << 8);
+    const uint32_t zero = ref_comp ? (uint32_t)'T' : (uint32_t)'A';          // classifies to base index 0
+    if (ty < 2u) info |= EMIT_F_REF | (ty == NS_OP_MIS ? EMIT_F_MIS : 0u) | (zero << 8);
+    else if (ty == NS_OP_LIT) info |= idx_base(((op >> 26) & 3u) ^ (ref_comp ? 2u : 0u)) << 8;
+    else info |= 3u | (zero << 8);
     return info;
 }
 
 struct EmitPiece {
     const uint8_t* cbase;    // first base of the chromosome
     uint32_t pos, clen;      // piece start within the chromosome, chromosome length
-    uint32_t rev;
+    uint32_t rdir;           // the reference is walked backwards (reverse read XOR minus-strand piece)
+    uint32_t ref_comp;       // reference bases are complemented on classification (minus-strand piece)
     uint32_t tbl;            // output characters of base indices 0..3 (complemented for reverse reads)
     uint32_t piece_in_read;
     uint64_t rid;
@@ -92,18 +96,18 @@ __device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiec
     const uint32_t within = x - e.x, info = e.w;
     uint32_t oi;
     if (info & EMIT_F_REF) {
-        uint32_t rabs = pc.rev ? e.y - within : e.y + within;
-        if (rabs >= pc.clen) rabs += pc.rev ? pc.clen : 0u - pc.clen;
+        uint32_t rabs = pc.rdir ? e.y - within : e.y + within;
+        if (rabs >= pc.clen) rabs += pc.rdir ? pc.clen : 0u - pc.clen;
         uint32_t c = __ldg(pc.cbase + rabs);
         if (c - 'a' < 26u) c -= 32;
         if (!acgt_fast(c)) {
             const uint32_t f = rabs >= pc.pos ? rabs - pc.pos : rabs + pc.clen - pc.pos;
             c = converted_ref_base(c, a.cfg.seed, pc.rid, pc.piece_in_read, f);
         }
-        oi = base_idx(c);
+        oi = base_idx(c) ^ (pc.ref_comp ? 2u : 0u);
         if (info & EMIT_F_MIS) oi = (oi + 1u + __umulhi(p, 3u)) & 3u;
     } else {
-        oi = (info & 3u) ? (w & 3u) : base_idx((info >> 8) & 0xffu);
+        oi = (info & 3u) ? (w & 3u) : (base_idx((info >> 8) & 0xffu) ^ (pc.ref_comp ? 2u : 0u));
     }
     uint32_t out = (pc.tbl >> (8u * oi)) & 0xffu;
     if (FASTQ) {
@@ -167,15 +171,16 @@ template <bool FASTQ>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ EmitArgs a) {
     extern __shared__ uint4 smem4[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem4);                          // FASTQ only
-    uint8_t* cvt = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));
+    uint8_t* cvt_tables = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4* ring = reinterpret_cast<uint4*>(cvt + 256) + warp * EMIT_RING;
+    uint4* ring = reinterpret_cast<uint4*>(cvt_tables + 512) + warp * EMIT_RING;
     if (FASTQ)
         for (int i = threadIdx.x; i < NS_N_QUAL_STATES * QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[i];
     {   // case_convert classification: base index 0..3 (A C T G), 4 = needs the IUPAC path
         uint32_t c = threadIdx.x;
         uint32_t u = (c - 'a' < 26u) ? c - 32u : c;
-        cvt[c] = (uint8_t)(acgt_fast(u) ? base_idx(u) : 4u);
+        cvt_tables[c] = (uint8_t)(acgt_fast(u) ? base_idx(u) : 4u);
+        cvt_tables[256 + c] = (uint8_t)(acgt_fast(u) ? base_idx(u) ^ 2u : 4u);     // complementing twin (NS_PIECE_REF_REV)
     }
     __syncthreads();
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
@@ -191,6 +196,11 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         if (pm.out_len == 0) continue;
         const NsReadMeta rm = a.reads[pm.read_slot];
         const bool rev = rm.reversed != 0;
+        // a minus-strand piece (intron retention, ns_reemit) reads the genome backwards and complemented: together with the
+        // read's own orientation that fixes the walking direction, and the complement moves into the classification table
+        const bool ref_comp = (pm.kind & NS_PIECE_REF_REV) != 0;
+        const bool rdir = rev != ref_comp;
+        const uint8_t* cvt = cvt_tables + (ref_comp ? 256 : 0);
         const uint32_t n_ops = pm.n_ops, ref_len = pm.ref_len;
         const uint32_t A = rev ? rm.seq_len - pm.out_rel - pm.out_len : pm.out_rel;    // piece start in read coordinates
         const uint32_t pad = A & 15u, P0 = A - pad;          // x = read coordinate - P0: chunks are x/16
@@ -200,7 +210,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         pc.cbase = a.ref.bases + cstart;
         pc.pos = pm.pos;
         pc.clen = (uint32_t)(a.ref.chrom_off[pm.chrom + 1] - cstart);
-        pc.rev = rev;
+        pc.rdir = rdir;
+        pc.ref_comp = ref_comp;
         {
             const uint32_t t = a.cfg.uracil ? 0x47554341u : 0x47544341u;             // "ACTG" / "ACUG"
             pc.tbl = rev ? __byte_perm(t, 0, 0x1032) : t;                            // complement: A<->T, C<->G
@@ -210,13 +221,13 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         const uint8_t* __restrict__ cbase = pc.cbase;
         const uint32_t clen = pc.clen, tbl = pc.tbl;
         const bool wraps = (uint64_t)pm.pos + ref_len > clen;                        // circular wrap (:1756-1760)
-        const uint32_t dir = rev ? 0xffffffffu : 1u, wrap_fix = rev ? clen : 0u - clen;
+        const uint32_t dir = rdir ? 0xffffffffu : 1u, wrap_fix = rdir ? clen : 0u - clen;
         const uint32_t* __restrict__ ops = a.ops + pm.op_off;
         uint8_t* seq_out = a.seq + rm.seq_off + P0;
         uint8_t* qual_out = FASTQ ? a.qual + rm.seq_off + P0 : nullptr;
-        const bool unmapped = pm.kind != NS_PIECE_SEGMENT;
+        const bool unmapped = NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT;
         const uint32_t id_lo = (uint32_t)pc.rid, id_hi = (uint32_t)(pc.rid >> 32);
-        const uint32_t info_pad = emit_op_info(NS_OP_HT << 28, unmapped);
+        const uint32_t info_pad = emit_op_info(NS_OP_HT << 28, unmapped, ref_comp);
 
         uint32_t t_loaded = 0, w_loaded = 0, w_ret = 0, out_loaded = pad, ref_loaded = 0, prog = 0;
         bool closed = false;
@@ -239,10 +250,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
                 const uint32_t bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const uint32_t rstart = ref_loaded + sr - r;                      // reference bases consumed before this op
-                    uint32_t ab = pm.pos + (rev ? ref_len - 1u - rstart : rstart);    // first base in walking order
+                    uint32_t ab = pm.pos + (rdir ? ref_len - 1u - rstart : rstart);   // first base in walking order
                     if (wraps && ab >= clen) ab -= clen;
                     ring[(w_loaded + __popc(bal & lane_lt)) & (EMIT_RING - 1)] =
-                        make_uint4(out_loaded + so - o, ab, len, emit_op_info(op, unmapped));
+                        make_uint4(out_loaded + so - o, ab, len, emit_op_info(op, unmapped, ref_comp));
                 }
                 out_loaded += __shfl_sync(0xffffffffu, so, 31);
                 ref_loaded += __shfl_sync(0xffffffffu, sr, 31);
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
                     const uint32_t within = cs - e.x;
                     rem = e.z - within;
                     info = e.w;
-                    rabs = rev ? e.y - within : e.y + within;
+                    rabs = rdir ? e.y - within : e.y + within;
                     if (wraps && rabs >= clen) rabs += wrap_fix;
                 }
                 // ---- all randomness of the chunk up front, position-indexed: base i owns one 32-bit word (FASTQ: low

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
         const uint32_t pi = atomicAdd(a.counter, 1u);
         if (pi >= a.n_pieces) break;
         NsPieceMeta& pm = a.pieces[pi];
-        if (pm.kind != NS_PIECE_SEGMENT) {
+        if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
             if (!WRITE) a.out_n_ops[pi] = 0;           // untouched pieces keep their script
             continue;
         }

@@ -209,7 +209,7 @@ __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* rea
     unsigned long long* evlen = st + 16;
     unsigned long long* run_h = evlen + 3 * (NS_STATS_EV_CAP + 1);
     unsigned long long* first_h = run_h + (NS_STATS_RUN_CAP + 1);
-    if (pm.kind != NS_PIECE_SEGMENT) {
+    if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
         atomicAdd(&st[4], 1ull);
         atomicAdd(&st[5], (unsigned long long)pm.out_len);
         return;
@@ -545,6 +545,7 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.transcriptome = cfg->mode == 2 ? 1u : 0u;
     ctx->dcfg.uracil = (cfg->flags & NS_FLAG_URACIL) ? 1u : 0u;
     ctx->dcfg.kde2d_n = cfg->kde2d_sample ? cfg->kde2d_sample : 1u;
+    ctx->dcfg.trx_records = cfg->trx_records;
     ctx->dcfg.polya_scale = cfg->polya_scale;
     ctx->dcfg.min_len = cfg->min_len;
     ctx->dcfg.max_len = cfg->max_len;
@@ -679,7 +680,7 @@ void assign_species_host(const std::vector<uint32_t>& n_seg, const std::vector<u
 
 __global__ void species_bases_kernel(const NsPieceMeta* pieces, uint32_t n, const uint32_t* chrom_species, double* acc) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && pieces[i].kind == NS_PIECE_SEGMENT) atomicAdd(&acc[chrom_species[pieces[i].chrom]], (double)pieces[i].ref_len);
+    if (i < n && NS_PIECE_KIND(pieces[i].kind) == NS_PIECE_SEGMENT) atomicAdd(&acc[chrom_species[pieces[i].chrom]], (double)pieces[i].ref_len);
 }
 }  // namespace
 
@@ -690,6 +691,59 @@ static int exclusive_scan_u64(NsContext* ctx, const uint64_t* in, uint64_t* out,
     CK(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, in, out, (int)n, ctx->stream));
     return NS_OK;
 }
+
+namespace {
+// emit_kernel over `n_pieces` pieces of the context's current batch (all of them, or the ones `order` lists)
+int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order) {
+    cudaStream_t st = ctx->stream;
+    EmitArgs ea;
+    ea.ref = ctx->dref;
+    ea.cfg = ctx->dcfg;
+    ea.kind = (uint32_t)kind;
+    ea.first_id = first_read_id;
+    ea.reads = ctx->reads.as<NsReadMeta>();
+    ea.pieces = ctx->pieces.as<NsPieceMeta>();
+    ea.ops = ctx->ops.as<uint32_t>();
+    ea.n_pieces = n_pieces;
+    ea.seq = ctx->seq.as<uint8_t>();
+    ea.qual = ctx->qual.as<uint8_t>();
+    ea.qlut = ctx->qlut.as<uint32_t>();
+    ea.qcdf = ctx->qcdf.as<uint32_t>();
+    ea.counter = ctx->counter.as<uint32_t>();
+    ea.order = order;
+    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+    const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 512;
+    if (ctx->hcfg.fastq) {
+        size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
+        CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<true>, EMIT_WARPS * 32, smem));
+        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
+        emit_kernel<true><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
+    } else {
+        size_t smem = ring_bytes;
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, EMIT_WARPS * 32, smem));
+        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
+        emit_kernel<false><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
+    }
+    CK(cudaGetLastError());
+    return NS_OK;
+}
+
+__global__ void replace_reads(NsReadMeta* reads, const uint32_t* slots, const NsReadMeta* repl, uint32_t n, uint32_t n_reads) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && slots[i] < n_reads) {
+        NsReadMeta r = repl[i];
+        r.seq_off = reads[slots[i]].seq_off;         // the bytes are overwritten in place
+        reads[slots[i]] = r;
+    }
+}
+__global__ void iota_from(uint32_t* v, uint32_t n, uint32_t first) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = first + i;
+}
+}  // namespace
 
 int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_reads, NsBatchInfo* info) {
     if (!ctx) return NS_EINVAL;
@@ -947,36 +1001,9 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     launches += 2;    // ev copy + emit
 
     // ---- emit
-    EmitArgs ea;
-    ea.ref = ctx->dref;
-    ea.cfg = ctx->dcfg;
-    ea.kind = (uint32_t)kind;
-    ea.first_id = first_read_id;
-    ea.reads = pa.reads;
-    ea.pieces = pa.pieces;
-    ea.ops = pa.ops;
-    ea.n_pieces = n_pieces;
-    ea.seq = ctx->seq.as<uint8_t>();
-    ea.qual = ctx->qual.as<uint8_t>();
-    ea.qlut = ctx->qlut.as<uint32_t>();
-    ea.qcdf = ctx->qcdf.as<uint32_t>();
-    ea.counter = ctx->counter.as<uint32_t>();
-    ea.order = chim ? nullptr : vals_out;        // one piece per read: the plan's longest-first order serves the emit too
-    CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-    const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 256;
-    if (ctx->hcfg.fastq) {
-        size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
-        CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<true>, EMIT_WARPS * 32, smem));
-        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
-        emit_kernel<true><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
-    } else {
-        size_t smem = ring_bytes;
-        int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, EMIT_WARPS * 32, smem));
-        unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
-        emit_kernel<false><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
+    {
+        int rc = launch_emit(ctx, kind, first_read_id, n_pieces, chim ? nullptr : vals_out);   // one piece per read: the plan's
+        if (rc) return rc;                                                                       // longest-first order serves the emit too
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -1136,6 +1163,54 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
     return NS_OK;
 }
 
+int ns_reemit(NsContext* ctx, const uint32_t* read_slots, const NsReadMeta* new_reads, uint32_t n_slots,
+              const NsPieceMeta* new_pieces, uint32_t n_new_pieces, const uint32_t* new_ops, uint64_t n_new_ops) {
+    if (!ctx) return NS_EINVAL;
+    if (!ctx->have_batch || ctx->last_kind != NS_KIND_ALIGNED) return fail(ctx, NS_ESTATE, "ns_reemit: no aligned batch to patch");
+    if (n_slots == 0 || n_new_pieces == 0) return NS_OK;
+    if (!read_slots || !new_reads || !new_pieces || (n_new_ops && !new_ops)) return fail(ctx, NS_EINVAL, "ns_reemit: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    NsBatchInfo& bi = ctx->last;
+    const uint32_t old_np = bi.n_pieces;
+    const uint64_t old_ops = bi.n_ops;
+    // the host built absolute indices against these totals: check the ones that would corrupt memory
+    for (uint32_t k = 0; k < n_slots; ++k) {
+        if (read_slots[k] >= bi.n_reads) return fail(ctx, NS_EINVAL, "ns_reemit: read slot %u out of range", read_slots[k]);
+        if (new_reads[k].piece_first < old_np || (uint64_t)new_reads[k].piece_first + new_reads[k].n_pieces > (uint64_t)old_np + n_new_pieces)
+            return fail(ctx, NS_EINVAL, "ns_reemit: read %u does not point into the new pieces", read_slots[k]);
+    }
+    for (uint32_t k = 0; k < n_new_pieces; ++k) {
+        const NsPieceMeta& p = new_pieces[k];
+        if (p.read_slot >= bi.n_reads || p.chrom >= ctx->dref.n_chrom || p.op_off < old_ops || p.op_off + p.n_ops > old_ops + n_new_ops ||
+            (uint64_t)p.pos + p.ref_len > ctx->h_chrom_off[p.chrom + 1] - ctx->h_chrom_off[p.chrom])
+            return fail(ctx, NS_EINVAL, "ns_reemit: piece %u is inconsistent with the batch or the reference", k);
+    }
+    CK(ctx->pieces.ensure_keep((size_t)(old_np + n_new_pieces + 1) * sizeof(NsPieceMeta), (size_t)old_np * sizeof(NsPieceMeta), st));
+    CK(ctx->ops.ensure_keep((size_t)(old_ops + n_new_ops + 4) * sizeof(uint32_t), (size_t)old_ops * sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(ctx->pieces.as<NsPieceMeta>() + old_np, new_pieces, (size_t)n_new_pieces * sizeof(NsPieceMeta), cudaMemcpyHostToDevice, st));
+    if (n_new_ops) CK(cudaMemcpyAsync(ctx->ops.as<uint32_t>() + old_ops, new_ops, (size_t)n_new_ops * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // staging for the slots / replacement reads / piece order: the scan buffers are free between batches
+    CK(ctx->scan_in.ensure((size_t)n_slots * sizeof(NsReadMeta)));
+    CK(ctx->scan_out.ensure((size_t)n_slots * sizeof(uint32_t)));
+    CK(ctx->sort_vals.ensure((size_t)n_new_pieces * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(ctx->scan_in.p, new_reads, (size_t)n_slots * sizeof(NsReadMeta), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->scan_out.p, read_slots, (size_t)n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    replace_reads<<<(n_slots + 255) / 256, 256, 0, st>>>(ctx->reads.as<NsReadMeta>(), ctx->scan_out.as<uint32_t>(),
+                                                         ctx->scan_in.as<NsReadMeta>(), n_slots, bi.n_reads);
+    iota_from<<<(n_new_pieces + 255) / 256, 256, 0, st>>>(ctx->sort_vals.as<uint32_t>(), n_new_pieces, old_np);
+    CK(cudaGetLastError());
+    {
+        int rc = launch_emit(ctx, NS_KIND_ALIGNED, ctx->last_first_id, n_new_pieces, ctx->sort_vals.as<uint32_t>());
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(st));
+    bi.n_pieces = old_np + n_new_pieces;
+    bi.n_ops = old_ops + n_new_ops;
+    bi.n_launches += 3;
+    return NS_OK;
+}
+
 int ns_device_buffers(NsContext* ctx, const uint8_t** seq, const uint8_t** qual, const NsReadMeta** reads,
                       const NsPieceMeta** pieces, const uint32_t** ops) {
     if (!ctx) return NS_EINVAL;
@@ -1252,7 +1327,8 @@ inline char* put_dec(char* p, uint64_t v) {
     return p;
 }
 struct EvRow {
-    uint32_t type, len, ref_start, out_start, index;
+    uint32_t type, len, ref_start, out_start, index, piece, ref_base;
+    bool rewritten;
 };
 }  // namespace
 
@@ -1277,29 +1353,21 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
         const bool rev = r.reversed != 0;
         uint64_t bytes = 0;
         std::vector<EvRow> ev;
-        for (uint32_t k = 0; k < r.n_pieces; k += 2) {
-            const NsPieceMeta& pc = pieces[r.piece_first + k];
-            if (pc.kind != NS_PIECE_SEGMENT) continue;
-            const uint32_t* sc = ops + pc.ev_off;
-            const bool rewritten = pc.ev_off != pc.op_off;
-            const uint64_t cstart = chrom_off[pc.chrom], clen = chrom_off[pc.chrom + 1] - cstart;
-            ev.clear();
-            uint32_t o = pc.out_rel, rf = 0;
-            for (uint32_t j = 0; j < pc.ev_n_ops; ++j) {
-                const uint32_t op = sc[j], ty = NS_OP_TYPE(op), ln = NS_OP_LEN(op);
-                if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && ln) ev.push_back(EvRow{ty, ln, rf, o, j});
-                if (ty != NS_OP_DEL) o += ln;
-                if (ty == NS_OP_COPY || ty == NS_OP_MIS || ty == NS_OP_DEL) rf += ln;
-            }
+        // the pieces of one mutate_read call: a segment plus the pieces that continue it (NS_PIECE_CONT, intron retention)
+        auto flush = [&]() {
             for (size_t e = ev.size(); e-- > 0;) {
                 const EvRow& w = ev[e];
-                const uint64_t row = nl + 1 + dec_len(w.ref_start) + 1 + 3 + 1 + dec_len(w.len) + 1 + (uint64_t)w.len + 1 + w.len + 1;
+                const NsPieceMeta& pc = pieces[r.piece_first + w.piece];
+                const uint64_t shown = (uint64_t)w.ref_base + w.ref_start;
+                const uint64_t row = nl + 1 + dec_len(shown) + 1 + 3 + 1 + dec_len(w.len) + 1 + (uint64_t)w.len + 1 + w.len + 1;
                 bytes += row;
                 if (!p) continue;
+                const uint64_t cstart = chrom_off[pc.chrom], clen = chrom_off[pc.chrom + 1] - cstart;
+                const bool back = (pc.kind & NS_PIECE_REF_REV) != 0;
                 memcpy(p, nm, nl);
                 p += nl;
                 *p++ = '\t';
-                p = put_dec(p, w.ref_start);
+                p = put_dec(p, shown);
                 *p++ = '\t';
                 memcpy(p, kTypes[w.type - 1], 3);
                 p += 3;
@@ -1311,20 +1379,21 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
                     memset(p, '-', w.len);
                 } else {
                     for (uint32_t t = 0; t < w.len; ++t) {
-                        uint64_t ab = (uint64_t)pc.pos + w.ref_start + t;
+                        const uint32_t f = w.ref_start + t;             // offset in the piece, in the direction of the read
+                        uint64_t ab = (uint64_t)pc.pos + (back ? pc.ref_len - 1 - f : f);
                         if (ab >= clen) ab -= clen;
                         uint8_t c = ref_bases[cstart + ab];
                         if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
-                        p[t] = (char)c;
+                        p[t] = (char)(back ? comp[c] : c);
                     }
                 }
                 p += w.len;
                 *p++ = '\t';
                 if (w.type == NS_OP_DEL) {
                     memset(p, '-', w.len);
-                } else if (rewritten) {
+                } else if (w.rewritten) {
                     for (uint32_t t = 0; t < w.len; ++t) {
-                        const uint4 blk = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, k),
+                        const uint4 blk = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece),
                                                                   (w.index << 8) + (t >> 4)), key);
                         const uint32_t word = ((t >> 2) & 3u) == 0 ? blk.x : (((t >> 2) & 3u) == 1 ? blk.y : (((t >> 2) & 3u) == 2 ? blk.z : blk.w));
                         const uint32_t r8 = (word >> (8u * (t & 3u))) & 0xffu;
@@ -1348,7 +1417,28 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
                 p += w.len;
                 *p++ = '\n';
             }
+            ev.clear();
+        };
+        uint32_t ref_base = 0;
+        for (uint32_t k = 0; k < r.n_pieces; k += 2) {
+            const NsPieceMeta& pc = pieces[r.piece_first + k];
+            if (NS_PIECE_KIND(pc.kind) != NS_PIECE_SEGMENT) continue;
+            if (!(pc.kind & NS_PIECE_CONT)) {
+                flush();
+                ref_base = 0;
+            }
+            const uint32_t* sc = ops + pc.ev_off;
+            const bool rewritten = pc.ev_off != pc.op_off;
+            uint32_t o = pc.out_rel, rf = 0;
+            for (uint32_t j = 0; j < pc.ev_n_ops; ++j) {
+                const uint32_t op = sc[j], ty = NS_OP_TYPE(op), ln = NS_OP_LEN(op);
+                if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && ln) ev.push_back(EvRow{ty, ln, rf, o, j, k, ref_base, rewritten});
+                if (ty != NS_OP_DEL) o += ln;
+                if (ty == NS_OP_COPY || ty == NS_OP_MIS || ty == NS_OP_DEL) rf += ln;
+            }
+            ref_base += pc.ref_len;
         }
+        flush();
         return bytes;
     };
     int nt = std::max(1, std::min(n_threads, 64));
@@ -1425,6 +1515,42 @@ int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint
             nm += "_0_";
             add_num(pc[0].ref_len);
             nm += "_0";
+        } else if (trx && (pc[0].kind & NS_PIECE_GENOME)) {
+            // intron-retention layout (:1188-1192, :1217-1219): transcript, genomic start of the first interval, the
+            // retained-intron intervals the read covers in genomic order
+            uint64_t first_pos = pc[0].pos, mid = 0;
+            for (uint32_t k = 0; k < r.n_pieces; k += 2) {
+                first_pos = std::min<uint64_t>(first_pos, pc[k].pos);
+                mid += pc[k].ref_len;
+            }
+            nm += chrom_names + chrom_name_off[pc[0].ref_req];
+            nm += '_';
+            add_num(first_pos);
+            nm += "_aligned_";
+            add_num(index_base + i);
+            bool any = false;
+            for (uint32_t k = 0; k < r.n_pieces; k += 2) any = any || (pc[k].kind & NS_PIECE_RETAINED);
+            if (any) {
+                nm += "_RetainedIntron_";
+                std::vector<std::pair<uint64_t, uint64_t>> ivs;              // in genomic order, whatever the strand
+                for (uint32_t k = 0; k < r.n_pieces; k += 2)
+                    if (pc[k].kind & NS_PIECE_RETAINED) ivs.emplace_back(pc[k].pos, (uint64_t)pc[k].pos + pc[k].ref_len);
+                std::stable_sort(ivs.begin(), ivs.end());
+                for (const auto& iv : ivs) {
+                    add_num(iv.first);
+                    nm += '-';
+                    add_num(iv.second);
+                    nm += ';';
+                }
+            }
+            nm += '_';
+            nm += strand;
+            nm += '_';
+            add_num(r.head);
+            nm += '_';
+            add_num(mid);
+            nm += '_';
+            add_num((uint64_t)r.tail + pc[0].polya_len);
         } else if (trx) {
             nm += chrom_names + chrom_name_off[pc[0].chrom];
             nm += '_';

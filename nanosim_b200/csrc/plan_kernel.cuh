@@ -189,9 +189,10 @@ __device__ __forceinline__ void draw_position_meta(const DevRef& ref, Rng& rng, 
 
 // extract_read, transcriptome branch (:1695-1703, unaligned reads): uniform transcript until it is longer than the
 // read, uniform start.
-__device__ __forceinline__ void draw_position_trx(const DevRef& ref, Rng& rng, uint32_t length, uint32_t& chrom, uint32_t& pos) {
+__device__ __forceinline__ void draw_position_trx(const DevRef& ref, uint32_t n_records, Rng& rng, uint32_t length, uint32_t& chrom,
+                                                  uint32_t& pos) {
     for (int it = 0; it < 1000000; ++it) {
-        const uint32_t c = (uint32_t)__umul64hi(rng.next64(), (uint64_t)ref.n_chrom);
+        const uint32_t c = (uint32_t)__umul64hi(rng.next64(), (uint64_t)n_records);
         const uint64_t clen = __ldg(&ref.chrom_off[c + 1]) - __ldg(&ref.chrom_off[c]);
         if ((uint64_t)length < clen) {
             chrom = c;
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                     const bool seg = !unal_kind && !(q & 1u);
                     draw_position_meta(a.ref, pr, seg ? (int)pm.chrom : -1, pm.ref_len, chrom, ppos);
                 } else if (cfg.transcriptome) {
-                    draw_position_trx(a.ref, pr, pm.ref_len, chrom, ppos);
+                    draw_position_trx(a.ref, cfg.trx_records ? cfg.trx_records : a.ref.n_chrom, pr, pm.ref_len, chrom, ppos);
                 } else if (pm.ref_len > 0) {
                     draw_position(a.ref, cfg, pr, pm.ref_len, chrom, ppos);
                 }

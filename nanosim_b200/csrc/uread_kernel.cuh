@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             pr.init(cfg.seed, rid, stream_word(ST_POS, NS_KIND_UNALIGNED, attempt));
             uint32_t chrom = 0, ppos = 0;
             if (cfg.metagenome) draw_position_meta(a.ref, pr, -1, middle_ref, chrom, ppos);
-            else if (cfg.transcriptome) draw_position_trx(a.ref, pr, middle_ref, chrom, ppos);
+            else if (cfg.transcriptome) draw_position_trx(a.ref, cfg.trx_records ? cfg.trx_records : a.ref.n_chrom, pr, middle_ref, chrom, ppos);
             else draw_position(a.ref, cfg, pr, middle_ref, chrom, ppos);
             if (lane == 0) {
                 const bool overflow = n_ops > cap;

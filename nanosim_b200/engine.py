@@ -157,13 +157,14 @@ class Engine:
 
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
                   max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False,
-                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0):
+                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0, trx_records=0):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
         flags = (L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0) | (L.NS_FLAG_URACIL if uracil else 0)
         cfg = L.NsRunConfig(2 if transcriptome else (1 if metagenome else 0), int(circular), int(perfect), int(fastq),
                             int(chimeric), int(kmer_bias or 0), int(min_len), int(min(max_len, 0x0fffffff)),
-                            float(median_len or 0.0), float(sd_len or 0.0), flags, int(kde2d_sample), float(polya_scale or 0.0))
+                            float(median_len or 0.0), float(sd_len or 0.0), flags, int(kde2d_sample), float(polya_scale or 0.0),
+                            int(trx_records), 0)
         self._check(self._lib.ns_configure(self._ctx, C.byref(cfg)))
         self.fastq = bool(fastq)
 
@@ -174,6 +175,27 @@ class Engine:
         self.info = info
         self._kind, self._first = kind, first_id
         return info
+
+    def reemit(self, slots, new_reads, new_pieces, new_ops):
+        """Intron retention (intron_retention.py): replaces the piece lists of reads `slots` of the last aligned batch and
+        emits those reads again in place (ns_reemit)."""
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        new_reads = np.ascontiguousarray(new_reads, dtype=L.READ_DTYPE)
+        new_pieces = np.ascontiguousarray(new_pieces, dtype=L.PIECE_DTYPE)
+        new_ops = np.ascontiguousarray(new_ops, dtype=np.uint32)
+        self._check(self._lib.ns_reemit(self._ctx, _ptr(slots), _ptr(new_reads), len(slots), _ptr(new_pieces), len(new_pieces),
+                                        _ptr(new_ops), C.c_uint64(len(new_ops))))
+        self.info.n_pieces += len(new_pieces)
+        self.info.n_ops += len(new_ops)
+
+    def fetch_meta(self, want_ops=True):
+        """reads / pieces / (ops) of the last batch without the sequence bytes."""
+        info = self.info
+        reads = np.empty(int(info.n_reads), dtype=L.READ_DTYPE)
+        pieces = np.empty(int(info.n_pieces), dtype=L.PIECE_DTYPE)
+        ops = np.empty(int(info.n_ops), dtype=np.uint32) if want_ops else None
+        self._check(self._lib.ns_fetch(self._ctx, None, None, _ptr(reads), _ptr(pieces), _ptr(ops)))
+        return reads, pieces, ops
 
     def fetch(self, want_ops=False, want_pieces=True):
         info = self.info

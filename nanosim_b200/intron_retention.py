@@ -242,8 +242,8 @@ class IntronRetention:
                     gap["op_off"] = gap["ev_off"] = op_cursor
                     new_pieces.append(gap)
                 q = pc.copy()
-                q["kind"] = (L.NS_PIECE_SEGMENT | (L.NS_PIECE_REF_REV if minus else 0) | (L.NS_PIECE_CONT if k else 0) |
-                             (L.NS_PIECE_RETAINED if is_ir else 0))
+                q["kind"] = (L.NS_PIECE_SEGMENT | L.NS_PIECE_GENOME | (L.NS_PIECE_REF_REV if minus else 0) |
+                             (L.NS_PIECE_CONT if k else 0) | (L.NS_PIECE_RETAINED if is_ir else 0))
                 q["chrom"] = self.g0 + g
                 q["pos"] = s
                 q["ref_len"] = e - s

@@ -34,6 +34,14 @@ def read_names(batch, ref_names, index_base, perfect=False, metagenome=False, tr
             names.append("%s_%d_unaligned_%d_%s_0_%d_0" % (ref_names[pc["chrom"]], pc["pos"], idx, strand, pc["ref_len"]))
             continue
         segs = [pieces[p0 + k] for k in range(0, npc, 2)]
+        if transcriptome and int(segs[0]["kind"]) & L.NS_PIECE_GENOME:
+            # intron-retention layout (:1188-1192): genomic start of the first interval, retained introns in genomic order
+            loc = sorted(segs, key=lambda x: int(x["pos"]))
+            ir = "".join("%d-%d;" % (x["pos"], int(x["pos"]) + int(x["ref_len"])) for x in loc if int(x["kind"]) & L.NS_PIECE_RETAINED)
+            names.append("%s_%d_aligned_%d%s_%s_%d_%d_%d" % (ref_names[segs[0]["ref_req"]], loc[0]["pos"], idx, "_RetainedIntron_" + ir if ir else "",
+                                                             strand, r["head"], sum(int(x["ref_len"]) for x in segs),
+                                                             int(r["tail"]) + int(segs[0]["polya_len"])))
+            continue
         if transcriptome:       # {trx}_{pos}_aligned|perfect_{idx}_{F|R}_{head}_{middle_ref}_{tail+polyA} (:1188-1219)
             pc = segs[0]
             names.append("%s_%d_%s_%d_%s_%d_%d_%d" % (ref_names[pc["chrom"]], pc["pos"], "perfect" if perfect else "aligned", idx,
@@ -221,28 +229,36 @@ def error_profile_rows(batch, names, ref, seed=0):
         if r["reversed"]:
             fwd = _COMP[fwd[::-1]]
         p0, npc = int(r["piece_first"]), int(r["n_pieces"])
+        group, ref_base = [], 0                 # rows of one mutate_read call: a segment and the pieces continuing it
         for k in range(0, npc, 2):
             pc = pieces[p0 + k]
-            if pc["kind"] != L.NS_PIECE_SEGMENT:
+            kind = int(pc["kind"])
+            if kind & L.NS_PIECE_KIND_MASK != L.NS_PIECE_SEGMENT:
                 continue
+            if not kind & L.NS_PIECE_CONT:
+                rows.extend(reversed(group))
+                group, ref_base = [], 0
+            back = bool(kind & L.NS_PIECE_REF_REV)
             ops = ops_all[int(pc["ev_off"]): int(pc["ev_off"]) + int(pc["ev_n_ops"])]    # the error-event script
             rewritten = int(pc["ev_off"]) != int(pc["op_off"])                        # -hp: bases fixed by the hp pass
             ty = (ops >> 28).astype(np.int64)
-            ln = (ops & 0x0fffffff).astype(np.int64)
+            ln = np.where(ty == L.NS_OP_LIT, ops & 0x00ffffff, ops & 0x0fffffff).astype(np.int64)
             out_adv = np.where(ty == L.NS_OP_DEL, 0, ln)
-            ref_adv = np.where((ty == L.NS_OP_INS) | (ty == L.NS_OP_HT), 0, ln)
+            ref_adv = np.where((ty == L.NS_OP_COPY) | (ty == L.NS_OP_MIS) | (ty == L.NS_OP_DEL), ln, 0)
             out_start = int(pc["out_rel"]) + np.concatenate([[0], np.cumsum(out_adv)[:-1]])
             ref_start = np.concatenate([[0], np.cumsum(ref_adv)[:-1]])
             cstart, clen = int(ref_off[pc["chrom"]]), int(ref_off[pc["chrom"] + 1] - ref_off[pc["chrom"]])
-            base = int(pc["pos"])
-            seg_rows = []
-            for j in np.nonzero((ty >= 1) & (ty <= 3))[0]:
+            base, plen = int(pc["pos"]), int(pc["ref_len"])
+            for j in np.nonzero((ty >= 1) & (ty <= 3) & (ln > 0))[0]:
                 t, n, rs, os_ = int(ty[j]), int(ln[j]), int(ref_start[j]), int(out_start[j])
                 if t == L.NS_OP_INS:
                     refb = "-" * n
                 else:
-                    idx = (base + rs + np.arange(n)) % clen if base + rs + n > clen else np.arange(base + rs, base + rs + n)
-                    refb = ref.bases[cstart + idx].tobytes().decode().upper()
+                    f = rs + np.arange(n)                      # offsets in the piece, in the direction of the read
+                    idx = (base + (plen - 1 - f if back else f)) % clen
+                    rb = ref.bases[cstart + idx]
+                    rb = np.where((rb >= 97) & (rb <= 122), rb - 32, rb).astype(np.uint8)
+                    refb = (_COMP[rb] if back else rb).tobytes().decode()
                 if t == L.NS_OP_DEL:
                     seqb = "-" * n
                 elif rewritten:
@@ -251,6 +267,7 @@ def error_profile_rows(batch, names, ref, seed=0):
                     seqb = _IDX_BASE[bi].tobytes().decode()
                 else:
                     seqb = fwd[os_:os_ + n].tobytes().decode()
-                seg_rows.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (names[i], rs, ("mis", "ins", "del")[t - 1], n, refb, seqb))
-            rows.extend(reversed(seg_rows))
+                group.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (names[i], ref_base + rs, ("mis", "ins", "del")[t - 1], n, refb, seqb))
+            ref_base += plen
+        rows.extend(reversed(group))
     return rows

@@ -204,6 +204,17 @@ def test_error_profile_formatter_matches_python_rows(rewritten):
         got = format_error_profile(b, names, ref, seed=77, n_threads=nt)
         assert got == want
     assert want.count(b"\n") > 1000
+    # intron-retention layout: the second segment continues the first (one mutate_read call: positions keep counting,
+    # rows right to left over both), minus-strand pieces show the complemented reference
+    from nanosim_b200 import _lib as L
+    two = np.flatnonzero(b.reads["n_pieces"] == 3)
+    for i in two.tolist():
+        p0 = int(b.reads["piece_first"][i])
+        flags = L.NS_PIECE_GENOME | (L.NS_PIECE_REF_REV if i % 2 else 0)
+        b.pieces["kind"][p0] |= flags
+        b.pieces["kind"][p0 + 2] |= flags | L.NS_PIECE_CONT
+    want_ir = "".join(error_profile_rows(b, names, ref, seed=77)).encode()
+    assert want_ir != want and format_error_profile(b, names, ref, seed=77, n_threads=3) == want_ir
 
 
 def test_name_formatter_matches_python_names():
@@ -221,6 +232,14 @@ def test_name_formatter_matches_python_names():
     b.reads["tail"] = rng.integers(0, 500, len(b.reads))
     for kw in ({}, {"metagenome": True}, {"perfect": True}, {"transcriptome": True}, {"transcriptome": True, "perfect": True}):
         assert name_table(b, ref.names, 12345, **kw).tolist() == read_names(b, ref.names, 12345, **kw), kw
+    two = np.flatnonzero(b.reads["n_pieces"] == 3)           # intron-retention layout of some reads
+    for i in two.tolist():
+        p0 = int(b.reads["piece_first"][i])
+        b.pieces["kind"][p0] |= L.NS_PIECE_GENOME | (L.NS_PIECE_REF_REV if i % 2 else 0) | (L.NS_PIECE_RETAINED if i % 3 else 0)
+        b.pieces["kind"][p0 + 2] |= L.NS_PIECE_GENOME | L.NS_PIECE_CONT | (L.NS_PIECE_REF_REV if i % 2 else 0) | (L.NS_PIECE_RETAINED if i % 5 == 0 else 0)
+        b.pieces["ref_req"][p0] = b.pieces["ref_req"][p0 + 2] = i % 2
+    got, want = name_table(b, ref.names, 99, transcriptome=True).tolist(), read_names(b, ref.names, 99, transcriptome=True)
+    assert got == want and any("_RetainedIntron_" in x for x in want)
     b.kind = L.NS_KIND_UNALIGNED
     t = name_table(b, ref.names, 7)
     assert t.tolist() == read_names(b, ref.names, 7) and t[3] == read_names(b, ref.names, 7)[3] and len(t) == 200
