@@ -222,7 +222,9 @@ class IntronRetention:
                              st.minus[a:b].tolist()))
             pc = pieces[int(p0[i])]
             length = int(pc["ref_len"])
-            ivs = extract_read_pos(length, int(self.trx_len[t]), feats, retained[i].tolist(), float(u[i, m]))
+            # the uniform after the read's own intron draws (not after the batch's longest chain: results must not
+            # depend on which reads share a batch)
+            ivs = extract_read_pos(length, int(self.trx_len[t]), feats, retained[i].tolist(), float(u[i, int(n_int[i])]))
             if not ivs or any(g < 0 for g, *_ in ivs) or sum(e - s for _, s, e, _, _ in ivs) != length:
                 continue                                     # a chromosome the genome file lacks (:1168-1170) / inconsistent annotation
             minus = bool(ivs[-1][3])                         # `interval.strand` after the loop (:1177)

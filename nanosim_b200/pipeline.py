@@ -104,11 +104,13 @@ class BatchPipeline:
         for t in threads:
             t.join()
 
-    def run(self, jobs, consume=None, static_assign=False):
+    def run(self, jobs, consume=None, static_assign=False, after_simulate=None):
         """jobs: iterable of (kind, first_read_id, n_reads).  consume(info, batch, job) runs on the calling thread in
         submission order; the batch's buffers are reused as soon as consume returns.  Returns the list of infos.
         static_assign: job j always runs on context j % depth (needed when a context carries state from batch to batch,
-        i.e. the metagenome species quotas) instead of on whichever context is free."""
+        i.e. the metagenome species quotas) instead of on whichever context is free.
+        after_simulate(engine, info, job) runs on the worker thread between the simulation and the fetch of a batch (the
+        intron-retention pass patches reads there)."""
         jobs = list(jobs)
         n = len(jobs)
         results = [None] * n
@@ -134,6 +136,9 @@ class BatchPipeline:
                                 return
                             cursor[0] += 1
                     info = self._simulate(slot, jobs[j])
+                    if after_simulate is not None:
+                        after_simulate(self.engines[slot], info, jobs[j])
+                        info = self.engines[slot].info
                     b = None
                     if self.fetch:
                         released[slot].wait()

@@ -17,8 +17,9 @@ def normalise_name(header):
 
 
 class PackedReference:
-    def __init__(self, names, bases, offsets):
+    def __init__(self, names, bases, offsets, raw_names=None):
         self.names = list(names)
+        self.raw_names = list(raw_names) if raw_names is not None else list(names)   # header up to the first blank (pysam's view)
         self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         assert len(self.offsets) == len(self.names) + 1
@@ -39,7 +40,7 @@ class PackedReference:
     @staticmethod
     def from_records(records):
         """records: iterable of (header, uint8 array or bytes or str)."""
-        names, parts, offs = [], [], [0]
+        names, parts, offs, raws = [], [], [0], []
         seen = {}
         for header, seq in records:
             if isinstance(seq, str):
@@ -52,11 +53,18 @@ class PackedReference:
             else:
                 seen[key] = len(names)
                 names.append(key)
+                raws.append(header.split()[0] if header.split() else header)
                 parts.append(arr)
         for p in parts:
             offs.append(offs[-1] + len(p))
         bases = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
-        return PackedReference(names, bases, np.asarray(offs, dtype=np.uint64))
+        return PackedReference(names, bases, np.asarray(offs, dtype=np.uint64), raws)
+
+    @staticmethod
+    def concat(a, b):
+        """Records of `a` followed by the records of `b` (transcripts + the genome intron retention reads from)."""
+        offs = np.concatenate([a.offsets, b.offsets[1:] + a.offsets[-1]]).astype(np.uint64)
+        return PackedReference(a.names + b.names, np.concatenate([a.bases, b.bases]), offs, a.raw_names + b.raw_names)
 
     @staticmethod
     def from_fasta(path):

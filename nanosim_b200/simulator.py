@@ -51,11 +51,10 @@ class Profile:
 
 def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
                  polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
-                 device=0, seed=0):
-    if mode == "transcriptome" and model_ir:
-        sys.stderr.write("nanosim_b200: intron retention simulation is not implemented; run with --no_model_ir\n")
-        sys.exit(1)
+                 device=0, seed=0, ir_files=None):
     prof = Profile()
+    prof.ir = None
+    prof.n_trx = 0
     _log("Read in reference ")
     if mode == "metagenome":
         try:
@@ -81,9 +80,28 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
         if polya:
             _log("Read in list of transcripts with polyA tails")
             prof.polya_flags = read_polya_list(polya, prof.ref)
+        prof.max_chrom = prof.ref.max_chrom
+        if model_ir:
+            # :404-453: the genome the retained introns are read from, the IR Markov model, the exon/intron structure
+            from .intron_retention import IntronRetention, TranscriptStructures, read_ir_markov_model
+            _log("Read in reference genome and create .fai index file")
+            trx = prof.ref
+            genome = PackedReference.from_fasta(ref_g)
+            _log("Read in IR markov model")
+            ir_files = ir_files or {}
+            base = model_prefix[:-4] if model_prefix.endswith(".npz") else model_prefix
+            p_no_ir = read_ir_markov_model(ir_files.get("markov") or base + "_IR_markov_model")
+            _log("Read in GFF3 annotation file")
+            st = TranscriptStructures.from_gff3(ir_files.get("gff3") or base + "_added_intron_final.gff3", trx.names, genome.raw_names)
+            prof.n_trx = len(trx.names)
+            prof.ir = IntronRetention(p_no_ir, st, trx.lengths, prof.n_trx)
+            prof.ref = PackedReference.concat(trx, genome)
+            if prof.polya_flags is not None:
+                prof.polya_flags = np.concatenate([prof.polya_flags, np.zeros(len(genome.names), dtype=np.uint8)])
     else:
         prof.ref = PackedReference.from_fasta(ref_g)
-    prof.max_chrom = prof.ref.max_chrom
+    if mode != "transcriptome":
+        prof.max_chrom = prof.ref.max_chrom
     if mode == "genome" and len(prof.ref.names) > 1 and dna_type == "circular":
         sys.stderr.write("Do not choose circular if there is more than one chromosome in the genome!\n")
         sys.exit(1)
@@ -125,7 +143,8 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                   metagenome=meta, transcriptome=trx, uracil=bool(uracil),
                   polya_scale=POLYA_SCALE.get(basecaller, POLYA_SCALE["guppy"]) if (trx and polya) else 0.0,
                   # the reference's 2-D KDE sample has one row per read of a WORKER (:1072): -t sets its size as it does there
-                  kde2d_sample=max(1, (hi_a - lo_a) // max(1, num_threads)))
+                  kde2d_sample=max(1, (hi_a - lo_a) // max(1, num_threads)),
+                  trx_records=prof.n_trx if (trx and prof.ir is not None) else 0)
     ext = ".fastq" if fastq else ".fasta"
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
@@ -147,7 +166,16 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
             if want_err:
                 f_err.write(format_error_profile(b, names, prof.ref, seed=prof.seed, n_threads=fmt_threads, as_array=True))
 
-        pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned, static_assign=meta)
+        def retain_introns(engine, info, job):
+            # intron retention (:1156-1183): decided on the host from the batch's metadata, the few affected reads are laid
+            # out on the genome and emitted again (intron_retention.py)
+            reads, pieces, ops = engine.fetch_meta()
+            patch = prof.ir.plan_batch(reads, pieces, ops, job[1], prof.seed, info.n_pieces, info.n_ops)
+            if patch is not None:
+                engine.reemit(*patch)
+
+        pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned, static_assign=meta,
+                 after_simulate=retain_introns if (trx and prof.ir is not None and not per) else None)
     if not per:
         _log("Start simulation of random reads")
         lo, hi = _shard(prof.number_unaligned, rank, world)
@@ -285,6 +313,9 @@ def build_parser():
     t.add_argument('-s', '--strandness', help='Proportion of sense sequences. Overrides the value profiled in '
                    'characterization stage. Should be between 0 and 1', type=float, default=None)
     t.add_argument('--no_model_ir', help='Ignore simulating intron retention events', action='store_false', default=True)
+    t.add_argument('--ir_markov_model', help='IR Markov model (Default = <model_prefix>_IR_markov_model)', default=None)
+    t.add_argument('--ir_gff3', help='GFF3 with exon and intron features (Default = <model_prefix>_added_intron_final.gff3)',
+                   default=None)
     t.add_argument('--perfect', help='Ignore profiles and simulate perfect reads', action='store_true', default=False)
     t.add_argument('--polya', help='Simulate polyA tails for given list of transcripts', default=None)
     t.add_argument('--fastq', help='Output fastq files instead of fasta files', action='store_true', default=False)
@@ -327,6 +358,9 @@ def main_transcriptome(args, parser_t):
         sys.stderr.write("\nMaximum read length must be longer than Minimum read length!\n")
         parser_t.print_help(sys.stderr)
         sys.exit(1)
+    if model_ir and args.homopolymer:
+        sys.stderr.write("\nnanosim_b200: -hp/-k cannot be combined with intron retention yet; add --no_model_ir\n")
+        sys.exit(1)
     if model_ir and args.ref_g == '':
         sys.stderr.write("\nPlease provide a reference genome to simulate intron retention events!\n")
         parser_t.print_help(sys.stderr)
@@ -345,7 +379,8 @@ def main_transcriptome(args, parser_t):
     number = [args.number]
     prof = read_profile(args.ref_g, number, args.model_prefix, args.perfect, "transcriptome", args.strandness,
                         ref_t=args.ref_t, dna_type="linear", model_ir=model_ir, polya=args.polya, exp=args.exp,
-                        homopolymer=args.homopolymer, fastq=args.fastq, device=device, seed=args.seed or 0)
+                        homopolymer=args.homopolymer, fastq=args.fastq, device=device, seed=args.seed or 0,
+                        ir_files={"markov": args.ir_markov_model, "gff3": args.ir_gff3})
     if args.coverage is not None:
         number[0] = coverage_to_reads(prof, prof.tables.cm, args.coverage)
         prof.number_aligned, prof.number_unaligned = prof.tables.split_counts(number[0], args.perfect)

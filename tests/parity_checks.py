@@ -80,7 +80,7 @@ def make_meta_engine(ref, abun, fastq=True, chimeric=True, perfect=False, seed=1
 
 
 def make_trx_engine(ref, expr_chrom, expr_weights, polya_flags=None, fastq=True, perfect=False, seed=1, polya_scale=0.0,
-                    uracil=False, kde2d_sample=400, min_len=50, model="drna", unaligned_scripts=False):
+                    uracil=False, kde2d_sample=400, min_len=50, model="drna", unaligned_scripts=False, trx_records=0, max_len=None):
     """Transcriptome-mode engine (no intron retention)."""
     from nanosim_b200.engine import Engine
     from nanosim_b200.model import build_alias
@@ -91,8 +91,8 @@ def make_trx_engine(ref, expr_chrom, expr_weights, polya_flags=None, fastq=True,
     eng.set_model(t, perfect=perfect)
     pr, al = build_alias(expr_weights)
     eng.set_expression(pr, al, expr_chrom, polya_flags)
-    eng.configure(perfect=perfect, fastq=fastq, min_len=min_len, max_len=ref.max_chrom, transcriptome=True, uracil=uracil,
-                  polya_scale=polya_scale, kde2d_sample=kde2d_sample, unaligned_scripts=unaligned_scripts)
+    eng.configure(perfect=perfect, fastq=fastq, min_len=min_len, max_len=max_len or ref.max_chrom, transcriptome=True, uracil=uracil,
+                  polya_scale=polya_scale, kde2d_sample=kde2d_sample, unaligned_scripts=unaligned_scripts, trx_records=trx_records)
     return eng, cm, t
 
 
@@ -157,7 +157,10 @@ def check_edit_scripts(batch, ref, fastq, max_reads=None):
                 per_ty = np.repeat(ty[use], ln[use])
                 ridx = np.repeat(ref_start[use], ln[use]) + (np.arange(int(ln[use].sum())) - np.repeat(np.cumsum(ln[use]) - ln[use], ln[use]))
                 oidx = np.repeat(out_start[use], ln[use]) + (np.arange(int(ln[use].sum())) - np.repeat(np.cumsum(ln[use]) - ln[use], ln[use]))
-                rb = _UPPER[ref.bases[cstart + (int(pc["pos"]) + ridx) % clen]]
+                if int(pc["kind"]) & 0x80000000:           # NS_PIECE_REF_REV: the genome read backwards, complemented
+                    rb = _COMP[_UPPER[ref.bases[cstart + (int(pc["pos"]) + int(pc["ref_len"]) - 1 - ridx) % clen]]]
+                else:
+                    rb = _UPPER[ref.bases[cstart + (int(pc["pos"]) + ridx) % clen]]
                 ob = seg[oidx]
                 cp = per_ty == 0
                 assert _MEMBER[rb[cp], ob[cp]].all(), "copied base differs from the reference (read %d piece %d)" % (i, k)

@@ -805,6 +805,103 @@ def test_med_sd_vs_unmodified_reference(ecoli, L):
     assert not fails, "\n".join(fails)
 
 
+@pytest.fixture(scope="module")
+def ir_fixture():
+    from nanosim_b200 import intron_retention as ir
+    from nanosim_b200.reference_fasta import PackedReference, read_expression, read_polya_list
+    D = os.path.join(GOLDEN, "ir")
+    trx = PackedReference.from_fasta(os.path.join(D, "transcripts.fa"))
+    genome = PackedReference.from_fasta(os.path.join(D, "genome.fa"))
+    ref = PackedReference.concat(trx, genome)
+    chrom, w = read_expression(os.path.join(D, "expression.tsv"), trx)
+    polya = np.concatenate([read_polya_list(os.path.join(D, "polya.txt"), trx), np.zeros(len(genome.names), dtype=np.uint8)])
+    st = ir.TranscriptStructures.from_gff3(os.path.join(D, "annotation.gff3"), trx.names, genome.raw_names)
+    irm = ir.IntronRetention(ir.read_ir_markov_model(os.path.join(D, "IR_markov_model")), st, trx.lengths, len(trx.names))
+    return D, trx, genome, ref, chrom, w, polya, irm
+
+
+def test_intron_retention_reemit(ir_fixture, L, monkeypatch):
+    """Transcriptome reads that retain introns (simulator.py:1156-1183): the host half decides and lays them out on the genome,
+    ns_reemit emits them again.  Untouched reads keep their bytes; patched reads keep length, qualities and every base
+    that does not come from the reference; their scripts re-applied to the GENOME reproduce the bases bit-exactly (minus
+    strand included); the intervals are the ones the pinned oracle extracts from the same uniforms."""
+    import random
+    import nanosim_oracle as no
+    from nanosim_b200 import intron_retention as ir
+    from nanosim_b200.records import error_profile_rows, format_error_profile, name_table, read_names
+    from nanosim_b200.reference_fasta import POLYA_SCALE
+    D, trx, genome, ref, chrom, w, polya, irm = ir_fixture
+    seed = 71
+    eng, cm, t = pc.make_trx_engine(ref, chrom, w, polya, fastq=True, seed=seed, polya_scale=POLYA_SCALE["guppy"],
+                                    trx_records=len(trx.names), max_len=trx.max_chrom)
+    eng.simulate(L.NS_KIND_ALIGNED, 500, 4000)
+    b0 = eng.fetch(want_ops=True)
+    assert (b0.pieces["chrom"] < len(trx.names)).all()
+    patch = irm.plan_batch(b0.reads, b0.pieces, b0.ops, 500, seed, eng.info.n_pieces, eng.info.n_ops)
+    assert patch is not None
+    slots = patch[0]
+    eng.reemit(*patch)
+    b1 = eng.fetch(want_ops=True)
+    assert 0.2 * 4000 < len(slots) < 0.95 * 4000                 # the fixture's IR model retains often
+    assert pc.check_edit_scripts(b1, ref, True) > 0
+    touched = np.zeros(4000, dtype=bool)
+    touched[slots] = True
+    oref = no.OracleTrxReference.from_files(os.path.join(D, "transcripts.fa"), os.path.join(D, "expression.tsv"), os.path.join(D, "polya.txt"))
+    oref.load_ir(os.path.join(D, "genome.fa"), os.path.join(D, "annotation.gff3"), os.path.join(D, "IR_markov_model"))
+    n_minus = n_named = 0
+    for i in range(4000):
+        a, n = int(b0.reads["seq_off"][i]), int(b0.reads["seq_len"][i])
+        assert int(b1.reads["seq_len"][i]) == n and int(b1.reads["seq_off"][i]) == a
+        assert np.array_equal(b0.qual[a:a + n], b1.qual[a:a + n])
+        if not touched[i]:
+            assert np.array_equal(b0.seq[a:a + n], b1.seq[a:a + n])
+            continue
+        p1 = b1.pieces[int(b1.reads["piece_first"][i]):int(b1.reads["piece_first"][i]) + int(b1.reads["n_pieces"][i])][::2]
+        assert (p1["chrom"] >= len(trx.names)).all() and (p1["kind"] & L.NS_PIECE_GENOME).all()
+        t0 = int(b0.pieces["chrom"][int(b0.reads["piece_first"][i])])
+        key, n_int = trx.names[t0], int(irm.st.n_introns[t0])
+        u = ir.ir_uniforms(seed, [500 + i], n_int + 1)[0]
+        feed = iter(u[:n_int].tolist())
+        monkeypatch.setattr(random, "random", lambda: next(feed))
+        monkeypatch.setattr(random, "randint", lambda lo, hi: min(int(u[n_int] * (hi + 1)), hi) if hi > 0 else 0)
+        flag, st_new = no.update_structure(oref.structure[key], oref.ir_model)
+        assert flag
+        ivs, _, ir_list = no.extract_read_pos(int(p1["ref_len"].sum()), oref.seq_len[key], st_new, False)
+        got = sorted((int(x["pos"]), int(x["pos"]) + int(x["ref_len"])) for x in p1)
+        assert got == [(s, e) for _, s, e, _ in ivs]
+        assert sorted((int(x["pos"]), int(x["pos"]) + int(x["ref_len"])) for x in p1 if int(x["kind"]) & L.NS_PIECE_RETAINED) == [tuple(x) for x in ir_list]
+        n_minus += bool(int(p1["kind"][0]) & L.NS_PIECE_REF_REV)
+    names = read_names(b1, ref.names, 500, transcriptome=True)
+    tab = name_table(b1, ref.names, 500, transcriptome=True)
+    assert tab.tolist() == names
+    n_named = sum("_RetainedIntron_" in x for x in names)
+    assert n_minus > 50 and n_named > 100
+    want = "".join(error_profile_rows(b1, names, ref, seed=seed)).encode()
+    assert format_error_profile(b1, tab, ref, seed=seed, n_threads=4) == want
+    eng.close()
+
+
+def test_cli_transcriptome_with_intron_retention(ir_fixture, tmp_path, L):
+    """The CLI with IR on (the reference's default): -rg genome, IR model and GFF3; output independent of the batch split."""
+    from nanosim_b200 import simulator
+    D = ir_fixture[0]
+    outs = []
+    for tag, batch in (("a", "100000"), ("b", "211")):
+        out = os.path.join(str(tmp_path), tag)
+        simulator.main(["transcriptome", "-rt", os.path.join(D, "transcripts.fa"), "-rg", os.path.join(D, "genome.fa"),
+                        "-e", os.path.join(D, "expression.tsv"), "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", "1500", "-o", out,
+                        "--fastq", "--polya", os.path.join(D, "polya.txt"), "-b", "guppy", "--seed", "9", "--batch_reads", batch,
+                        "--ir_markov_model", os.path.join(D, "IR_markov_model"), "--ir_gff3", os.path.join(D, "annotation.gff3")])
+        outs.append(out)
+    for suffix in ("_aligned_reads.fastq", "_unaligned_reads.fastq", "_aligned_error_profile"):
+        a, b = open(outs[0] + suffix, "rb").read(), open(outs[1] + suffix, "rb").read()
+        assert a == b and len(a) > 1000, suffix
+    heads = [l for l in open(outs[0] + "_aligned_reads.fastq") if l.startswith("@ENST")]
+    assert sum("_RetainedIntron_" in h for h in heads) > 50
+    s = rs.stats_from_prefix(outs[0], True)
+    assert s["n_aligned"] + s["n_unaligned"] == 1500
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
