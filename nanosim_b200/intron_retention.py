@@ -5,7 +5,7 @@ Mirrors ``read_profile``'s model_ir block (/root/reference/src/simulator.py:404-
 
 Division of labour.  The device simulates every aligned read against its transcript as usual.  Per batch the host then
 draws, from the read metadata alone, the IR / no_IR state of every intron of every read's transcript (two-state Markov
-chain, vectorised over the batch, Philox keyed by the read id), and for the few reads that retain an intron (~2 % with the
+chain, vectorised over the batch, uniforms a pure function of seed and read id), and for the few reads that retain an intron (~2 % with the
 shipped models) it lays the read out on the GENOME instead: the exon / retained-intron intervals the read covers become
 the read's pieces (one per interval, walked backwards for transcripts on the minus strand) and the read's edit script is
 cut at the interval boundaries.  ``ns_reemit`` uploads those pieces and runs the emit kernel on them again; as all emit
@@ -19,9 +19,8 @@ it from the genomic end of the last feature, :186-189, which would change the re
 import numpy as np
 
 from . import _lib as L
-from .records import _philox4x32
 
-ST_IR = 9                      # Philox stream word purpose of the IR draws (device streams use 1..8)
+ST_IR = 9                      # stream tag of the IR draws (the device's Philox streams use purposes 1..8)
 EXON, INTRON = 0, 1
 
 
@@ -98,16 +97,24 @@ class TranscriptStructures:
         return TranscriptStructures(first, ftype, chrom, start, end, minus)
 
 
-def ir_uniforms(seed, rids, n):
-    """n uniforms in [0, 1) per read id: word j of the read's Philox-10 stream ST_IR (block j >> 2)."""
+def ir_uniforms(seed, rids, n, counts=None):
+    """n uniforms in [0, 1) per read id, a pure function of (seed, read id, column): SplitMix64's finaliser over a counter
+    built from the three (host-side draws: a handful per read, no need for the device's Philox streams).  counts[i]
+    (optional): only the first counts[i] uniforms of read i are needed -- most transcripts have few introns, a few hundreds."""
     rids = np.asarray(rids, dtype=np.uint64)
-    out = np.empty((len(rids), n), dtype=np.float64)
-    for blk in range((n + 3) // 4):
-        ctr = np.stack([rids & np.uint64(0xFFFFFFFF), rids >> np.uint64(32), np.full(len(rids), ST_IR << 28, dtype=np.uint64),
-                        np.full(len(rids), blk, dtype=np.uint64)], axis=1)
-        w = _philox4x32(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF), 10)
-        k = min(4, n - 4 * blk)
-        out[:, 4 * blk:4 * blk + k] = w[:, :k].astype(np.float64) / 4294967296.0
+    counts = np.full(len(rids), n, dtype=np.int64) if counts is None else np.minimum(np.asarray(counts, dtype=np.int64), n)
+    rows = np.repeat(np.arange(len(rids)), counts)
+    cols = np.arange(int(counts.sum())) - np.repeat(np.cumsum(counts) - counts, counts)
+    with np.errstate(over="ignore"):
+        z = (rids[rows] * np.uint64(0x9E3779B97F4A7C15) + (cols.astype(np.uint64) + np.uint64(1)) * np.uint64(0xD1B54A32D192ED03)
+             + np.uint64(seed & 0xFFFFFFFFFFFFFFFF) * np.uint64(0x8CB92BA72F3D8DD7) + np.uint64(ST_IR))
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    out = np.zeros((len(rids), n), dtype=np.float64)
+    out[rows, cols] = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
     return out
 
 
@@ -207,24 +214,34 @@ class IntronRetention:
         p0 = reads["piece_first"].astype(np.int64)
         trx = pieces["chrom"][p0].astype(np.int64)
         n_int = st.n_introns[trx]
-        m = int(n_int.max()) if len(n_int) else 0
-        if m == 0:
+        if len(n_int) == 0 or int(n_int.max()) == 0:
             return None
-        u = ir_uniforms(seed, first_id + np.arange(len(reads), dtype=np.uint64), m + 1)
-        retained = draw_ir_states(self.p_no_ir, n_int, u[:, :m])
-        hit = np.flatnonzero(retained.any(axis=1))
+        rids = first_id + np.arange(len(reads), dtype=np.uint64)
+        # most transcripts have a handful of introns, a few have hundreds: two groups keep the uniform matrices small
+        decided = {}
+        for sel in (np.flatnonzero((n_int > 0) & (n_int <= 31)), np.flatnonzero(n_int > 31)):
+            if len(sel) == 0:
+                continue
+            m = int(n_int[sel].max())
+            u = ir_uniforms(seed, rids[sel], m + 1, counts=n_int[sel] + 1)
+            ret = draw_ir_states(self.p_no_ir, n_int[sel], u[:, :m])
+            for k in np.flatnonzero(ret.any(axis=1)).tolist():
+                i = int(sel[k])
+                decided[i] = (ret[k, :int(n_int[i])].tolist(), float(u[k, int(n_int[i])]))
+        hit = sorted(decided)
         slots, new_reads, new_pieces, new_ops = [], [], [], []
         piece_cursor, op_cursor = int(n_pieces_total), int(n_ops_total)
-        for i in hit.tolist():
+        for i in hit:
+            retained_i, u_start = decided[i]
             t = int(trx[i])
             a, b = int(st.first[t]), int(st.first[t + 1])
             feats = list(zip(st.ftype[a:b].tolist(), st.chrom[a:b].tolist(), st.start[a:b].tolist(), st.end[a:b].tolist(),
                              st.minus[a:b].tolist()))
             pc = pieces[int(p0[i])]
             length = int(pc["ref_len"])
-            # the uniform after the read's own intron draws (not after the batch's longest chain: results must not
+            # u_start: the uniform after the read's own intron draws (not after the batch's longest chain: results must not
             # depend on which reads share a batch)
-            ivs = extract_read_pos(length, int(self.trx_len[t]), feats, retained[i].tolist(), float(u[i, int(n_int[i])]))
+            ivs = extract_read_pos(length, int(self.trx_len[t]), feats, retained_i, u_start)
             if not ivs or any(g < 0 for g, *_ in ivs) or sum(e - s for _, s, e, _, _ in ivs) != length:
                 continue                                     # a chromosome the genome file lacks (:1168-1170) / inconsistent annotation
             minus = bool(ivs[-1][3])                         # `interval.strand` after the loop (:1177)
