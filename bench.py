@@ -52,36 +52,43 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from the warm-up on (nvidia-smi itself needs ~0.1 s to
+    start, longer than a short timed region); samples are time-stamped and only the ones inside a timed region count."""
 
     def __init__(self, device):
         self.rows = []
         self.device = device
         self.proc = None
+        self.windows = []
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1, label):
+        self.windows.append((t0, t1, label))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        inside = [r for t, r in self.rows if any(a <= t <= b + 0.06 for a, b, _ in self.windows)]
+        sm = [float(r[0]) for r in inside if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for _, r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = sorted({names[i] for r in inside if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm),
+                "windows": "samples inside the timed regions: " + ", ".join("%s %.0f ms" % (lab, 1e3 * (b - a)) for a, b, lab in self.windows)}
 
 
 def synth_reference_gpu(device, scale=1.0):
@@ -261,17 +268,17 @@ def main():
     #      of one batch's plan / unaligned kernels overlap the emit kernel of another.  Every step simulates new read ids;
     #      a batch's working set (>2 GB written + a 3 GB reference sampled at random) is far larger than the 126 MB L2.
     pipe = BatchPipeline(eng, depth=args.depth, fetch=False)
-    pipe.warm(jobs_for(range(1)))                   # every context sizes its buffers once (untimed)
-    pipe.run(jobs_for(range(args.warmup)))
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    pipe.warm(jobs_for(range(1)))                   # every context sizes its buffers once (untimed)
+    pipe.run(jobs_for(range(args.warmup)))
+    barrier()
     t0 = time.perf_counter()
     rows = [row(i) for i in pipe.run(jobs_for(range(args.warmup, total_steps)))]
     barrier()
     wall = time.perf_counter() - t0
-    clk = clocks.stop() if rank == 0 else None
+    clocks.window(t0, t0 + wall, "kernel-only arm")
     pipe.close()
     if args.timeline and rank == 0:
         with open(args.timeline, "w") as f:       # phases are back to back on a context's stream: begin + cumulative durations
@@ -324,6 +331,8 @@ def main():
     rows_e = [row(i) for i in pipe_e.run(jobs_for(range(base_step + e_warm, base_step + e_warm + args.steps)))]
     barrier()
     wall_e = time.perf_counter() - t0
+    clocks.window(t0, t0 + wall_e, "end-to-end arm")
+    clk = clocks.stop() if rank == 0 else None
     pipe_e.close()
     bases_e = sum(r[0] for r in rows_e)
     # bytes that cross PCIe: qualities as ASCII, bases as 2 bits (packed on the device, expanded by host threads inside

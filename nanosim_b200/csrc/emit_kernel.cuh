@@ -120,12 +120,13 @@ __device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiec
 
 // The branch-free 16-base walk of one chunk (see the header comment).  WRAPS: the piece crosses the origin of a circular
 // chromosome (:1756-1760).
-template <bool FASTQ, bool WRAPS>
-__device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* lut, const uint8_t* cvt,
+template <bool FASTQ, bool WRAPS, bool COMP>
+__device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* lut, const uint8_t* cvt_tables,
                                              const uint8_t* __restrict__ cbase, const uint32_t (&W)[FASTQ ? 16 : 4], uint32_t& k,
                                              uint32_t& rem, uint32_t& rabs, uint32_t& info, uint32_t dir, uint32_t clen,
                                              uint32_t wrap_fix, uint32_t tbl, uint32_t (&sb)[4], uint32_t (&sq)[4], uint32_t& bad,
                                              uint32_t& slow) {
+    const uint8_t* cvt = cvt_tables + (COMP ? 256 : 0);    // compile-time offset: the lookup stays [register + immediate]
     uint32_t sel = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -200,7 +201,6 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         // read's own orientation that fixes the walking direction, and the complement moves into the classification table
         const bool ref_comp = (pm.kind & NS_PIECE_REF_REV) != 0;
         const bool rdir = rev != ref_comp;
-        const uint8_t* cvt = cvt_tables + (ref_comp ? 256 : 0);
         const uint32_t n_ops = pm.n_ops, ref_len = pm.ref_len;
         const uint32_t A = rev ? rm.seq_len - pm.out_rel - pm.out_len : pm.out_rel;    // piece start in read coordinates
         const uint32_t pad = A & 15u, P0 = A - pad;          // x = read coordinate - P0: chunks are x/16
@@ -307,8 +307,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
                 }
                 uint32_t sb[4], sq[4] = {0, 0, 0, 0};
                 uint32_t bad = 0, slow = 0;
-                if (wraps) emit_chunk16<FASTQ, true>(ring, lut, cvt, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
-                else emit_chunk16<FASTQ, false>(ring, lut, cvt, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
+                // three instantiations: plain, circular wrap, complementing (minus-strand genome pieces; keeps the wrap check)
+                if (ref_comp) emit_chunk16<FASTQ, true, true>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
+                else if (wraps) emit_chunk16<FASTQ, true, false>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
+                else emit_chunk16<FASTQ, false, false>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
                 // ---- rare exact paths, one base at a time
                 if ((bad & 4u) || (FASTQ && (slow & 0x80u))) {
 #pragma unroll
