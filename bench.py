@@ -38,9 +38,9 @@ CHROM_NAMES = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
 MODEL = os.path.join(ROOT, "nanosim_b200", "data", "guppy_fab49712_plusq.npz")
 ALGO_BYTES_PER_BASE = 3.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE emit_kernel<FASTQ> launch of this workload (235536 aligned reads,
-# 2.04 Gbases): 3.223 GB + 4.319 GB, from `ncu --set full -k regex:emit_kernel -c 1 python bench.py --steps 1 --warmup 1
-# --depth 1 --no_cpu_baseline` (profiles/r1_emit_ncu_summary.txt) = 3.69 B/base against 3 B/base algorithmic.
-TRAFFIC_BYTES_PER_LAUNCH = 7.542e9
+# 2.04 Gbases): 3.226 GB + 4.401 GB, from `ncu --set full -k regex:emit_kernel -c 1 python bench.py --steps 1 --warmup 1
+# --depth 1 --no_cpu_baseline` (profiles/r1_emit_ncu_summary.txt) = 3.73 B/base against 3 B/base algorithmic.
+TRAFFIC_BYTES_PER_LAUNCH = 7.627e9
 
 
 def measured_peak():
