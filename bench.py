@@ -234,7 +234,7 @@ def main():
     tables = DeviceTables(cm, fastq=True)
     eng = Engine(device=local, seed=20260924)
     eng.set_reference_ptr(ref_t.data_ptr(), int(offsets[-1]), offsets)
-    host_ref = ref_t.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+    host_ref = ref_t.cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None     # CPU baseline: N=1 only
     del ref_t
     torch.cuda.empty_cache()
     eng.set_model(tables)
