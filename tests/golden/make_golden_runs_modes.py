@@ -4,6 +4,8 @@ tests/run_stats.py, accumulated into tests/golden/ref_stats_<config>.json).
 
     python tests/golden/make_golden_runs_modes.py meta_even_fastq_chimeric 200000 20000 [/tmp/models]
     python tests/golden/make_golden_runs_modes.py trx_drna_fasta 200000 8000 [/tmp/models]
+    python tests/golden/make_golden_runs_modes.py trx_ir_drna_fasta 100000 8000 [/tmp/models]     (intron retention on; HTSeq /
+                                                  pysam calls served by the stand-ins of oracle/ref_shim.py, fixture tests/golden/ir)
 
 Besides the run_stats histograms the JSON holds ``by_chrom_reads`` / ``by_chrom_bases``: aligned reads and their emitted
 bases per reference record of the read's FIRST segment (species-chromosome, or transcript).
@@ -67,6 +69,16 @@ def main():
         fastq, prefix = False, out
         shown = "simulator.py transcriptome -rt trx/transcripts.fa -e trx/expression.tsv -c %s/training -n %d --no_model_ir " \
                 "-b guppy --polya trx/polya.txt -t 8" % (DRNA, chunk)
+    elif cfg == "trx_ir_drna_fasta":
+        sys.path.insert(0, HERE)
+        from make_golden_ir import IR, model_dir
+        mp_ = model_dir(models)
+        cmd = [sys.executable, shim, "transcriptome", "-rt", os.path.join(IR, "transcripts.fa"), "-rg", os.path.join(IR, "genome.fa"),
+               "-e", os.path.join(IR, "expression.tsv"), "-c", mp_, "-o", out, "-n", str(chunk), "-b", "guppy",
+               "--polya", os.path.join(IR, "polya.txt"), "-t", "8"]
+        fastq, prefix = False, out
+        shown = "simulator.py transcriptome -rt ir/transcripts.fa -rg ir/genome.fa -e ir/expression.tsv -c <%s + ir/IR_markov_model + " \
+                "ir/annotation.gff3>/training -n %d -b guppy --polya ir/polya.txt -t 8" % (DRNA, chunk)
     else:
         raise SystemExit("unknown config " + cfg)
     out_json = os.path.join(HERE, "ref_stats_%s.json" % cfg)
@@ -82,6 +94,14 @@ def main():
         t1 = time.time()
         s = rs.stats_from_prefix(prefix, fastq)
         r, b = by_chrom(prefix + "_aligned_reads." + ("fastq" if fastq else "fasta"), fastq)
+        if cfg.startswith("trx_ir"):
+            n_ir = n_iv = 0
+            for name, _, _ in rs._records(prefix + "_aligned_reads." + ("fastq" if fastq else "fasta"), fastq):
+                if "_RetainedIntron_" in name:
+                    n_ir += 1
+                    n_iv += name.split("_RetainedIntron_")[1].split("_")[0].count(";")
+            acc["ir_reads"] = acc.get("ir_reads", 0) + n_ir
+            acc["ir_intervals"] = acc.get("ir_intervals", 0) + n_iv
         for k in r:
             acc["by_chrom_reads"][k] = acc["by_chrom_reads"].get(k, 0) + r[k]
             acc["by_chrom_bases"][k] = acc["by_chrom_bases"].get(k, 0) + b[k]

@@ -902,6 +902,47 @@ def test_cli_transcriptome_with_intron_retention(ir_fixture, tmp_path, L):
     assert s["n_aligned"] + s["n_unaligned"] == 1500
 
 
+def test_intron_retention_vs_unmodified_reference(ir_fixture, tmp_path, L):
+    """96k reads of the unmodified `simulator.py transcriptome` with intron retention ON (its HTSeq / pysam calls served by the
+    stand-ins of oracle/ref_shim.py) on the IR fixture, against this CLI: read-level histograms, error rates, the share
+    of reads that retain an intron and how many retained intervals they cover."""
+    from nanosim_b200 import simulator
+    path = os.path.join(GOLDEN, "ref_stats_trx_ir_drna_fasta.json")
+    if not os.path.exists(path):
+        pytest.skip("golden reference histograms not generated")
+    gold, _ = rs.load(path)
+    D = ir_fixture[0]
+    out = os.path.join(str(tmp_path), "ir")
+    n = 96000
+    simulator.main(["transcriptome", "-rt", os.path.join(D, "transcripts.fa"), "-rg", os.path.join(D, "genome.fa"),
+                    "-e", os.path.join(D, "expression.tsv"), "-c", os.path.join(pc.DATA, pc.MODELS["drna"]), "-n", str(n), "-o", out,
+                    "--polya", os.path.join(D, "polya.txt"), "-b", "guppy", "--seed", "29", "-t", str(n // 8000 * 8),
+                    "--ir_markov_model", os.path.join(D, "IR_markov_model"), "--ir_gff3", os.path.join(D, "annotation.gff3")])
+    s = rs.stats_from_prefix(out, False)
+    rd, rg = pc.rates(s), pc.rates(gold)
+    print("IR per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
+    # Two documented deviations show on this 16-transcript fixture where half of the reads retain an intron: (1) len_tail is
+    # left out -- the name's last field is tail + polyA, and a retained-intron read keeps the polyA decision of its first
+    # pass while the reference re-decides it from the genomic end of the last feature (simulator.py:186-189); (2) transcript
+    # usage differs slightly (shared 2-D KDE sample, see test_transcriptome_vs_unmodified_reference), which moves the read
+    # length mix and with it the per-base rates by a few 1e-3.
+    fails = pc.compare_stats(s, gold, rate_tol=8e-3, p_min=1e-6, label="trx-ir",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "match_run", "first_match", "events_per_read"])
+    n_ir = n_iv = 0
+    for name, _, _ in rs._records(out + "_aligned_reads.fasta", False):
+        if "_RetainedIntron_" in name:
+            n_ir += 1
+            n_iv += name.split("_RetainedIntron_")[1].split("_")[0].count(";")
+    f_d, f_g = n_ir / s["n_aligned"], gold["ir_reads"] / gold["n_aligned"]
+    k_d, k_g = n_iv / max(n_ir, 1), gold["ir_intervals"] / max(gold["ir_reads"], 1)
+    print("reads with a retained intron: device %.4f reference %.4f; intervals per such read %.3f vs %.3f" % (f_d, f_g, k_d, k_g))
+    if abs(f_d - f_g) > 5 * np.sqrt(f_g * (1 - f_g) * (1 / s["n_aligned"] + 1 / gold["n_aligned"])) + 2e-3:
+        fails.append("share of IR reads %.4f vs %.4f" % (f_d, f_g))
+    if abs(k_d / k_g - 1) > 0.03:
+        fails.append("retained intervals per IR read %.3f vs %.3f" % (k_d, k_g))
+    assert not fails, "\n".join(fails)
+
+
 def test_lognormal_lengths_med_sd(ecoli, L):
     """-med / -sd (simulator.py:1285-1295, 1494-1495): log-normal read lengths."""
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=5)
