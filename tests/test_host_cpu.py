@@ -299,3 +299,125 @@ def test_intron_retention_host_logic_matches_oracle(monkeypatch):
     assert ref_used == [30, 11, 19]
     assert sum(ir._out_len(p) for p in parts) == ir._out_len(ops)
     assert parts[0][0] == ops[0] and parts[-1][-1] == ops[-1] and (parts[0][2] >> 28) == L.NS_OP_INS
+
+
+class _FakeEngine:
+    """Stands in for Engine in the pipeline tests: simulate() sleeps a job-dependent time, records what ran where."""
+
+    def __init__(self, slot, log, fail_on=None):
+        self.slot, self.log, self.fail_on, self.fastq, self.info = slot, log, fail_on, False, None
+
+    def clone(self):
+        raise AssertionError("not used")
+
+    def simulate(self, kind, first, n):
+        import time
+        if self.fail_on is not None and first == self.fail_on:
+            raise RuntimeError("boom at %d" % first)
+        time.sleep(0.001 * (1 + (first * 7) % 5))
+        self.log.append((self.slot, first))
+        self.info = type("I", (), {"first": first, "n_reads": n, "seq_bytes": 0, "n_pieces": 0, "n_ops": 0})()
+        return self.info
+
+    def close(self):
+        pass
+
+
+def _fake_pipeline(depth, fail_on=None):
+    from nanosim_b200.pipeline import BatchPipeline
+    log = []
+    pipe = BatchPipeline.__new__(BatchPipeline)
+    pipe.engines = [_FakeEngine(s, log, fail_on) for s in range(depth)]
+    pipe.depth, pipe.fetch, pipe.want_ops, pipe.want_pieces = depth, False, False, True
+    pipe.bufs, pipe.hint = [None] * depth, {"seq": 0, "reads": 0, "pieces": 0, "ops": 0}
+    return pipe, log
+
+
+def test_pipeline_orders_results_and_assigns_contexts():
+    """BatchPipeline: results are consumed in submission order whatever the completion order; static_assign pins job j to
+    context j % depth; the after_simulate hook runs once per job on the job's context; a failing job surfaces."""
+    jobs = [(0, i, 1) for i in range(40)]
+    pipe, log = _fake_pipeline(3)
+    seen, hooked = [], []
+    infos = pipe.run(jobs, consume=lambda info, b, job: seen.append(job[1]), after_simulate=lambda e, info, job: hooked.append((e.slot, job[1])))
+    assert seen == list(range(40)) and [i.first for i in infos] == list(range(40))
+    assert sorted(f for _, f in log) == list(range(40)) and sorted(f for _, f in hooked) == list(range(40))
+    assert dict((f, s) for s, f in log) == dict((f, s) for s, f in hooked)
+    pipe, log = _fake_pipeline(3)
+    pipe.run(jobs, static_assign=True)
+    assert all(slot == first % 3 for slot, first in log)
+    pipe, log = _fake_pipeline(2, fail_on=7)
+    with pytest.raises(RuntimeError, match="boom at 7"):
+        pipe.run(jobs)
+    assert pipe.run([]) == []
+
+
+def test_intron_retention_patch_is_consistent():
+    """IntronRetention.plan_batch on a hand-built transcriptome batch (no GPU): every patched read keeps its length, its new
+    pieces tile the extracted genomic intervals, the cut scripts consume exactly those intervals and produce the same number
+    of bases, offsets point behind the batch, and the decision does not depend on which reads share a batch."""
+    from nanosim_b200 import _lib as L
+    from nanosim_b200 import intron_retention as ir
+    from nanosim_b200.reference_fasta import PackedReference
+    D = os.path.join(GOLDEN, "ir")
+    trx = PackedReference.from_fasta(os.path.join(D, "transcripts.fa"))
+    genome = PackedReference.from_fasta(os.path.join(D, "genome.fa"))
+    ref = PackedReference.concat(trx, genome)
+    assert ref.names[:len(trx.names)] == trx.names and ref.raw_names[len(trx.names):] == ["chr1", "chr2"]
+    assert int(ref.offsets[len(trx.names)]) == trx.genome_len and ref.genome_len == trx.genome_len + genome.genome_len
+    st = ir.TranscriptStructures.from_gff3(os.path.join(D, "annotation.gff3"), trx.names, genome.raw_names)
+    irm = ir.IntronRetention(ir.read_ir_markov_model(os.path.join(D, "IR_markov_model")), st, trx.lengths, len(trx.names))
+    rng = np.random.default_rng(11)
+    n = 400
+    reads = np.zeros(n, dtype=L.READ_DTYPE)
+    pieces = np.zeros(n, dtype=L.PIECE_DTYPE)
+    ops = []
+    for i in range(n):
+        t = int(rng.integers(0, len(trx.names)))
+        tl = int(trx.lengths[t])
+        script, rf, out = [(L.NS_OP_HT << 28) | 4], 0, 4
+        want = int(rng.integers(20, tl - 5))
+        while rf < want:
+            ty = int(rng.choice([L.NS_OP_COPY, L.NS_OP_COPY, L.NS_OP_MIS, L.NS_OP_INS, L.NS_OP_DEL]))
+            ln = int(rng.integers(1, 25 if ty == L.NS_OP_COPY else 4))
+            if ty != L.NS_OP_INS:
+                ln = min(ln, want - rf)
+                rf += ln
+            if ty != L.NS_OP_DEL:
+                out += ln
+            script.append((ty << 28) | ln)
+        script += [(L.NS_OP_LIT << 28) | (3 << 24) | 6, (L.NS_OP_HT << 28) | 3]
+        out += 9
+        reads[i]["piece_first"], reads[i]["n_pieces"], reads[i]["seq_len"], reads[i]["head"], reads[i]["tail"] = i, 1, out, 4, 3
+        pieces[i]["chrom"], pieces[i]["pos"], pieces[i]["ref_len"], pieces[i]["out_len"], pieces[i]["read_slot"] = t, 0, rf, out, i
+        pieces[i]["op_off"] = pieces[i]["ev_off"] = len(ops)
+        pieces[i]["n_ops"] = pieces[i]["ev_n_ops"] = len(script)
+        pieces[i]["polya_len"] = 6
+        ops += script
+    ops = np.asarray(ops, dtype=np.uint32)
+    patch = irm.plan_batch(reads, pieces, ops, 1000, 5, n, len(ops))
+    slots, nr, npc, nops = patch
+    assert 0.15 * n < len(slots) < 0.95 * n and len(nr) == len(slots)
+    for k, i in enumerate(slots.tolist()):
+        r = nr[k]
+        assert int(r["seq_len"]) == int(reads[i]["seq_len"]) and int(r["piece_first"]) >= n
+        own = npc[int(r["piece_first"]) - n: int(r["piece_first"]) - n + int(r["n_pieces"])]
+        segs, gaps = own[::2], own[1::2]
+        assert (gaps["kind"] == L.NS_PIECE_GAP).all() and (gaps["out_len"] == 0).all()
+        assert (segs["kind"] & L.NS_PIECE_GENOME).all() and (segs["chrom"] >= len(trx.names)).all() and (segs["read_slot"] == i).all()
+        assert int(segs["ref_len"].sum()) == int(pieces[i]["ref_len"]) and int(segs["out_len"].sum()) == int(reads[i]["seq_len"])
+        assert (segs["kind"][1:] & L.NS_PIECE_CONT).all() and not int(segs["kind"][0]) & L.NS_PIECE_CONT
+        rel = 0
+        for q in segs:
+            part = nops[int(q["op_off"]) - len(ops): int(q["op_off"]) - len(ops) + int(q["n_ops"])]
+            ty = part >> 28
+            assert int(sum(int(o & 0x0fffffff) for o, t_ in zip(part.tolist(), ty.tolist()) if t_ in (0, 1, 3))) == int(q["ref_len"])
+            assert ir._out_len(part) == int(q["out_len"]) and int(q["out_rel"]) == rel
+            rel += int(q["out_len"])
+            g = int(q["chrom"]) - len(trx.names)
+            assert 0 <= int(q["pos"]) and int(q["pos"]) + int(q["ref_len"]) <= int(genome.lengths[g])
+    # the same reads in a different batch split decide the same way
+    half = irm.plan_batch(reads[:200], pieces[:200], ops, 1000, 5, 200, len(ops))
+    assert half[0].tolist() == [s for s in slots.tolist() if s < 200]
+    a = npc[:len(half[2])]
+    assert np.array_equal(a["pos"], half[2]["pos"]) and np.array_equal(a["ref_len"], half[2]["ref_len"])
