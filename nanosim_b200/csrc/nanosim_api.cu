@@ -205,6 +205,10 @@ __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* rea
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const NsPieceMeta pm = pieces[i];
+    {   // pieces a read no longer owns (its piece list was replaced by ns_reemit) are not counted
+        const NsReadMeta rm = reads[pm.read_slot];
+        if (i < rm.piece_first || i >= rm.piece_first + rm.n_pieces) return;
+    }
     unsigned long long* ev = st + 8;
     unsigned long long* evlen = st + 16;
     unsigned long long* run_h = evlen + 3 * (NS_STATS_EV_CAP + 1);
