@@ -337,7 +337,8 @@ def main():
     bases_e = sum(r[0] for r in rows_e)
     # bytes that cross PCIe: qualities as ASCII, bases as 2 bits (packed on the device, expanded by host threads inside
     # ns_fetch unless NANOSIM_B200_UNPACK_THREADS=0) + read / piece metadata
-    packed = os.environ.get("NANOSIM_B200_UNPACK_THREADS", "") != "0"
+    env_t = os.environ.get("NANOSIM_B200_UNPACK_THREADS", "")          # same rule as unpack_threads() in nanosim_api.cu
+    packed = int(env_t) > 0 if env_t else (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) >= 48
     d2h = sum((1.25 if packed and r[1] >= (1 << 20) else 2.0) * r[1] + 32 * r[2] + 64 * r[3] for r in rows_e) / max(args.steps, 1)
     stat = torch.tensor([bases_e, wall_e], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
@@ -366,8 +367,8 @@ def main():
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": int(d2h),
                 "note": "reference + model are resident in HBM (uploaded once at init); per-step input is the read-id range; the "
-                        "timed region ends with ASCII bases + qualities + metadata in pinned host buffers (bases cross PCIe as "
-                        "2 bits and are expanded by host threads inside ns_fetch)"},
+                        "timed region ends with ASCII bases + qualities + metadata in pinned host buffers" +
+                        (" (bases cross PCIe as 2 bits and are expanded by host threads inside ns_fetch)" if packed else "")},
         "gpu_launches": int(launches),
         "phase_ms_per_step": {"plan": sum(r[6] for r in rows) / args.steps, "scan": sum(r[7] for r in rows) / args.steps,
                               "script": sum(r[8] for r in rows) / args.steps, "emit": emit_ms / args.steps,

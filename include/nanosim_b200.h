@@ -232,7 +232,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
 /* Device->host copy of the last batch into caller buffers (pinned memory recommended).  qual / pieces / ops may be
  * NULL.  seq and qual need info.seq_bytes bytes, reads n_reads entries, pieces n_pieces, ops n_ops uint32.
  * seq arrives as ASCII as always; on the wire large batches travel as 2 bits per base (packed by a kernel, expanded by
- * host threads inside this call: NANOSIM_B200_UNPACK_THREADS, default min(16, cores/4); 0 copies plain ASCII). */
+ * host threads inside this call: NANOSIM_B200_UNPACK_THREADS; default 16 when the host has >= 48 cores per GPU process
+ * (cores / LOCAL_WORLD_SIZE), else 0 = plain ASCII copies). */
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
 
 /* Intron retention (simulator.py:1156-1183), second half: replaces the piece lists of `n_slots` reads of the last batch and

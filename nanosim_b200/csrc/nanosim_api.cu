@@ -1109,8 +1109,12 @@ int unpack_threads() {
     static const int n = [] {
         const char* e = getenv("NANOSIM_B200_UNPACK_THREADS");     // 0: copy the bases as ASCII (no packing)
         if (e && *e) return std::max(0, atoi(e));
+        // packing only pays when the host can expand faster than PCIe delivers: with fewer than 48 cores per GPU process
+        // (torchrun exports LOCAL_WORLD_SIZE) every GPU's own PCIe link is the better deal and the bases travel as ASCII
         const unsigned hc = std::thread::hardware_concurrency();
-        return (int)std::max(1u, std::min(16u, hc ? hc / 4 : 4u));
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        const unsigned ranks = (lw && *lw) ? (unsigned)std::max(1, atoi(lw)) : 1u;
+        return ((hc ? hc : 4u) / ranks >= 48u) ? 16 : 0;
     }();
     return n;
 }
