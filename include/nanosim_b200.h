@@ -255,7 +255,17 @@ int ns_device_buffers(NsContext* ctx, const uint8_t** seq, const uint8_t** qual,
  * the reference's <out>_aligned_error_profile).  out must hold NS_STATS_WORDS uint64. */
 #define NS_STATS_EV_CAP 64
 #define NS_STATS_RUN_CAP 512
-#define NS_STATS_WORDS (8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1))
+#define NS_STATS_EPR_CAP 131072   /* error events per aligned segment (mutate_read call), exact counts 0..cap-1, cap+ */
+/* layout (uint64 words): [0..7] totals (segments, reference bases, segment output bases, head/tail bases, gaps, gap bases,
+ * events, -), [8..15] events / event bases by type (mis ins del), 3 event-length histograms, match-run and first-match
+ * histograms, then NS_STATS_EPR_OFF: events-per-segment histogram (segments with at least one event, as the error profile
+ * shows them), NS_STATS_SUB_OFF: 4x4 reference base x read base of 1-base mismatches (A C G T order, read taken in the
+ * reference's orientation), NS_STATS_INS_OFF: inserted bases by A C G T, NS_STATS_COMP_OFF: base composition of the reads */
+#define NS_STATS_EPR_OFF (8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1))
+#define NS_STATS_SUB_OFF (NS_STATS_EPR_OFF + NS_STATS_EPR_CAP + 1)
+#define NS_STATS_INS_OFF (NS_STATS_SUB_OFF + 16)
+#define NS_STATS_COMP_OFF (NS_STATS_INS_OFF + 4)
+#define NS_STATS_WORDS (NS_STATS_COMP_OFF + 4)
 int ns_op_stats(NsContext* ctx, uint64_t* out);
 
 /* Host-side record formatting of a fetched batch into the reference's FASTA/FASTQ text (:1437-1443); multi-threaded.

@@ -15,7 +15,12 @@ NS_PIECE_SEGMENT, NS_PIECE_GAP, NS_PIECE_UNALIGNED = 0, 1, 2
 NS_PIECE_REF_REV, NS_PIECE_CONT, NS_PIECE_RETAINED, NS_PIECE_GENOME, NS_PIECE_KIND_MASK = 0x80000000, 0x40000000, 0x20000000, 0x10000000, 0xffff
 NS_OP_COPY, NS_OP_MIS, NS_OP_INS, NS_OP_DEL, NS_OP_HT, NS_OP_LIT = 0, 1, 2, 3, 4, 5
 NS_STATS_EV_CAP, NS_STATS_RUN_CAP = 64, 512
-NS_STATS_WORDS = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
+NS_STATS_EPR_CAP = 131072
+NS_STATS_EPR_OFF = 8 + 8 + 3 * (NS_STATS_EV_CAP + 1) + 2 * (NS_STATS_RUN_CAP + 1)
+NS_STATS_SUB_OFF = NS_STATS_EPR_OFF + NS_STATS_EPR_CAP + 1
+NS_STATS_INS_OFF = NS_STATS_SUB_OFF + 16
+NS_STATS_COMP_OFF = NS_STATS_INS_OFF + 4
+NS_STATS_WORDS = NS_STATS_COMP_OFF + 4
 
 EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
            "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names"]

@@ -200,15 +200,18 @@ __global__ void sum_bases(const NsReadMeta* reads, uint32_t n, unsigned long lon
 }
 
 // op-list histograms (ns_op_stats)
+__device__ __forceinline__ int acgt_index(uint32_t c) {          // A C G T(U) -> 0 1 2 3, anything else -1
+    if (c - 'a' < 26u) c -= 32;
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : (c == 'T' || c == 'U') ? 3 : -1;
+}
 __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* reads, const uint32_t* ops, uint32_t n,
-                                unsigned long long* st) {
+                                DevRef ref, const uint8_t* seq, unsigned long long* st) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const NsPieceMeta pm = pieces[i];
-    {   // pieces a read no longer owns (its piece list was replaced by ns_reemit) are not counted
-        const NsReadMeta rm = reads[pm.read_slot];
-        if (i < rm.piece_first || i >= rm.piece_first + rm.n_pieces) return;
-    }
+    const NsReadMeta rm = reads[pm.read_slot];
+    // pieces a read no longer owns (its piece list was replaced by ns_reemit) are not counted
+    if (i < rm.piece_first || i >= rm.piece_first + rm.n_pieces) return;
     unsigned long long* ev = st + 8;
     unsigned long long* evlen = st + 16;
     unsigned long long* run_h = evlen + 3 * (NS_STATS_EV_CAP + 1);
@@ -222,14 +225,31 @@ __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* rea
     atomicAdd(&st[1], (unsigned long long)pm.ref_len);
     uint64_t run = 0, ht = 0, n_ev = 0;
     bool first = true;
+    // substituted / inserted bases are read back from the sequence: only when the event script is the emitted script
+    // (-hp rewrites it) and the piece reads the reference forwards
+    const bool bases_ok = seq != nullptr && pm.ev_off == pm.op_off && !(pm.kind & NS_PIECE_REF_REV);
+    const uint64_t cstart = ref.chrom_off[pm.chrom];
+    const uint32_t clen = (uint32_t)(ref.chrom_off[pm.chrom + 1] - cstart);
+    const uint8_t* rs = seq ? seq + rm.seq_off : nullptr;
+    uint32_t sub[16], insb[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sub[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) insb[k] = 0;
+    auto read_base = [&](uint32_t x) -> int {                    // base x of the read in the reference's orientation
+        if (!rm.reversed) return acgt_index(rs[x]);
+        const int b = acgt_index(rs[rm.seq_len - 1u - x]);
+        return b < 0 ? b : 3 - b;
+    };
+    uint32_t o = pm.out_rel, rf = 0;
     for (uint32_t k = 0; k < pm.ev_n_ops; ++k) {         // the event script (== op script unless -hp rewrote it)
         uint32_t op = ops[pm.ev_off + k];
-        uint32_t ty = op >> 28, len = op & 0x0fffffffu;
+        uint32_t ty = op >> 28, len = op_len(op);
         if (ty == NS_OP_HT) {
             ht += len;
         } else if (ty == NS_OP_COPY) {
             run += len;
-        } else {
+        } else if (ty <= NS_OP_DEL) {
             uint32_t t = ty - 1;   // 0 mis 1 ins 2 del
             atomicAdd(&ev[t], 1ull);
             atomicAdd(&ev[3 + t], (unsigned long long)len);
@@ -239,11 +259,49 @@ __global__ void op_stats_kernel(const NsPieceMeta* pieces, const NsReadMeta* rea
             first = false;
             run = 0;
             ++n_ev;
+            if (bases_ok && ty == NS_OP_MIS && len == 1) {
+                uint32_t ab = pm.pos + rf;
+                if (ab >= clen) ab -= clen;
+                const int a = acgt_index(ref.bases[cstart + ab]), b = read_base(o);
+                if (a >= 0 && b >= 0) ++sub[a * 4 + b];
+            } else if (bases_ok && ty == NS_OP_INS) {
+                for (uint32_t t2 = 0; t2 < len; ++t2) {
+                    const int b = read_base(o + t2);
+                    if (b >= 0) ++insb[b];
+                }
+            }
         }
+        if (ty != NS_OP_DEL) o += len;
+        if (ty == NS_OP_COPY || ty == NS_OP_MIS || ty == NS_OP_DEL) rf += len;
     }
     atomicAdd(&st[2], (unsigned long long)(pm.out_len - ht));
     atomicAdd(&st[3], (unsigned long long)ht);
     atomicAdd(&st[6], (unsigned long long)n_ev);
+    if (n_ev) atomicAdd(&st[NS_STATS_EPR_OFF + (n_ev < NS_STATS_EPR_CAP ? n_ev : NS_STATS_EPR_CAP)], 1ull);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (sub[k]) atomicAdd(&st[NS_STATS_SUB_OFF + k], (unsigned long long)sub[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (insb[k]) atomicAdd(&st[NS_STATS_INS_OFF + k], (unsigned long long)insb[k]);
+}
+// base composition of the batch's reads (as emitted; U counts as T): one warp per read
+__global__ void base_comp_kernel(const NsReadMeta* reads, uint32_t n, const uint8_t* seq, unsigned long long* st) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const NsReadMeta rm = reads[w];
+    const uint8_t* rs = seq + rm.seq_off;
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (uint32_t x = lane; x < rm.seq_len; x += 32) {
+        const int b = acgt_index(rs[x]);
+        if (b >= 0) ++c[b];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t v = c[k];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0 && v) atomicAdd(&st[NS_STATS_COMP_OFF + k], (unsigned long long)v);
+    }
 }
 
 cudaError_t upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
@@ -1241,8 +1299,12 @@ int ns_op_stats(NsContext* ctx, uint64_t* out) {
     const uint32_t n = ctx->last.n_pieces;
     if (n) {
         op_stats_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->pieces.as<NsPieceMeta>(), ctx->reads.as<NsReadMeta>(),
-                                                                   ctx->ops.as<uint32_t>(), n,
+                                                                   ctx->ops.as<uint32_t>(), n, ctx->dref, ctx->seq.as<uint8_t>(),
                                                                    (unsigned long long*)ctx->stats.p);
+        const uint32_t nr = ctx->last.n_reads;
+        if (nr && ctx->seq.p)
+            base_comp_kernel<<<(nr + 3) / 4, 128, 0, ctx->stream>>>(ctx->reads.as<NsReadMeta>(), nr, ctx->seq.as<uint8_t>(),
+                                                                     (unsigned long long*)ctx->stats.p);
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(out, ctx->stats.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));

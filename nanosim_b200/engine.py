@@ -229,5 +229,11 @@ class Engine:
              "event_bases": {"mis": int(o[11]), "ins": int(o[12]), "del": int(o[13])},
              "ev_len": {k: o[16 + i * ev: 16 + (i + 1) * ev].copy() for i, k in enumerate(("mis", "ins", "del"))},
              "match_run": o[16 + 3 * ev: 16 + 3 * ev + run].copy(),
-             "first_match": o[16 + 3 * ev + run: 16 + 3 * ev + 2 * run].copy()}
+             "first_match": o[16 + 3 * ev + run: 16 + 3 * ev + 2 * run].copy(),
+             # error events per aligned segment (exact counts; the last slot collects >= NS_STATS_EPR_CAP)
+             "events_per_segment": o[L.NS_STATS_EPR_OFF: L.NS_STATS_EPR_OFF + L.NS_STATS_EPR_CAP + 1].copy(),
+             # 1-base mismatches: reference base x read base, inserted bases, read composition (A C G T order)
+             "mis_sub": o[L.NS_STATS_SUB_OFF: L.NS_STATS_SUB_OFF + 16].reshape(4, 4).copy(),
+             "ins_base": o[L.NS_STATS_INS_OFF: L.NS_STATS_INS_OFF + 4].copy(),
+             "base_comp": o[L.NS_STATS_COMP_OFF: L.NS_STATS_COMP_OFF + 4].copy()}
         return d

@@ -97,6 +97,22 @@ class TranscriptStructures:
         return TranscriptStructures(first, ftype, chrom, start, end, minus)
 
 
+def expressed_with_structure(expr_chrom, expr_weights, st, trx_lengths):
+    """With intron retention on, the reference only accepts a drawn transcript that has features in the GFF3 and whose
+    exon lengths add up to its length in the transcriptome FASTA (simulator.py:1094-1099, ref_len_from_structure :100-105);
+    anything else is drawn again.  Redrawing from fixed weights == dropping those transcripts from the expressed set."""
+    expr_chrom = np.asarray(expr_chrom)
+    n = len(st.first) - 1
+    is_exon = st.ftype == EXON
+    exon_len = np.zeros(n, dtype=np.int64)
+    owner = np.repeat(np.arange(n), np.diff(st.first))
+    np.add.at(exon_len, owner[is_exon], (st.end - st.start)[is_exon])
+    has = np.diff(st.first) > 0
+    t = expr_chrom.astype(np.int64)
+    keep = has[t] & (exon_len[t] == np.asarray(trx_lengths, dtype=np.int64)[t])
+    return expr_chrom[keep], np.asarray(expr_weights)[keep], int((~keep).sum())
+
+
 def ir_uniforms(seed, rids, n, counts=None):
     """n uniforms in [0, 1) per read id, a pure function of (seed, read id, column): SplitMix64's finaliser over a counter
     built from the three (host-side draws: a handful per read, no need for the device's Philox streams).  counts[i]

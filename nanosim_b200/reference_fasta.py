@@ -174,7 +174,8 @@ def read_abundance(path, species):
             if sp not in species:
                 raise KeyError("You didn't provide a reference genome for " + sp)
             table[sp] = [float(x) for x in fields[1:]]
-    samples = [[table[sp][i] for sp in species] for i in range(len(numbers))]
+    # a species with a genome but no abundance row is simply not simulated (the reference leaves it out of dict_abun)
+    samples = [[table[sp][i] if sp in table else 0.0 for sp in species] for i in range(len(numbers))]
     return numbers, samples
 
 

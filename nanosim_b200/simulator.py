@@ -70,6 +70,7 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
         prof.number_list = number_list
     elif mode == "transcriptome":
         prof.ref = PackedReference.from_fasta(ref_t)
+        prof.coverage_ref_len = prof.ref.genome_len      # -x counts the transcriptome only (:2348), not the IR genome
         _log("Read in expression profile")
         try:
             prof.expr_chrom, prof.expr_weights = read_expression(exp, prof.ref)
@@ -95,6 +96,14 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
             st = TranscriptStructures.from_gff3(ir_files.get("gff3") or base + "_added_intron_final.gff3", trx.names, genome.raw_names)
             prof.n_trx = len(trx.names)
             prof.ir = IntronRetention(p_no_ir, st, trx.lengths, prof.n_trx)
+            # :1094-1099: only transcripts whose GFF3 exons add up to their FASTA length are ever simulated
+            from .intron_retention import expressed_with_structure
+            prof.expr_chrom, prof.expr_weights, dropped = expressed_with_structure(prof.expr_chrom, prof.expr_weights, st, trx.lengths)
+            if len(prof.expr_chrom) == 0:
+                sys.stderr.write("No expressed transcript has a matching exon structure in the GFF3 annotation!\n")
+                sys.exit(1)
+            if dropped:
+                _log("%d expressed transcripts without a matching exon structure are never drawn" % dropped)
             prof.ref = PackedReference.concat(trx, genome)
             if prof.polya_flags is not None:
                 prof.polya_flags = np.concatenate([prof.polya_flags, np.zeros(len(genome.names), dtype=np.uint8)])
@@ -149,7 +158,13 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
     pipe = BatchPipeline(eng, depth=2, fetch=True, want_ops=want_err)
+    try:
+        _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads)
+    finally:
+        pipe.close()         # the cloned contexts own device batch buffers and pinned staging
 
+
+def _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads):
     def jobs(kind, lo, hi):
         return [(kind, start, min(batch_reads, hi - start)) for start in range(lo, hi, batch_reads)]
 
@@ -188,7 +203,6 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
                 f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads, as_array=True))
 
             pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned, static_assign=meta)
-    pipe.close()
 
 
 def merge_rank_files(out, fastq, per, world):
@@ -472,7 +486,8 @@ def coverage_to_reads(prof, cm, coverage):
     mean = w_al * cm.kde["aligned_reads"][0].mean()
     if "unaligned_length" in cm.kde:
         mean += (1 - w_al) * cm.kde["unaligned_length"][0].mean()
-    return int(prof.ref.genome_len / mean * coverage)
+    ref_len = getattr(prof, "coverage_ref_len", None) or prof.ref.genome_len
+    return int(ref_len / mean * coverage)
 
 
 def main(argv=None):

@@ -1294,6 +1294,13 @@ def simulation_aligned_transcriptome(ref, model, sink, kmer_bias, basecaller, nu
             if ref_trx in trx_sampled:
                 sampled = kde_lengths(model.kde_aligned_2d, num_simulate, False, False)
                 trx_sampled = set()
+            if model_ir:
+                # simulator.py:1094-1099: a transcript without GFF3 features, or whose exons do not add up to its length,
+                # is drawn again (ref_len_from_structure :100-105)
+                if ref_trx not in ref.structure:
+                    continue
+                if ref_trx_len != sum(item[-2] for item in ref.structure[ref_trx] if item[0] == "exon"):
+                    continue
             ref_len_aligned = select_nearest_kde2d(sampled, ref_trx_len)
             if ref_len_aligned < ref_trx_len:
                 break

@@ -283,7 +283,7 @@ def batch_stats(batch, ref, fastq, s=None):
     return s
 
 
-def merge_op_stats(s, d):
+def merge_op_stats(s, d, aligned_comp=False):
     """Fold Engine.op_stats() (device histograms of a whole batch) into a run_stats dict."""
     for k in ("mis", "ins", "del"):
         s["events"][k] += d["events"][k]
@@ -291,6 +291,15 @@ def merge_op_stats(s, d):
         s["ev_len"][k] += d["ev_len"][k]
     s["match_run"] += d["match_run"]
     s["first_match"] += d["first_match"]
+    # events per segment: exact device counts re-binned on run_stats' edges (the error profile only shows segments
+    # with at least one event, so slot 0 stays empty on both sides)
+    eps = d["events_per_segment"]
+    nz = np.nonzero(eps)[0]
+    np.add.at(s["events_per_read"], np.searchsorted(rs.EPR_EDGES, nz, side="right"), eps[nz])
+    s["mis_sub"] += d["mis_sub"]
+    s["ins_base"] += d["ins_base"]
+    if aligned_comp:
+        s["base_comp_aligned"] += d["base_comp"]
     return s
 
 
@@ -372,16 +381,135 @@ def compare_stats(a, b, rate_tol, p_min, keys=None, label=""):
                          "events_per_read", "len_unaligned"]
     for k in hist_keys:
         if a[k].sum() == 0 or b[k].sum() == 0:
+            # an unfilled histogram is a hole in the comparison, not a pass
+            fails.append("%s histogram %s is empty on %s" % (label, k, "both sides" if a[k].sum() == b[k].sum() else
+                                                             ("the first side" if a[k].sum() == 0 else "the second side")))
             continue
         st, dof, p = chi2_two_sample(a[k], b[k])
         if p < p_min:
             fails.append("%s histogram %s: chi2 %.1f dof %d p %.3g" % (label, k, st, dof, p))
     for k in ("mis", "ins", "del"):
-        if a["ev_len"][k].sum() and b["ev_len"][k].sum():
+        na, nb = a["ev_len"][k].sum(), b["ev_len"][k].sum()
+        if na and nb:
             st, dof, p = chi2_two_sample(a["ev_len"][k], b["ev_len"][k])
             if p < p_min:
                 fails.append("%s event-length %s: chi2 %.1f dof %d p %.3g" % (label, k, st, dof, p))
+        elif na != nb:
+            fails.append("%s event-length %s: %d events on one side, %d on the other" % (label, k, na, nb))
     return fails
+
+
+def compare_base_choices(a, b, p_min, label=""):
+    """Substituted / inserted base choices and read composition (run_stats mis_sub, ins_base, base_comp_aligned).
+    mutate_read draws a substituted base uniformly from the three others (simulator.py:1968-1973) and an inserted base
+    uniformly from ACGT (:1989-1991)."""
+    fails = []
+    off = ~np.eye(4, dtype=bool)
+    for name, x, y in (("mis_sub", a["mis_sub"][off], b["mis_sub"][off]), ("ins_base", a["ins_base"], b["ins_base"]),
+                       ("base_comp_aligned", a["base_comp_aligned"], b["base_comp_aligned"])):
+        if x.sum() == 0 or y.sum() == 0:
+            fails.append("%s %s is empty on one side" % (label, name))
+            continue
+        st, dof, p = chi2_two_sample(x, y)
+        print(label, name, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < p_min:
+            fails.append("%s %s: chi2 %.1f dof %d p %.3g" % (label, name, st, dof, p))
+    if np.trace(a["mis_sub"]) != 0:
+        fails.append("%s a substituted base equals its reference base" % label)
+    return fails
+
+
+def golden(path):
+    """Golden files are part of the repository: a missing one is a failure, never a skip."""
+    assert os.path.exists(path), "golden file %s is missing (regenerate with tests/golden/make_golden_*.py)" % path
+    return rs.load(path)
+
+
+# --------------------------------------------------------------------------------------
+# unaligned reads: unaligned_error_list + mutate_read (simulator.py:1784-1830, 1957-1995) as edit statistics
+# --------------------------------------------------------------------------------------
+def apply_edict_to_tags(e_dict, middle_ref):
+    """The string splices of mutate_read (simulator.py:1960-1995: keys right to left, ceil(key), mis replaces, del cuts,
+    ins inserts) on a list of provenance tags instead of characters: int k = reference base k, "I" = inserted base,
+    ("M", t) = substituted base that replaced tag t."""
+    import math
+
+    tags = list(range(middle_ref))
+    for key in sorted(e_dict.keys(), reverse=True):
+        kind, length = e_dict[key]
+        k = math.ceil(key)
+        if kind == "mis":
+            tags[k:k + length] = [("M", t) for t in tags[k:k + length]]
+        elif kind == "del":
+            del tags[k:k + length]
+        else:
+            tags[k:k] = ["I"] * length
+    return tags
+
+
+def tags_to_ops(tags, middle_ref):
+    """Provenance tags -> [(type, length)] with the device's op types (COPY 0, MIS 1, INS 2, DEL 3), adjacent equal types
+    merged.  A substituted inserted base is still an inserted (random) base."""
+    ops = []
+
+    def put(t, n):
+        if n <= 0:
+            return
+        if ops and ops[-1][0] == t:
+            ops[-1][1] += n
+        else:
+            ops.append([t, n])
+
+    nxt = 0
+    for t in tags:
+        if t == "I" or (isinstance(t, tuple) and t[1] == "I"):
+            put(2, 1)
+            continue
+        mis = isinstance(t, tuple)
+        r = t[1] if mis else t
+        put(3, r - nxt)
+        put(1 if mis else 0, 1)
+        nxt = r + 1
+    put(3, middle_ref - nxt)
+    return ops
+
+
+def script_stats(op_lists):
+    """Event statistics of a list of op lists [(type, len), ...]: the run_stats event keys."""
+    s = rs.empty()
+    for ops in op_lists:
+        merged = []
+        for t, n in ops:
+            if n == 0:
+                continue
+            if merged and merged[-1][0] == t:
+                merged[-1][1] += n
+            else:
+                merged.append([t, n])
+        run, first, n_ev, ref = 0, True, 0, 0
+        for t, n in merged:
+            if t == 0:
+                run += n
+                ref += n
+                continue
+            name = ("mis", "ins", "del")[t - 1]
+            s["events"][name] += 1
+            s["event_bases"][name] += n
+            s["ev_len"][name][min(n, rs.EV_CAP)] += 1
+            (s["first_match"] if first else s["match_run"])[min(run, rs.RUN_CAP)] += 1
+            first, run = False, 0
+            n_ev += 1
+            if t != 2:
+                ref += n
+        s["ref_bases"] += ref
+        if n_ev:
+            s["events_per_read"][rs._bin(rs.EPR_EDGES, n_ev)] += 1
+    return s
+
+
+def device_piece_ops(batch, pc, events=True):
+    ty, ln, _, _, _, _ = _piece_layout(batch, pc, events=events)
+    return [(int(t), int(n)) for t, n in zip(ty, ln)]
 
 
 # --------------------------------------------------------------------------------------

@@ -82,6 +82,67 @@ def test_unaligned_fast_path_equals_scripted_path(model, fastq, mini_ref, L):
     assert bf.reads["attempts"].max() > 0
 
 
+def test_unaligned_event_scripts_vs_oracle(ecoli, L, tmp_path):
+    """unaligned_error_list (simulator.py:1784-1830: 0.4/0.3/0.15/0.15 step mix, insertions merged at pos+0.1) and what
+    mutate_read makes of its e_dict (:1957-1995) against the pinned oracle: the device's scripted unaligned path on 2500
+    reads vs oracle.unaligned_error_list on the same drawn lengths.  The oracle's e_dict is turned into per-base
+    provenance by the splice arithmetic of mutate_read on tags, and that is checked against oracle.mutate_read on a
+    random string for every read, so the comparison stands on the oracle alone."""
+    import random
+    import nanosim_oracle as no
+    from conftest import oracle_model
+    eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=57, unaligned_scripts=True, max_len=30000)
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 2500)
+    b = eng.fetch(want_ops=True)
+    eng.close()
+    assert pc.check_edit_scripts(b, ecoli, False) > 0
+    dev_ops = [pc.device_piece_ops(b, pcs) for pcs in b.pieces]
+    s_dev = pc.script_stats(dev_ops)
+    m = oracle_model(cm, tmp_path, fastq=False)
+    random.seed(99)
+    np.random.seed(99)
+    or_ops, d_len_dev, d_len_or = [], [], []
+    alphabet = "ACGT"
+    for pcs in b.pieces:
+        m_ref = int(pcs["ref_req"])
+        l_new, middle_ref, e_dict, e_count = no.unaligned_error_list(m_ref, m)
+        tags = pc.apply_edict_to_tags(e_dict, middle_ref)
+        read = "".join(random.choice(alphabet) for _ in range(middle_ref))
+        mutated, _ = no.mutate_read(read, "x", None, dict(e_dict), e_count, False, False, m)
+        assert len(mutated) == len(tags)
+        for ch, tg in zip(mutated, tags):                      # the tag interpreter agrees with the oracle's strings
+            if isinstance(tg, int):
+                assert ch == read[tg]
+            elif isinstance(tg, tuple) and isinstance(tg[1], int):
+                assert ch != read[tg[1]]
+        or_ops.append(pc.tags_to_ops(tags, middle_ref))
+        d_len_or.append((len(tags) - m_ref, middle_ref - m_ref))
+        d_len_dev.append((int(pcs["out_len"]) - m_ref, int(pcs["ref_len"]) - m_ref))
+    s_or = pc.script_stats(or_ops)
+    rd, ro = pc.rates(s_dev), pc.rates(s_or)
+    print("unaligned per-reference-base event bases device", rd, "oracle", ro)
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.02, p_min=1e-5, label="unaligned-scripts",
+                             keys=["match_run", "first_match", "events_per_read"])
+    for k in ("mis", "ins", "del"):
+        a, o = s_dev["events"][k] / s_dev["ref_bases"], s_or["events"][k] / s_or["ref_bases"]
+        if abs(a / o - 1) > 0.02:
+            fails.append("unaligned %s events per reference base %.5f vs %.5f" % (k, a, o))
+    # read length minus drawn length, and the overshoot of the last step (:1826-1828)
+    d_len_dev, d_len_or = np.asarray(d_len_dev, dtype=np.float64), np.asarray(d_len_or, dtype=np.float64)
+    scale = np.sqrt(np.maximum(b.pieces["ref_req"].astype(np.float64), 1.0))
+    edges = np.linspace(-6, 6, 41)
+    st, dof, p = pc.chi2_two_sample(np.histogram(d_len_dev[:, 0] / scale, edges)[0], np.histogram(d_len_or[:, 0] / scale, edges)[0])
+    print("normalised length change chi2 %.1f dof %d p %.3g; mean %.2f vs %.2f" % (st, dof, p, d_len_dev[:, 0].mean(), d_len_or[:, 0].mean()))
+    if p < 1e-5:
+        fails.append("unaligned length change: chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    st, dof, p = pc.chi2_two_sample(np.bincount(d_len_dev[:, 1].astype(np.int64), minlength=12)[:12],
+                                    np.bincount(d_len_or[:, 1].astype(np.int64), minlength=12)[:12], min_count=10)
+    print("overshoot of the last step chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    if p < 1e-5:
+        fails.append("unaligned overshoot: chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    assert not fails, "\n".join(fails)
+
+
 def test_circular_reference_wraps(L):
     from nanosim_b200.reference_fasta import PackedReference
     ref = PackedReference.from_fasta(os.path.join(GOLDEN, "mini_circular.fa"))
@@ -152,6 +213,9 @@ def test_device_op_stats_equal_host_stats(ecoli, L):
     for k in ("mis", "ins", "del"):
         assert np.array_equal(dev["ev_len"][k], host["ev_len"][k])
     assert np.array_equal(dev["match_run"], host["match_run"]) and np.array_equal(dev["first_match"], host["first_match"])
+    merged = pc.merge_op_stats(rs.empty(), dev, aligned_comp=True)
+    for k in ("events_per_read", "mis_sub", "ins_base", "base_comp_aligned"):
+        assert host[k].sum() > 0 and np.array_equal(merged[k], host[k]), k
     eng.close()
 
 
@@ -186,7 +250,7 @@ def _device_run_stats(eng, ref, L, n_aligned, n_unaligned, batch, fastq):
         eng.simulate(L.NS_KIND_ALIGNED, start, n)
         b = eng.fetch(want_ops=False)
         pc.meta_stats(b, s)
-        pc.merge_op_stats(s, eng.op_stats())
+        pc.merge_op_stats(s, eng.op_stats(), aligned_comp=True)
     for start in range(0, n_unaligned, batch):
         n = min(batch, n_unaligned - start)
         eng.simulate(L.NS_KIND_UNALIGNED, start, n)
@@ -198,9 +262,7 @@ def test_vs_unmodified_reference_1M_reads(ecoli, L):
     """BASELINE config-1 reference/model at 1M reads, against histograms of the unmodified reference
     (tests/golden/ref_stats_guppy_fasta.json).  north_star: per-base edit-type counts within +-0.1 %."""
     path = os.path.join(GOLDEN, "ref_stats_guppy_fasta.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated yet")
-    gold, meta = rs.load(path)
+    gold, meta = pc.golden(path)
     n_al, n_un = int(gold["n_aligned"]), int(gold["n_unaligned"])
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=2024)
     s = _device_run_stats(eng, ecoli, L, n_al, n_un, 125000, False)
@@ -208,20 +270,23 @@ def test_vs_unmodified_reference_1M_reads(ecoli, L):
     rd, rg = pc.rates(s), pc.rates(gold)
     print("per-base rates device", rd, "reference", rg, "rel", {k: rd[k] / rg[k] - 1 for k in rd})
     # the reference's own chunk-to-chunk noise bounds what +-0.1 % can mean
+    # north_star: identical read-length and per-read error-count histograms, per-base edit-type counts within +-0.1 %
     fails = pc.compare_stats(s, gold, rate_tol=1e-3, p_min=1e-6, label="1M",
-                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match",
+                                   "events_per_read"])
+    # which base a mismatch / an insertion produces (simulator.py:1968-1973, 1989-1991) and the reads' composition
+    fails += pc.compare_base_choices(s, gold, 1e-6, label="1M")
     # unaligned lengths: the reference forks its unaligned workers WITHOUT reseeding numpy (simulator.py:1648-1660), so
     # with -t 8 all eight workers draw the same KDE lengths (8-fold duplicated sample).  They are compared against a
     # separate golden run made of independent -t 1 processes.
-    p1 = os.path.join(GOLDEN, "ref_stats_guppy_fasta_t1.json")
-    if os.path.exists(p1):
-        g1, _ = rs.load(p1)
-        st, dof, p = pc.chi2_two_sample(s["len_unaligned"], g1["len_unaligned"])
-        print("len_unaligned vs -t 1 golden: chi2 %.1f dof %d p %.3g" % (st, dof, p))
-        if p < 1e-6:
-            fails.append("1M histogram len_unaligned (vs -t 1 golden): chi2 %.1f dof %d p %.3g" % (st, dof, p))
-        fr_d, fr_g = s["strand_R_unaligned"] / s["n_unaligned"], g1["strand_R_unaligned"] / g1["n_unaligned"]
-        assert abs(fr_d - fr_g) < 0.02
+    g1, _ = pc.golden(os.path.join(GOLDEN, "ref_stats_guppy_fasta_t1.json"))
+    assert s["len_unaligned"].sum() > 0 and g1["len_unaligned"].sum() > 0
+    st, dof, p = pc.chi2_two_sample(s["len_unaligned"], g1["len_unaligned"])
+    print("len_unaligned vs -t 1 golden: chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    if p < 1e-6:
+        fails.append("1M histogram len_unaligned (vs -t 1 golden): chi2 %.1f dof %d p %.3g" % (st, dof, p))
+    fr_d, fr_g = s["strand_R_unaligned"] / s["n_unaligned"], g1["strand_R_unaligned"] / g1["n_unaligned"]
+    assert abs(fr_d - fr_g) < 0.02
     mean_dev, mean_ref = s["aligned_bases"] / s["n_aligned"], gold["aligned_bases"] / gold["n_aligned"]
     assert abs(mean_dev / mean_ref - 1) < 5e-3, (mean_dev, mean_ref)
     assert abs(s["strand_R_aligned"] / s["n_aligned"] - gold["strand_R_aligned"] / gold["n_aligned"]) < 3e-3
@@ -246,9 +311,7 @@ def test_vs_unmodified_reference_dorado_fastq_chimeric(ecoli, L):
     """100k reads of `simulator.py genome --fastq --chimeric` with the dorado kit-v14 model (unmodified reference) vs
     the device: chimeric fraction, segments per read, per-base rates, length/event/quality histograms."""
     path = os.path.join(GOLDEN, "ref_stats_dorado_fastq_chimeric.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     eng, cm, t = pc.make_engine("dorado", ecoli, fastq=True, chimeric=True, seed=77)
     s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
     eng.close()
@@ -272,9 +335,7 @@ def test_qualities_vs_unmodified_reference_guppyq(ecoli, L):
     """50k FASTQ reads of the unmodified reference with the config-2 model (guppy + dorado quality table): quality
     histograms of aligned middles (match/mis/ins mixture), head/tail regions and unaligned reads."""
     path = os.path.join(GOLDEN, "ref_stats_guppyq_fastq.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=True, seed=78)
     s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
     eng.close()
@@ -282,11 +343,9 @@ def test_qualities_vs_unmodified_reference_guppyq(ecoli, L):
                              keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
     # unaligned qualities: with -t 8 the reference's unaligned workers share one numpy stream (simulator.py:1648-1660),
     # i.e. identical quality draws in all eight workers; they are compared with independent -t 1 processes instead.
-    p1 = os.path.join(GOLDEN, "ref_stats_guppyq_fastq_t1.json")
-    g1 = rs.load(p1)[0] if os.path.exists(p1) else None
+    g1, _ = pc.golden(os.path.join(GOLDEN, "ref_stats_guppyq_fastq_t1.json"))
     for k, g in (("qual_middle", gold), ("qual_ht", gold), ("qual_unaligned", g1)):
-        if g is None:
-            continue
+        assert s[k].sum() > 0 and g[k].sum() > 0, k
         st, dof, p = pc.chi2_two_sample(s[k], g[k])
         print(k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
         if p < 1e-6:
@@ -369,11 +428,8 @@ def test_homopolymer_statistics_vs_oracle(L, tmp_path):
 def test_homopolymer_vs_unmodified_reference(ecoli, L):
     """50k reads of `simulator.py genome --fastq --chimeric -hp -k 6` (dorado model, unmodified reference)."""
     path = os.path.join(GOLDEN, "ref_stats_dorado_fastq_hp6_chimeric.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
-    if "hp_runs" not in gold:
-        pytest.skip("golden file predates the homopolymer histogram")
+    gold, _ = pc.golden(path)
+    assert "hp_runs" in gold, "golden file predates the homopolymer histogram: regenerate it"
     eng, cm, t = pc.make_engine("dorado", ecoli, fastq=True, chimeric=True, kmer_bias=6, seed=79)
     s = _run_with_quals(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 25000)
     eng.close()
@@ -644,9 +700,7 @@ def test_transcriptome_vs_unmodified_reference(trx_ref, tmp_path, L):
     length-KDE sample has the reference's 623 rows per worker."""
     from nanosim_b200 import simulator
     path = os.path.join(GOLDEN, "ref_stats_trx_drna_fasta.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     T = os.path.join(GOLDEN, "trx")
     out = os.path.join(str(tmp_path), "tx")
     n = 200000
@@ -687,9 +741,7 @@ def test_metagenome_vs_unmodified_reference(meta_ref, tmp_path, L):
     against this CLI on the same 4-species fixture: histograms, rates, qualities, species and chromosome shares."""
     from nanosim_b200 import simulator
     path = os.path.join(GOLDEN, "ref_stats_meta_even_fastq_chimeric.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     meta = os.path.join(GOLDEN, "meta")
     ab = os.path.join(str(tmp_path), "abun.tsv")
     with open(os.path.join(meta, "abundance.tsv")) as f, open(ab, "w") as o:
@@ -764,9 +816,7 @@ def test_perfect_reads_vs_unmodified_reference(ecoli, L):
     """100k reads of `simulator.py genome --perfect` (unmodified reference): length law (kde_aligned_reads within
     [min_l, max_l], :1285-1299), strand, no errors, no head/tail."""
     path = os.path.join(GOLDEN, "ref_stats_guppy_perfect.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, perfect=True, seed=91)
     s = _device_run_stats(eng, ecoli, L, int(gold["n_aligned"]), 0, 50000, False)
     eng.close()
@@ -788,9 +838,7 @@ def test_med_sd_vs_unmodified_reference(ecoli, L):
     remainder from a log-normal total and then filters the list, which breaks the pairing with the remainder a read
     later gets (:1285-1296); the device subtracts an independent remainder.  Read-level laws must agree."""
     path = os.path.join(GOLDEN, "ref_stats_guppy_medsd.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     eng, cm, t = pc.make_engine("guppy", ecoli, fastq=False, seed=93)
     eng.configure(fastq=False, min_len=50, max_len=ecoli.max_chrom, median_len=5000, sd_len=1.05)
     s = _device_run_stats(eng, ecoli, L, int(gold["n_aligned"]), int(gold["n_unaligned"]), 50000, False)
@@ -908,9 +956,7 @@ def test_intron_retention_vs_unmodified_reference(ir_fixture, tmp_path, L):
     of reads that retain an intron and how many retained intervals they cover."""
     from nanosim_b200 import simulator
     path = os.path.join(GOLDEN, "ref_stats_trx_ir_drna_fasta.json")
-    if not os.path.exists(path):
-        pytest.skip("golden reference histograms not generated")
-    gold, _ = rs.load(path)
+    gold, _ = pc.golden(path)
     D = ir_fixture[0]
     out = os.path.join(str(tmp_path), "ir")
     n = 96000

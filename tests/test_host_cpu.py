@@ -421,3 +421,82 @@ def test_intron_retention_patch_is_consistent():
     assert half[0].tolist() == [s for s in slots.tolist() if s < 200]
     a = npc[:len(half[2])]
     assert np.array_equal(a["pos"], half[2]["pos"]) and np.array_equal(a["ref_len"], half[2]["ref_len"])
+
+
+def test_ir_expressed_set_needs_matching_exon_structure(tmp_path):
+    """simulator.py:1094-1099: with intron retention on, a transcript that is missing from the GFF3, or whose exons do
+    not add up to its FASTA length, is drawn again and again -- i.e. never simulated.  The host drops such transcripts
+    from the expressed set; the oracle carries the same guard."""
+    import random
+    from nanosim_b200 import intron_retention as ir
+    from nanosim_b200.reference_fasta import PackedReference, read_expression
+    D = os.path.join(GOLDEN, "ir")
+    fa = open(os.path.join(D, "transcripts.fa")).read()
+    # a transcript the annotation does not know, and one whose sequence is one base longer than its exons
+    recs = fa.split(">")[1:]
+    name0 = recs[0].split("\n", 1)[0].split()[0]
+    longer = ">" + recs[0].split("\n", 1)[0] + "\n" + "".join(recs[0].split("\n")[1:]) + "A\n"
+    fa2 = longer + "".join(">" + r for r in recs[1:]) + ">ENST00000009999.1\n" + "ACGT" * 300 + "\n"
+    tfa = os.path.join(str(tmp_path), "t.fa")
+    open(tfa, "w").write(fa2)
+    texp = os.path.join(str(tmp_path), "e.tsv")
+    open(texp, "w").write(open(os.path.join(D, "expression.tsv")).read() + "ENST00000009999.1\t10.00\t50.0\n")
+    trx = PackedReference.from_fasta(tfa)
+    chrom, w = read_expression(texp, trx)
+    genome = PackedReference.from_fasta(os.path.join(D, "genome.fa"))
+    st = ir.TranscriptStructures.from_gff3(os.path.join(D, "annotation.gff3"), trx.names, genome.raw_names)
+    c2, w2, dropped = ir.expressed_with_structure(chrom, w, st, trx.lengths)
+    bad = {trx.names.index("ENST00000009999"), trx.names.index(name0.split(".")[0])}
+    assert dropped == 2 and not (set(c2.tolist()) & bad) and set(c2.tolist()) | bad == set(chrom.tolist())
+    assert np.array_equal(w2, w[~np.isin(chrom, list(bad))])
+    # the oracle never emits them either (and does not raise KeyError on the unknown transcript)
+    from conftest import oracle_model
+    from nanosim_b200.model import CompiledModel
+    cm = CompiledModel.load(os.path.join(ROOT, "nanosim_b200", "data", "drna_bham1_guppy_plusq.npz"))
+    m = oracle_model(cm, tmp_path, fastq=False)
+    oref = no.OracleTrxReference.from_files(tfa, texp, os.path.join(D, "polya.txt"))
+    oref.load_ir(os.path.join(D, "genome.fa"), os.path.join(D, "annotation.gff3"), os.path.join(D, "IR_markov_model"))
+    random.seed(5)
+    np.random.seed(5)
+    sink = no.ReadSink()
+    no.simulation_aligned_transcriptome(oref, m, sink, None, "guppy", 60, False, False, False, False, True)
+    used = {name.split("_")[0] for name, _, _ in sink.records}
+    assert len(sink.records) == 60 and "ENST00000009999" not in used and name0.split(".")[0] not in used
+
+
+def test_coverage_counts_the_transcriptome_only_and_abundance_rows_may_be_missing(tmp_path):
+    """-x (calculate_read_number_from_coverage, simulator.py:2024-2068, called with ref_t at :2348): the reference size is the
+    transcriptome's even when the genome is concatenated behind it for intron retention; the closed-form mean equals the
+    reference's Monte-Carlo estimate.  A species without an abundance row is left out (zero), not an error."""
+    from types import SimpleNamespace
+    from nanosim_b200 import simulator
+    from nanosim_b200.model import CompiledModel, DeviceTables
+    from nanosim_b200.reference_fasta import MetaReference, PackedReference, read_abundance
+    D = os.path.join(GOLDEN, "ir")
+    trx = PackedReference.from_fasta(os.path.join(D, "transcripts.fa"))
+    genome = PackedReference.from_fasta(os.path.join(D, "genome.fa"))
+    cm = CompiledModel.load(os.path.join(ROOT, "nanosim_b200", "data", "drna_bham1_guppy_plusq.npz"))
+    t = DeviceTables(cm, fastq=False)
+    prof = SimpleNamespace(ref=PackedReference.concat(trx, genome), tables=t, coverage_ref_len=trx.genome_len)
+    n = simulator.coverage_to_reads(prof, cm, 30.0)
+    # Monte-Carlo estimate as the reference does it (KernelDensity.sample == data[randint] + N(0, bw)), 2M draws
+    rng = np.random.default_rng(0)
+    rate = t.aligned_ratio
+    n_al = int(2000000 * rate / (rate + 1))
+    al, bw_al = cm.kde["aligned_reads"]
+    un, bw_un = cm.kde["unaligned_length"]
+    draws = np.concatenate([al.reshape(-1)[rng.integers(0, al.size, n_al)] + rng.normal(0, bw_al, n_al),
+                            un.reshape(-1)[rng.integers(0, un.size, 2000000 - n_al)] + rng.normal(0, bw_un, 2000000 - n_al)])
+    want = trx.genome_len / draws.mean() * 30.0
+    assert abs(n / want - 1) < 5e-3, (n, want)
+    assert n < 0.5 * int(prof.ref.genome_len / draws.mean() * 30.0)          # the genome is not counted
+    meta = os.path.join(GOLDEN, "meta")
+    from conftest import meta_fixture
+    meta_fixture()
+    ref = MetaReference.from_genome_list(os.path.join(meta, "genome_list_local.tsv"), os.path.join(meta, "dna_type.tsv"))
+    lines = open(os.path.join(meta, "abundance.tsv")).read().splitlines()
+    ab = os.path.join(str(tmp_path), "abun.tsv")
+    open(ab, "w").write("\n".join(lines[:-1]) + "\n")                        # the last species has no row
+    numbers, samples = read_abundance(ab, ref.species)
+    missing = MetaReference.species_key(lines[-1].split("\t")[0])
+    assert samples[0][ref.species.index(missing)] == 0.0 and sum(samples[0]) > 0
