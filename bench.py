@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the per-read simulation hot path (BASELINE.json metric: simulated bases/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch_reads B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2] [--batch_reads B]
 
-Workload (BASELINE config 2): genome mode, human_NA12878_DNA_FAB49712_guppy error/length model with the
-dorado_v3.2.1 base-quality table (the shipped guppy model has none), FASTQ, on a 3.09 Gb synthetic
-reference (24 chromosomes with hg38 lengths, i.i.d. ACGT).  The whole job is 10M reads; ONE STEP is one batch of
-``--batch_reads`` reads (aligned + unaligned in the model's 8.85:1 ratio) = the unit the job is made of, so
-bases/sec over K steps is the job's throughput.  Under torchrun every rank simulates its own batch per step
-(weak scaling; read ids are disjoint shards) after ONE NCCL broadcast of the reference at init.
+Workloads = the BASELINE.json configs, built by the SURVEY.md 8(d) generators (tests/synth.py):
+
+  config1  genome, 5 Mb synthetic E. coli-sized reference, guppy FAB49712 model, FASTA, 1000 reads per step
+  config2  (default; the config the metric is quoted on) genome, guppy model + dorado_v3.2.1 quality table (the shipped
+           guppy model has none), FASTQ, 3.09 Gb synthetic reference (24 chromosomes with hg38 lengths)
+  config3  transcriptome directRNA (dRNA_Bham1_guppy), 200k-transcript synthetic reference + expression profile, FASTA,
+           --no_model_ir
+  config4  metagenome, 50 species x 1-3 circular chromosomes of 2-6 Mb, Even abundance, ERR3152364_Even model, FASTQ,
+           --chimeric
+  config5  genome, dorado kit-v14 model, FASTQ -hp -k 6 --chimeric on the config-2 reference
+
+ONE STEP is one batch of ``--batch_reads`` reads (aligned + unaligned in the model's ratio) = the unit the job is made
+of, so bases/sec over K steps is the job's throughput.  Under torchrun every rank simulates its own batch per step (weak
+scaling; read ids are disjoint shards) after ONE NCCL broadcast of the reference at init.
 
 Printed JSON line: see the task contract.  ``value`` = bases / device time of the kernels (outputs stay in HBM);
 ``e2e`` = the same through ns_simulate + ns_fetch into pinned host buffers (D2H inside the timed region);
-``roofline`` = emit kernel, 3 algorithmic bytes per base (1 reference byte read + 1 base + 1 quality written);
-``cpu_baseline`` = the oracle port (pure Python, like the reference) on a bounded sample with all host cores.
+``roofline`` = emit kernel, 3 algorithmic bytes per base for FASTQ (1 reference byte read + 1 base + 1 quality written),
+2 for FASTA; ``cpu_baseline`` / ``--impl reference`` = the oracle port (pure Python, like the reference) in a pool of
+worker processes forked ONCE (one per host core, like ``simulator.py -t <cores>``), timed in steady state.
 """
 import argparse
 import json
@@ -31,16 +40,27 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-HG38_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
-                133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
-                58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
-CHROM_NAMES = ["chr%d" % i for i in range(1, 23)] + ["chrX", "chrY"]
-MODEL = os.path.join(ROOT, "nanosim_b200", "data", "guppy_fab49712_plusq.npz")
-ALGO_BYTES_PER_BASE = 3.0
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE emit_kernel<FASTQ> launch of this workload (235536 aligned reads,
-# 2.04 Gbases): 3.226 GB + 4.401 GB, from `ncu --set full -k regex:emit_kernel -c 1 python bench.py --steps 1 --warmup 1
-# --depth 1 --no_cpu_baseline` (profiles/r1_emit_ncu_summary.txt) = 3.73 B/base against 3 B/base algorithmic.
-TRAFFIC_BYTES_PER_LAUNCH = 7.627e9
+import synth  # noqa: E402  (tests/synth.py: the SURVEY 8d generators)
+
+DATA = os.path.join(ROOT, "nanosim_b200", "data")
+
+WORKLOADS = {
+    "config1": dict(mode="genome", model="guppy_fab49712_plusq.npz", fastq=False, chimeric=False, kmer_bias=0, batch=1000,
+                    text="genome FASTA, guppy FAB49712 model, 5 Mb synthetic reference (1 chr, i.i.d. ACGT, default_rng(0)), "
+                         "1k-read job = one step"),
+    "config2": dict(mode="genome", model="guppy_fab49712_plusq.npz", fastq=True, chimeric=False, kmer_bias=0, batch=262144,
+                    text="genome FASTQ, guppy FAB49712 model + dorado_v3.2.1 quality table, 3.09 Gb synthetic hg38-sized reference "
+                         "(24 chr, i.i.d. ACGT), 10M-read job"),
+    "config3": dict(mode="transcriptome", model="drna_bham1_guppy_plusq.npz", fastq=False, chimeric=False, kmer_bias=0, batch=262144,
+                    text="transcriptome directRNA FASTA (--no_model_ir), dRNA_Bham1_guppy model, 200k-transcript synthetic reference "
+                         "(354 Mb, lengths clip(lognormal(7.3,0.6),300,20000)) + expression profile tpm~lognormal(2,1.5), 5M-read job"),
+    "config4": dict(mode="metagenome", model="even_err3152364_v3.2.2.npz", fastq=True, chimeric=True, kmer_bias=0, batch=262144,
+                    text="metagenome FASTQ --chimeric, ERR3152364_Even model, 50 species x 1-3 circular chromosomes of 2-6 Mb "
+                         "(406 Mb, i.i.d. ACGT), Even abundance, 20M-read job"),
+    "config5": dict(mode="genome", model="dorado_kitv14_v3.2.1.npz", fastq=True, chimeric=True, kmer_bias=6, batch=131072,
+                    text="genome FASTQ -hp -k 6 --chimeric, dorado kit-v14 v3.2.1 model, 3.09 Gb synthetic hg38-sized reference, "
+                         "240M-read job"),
+}
 
 
 def measured_peak():
@@ -91,67 +111,173 @@ class ClockSampler:
                 "windows": "samples inside the timed regions: " + ", ".join("%s %.0f ms" % (lab, 1e3 * (b - a)) for a, b, lab in self.windows)}
 
 
-def synth_reference_gpu(device, scale=1.0):
-    """24 chromosomes, i.i.d. uniform ACGT, generated on the GPU (torch is plumbing here)."""
+# --------------------------------------------------------------------------------------------------------------------
+# synthetic references
+# --------------------------------------------------------------------------------------------------------------------
+class SynthRef:
+    """What a workload's reference looks like on the host side of the C ABI: base bytes (a CUDA tensor for the 3 Gb
+    genome, numpy otherwise), chromosome offsets, and the mode's extras."""
+
+    def __init__(self, bases, offsets, names, species=None, chrom_species=None, chrom_circular=None, tpm=None):
+        self.bases, self.offsets, self.names = bases, np.ascontiguousarray(offsets, dtype=np.uint64), names
+        self.species, self.chrom_species, self.chrom_circular, self.tpm = species, chrom_species, chrom_circular, tpm
+
+    @property
+    def max_chrom(self):
+        return int(np.diff(self.offsets.astype(np.int64)).max())
+
+
+def synth_genome_gpu(device, scale=1.0):
+    """configs 2 and 5: 24 chromosomes with hg38 lengths, i.i.d. uniform ACGT, generated on the GPU (torch is plumbing)."""
     import torch
 
-    lengths = [max(1000, int(x * scale)) for x in HG38_LENGTHS]
+    lengths = [max(1000, int(x * scale)) for x in synth.HG38_LENGTHS]
     total = sum(lengths)
-    g = torch.Generator(device="cuda:%d" % device)
+    dev = "cuda:%d" % device
+    g = torch.Generator(device=dev)
     g.manual_seed(1)
-    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda:%d" % device)
-    out = torch.empty(total, dtype=torch.uint8, device="cuda:%d" % device)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    out = torch.empty(total, dtype=torch.uint8, device=dev)
     step = 1 << 28
     for s in range(0, total, step):
         e = min(total, s + step)
-        idx = torch.randint(0, 4, (e - s,), generator=g, device="cuda:%d" % device, dtype=torch.uint8)
+        idx = torch.randint(0, 4, (e - s,), generator=g, device=dev, dtype=torch.uint8)
         out[s:e] = lut[idx.long()]
         del idx
-    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-    return out, offsets
+    return SynthRef(out, np.concatenate([[0], np.cumsum(lengths)]), list(synth.HG38_NAMES))
 
 
-def cpu_oracle_sample(ref_strs, n_reads, n_procs, fastq=True):
-    """Times the oracle port (pure Python, same algorithm and data structures as the reference) on ``n_reads`` reads
-    split over ``n_procs`` forked workers, like ``simulator.py -t``.  Returns (bases, seconds)."""
-    import multiprocessing as mp
+def synth_genome_host(scale=1.0):
+    rng = np.random.default_rng(1)
+    lengths = [max(1000, int(x * scale)) for x in synth.HG38_LENGTHS]
+    bases = np.concatenate([synth.synth_chrom(rng, n) for n in lengths])
+    return SynthRef(bases, np.concatenate([[0], np.cumsum(lengths)]), list(synth.HG38_NAMES))
 
-    from conftest import oracle_model
-    from nanosim_b200.model import CompiledModel
-    import nanosim_oracle as no
 
-    cm = CompiledModel.load(MODEL)
-    tmp = tempfile.mkdtemp(prefix="bench_oracle_")
-    m = oracle_model(cm, tmp, fastq=fastq)
-    oref = no.OracleReference(ref_strs)
-    n_al, n_un = m.split_counts(n_reads)
-    ctx = mp.get_context("fork")
-    q = ctx.Queue()
+def build_reference(name, device, scale, on_gpu):
+    mode = WORKLOADS[name]["mode"]
+    if name == "config1":
+        (nm, arr), = synth.ecoli5m()
+        return SynthRef(arr, [0, len(arr)], [nm])
+    if mode == "genome":
+        return synth_genome_gpu(device, scale) if on_gpu else synth_genome_host(scale)
+    if mode == "transcriptome":
+        names, lengths, bases, tpm = synth.config3_transcriptome(max(100, int(200000 * scale)))
+        return SynthRef(bases, np.concatenate([[0], np.cumsum(lengths)]), [n.split(".")[0] for n in names], tpm=tpm)
+    genomes = synth.config4_metagenome(max(2, int(50 * scale)))
+    from nanosim_b200.reference_fasta import MetaReference
+    m = MetaReference.from_genomes(genomes)
+    return SynthRef(m.bases, m.offsets, m.names, species=m.species, chrom_species=m.chrom_species, chrom_circular=m.chrom_circular)
 
-    def work(i, na, nu):
-        import random
-        random.seed(1000 + i)
-        np.random.seed(1000 + i)
-        s1, s2 = no.ReadSink(), no.ReadSink()
-        no.simulation_aligned_genome(oref, m, s1, "linear", 50, oref.max_chrom, None, None, None, fastq, na, False, False)
-        if nu:
-            no.simulation_unaligned(oref, m, s2, "linear", 50, oref.max_chrom, None, None, fastq, nu)
-        txt = no.format_records(s1.records + s2.records, fastq)      # the reference also formats and writes records
-        q.put((sum(len(r[1]) for r in s1.records + s2.records), len(txt)))
 
-    t0 = time.time()
-    procs = []
-    for i in range(n_procs):
-        na = n_al // n_procs + (n_al % n_procs if i == n_procs - 1 else 0)
-        nu = n_un // n_procs + (n_un % n_procs if i == n_procs - 1 else 0)
-        p = ctx.Process(target=work, args=(i, na, nu))
-        p.start()
-        procs.append(p)
-    res = [q.get() for _ in procs]
-    for p in procs:
-        p.join()
-    dt = time.time() - t0
-    return sum(r[0] for r in res), dt
+# --------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation of the path == the oracle port, in a pool of workers forked once
+# --------------------------------------------------------------------------------------------------------------------
+class OraclePool:
+    """``n_procs`` worker processes forked ONCE from a parent that already holds the reference (as Python strings, like the
+    reference's seq_dict) and the parsed model -- the reference's ``-t n_procs`` fan-out (simulator.py:1590-1622) without
+    paying the fork, the scipy import and the model parsing again at every step.  A step hands every worker its share of
+    reads; the step's time is the wall clock until the last worker has answered."""
+
+    def __init__(self, name, sref, n_procs):
+        import multiprocessing as mp
+
+        import scipy.stats  # noqa: F401  (imported before the fork: the oracle needs it for every quality draw)
+        from conftest import oracle_model
+        from nanosim_b200.model import CompiledModel
+        import nanosim_oracle as no
+
+        w = WORKLOADS[name]
+        self.w, self.n = w, n_procs
+        cm = CompiledModel.load(os.path.join(DATA, w["model"]))
+        tmp = tempfile.mkdtemp(prefix="bench_oracle_")
+        m = oracle_model(cm, tmp, fastq=w["fastq"], chimeric=w["chimeric"], homopolymer=bool(w["kmer_bias"]), mode=w["mode"])
+        host = sref.bases if isinstance(sref.bases, np.ndarray) else sref.bases.cpu().numpy()
+        offs = sref.offsets.astype(np.int64)
+        seqs = [host[offs[i]:offs[i + 1]].tobytes().decode() for i in range(len(offs) - 1)]
+        fastq, chim, kb = w["fastq"], w["chimeric"], (w["kmer_bias"] or None)
+        if w["mode"] == "genome":
+            oref = no.OracleReference(list(zip(sref.names, seqs)))
+
+            def run(na, nu):
+                s1, s2 = no.ReadSink(), no.ReadSink()
+                no.simulation_aligned_genome(oref, m, s1, "linear", 50, oref.max_chrom, None, None, kb, fastq, na, False, chim)
+                if nu:
+                    no.simulation_unaligned(oref, m, s2, "linear", 50, oref.max_chrom, None, None, fastq, nu)
+                return s1.records + s2.records
+        elif w["mode"] == "transcriptome":
+            oref = no.OracleTrxReference(list(zip(sref.names, seqs)), dict(zip(sref.names, sref.tpm.tolist())))
+
+            def run(na, nu):
+                s1, s2 = no.ReadSink(), no.ReadSink()
+                no.simulation_aligned_transcriptome(oref, m, s1, None, "guppy", na, False, fastq, False, False, False)
+                if nu:
+                    no.simulation_unaligned_transcriptome(oref, m, s2, 50, oref.max_chrom, fastq, nu)
+                return s1.records + s2.records
+        else:
+            genomes = {}
+            for nm, sq, si in zip(sref.names, seqs, sref.chrom_species):
+                sp = sref.species[int(si)]
+                genomes.setdefault(sp, []).append((nm[len(sp) + 1:], sq))
+            oref = no.OracleMetaReference(genomes)
+            abun = {sp: 100.0 / len(sref.species) for sp in sref.species}
+            infl = {sp: no.inflate_abun(abun, sp, m.abun_inflation) for sp in abun}
+            mx = max(oref.max_chrom.values())
+
+            def run(na, nu):
+                s1, s2 = no.ReadSink(), no.ReadSink()
+                no.simulation_aligned_metagenome(oref, m, s1, abun, infl, 50, mx, None, fastq, na, False, chim)
+                if nu:
+                    no.simulation_unaligned_meta(oref, m, s2, 50, mx, fastq, nu)
+                return s1.records + s2.records
+        self.split = m.split_counts
+        ctx = mp.get_context("fork")
+        self.res = ctx.Queue()
+        self.cmd = [ctx.Queue() for _ in range(n_procs)]
+
+        def loop(i):
+            import random
+            k = 0
+            while True:
+                job = self.cmd[i].get()
+                if job is None:
+                    return
+                random.seed(1000003 * i + k)
+                np.random.seed((1000003 * i + k) % (2 ** 31))
+                k += 1
+                t0 = time.perf_counter()
+                recs = run(*job)
+                txt = no.format_records(recs, fastq)        # the reference also formats (and writes) its records
+                self.res.put((sum(len(r[1]) for r in recs), len(recs), time.perf_counter() - t0, len(txt)))
+
+        self.procs = [ctx.Process(target=loop, args=(i,), daemon=True) for i in range(n_procs)]
+        for p in self.procs:
+            p.start()
+
+    def step(self, reads_per_worker):
+        na, nu = self.split(reads_per_worker)
+        t0 = time.perf_counter()
+        for q in self.cmd:
+            q.put((na, nu))
+        out = [self.res.get() for _ in self.procs]
+        wall = time.perf_counter() - t0
+        return sum(o[0] for o in out), sum(o[1] for o in out), wall, sum(o[2] for o in out)
+
+    def close(self):
+        for q in self.cmd:
+            q.put(None)
+        for p in self.procs:
+            p.join(timeout=10)
+
+
+def cpu_sample_text(name, n_workers, per_worker, wall, worker_s, bases):
+    extra = ""
+    if WORKLOADS[name]["mode"] == "transcriptome":
+        extra = "; the reference's select_nearest_kde2d is O(N) per read in the reads of a worker (N = %d here; at the job's " \
+                "5M/%d reads per worker it is ~%dx slower per read)" % (per_worker, n_workers, max(1, 5000000 // n_workers // max(per_worker, 1)))
+    return ("pure-Python oracle port of simulator.py (same algorithm as the reference, record formatting included, no file I/O), "
+            "%d worker processes forked once, %d reads per worker in steady state, %.1f s wall; per core %.3g bases/s%s"
+            % (n_workers, per_worker, wall, bases / max(worker_s, 1e-9), extra))
 
 
 def main():
@@ -160,11 +286,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch_reads", type=int, default=262144)
-    ap.add_argument("--ref_scale", type=float, default=1.0, help="scale the 3.09 Gb reference (tests only)")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch_reads", type=int, default=0, help="reads per step per GPU (0 = the workload's default)")
+    ap.add_argument("--ref_scale", type=float, default=1.0, help="scale the synthetic reference (tests only)")
     ap.add_argument("--depth", type=int, default=4, help="overlapped contexts per GPU")
     ap.add_argument("--timeline", default=None, help="write the per-batch phase intervals of the timed steps to this file")
-    ap.add_argument("--cpu_reads", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--cpu_reads", type=int, default=0, help="reads PER WORKER in a CPU-baseline step (0 = auto)")
+    ap.add_argument("--cpu_procs", type=int, default=0, help="CPU-baseline worker processes (0 = all host cores)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
 
@@ -172,75 +300,94 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    workload = "genome FASTQ, guppy FAB49712 model + dorado_v3.2.1 quality table, 3.09 Gb synthetic hg38-sized reference " \
-               "(24 chr, i.i.d. ACGT), 10M-read job, %d reads per step" % args.batch_reads
+    n_procs = args.cpu_procs or cores
+    W = WORKLOADS[args.workload]
+    batch_reads = args.batch_reads or W["batch"]
+    workload = "%s: %s, %d reads per step" % (args.workload, W["text"], batch_reads)
+    algo_bytes = 3.0 if W["fastq"] else 2.0
 
     import torch
 
     if args.impl == "reference":
-        # the reference's CPU implementation of the path == the oracle port (Python, multiprocessing over all cores)
+        # the reference's CPU implementation of the path == the oracle port (Python, one process per host core)
         if rank != 0:
             return
-        ref_t, offsets = synth_reference_gpu(local, args.ref_scale) if torch.cuda.is_available() else (None, None)
-        if ref_t is None:
-            rng = np.random.default_rng(1)
-            lengths = [max(1000, int(x * args.ref_scale)) for x in HG38_LENGTHS]
-            host = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n, dtype=np.uint8)] for n in lengths]
-            ref_strs = [(nm, a.tobytes().decode()) for nm, a in zip(CHROM_NAMES, host)]
-        else:
-            host = ref_t.cpu().numpy()
-            ref_strs = [(nm, host[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()) for i, nm in enumerate(CHROM_NAMES)]
-            del ref_t
-        per_step = args.cpu_reads or 40 * cores
+        sref = build_reference(args.workload, local, args.ref_scale, torch.cuda.is_available())
+        pool = OraclePool(args.workload, sref, n_procs)
+        del sref
+        per_worker = args.cpu_reads or (400 if W["mode"] != "transcriptome" else 1500)
         vals = []
         for s in range(args.warmup + args.steps):
-            bases, dt = cpu_oracle_sample(ref_strs, per_step, cores)
+            bases, nreads, wall, wsum = pool.step(per_worker if s >= args.warmup else max(8, per_worker // 10))
             if s >= args.warmup:
-                vals.append((bases, dt))
-        tb, tt = sum(v[0] for v in vals), sum(v[1] for v in vals)
+                vals.append((bases, nreads, wall, wsum))
+        pool.close()
+        tb, tt, tw = sum(v[0] for v in vals), sum(v[2] for v in vals), sum(v[3] for v in vals)
         v = tb / tt
         print(json.dumps({"impl": "reference", "metric": "simulated_bases_per_sec", "value": v, "unit": "bases/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * tt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": {"workload": workload},
-                          "cpu_baseline": {"value": v, "unit": "bases/s", "cores": cores, "kind": "port",
-                                           "sample": "%d reads per step, %d forked workers, pure-Python oracle port of simulator.py "
-                                                     "(same algorithm as the reference, incl. record formatting)" % (per_step, cores)},
+                          "reads_per_sec": sum(v[1] for v in vals) / tt,
+                          "cpu_baseline": {"value": v, "unit": "bases/s", "cores": n_procs, "kind": "port",
+                                           "per_core": tb / max(tw, 1e-9), "reads_per_step": per_worker * n_procs,
+                                           "sample": cpu_sample_text(args.workload, n_procs, per_worker, tt / max(args.steps, 1), tw, tb) + " per step"},
                           "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     from nanosim_b200 import _lib as L
     from nanosim_b200.engine import Engine
-    from nanosim_b200.model import CompiledModel, DeviceTables
+    from nanosim_b200.model import CompiledModel, DeviceTables, build_alias
 
     torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+        dist.init_process_group("nccl", device_id=torch.device(dev))
 
     # ---- init (not timed): reference generated on rank 0, ONE broadcast over NCCL, model tables to HBM
     if rank == 0:
-        ref_t, offsets = synth_reference_gpu(local, args.ref_scale)
+        sref = build_reference(args.workload, local, args.ref_scale, True)
+        meta = [sref.offsets, sref.names, sref.species, sref.chrom_species, sref.chrom_circular, sref.tpm]
     else:
-        lengths = [max(1000, int(x * args.ref_scale)) for x in HG38_LENGTHS]
-        offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-        ref_t = torch.empty(int(offsets[-1]), dtype=torch.uint8, device="cuda:%d" % local)
+        sref, meta = None, [None] * 6
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    n_bases = int(meta[0][-1])
+    if rank == 0:
+        ref_t = sref.bases if not isinstance(sref.bases, np.ndarray) else torch.from_numpy(sref.bases).to(dev)
+    else:
+        ref_t = torch.empty(n_bases, dtype=torch.uint8, device=dev)
+        sref = SynthRef(None, *meta)
     if world > 1:
         dist.broadcast(ref_t, src=0)
     torch.cuda.synchronize()
-    cm = CompiledModel.load(MODEL)
-    tables = DeviceTables(cm, fastq=True)
+    cm = CompiledModel.load(os.path.join(DATA, W["model"]))
+    tables = DeviceTables(cm, fastq=W["fastq"], chimeric=W["chimeric"], homopolymer=bool(W["kmer_bias"]), mode=W["mode"])
     eng = Engine(device=local, seed=20260924)
-    eng.set_reference_ptr(ref_t.data_ptr(), int(offsets[-1]), offsets)
-    host_ref = ref_t.cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None     # CPU baseline: N=1 only
+    eng.set_reference_ptr(ref_t.data_ptr(), n_bases, sref.offsets, chrom_species=sref.chrom_species,
+                          chrom_circular=sref.chrom_circular, n_species=len(sref.species) if sref.species else 0)
+    keep_host = rank == 0 and world == 1 and not args.no_cpu_baseline          # CPU baseline: N=1 only
+    if keep_host and not isinstance(sref.bases, np.ndarray):
+        sref.bases = ref_t.cpu().numpy()
     del ref_t
     torch.cuda.empty_cache()
     eng.set_model(tables)
-    eng.configure(fastq=True, min_len=50, max_len=int(np.diff(offsets.astype(np.int64)).max()))
+    n_al, n_un = tables.split_counts(batch_reads)
+    if W["mode"] == "transcriptome":
+        pr, al = build_alias(sref.tpm)
+        eng.set_expression(pr, al, np.arange(len(sref.tpm), dtype=np.uint32), None)
+    if W["mode"] == "metagenome":
+        abun = [100.0 / len(sref.species)] * len(sref.species)
+        eng.set_abundance(abun, [1 - (1 - a) * tables.abun_inflation for a in abun] if W["chimeric"] else None)
+    eng.configure(fastq=W["fastq"], chimeric=W["chimeric"], kmer_bias=W["kmer_bias"], min_len=50, max_len=sref.max_chrom,
+                  metagenome=W["mode"] == "metagenome", transcriptome=W["mode"] == "transcriptome",
+                  # the reference's 2-D KDE sample has one row per aligned read of a worker (simulator.py:1072): 5M-read job / cores
+                  kde2d_sample=max(1, int(5000000 * n_al / max(batch_reads, 1)) // cores) if W["mode"] == "transcriptome" else 0)
+    static = W["mode"] == "metagenome"           # species quotas live in a context: job j -> context j % depth
 
-    n_al, n_un = tables.split_counts(args.batch_reads)
     total_steps = args.warmup + args.steps
     from nanosim_b200.pipeline import BatchPipeline
 
@@ -266,16 +413,17 @@ def main():
 
     # ---- kernel-only arm: outputs stay in HBM.  `depth` contexts (ns_clone) share the reference; the latency-bound tails
     #      of one batch's plan / unaligned kernels overlap the emit kernel of another.  Every step simulates new read ids;
-    #      a batch's working set (>2 GB written + a 3 GB reference sampled at random) is far larger than the 126 MB L2.
+    #      a batch's working set (GBs written + a reference sampled at random) is far larger than the 126 MB L2 (config 1,
+    #      a 5 Mb reference and 9 MB of output per step, is the exception: the reference's own tiny case).
     pipe = BatchPipeline(eng, depth=args.depth, fetch=False)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     pipe.warm(jobs_for(range(1)))                   # every context sizes its buffers once (untimed)
-    pipe.run(jobs_for(range(args.warmup)))
+    pipe.run(jobs_for(range(args.warmup)), static_assign=static)
     barrier()
     t0 = time.perf_counter()
-    rows = [row(i) for i in pipe.run(jobs_for(range(args.warmup, total_steps)))]
+    rows = [row(i) for i in pipe.run(jobs_for(range(args.warmup, total_steps)), static_assign=static)]
     barrier()
     wall = time.perf_counter() - t0
     clocks.window(t0, t0 + wall, "kernel-only arm")
@@ -293,7 +441,7 @@ def main():
     emit_ms = sum(r[9] for r in rows)
     launches = sum(r[4] for r in rows)
     n_reads_done = sum(r[2] for r in rows)
-    stat = torch.tensor([bases, dev_ms, wall * 1e3, n_reads_done], dtype=torch.float64, device="cuda:%d" % local)
+    stat = torch.tensor([bases, dev_ms, wall * 1e3, n_reads_done], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -314,10 +462,11 @@ def main():
     rows1 = [row(i) for i in pipe1.run(jobs_for(range(total_steps + 1, total_steps + 1 + n_roof)))]
     barrier()
     pipe1.close()
-    al1 = [r for r in rows1 if r[2] == n_al]                         # aligned batches -> emit_kernel<FASTQ> launches
+    al1 = [r for r in rows1 if r[2] == n_al]                         # aligned batches -> the emit kernel's big launches
     emit_alone_ms = sum(r[9] for r in al1) / max(len(al1), 1)
     emit_alone_bases = sum(r[0] for r in al1) / max(len(al1), 1)
     plan_alone_ms = sum(r[6] for r in al1) / max(len(al1), 1)
+    un1 = [r for r in rows1 if r[2] != n_al]
     total_steps += 1 + n_roof
 
     # ---- end-to-end arm: the public API (BatchPipeline): ns_simulate + ns_fetch into pinned host buffers every batch
@@ -325,22 +474,21 @@ def main():
     base_step = total_steps                          # fresh read ids
     e_warm = max(3, args.depth + 1)                  # every context's pinned buffers must have seen an aligned batch
     pipe_e.warm(jobs_for(range(base_step, base_step + 1)))
-    pipe_e.run(jobs_for(range(base_step, base_step + e_warm)))
+    pipe_e.run(jobs_for(range(base_step, base_step + e_warm)), static_assign=static)
     barrier()
     t0 = time.perf_counter()
-    rows_e = [row(i) for i in pipe_e.run(jobs_for(range(base_step + e_warm, base_step + e_warm + args.steps)))]
+    rows_e = [row(i) for i in pipe_e.run(jobs_for(range(base_step + e_warm, base_step + e_warm + args.steps)), static_assign=static)]
     barrier()
     wall_e = time.perf_counter() - t0
     clocks.window(t0, t0 + wall_e, "end-to-end arm")
     clk = clocks.stop() if rank == 0 else None
     pipe_e.close()
     bases_e = sum(r[0] for r in rows_e)
-    # bytes that cross PCIe: qualities as ASCII, bases as 2 bits (packed on the device, expanded by host threads inside
-    # ns_fetch unless NANOSIM_B200_UNPACK_THREADS=0) + read / piece metadata
-    env_t = os.environ.get("NANOSIM_B200_UNPACK_THREADS", "")          # same rule as unpack_threads() in nanosim_api.cu
-    packed = int(env_t) > 0 if env_t else (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) >= 48
-    d2h = sum((1.25 if packed and r[1] >= (1 << 20) else 2.0) * r[1] + 32 * r[2] + 64 * r[3] for r in rows_e) / max(args.steps, 1)
-    stat = torch.tensor([bases_e, wall_e], dtype=torch.float64, device="cuda:%d" % local)
+    # bytes that cross PCIe: qualities as ASCII, bases as 2 bits when the library packs them (ns_fetch) + read / piece metadata
+    packed = bool(eng.fetch_packs_bases())
+    per_base = (1.25 if packed else 2.0) if W["fastq"] else (0.25 if packed else 1.0)
+    d2h = sum((per_base if r[1] >= (1 << 20) else (2.0 if W["fastq"] else 1.0)) * r[1] + 32 * r[2] + 64 * r[3] for r in rows_e) / max(args.steps, 1)
+    stat = torch.tensor([bases_e, wall_e], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -353,19 +501,27 @@ def main():
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_BASE * emit_alone_bases / (emit_alone_ms * 1e-3) / 1e9
+    achieved = algo_bytes * emit_alone_bases / (emit_alone_ms * 1e-3) / 1e9
+    kernel = "emit_kernel<%s>" % ("FASTQ" if W["fastq"] else "FASTA")
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)   # written by tools/ncu_traffic.py from an ncu --set full capture
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f)
     line = {
         "metric": "simulated_bases_per_sec", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_step_per_gpu": args.batch_reads, "aligned_per_step": n_al,
-                   "unaligned_per_step": n_un, "l2": "inputs larger than L2 (3.09 GB reference sampled at random, >2 GB written per step)",
+        "config": {"workload": workload, "reads_per_step_per_gpu": batch_reads, "aligned_per_step": n_al,
+                   "unaligned_per_step": n_un, "l2": "inputs larger than L2 (reference sampled at random, GBs written per step)"
+                   if args.workload != "config1" else "config 1 is the reference's tiny case: 5 Mb reference, 9 MB written per step (fits L2)",
                    "contexts_per_gpu": args.depth,
                    "timing": "device timeline (CUDA events vs a common base event): first batch start to last batch end of the K "
                              "timed steps, %d overlapped contexts per GPU, max over ranks" % args.depth},
         "reads_per_sec": total_reads / (t_ms * 1e-3),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": int(d2h),
+                "d2h_gb_per_s_per_gpu": d2h * args.steps / wall_e / 1e9,
                 "note": "reference + model are resident in HBM (uploaded once at init); per-step input is the read-id range; the "
                         "timed region ends with ASCII bases + qualities + metadata in pinned host buffers" +
                         (" (bases cross PCIe as 2 bits and are expanded by host threads inside ns_fetch)" if packed else "")},
@@ -375,23 +531,32 @@ def main():
                               "setup": sum(r[10] for r in rows) / args.steps,
                               "note": "sums of per-batch CUDA-event durations; batches of the overlapped contexts share the GPU, so these add up to more than ms_per_step"},
         "wall_ms_per_step": 1e3 * wall / max(args.steps, 1),
-        "roofline": {"bound": "hbm", "kernel": "emit_kernel<FASTQ>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                     "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else "no ncu --set full capture of this workload committed",
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_base": algo_bytes,
                      "bases_per_launch": emit_alone_bases, "ms_per_launch": emit_alone_ms,
                      "plan_kernel_ms_per_launch": plan_alone_ms,
-                     "measured": "CUDA events on the launching stream around emit_kernel<FASTQ>, %d aligned batches of %d reads run "
+                     "alone_ms": {"aligned_batch_total": sum(r[5] for r in al1) / max(len(al1), 1),
+                                  "unaligned_batch_total": sum(r[5] for r in un1) / max(len(un1), 1),
+                                  "unaligned_plan": sum(r[6] for r in un1) / max(len(un1), 1),
+                                  "unaligned_emit": sum(r[9] for r in un1) / max(len(un1), 1)},
+                     "measured": "CUDA events on the launching stream around %s, %d aligned batches of %d reads run "
                                  "through ONE context after the timed region (kernels of overlapped contexts share SMs, which "
-                                 "stretches every per-launch duration)" % (len(al1), n_al),
-                     "whole_path_frac": ALGO_BYTES_PER_BASE * total_bases / (t_ms * 1e-3) / 1e9 / peak / max(world, 1)},
+                                 "stretches every per-launch duration)" % (kernel, len(al1), n_al),
+                     "whole_path_frac": algo_bytes * total_bases / (t_ms * 1e-3) / 1e9 / peak / max(world, 1)},
     }
-    if not args.no_cpu_baseline and host_ref is not None:
-        ref_strs = [(nm, host_ref[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()) for i, nm in enumerate(CHROM_NAMES)]
-        n_cpu = args.cpu_reads or 40 * cores
-        cb, ct = cpu_oracle_sample(ref_strs, n_cpu, cores)
-        line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": cores, "kind": "port",
-                                "sample": "%d reads of the same workload, %d forked workers, pure-Python oracle port of simulator.py "
-                                          "(record formatting included, no file I/O); %.1f s" % (n_cpu, cores, ct)}
+    if keep_host:
+        pool = OraclePool(args.workload, sref, n_procs)
+        per_worker = args.cpu_reads or (1000 if W["mode"] != "transcriptome" else 3000)
+        pool.step(max(8, per_worker // 20))                      # the workers' first call (lazy imports, page faults)
+        cb, cr, ct, cw = pool.step(per_worker)
+        pool.close()
+        line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": n_procs, "kind": "port", "per_core": cb / max(cw, 1e-9),
+                                "reads_per_sec": cr / ct,
+                                "sample": cpu_sample_text(args.workload, n_procs, per_worker, ct, cw, cb)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -133,6 +133,10 @@ typedef struct {
  * positions; used by the tests to check the fast path against re-applied edit scripts). */
 #define NS_FLAG_UNALIGNED_SCRIPTS 1u
 #define NS_FLAG_URACIL 2u            /* --uracil: T -> U in the emitted reads (:1247-1248) */
+/* The emit kernel reads plain-ACGT stretches of the reference from a 2-bit copy (fast route) and everything else byte by
+ * byte (exact route: IUPAC codes, circular wrap-around, minus-strand genome pieces).  Both give the same bytes; this flag
+ * sends every piece down the exact route (tests compare the two). */
+#define NS_FLAG_EMIT_EXACT 4u
 
 #define NS_KIND_ALIGNED 0
 #define NS_KIND_UNALIGNED 1
@@ -235,6 +239,11 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
  * host threads inside this call: NANOSIM_B200_UNPACK_THREADS; default 16 when the host has >= 48 cores per GPU process
  * (cores / LOCAL_WORLD_SIZE), else 0 = plain ASCII copies). */
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
+
+/* How ns_fetch moves the bases of large batches: *packed_bases = 1 when they cross PCIe as 2 bits each (every byte of the
+ * reference is an IUPAC nucleotide code, so reads hold A C G T/U only, and the host has threads to expand them),
+ * *unpack_threads = host threads ns_fetch uses for the expansion.  (No reference counterpart: its workers write files.) */
+int ns_transfer_info(NsContext* ctx, uint32_t* packed_bases, uint32_t* unpack_threads);
 
 /* Intron retention (simulator.py:1156-1183), second half: replaces the piece lists of `n_slots` reads of the last batch and
  * emits those reads again.  The host decides which reads retain introns (nanosim_b200/intron_retention.py) and lays each of

@@ -46,7 +46,17 @@ struct DevRef {
     const uint32_t* expr_chrom;         // expressed transcript -> reference record
     uint32_t n_expressed;
     const uint8_t* chrom_has_polya;     // per reference record (nullptr: no polyA list)
+    // 2-bit copy of the reference for the emit kernel's fast path (built once by ns_set_reference): 16 bases per 32-bit
+    // word, base j of a word in bits [2j+1:2j], code (c >> 1) & 3 of the upper-cased base (A 0, C 1, T 2, G 3); every
+    // chromosome starts at a word boundary (pk_off[chrom], in words); one guard word in front, two behind.  Bytes that
+    // case_convert does not map to exactly one of ACGT (IUPAC codes, anything else) are "exceptions" and get code 0:
+    // exc_pre[b] = exceptions in packed words [0, 256 b) -- a piece whose words touch none takes the fast path.
+    const uint32_t* packed;
+    const uint64_t* pk_off;
+    const uint32_t* exc_pre;
+    uint32_t all_iupac;                 // every reference byte is a nucleotide code case_convert turns into A C G T
 };
+#define REF_EXC_BLOCK_SHIFT 8           // 256 packed words = 4096 bases per exception-count block
 
 struct DevCfg {
     uint32_t circular, perfect, fastq, chimeric, kmer_bias, metagenome, transcriptome, uracil, kde2d_n, trx_records;
@@ -169,24 +179,10 @@ __device__ __forceinline__ bool acgt_fast(uint32_t c) {
     uint32_t d = c - 'A';
     return d < 26u && ((0x80045u >> d) & 1u);
 }
-// Base-quality bucket table over 24-bit uniforms (built on the host, nanosim_api.cu:build_qlut).  A random word w carries
-// the uniform in its high 24 bits; bucket = w >> 21.  Entry: [7:0] ASCII character of the bucket's lower value (minus one
-// when the bucket holds a single value), [31:19] 13-bit threshold on the fraction: char += (fraction >= threshold).
-// A bucket with more than two values has entry 0x80 | lowest value << 8 (an impossible character) and is resolved by
-// qual_char_exact.
+// Base qualities: per quality state a Walker alias table with 2^QLUT_BITS slots over the state's 24-bit pmf (built on the
+// host, nanosim_api.cu:build_qlut; sampled in emit_kernel.cuh:qual_pick).
 #define QLUT_BITS 11
 #define QLUT_SIZE (1 << QLUT_BITS)
-#define QLUT_FRAC_BITS (24 - QLUT_BITS)
-__device__ __forceinline__ uint32_t qual_char_fast(uint32_t e, uint32_t w) {
-    return (e & 0xffu) + (((w << QLUT_BITS) >= (e & 0xfff80000u)) ? 1u : 0u);
-}
-// exact scan for a flagged bucket; bits [14:8] of its entry hold the bucket's lowest quality value
-__device__ __forceinline__ uint32_t qual_char_exact(const uint32_t* cdf24, uint32_t w, uint32_t e) {
-    const uint32_t u24 = w >> 8;
-    uint32_t q = (e >> 8) & 0x7fu;
-    while (q < NS_QUAL_SLOTS - 1 && u24 >= __ldg(&cdf24[q])) ++q;
-    return q + 33u;
-}
 
 __device__ __forceinline__ uint32_t op_len(uint32_t op) { return (op >> 28) == NS_OP_LIT ? (op & 0x00ffffffu) : (op & 0x0fffffffu); }
 

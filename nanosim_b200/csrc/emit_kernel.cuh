@@ -5,18 +5,32 @@
 // (:1433-1435, :1675-1680) and the per-state quality draws (model_base_qualities.py:120-130) in ONE pass:
 //
 //   * a warp owns one piece (an aligned segment with its head/tail, a chimeric gap, or an unaligned read) and
-//     streams its ops 32 at a time; a warp-wide scan turns them into ring entries {output start, absolute reference
-//     offset, length, per-op constants} in shared memory (deletions only advance the reference offset and get no
-//     entry; a pad entry aligns the piece to its first 16-byte chunk, a sentinel closes it);
-//   * every lane produces one 16-byte output chunk per step: it binary-searches the ring for the entry covering its
-//     first base, then runs a BRANCH-FREE, fully unrolled 16-base loop: a predicated ring advance, a predicated
-//     reference byte load, one table lookup for case/IUPAC classification, one for the quality bucket.  Lanes of a
-//     warp sit in different ops, so anything branchy would be executed by everybody anyway; the rare cases (IUPAC
-//     codes, quality buckets that hold more than two values) only raise a flag and are patched afterwards;
+//     streams its ops 32 at a time; a warp-wide scan turns them into ring entries {output start, reference offset
+//     within the chromosome, length, per-op constants} in shared memory (deletions only advance the reference offset
+//     and get no entry; a pad entry aligns the piece to its first 16-byte chunk, a sentinel closes it);
+//   * every lane produces one 16-byte output chunk per step.  It binary-searches the ring for the entry covering its
+//     first base and then takes one of two routes, chosen per piece (warp-uniform):
+//       FAST  the piece's reference span holds plain a/c/g/t only (DevRef::exc_pre) and does not wrap: the lane walks
+//             the ENTRIES that overlap its chunk.  For an entry that reads the reference it fetches the 16 bases that
+//             start at its first base from the 2-bit copy of the reference (two 32-bit loads + one funnel shift; a BREV
+//             and a pair swap for a backward walk), shifts them into place and merges them under a mask into a 32-bit
+//             accumulator of 16 2-bit bases; inserted / head-tail bases are one AND with the chunk's random word,
+//             substituted bases are patched afterwards in a short loop over a bit mask, and the quality state of every
+//             base is merged the same way into a second 2-bit word.  Four PRMTs turn the accumulator into ASCII.
+//       EXACT a branch-free 16-base walk over the reference BYTES (case, IUPAC codes, circular wrap-around, the
+//             complemented backward walk of minus-strand genome pieces): a predicated ring advance, a predicated byte
+//             load and one table lookup for the case / IUPAC class per base; IUPAC codes raise a flag and are
+//             resolved by a per-base routine.
+//     Both routes draw the same random bits for the same base, so a read's bytes do not depend on the route (tested
+//     by forcing the exact route: NS_FLAG_EMIT_EXACT);
+//   * base qualities: one shared-memory lookup per base in a 2048-slot Walker alias table per quality state, built on
+//     the host from the state's 24-bit pmf (slot = 11 bits, acceptance threshold = 13 bits: exact to 2^-24);
 //   * reverse-strand reads are produced directly in output order by walking the edit script and the reference
 //     backwards with a complemented character table (no second pass over the read);
-//   * all randomness is Philox keyed by (seed, read id, chunk index): one 32-bit word per base (8 bits base choice,
-//     24 bits quality uniform), so the bytes do not depend on the batch, the launch geometry or the GPU count.
+//   * all randomness is Philox-7 keyed by (seed, read id, chunk index): per chunk of 16 bases, FASTQ draws 16 quality
+//     words (slot 11 bits | threshold 13 bits | 8 bits for a substitution) + one block {2 bits per base for inserted
+//     bases, 6 more bits per base for substitutions}; FASTA draws that block + 16 substitution bytes.  The bytes of a
+//     read therefore do not depend on the batch, the launch geometry or the GPU count.
 #pragma once
 #include "device_common.cuh"
 
@@ -26,6 +40,7 @@
 #define EMIT_MIN_BLOCKS 3     // resident blocks per SM the register allocation aims for
 #endif
 
+#define EMIT_F_RND 1u        // info bit: random base (INS, HT, pad); bit 1 is set with it (info & 3 == 3)
 #define EMIT_F_REF 4u        // info bit: the base is read from the reference (COPY, MIS)
 #define EMIT_F_MIS 8u        // info bit: ... and substituted by one of the three other bases
 
@@ -33,6 +48,7 @@ struct EmitArgs {
     DevRef ref;
     DevCfg cfg;
     uint32_t kind;
+    uint32_t force_exact;        // debugging / tests: every piece takes the exact route
     uint64_t first_id;
     const NsReadMeta* reads;
     const NsPieceMeta* pieces;
@@ -40,8 +56,7 @@ struct EmitArgs {
     uint32_t n_pieces;
     uint8_t* seq;
     uint8_t* qual;
-    const uint32_t* qlut;        // [5][QLUT_SIZE] packed bucket table (built on the host from qual_cdf)
-    const uint32_t* qcdf;        // [5][94], 24-bit fixed point
+    const uint32_t* qlut;        // [5][QLUT_SIZE] alias table entries (built on the host from qual_cdf)
     uint32_t* counter;
     const uint32_t* order;       // piece processing order (longest first) or null
 };
@@ -57,7 +72,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 // Per-op constants of a ring entry: [1:0] 3 when the base is random (INS, HT, pad), [2] EMIT_F_REF, [3] EMIT_F_MIS,
 // [15:8] the character classified when the reference is not read ('A' -> index 0, or the literal base of a LIT op),
-// [31:16] byte offset of the quality state's bucket table.
+// [31:16] byte offset of the quality state's alias table (state << 13).
 // ref_comp: the piece classifies reference bytes with the COMPLEMENTING table (NS_PIECE_REF_REV); the characters stored for
 // ops that do not read the reference are then pre-complemented so that they classify to the intended base.
 __device__ __forceinline__ uint32_t emit_op_info(uint32_t op, bool unmapped, bool ref_comp = false) {
@@ -72,6 +87,60 @@ __device__ __forceinline__ uint32_t emit_op_info(uint32_t op, bool unmapped, boo
     return info;
 }
 
+// ---- the random bits of one 16-base chunk -------------------------------------------------------------------------
+// Drawn in two parts so that the 16 quality words are not live while the chunk's entries are walked.
+struct ChunkAux {
+    uint32_t RB;                  // base i's random base index in bits [2i+1:2i] (inserted, head/tail, pad bases)
+    uint32_t M[3];                // base i's low 6 substitution bits at bit 6i of this 96-bit string
+};
+template <bool FASTQ>
+struct ChunkQual {
+    uint32_t W[FASTQ ? 16 : 1];   // FASTQ: base i's quality word (alias slot in bits [18:8], threshold draw in [31:19])
+    uint32_t LB[4];               // base i's high 8 substitution bits = byte i (FASTQ: the low bytes of the quality words)
+};
+
+template <bool FASTQ>
+__device__ __forceinline__ void draw_chunk_aux(ChunkAux& r, uint32_t id_lo, uint32_t id_hi, uint32_t kind, uint32_t chunk, uint2 key) {
+    const uint4 a = FASTQ ? philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_Q, kind, chunk), 4u), key)
+                          : philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, kind, chunk), 0u), key);
+    r.RB = a.x; r.M[0] = a.y; r.M[1] = a.z; r.M[2] = a.w;
+}
+template <bool FASTQ>
+__device__ __forceinline__ void draw_chunk_qual(ChunkQual<FASTQ>& r, uint32_t id_lo, uint32_t id_hi, uint32_t kind, uint32_t chunk, uint2 key) {
+    if (FASTQ) {
+        const uint32_t sw = stream_word(ST_EMIT_Q, kind, chunk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
+            r.W[4 * j] = t.x; r.W[4 * j + 1] = t.y; r.W[4 * j + 2] = t.z; r.W[4 * j + 3] = t.w;
+            r.LB[j] = __byte_perm(__byte_perm(t.x, t.y, 0x0040), __byte_perm(t.z, t.w, 0x0040), 0x5410);
+        }
+    } else {
+        const uint4 b = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, kind, chunk), 1u), key);
+        r.LB[0] = b.x; r.LB[1] = b.y; r.LB[2] = b.z; r.LB[3] = b.w;
+        r.W[0] = 0;
+    }
+}
+
+// 1 + uniform{0,1,2}: what is added (mod 4) to a base index to substitute it by one of the three others
+// (random.choice of the remaining bases, simulator.py:1968-1973).  14 random bits, MSB-aligned: bias 2^-14.
+__device__ __forceinline__ uint32_t mis_offset(const ChunkAux& r, const uint32_t (&LB)[4], uint32_t i) {
+    const uint32_t wsel = i >> 2;
+    const uint32_t lbw = wsel == 0 ? LB[0] : (wsel == 1 ? LB[1] : (wsel == 2 ? LB[2] : LB[3]));
+    const uint32_t b8 = (lbw >> (8u * (i & 3u))) & 0xffu;
+    const uint32_t off = 6u * i, mw = off >> 5;
+    const uint32_t lo = mw == 0 ? r.M[0] : (mw == 1 ? r.M[1] : r.M[2]);
+    const uint32_t hi = mw == 0 ? r.M[1] : (mw == 1 ? r.M[2] : 0u);
+    const uint32_t m6 = __funnelshift_r(lo, hi, off & 31u) & 63u;
+    return 1u + __umulhi((b8 << 24) | (m6 << 18), 3u);
+}
+
+// Base quality from an alias-table entry: [31:19] 13-bit acceptance threshold, [15:8] alias character, [7:0] primary
+// character (nanosim_api.cu:build_qlut).  The draw w carries the slot in bits [18:8] and the threshold draw in [31:19].
+__device__ __forceinline__ uint32_t qual_pick(uint32_t e, uint32_t w) {
+    return ((w | 0x7ffffu) < e) ? e : (e >> 8);          // the character is the low byte of the result
+}
+
 struct EmitPiece {
     const uint8_t* cbase;    // first base of the chromosome
     uint32_t pos, clen;      // piece start within the chromosome, chromosome length
@@ -82,11 +151,10 @@ struct EmitPiece {
     uint64_t rid;
 };
 
-// Exact slow path for ONE base (IUPAC reference codes, quality buckets with more than two values): locates the ring
-// entry of padded piece coordinate x again and redoes the base with the same random word.  Returns char | qchar << 8.
-template <bool FASTQ>
+// Exact path for ONE base whose reference byte is not plain ACGT (IUPAC codes): locates the ring entry of padded piece
+// coordinate x again and redoes the base with the same random bits.  Returns the character.
 __device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiece& pc, const uint4* ring, uint32_t w_ret,
-                                               uint32_t w_loaded, uint32_t x, uint32_t w, uint32_t p) {
+                                               uint32_t w_loaded, uint32_t x, uint32_t rb2, uint32_t misoff) {
     uint32_t l = w_ret, h = w_loaded;
     while (h - l > 1) {
         uint32_t mid = (l + h) >> 1;
@@ -105,27 +173,20 @@ __device__ __noinline__ uint32_t emit_fix_base(const EmitArgs& a, const EmitPiec
             c = converted_ref_base(c, a.cfg.seed, pc.rid, pc.piece_in_read, f);
         }
         oi = base_idx(c) ^ (pc.ref_comp ? 2u : 0u);
-        if (info & EMIT_F_MIS) oi = (oi + 1u + __umulhi(p, 3u)) & 3u;
+        if (info & EMIT_F_MIS) oi = (oi + misoff) & 3u;
     } else {
-        oi = (info & 3u) ? (w & 3u) : (base_idx((info >> 8) & 0xffu) ^ (pc.ref_comp ? 2u : 0u));
+        oi = (info & 3u) ? rb2 : (base_idx((info >> 8) & 0xffu) ^ (pc.ref_comp ? 2u : 0u));
     }
-    uint32_t out = (pc.tbl >> (8u * oi)) & 0xffu;
-    if (FASTQ) {
-        const uint32_t qs = (info >> 16) / (QLUT_SIZE * 4u);
-        const uint32_t qe = __ldg(&a.qlut[qs * QLUT_SIZE + (w >> (32 - QLUT_BITS))]);
-        out |= ((qe & 0x80u) ? qual_char_exact(a.qcdf + qs * NS_QUAL_SLOTS, w, qe) : qual_char_fast(qe, w)) << 8;
-    }
-    return out;
+    return (pc.tbl >> (8u * oi)) & 0xffu;
 }
 
-// The branch-free 16-base walk of one chunk (see the header comment).  WRAPS: the piece crosses the origin of a circular
-// chromosome (:1756-1760).
+// ---- EXACT route: the branch-free 16-base walk of one chunk over the reference bytes.  WRAPS: the piece crosses the
+// origin of a circular chromosome (:1756-1760).  COMP: complementing classification (minus-strand genome pieces).
 template <bool FASTQ, bool WRAPS, bool COMP>
 __device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* lut, const uint8_t* cvt_tables,
-                                             const uint8_t* __restrict__ cbase, const uint32_t (&W)[FASTQ ? 16 : 4], uint32_t& k,
+                                             const uint8_t* __restrict__ cbase, const ChunkAux& R, const ChunkQual<FASTQ>& Q, uint32_t& k,
                                              uint32_t& rem, uint32_t& rabs, uint32_t& info, uint32_t dir, uint32_t clen,
-                                             uint32_t wrap_fix, uint32_t tbl, uint32_t (&sb)[4], uint32_t (&sq)[4], uint32_t& bad,
-                                             uint32_t& slow) {
+                                             uint32_t wrap_fix, uint32_t tbl, uint32_t (&sb)[4], uint32_t (&sq)[4], uint32_t& bad) {
     const uint8_t* cvt = cvt_tables + (COMP ? 256 : 0);    // compile-time offset: the lookup stays [register + immediate]
     uint32_t sel = 0;
 #pragma unroll
@@ -138,11 +199,6 @@ __device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* 
             info = e.w;
         }
         --rem;
-        // base i's random bits: rb low 2 bits = random.choice(BASES); rp = 16+ uniform bits, MSB-aligned, whose
-        // product with 3 picks one of the three other bases (bias 2^-16)
-        const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
-        const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
-                                  : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2], ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
         uint32_t c = (info >> 8) & 0xffu;
         if (info & EMIT_F_REF) {
             c = __ldg(cbase + rabs);
@@ -151,20 +207,121 @@ __device__ __forceinline__ void emit_chunk16(const uint4* ring, const uint32_t* 
         }
         const uint32_t code = cvt[c];
         bad |= code;
-        uint32_t v = code | (rb & info & 3u);
-        if (info & EMIT_F_MIS) v += 1u + __umulhi(rp, 3u);
+        uint32_t v = code | ((R.RB >> (2 * i)) & info & 3u);
+        if (info & EMIT_F_MIS) v += mis_offset(R, Q.LB, (uint32_t)i);
         sel += v << (4 * (i & 3));
         if (FASTQ) {
-            const uint32_t w = W[i];
+            const uint32_t w = Q.W[i];
             const uint32_t e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(lut) + (info >> 16) +
-                                                                  ((w >> 19) & 0x1ffcu));
-            slow |= e;
-            sq[i >> 2] |= qual_char_fast(e, w) << (8 * (i & 3));
+                                                                  ((w >> 6) & 0x1ffcu));
+            sq[i >> 2] |= (qual_pick(e, w) & 0xffu) << (8 * (i & 3));
         }
         if ((i & 3) == 3) {
             sb[i >> 2] = __byte_perm(tbl, 0, sel & 0x3333u);
             sel = 0;
         }
+    }
+}
+
+// 16 2-bit fields -> reversed order (field 15 first)
+__device__ __forceinline__ uint32_t reverse_pairs(uint32_t x) {
+    x = __brev(x);
+    return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+// the low 16 bits hold 8 2-bit base indices -> one index per nibble (PRMT selectors for two output words)
+__device__ __forceinline__ uint32_t spread_pairs(uint32_t h) {
+    uint32_t t = (h | (h << 8)) & 0x00ff00ffu;
+    t = (t | (t << 4)) & 0x0f0f0f0fu;
+    return (t | (t << 2)) & 0x33333333u;
+}
+
+// ---- FAST route: one chunk from the 2-bit reference copy, entry by entry (see the header comment).
+// pk = the packed reference, pk0w = the chromosome's first word in it; ring_s = shared-memory address of the warp's ring; k = ring index of the entry
+// covering the chunk's first base; cs = padded piece coordinate of that base.  RDIR: the reference is walked backwards.
+// Returns the accumulator of 16 2-bit base indices; S = their 2-bit quality states, mism = mask of substituted bases.
+template <bool RDIR>
+__device__ __forceinline__ uint32_t emit_walk_entries(uint32_t ring_s, const uint32_t* __restrict__ pk, uint32_t pk0w, uint32_t RB,
+                                                      uint32_t& k, uint32_t cs, uint32_t& S, uint32_t& mism) {
+    uint32_t acc = 0;
+    S = 0;
+    mism = 0;
+    for (;;) {
+        uint4 e;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(ring_s + ((k & (EMIT_RING - 1)) << 4)));
+        const uint32_t x0 = e.x, x1 = e.x + e.z, info = e.w;
+        const uint32_t lo = (x0 > cs ? x0 : cs) - cs;                       // first chunk position of the entry
+        const uint32_t hi = (x1 < cs + 16u ? x1 : cs + 16u) - cs;           // one past its last
+        const uint32_t m = (0xffffffffu >> (32u - 2u * (hi - lo))) << (2u * lo);
+        uint32_t v;
+        if (info & EMIT_F_REF) {
+            const uint32_t within = cs + lo - x0;
+            uint32_t r16;
+            // packed word index = first word of the chromosome + base offset / 16 (32-bit: < 2^32 words = 68 Gbases)
+            if (!RDIR) {
+                const uint32_t l = e.y + within;
+                const uint32_t* q = pk + (pk0w + (l >> 4));
+                r16 = __funnelshift_r(__ldg(q), __ldg(q + 1), (l + l) & 30u);
+            } else {
+                // the 16 bases ENDING at e.y - within, i.e. starting at l - 15 = (l + 1) - 16; for l < 15 the window reaches into
+                // the guard word / the previous chromosome's padding: those bases are masked out
+                const uint32_t l1 = e.y - within + 1u;
+                const uint32_t* q = pk + (pk0w + (l1 >> 4) - 1u);
+                r16 = reverse_pairs(__funnelshift_r(__ldg(q), __ldg(q + 1), (l1 + l1) & 30u));
+            }
+            v = r16 << (2u * lo);
+            if (info & EMIT_F_MIS) mism |= m;
+        } else if (info & EMIT_F_RND) {
+            v = RB;
+        } else {
+            v = ((info >> 9) & 3u) * 0x55555555u;                            // literal run (polyA, homopolymer rewrite)
+        }
+        acc = (acc & ~m) | (v & m);
+        S = (S & ~m) | (((info >> 29) * 0x55555555u) & m);
+        if (x1 >= cs + 16u) break;
+        ++k;
+    }
+    return acc;
+}
+
+template <bool FASTQ>
+__device__ __forceinline__ void emit_chunk16_fast(uint32_t ring_s, const char* lut_s, const uint32_t* __restrict__ pk, uint32_t pk0w, uint32_t& k,
+                                                  uint32_t cs, bool rdir, bool unmapped, uint32_t tbl, uint32_t id_lo, uint32_t id_hi,
+                                                  uint32_t kind, uint32_t chunk, uint2 key, uint32_t (&sb)[4], uint32_t (&sq)[4]) {
+    ChunkAux R;
+    draw_chunk_aux<FASTQ>(R, id_lo, id_hi, kind, chunk, key);
+    uint32_t S, mism;
+    uint32_t acc = rdir ? emit_walk_entries<true>(ring_s, pk, pk0w, R.RB, k, cs, S, mism) : emit_walk_entries<false>(ring_s, pk, pk0w, R.RB, k, cs, S, mism);
+    ChunkQual<FASTQ> Q;                                                     // after the walk: 16 fewer live registers in it
+    draw_chunk_qual<FASTQ>(Q, id_lo, id_hi, kind, chunk, key);
+    // substituted bases: index + 1 + uniform{0,1,2} (mod 4)
+    while (mism) {
+        const uint32_t b = (uint32_t)__ffs((int)mism) - 1u;                  // even bit position = 2 * base
+        mism &= ~(3u << b);
+        const uint32_t orig = (acc >> b) & 3u;
+        const uint32_t nw = (orig + mis_offset(R, Q.LB, b >> 1)) & 3u;
+        acc ^= (orig ^ nw) << b;
+    }
+    {
+        const uint32_t s0 = spread_pairs(acc & 0xffffu), s1 = spread_pairs(acc >> 16);
+        sb[0] = __byte_perm(tbl, 0, s0);
+        sb[1] = __byte_perm(tbl, 0, s0 >> 16);
+        sb[2] = __byte_perm(tbl, 0, s1);
+        sb[3] = __byte_perm(tbl, 0, s1 >> 16);
+    }
+    if (FASTQ) {
+        if (unmapped) S = 0;
+        uint32_t q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t w = Q.W[i];
+            // state << 13 | slot << 2
+            const uint32_t st = (2 * i <= 13) ? (S << (13 - 2 * i)) : (S >> (2 * i - 13));
+            const uint32_t off = (st & 0x6000u) | ((w >> 6) & 0x1ffcu);
+            q[i] = qual_pick(*reinterpret_cast<const uint32_t*>(lut_s + off), w);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            sq[g] = __byte_perm(__byte_perm(q[4 * g], q[4 * g + 1], 0x0040), __byte_perm(q[4 * g + 2], q[4 * g + 3], 0x0040), 0x5410);
     }
 }
 
@@ -175,6 +332,8 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
     uint8_t* cvt_tables = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = reinterpret_cast<uint4*>(cvt_tables + 512) + warp * EMIT_RING;
+    uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    asm volatile("" : "+r"(ring_s));       // opaque: kept in a register instead of being re-derived from threadIdx in the walk loop
     if (FASTQ)
         for (int i = threadIdx.x; i < NS_N_QUAL_STATES * QLUT_SIZE; i += blockDim.x) lut[i] = a.qlut[i];
     {   // case_convert classification: base index 0..3 (A C T G), 4 = needs the IUPAC path
@@ -228,6 +387,15 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         const bool unmapped = NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT;
         const uint32_t id_lo = (uint32_t)pc.rid, id_hi = (uint32_t)(pc.rid >> 32);
         const uint32_t info_pad = emit_op_info(NS_OP_HT << 28, unmapped, ref_comp);
+        // route: the fast one needs a forward-complement piece that stays inside its chromosome and whose packed words hold
+        // no exception (IUPAC code, other character)
+        const uint64_t pk0 = a.ref.pk_off[pm.chrom];
+        bool fast = !wraps && !ref_comp && !a.force_exact;
+        if (fast && ref_len) {
+            const uint64_t w_lo = pk0 + (pm.pos >> 4), w_hi = pk0 + ((pm.pos + ref_len - 1u) >> 4);
+            fast = __ldg(&a.ref.exc_pre[(w_hi >> REF_EXC_BLOCK_SHIFT) + 1]) == __ldg(&a.ref.exc_pre[w_lo >> REF_EXC_BLOCK_SHIFT]);
+        }
+        const char* lut_s = reinterpret_cast<const char*>(lut) + (unmapped ? 4u * QLUT_SIZE * 4u : 0u);
 
         uint32_t t_loaded = 0, w_loaded = 0, w_ret = 0, out_loaded = pad, ref_loaded = 0, prog = 0;
         bool closed = false;
@@ -281,50 +449,38 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
                     if (ring[mid & (EMIT_RING - 1)].x <= cs) l = mid; else h = mid;
                 }
                 k = l;
-                uint32_t rem, rabs, info;
-                {
-                    const uint4 e = ring[k & (EMIT_RING - 1)];
-                    const uint32_t within = cs - e.x;
-                    rem = e.z - within;
-                    info = e.w;
-                    rabs = rdir ? e.y - within : e.y + within;
-                    if (wraps && rabs >= clen) rabs += wrap_fix;
-                }
-                // ---- all randomness of the chunk up front, position-indexed: base i owns one 32-bit word (FASTQ: low
-                //      byte = base choice, high 24 bits = quality uniform) or one byte (FASTA)
+                // ---- all randomness of the chunk is position-indexed: (read id, chunk index in read coordinates)
                 const uint32_t chunk = (P0 + cs) >> 4;
-                uint32_t W[FASTQ ? 16 : 4];
-                if (FASTQ) {
-                    const uint32_t sw = stream_word(ST_EMIT_Q, a.kind, chunk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, sw, (uint32_t)j), key);
-                        W[4 * j] = t.x; W[4 * j + 1] = t.y; W[4 * j + 2] = t.z; W[4 * j + 3] = t.w;
-                    }
-                } else {
-                    const uint4 t = philox4x32_7(make_uint4(id_lo, id_hi, stream_word(ST_EMIT_B, a.kind, chunk), 0u), key);
-                    W[0] = t.x; W[1] = t.y; W[2] = t.z; W[3] = t.w;
-                }
                 uint32_t sb[4], sq[4] = {0, 0, 0, 0};
-                uint32_t bad = 0, slow = 0;
-                // three instantiations: plain, circular wrap, complementing (minus-strand genome pieces; keeps the wrap check)
-                if (ref_comp) emit_chunk16<FASTQ, true, true>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
-                else if (wraps) emit_chunk16<FASTQ, true, false>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
-                else emit_chunk16<FASTQ, false, false>(ring, lut, cvt_tables, cbase, W, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad, slow);
-                // ---- rare exact paths, one base at a time
-                if ((bad & 4u) || (FASTQ && (slow & 0x80u))) {
+                if (fast) {
+                    emit_chunk16_fast<FASTQ>(ring_s, lut_s, a.ref.packed, (uint32_t)pk0, k, cs, rdir, unmapped, tbl, id_lo, id_hi, a.kind, chunk, key, sb, sq);
+                } else {
+                    ChunkAux R;
+                    ChunkQual<FASTQ> Q;
+                    draw_chunk_aux<FASTQ>(R, id_lo, id_hi, a.kind, chunk, key);
+                    draw_chunk_qual<FASTQ>(Q, id_lo, id_hi, a.kind, chunk, key);
+                    uint32_t rem, rabs, info;
+                    {
+                        const uint4 e = ring[k & (EMIT_RING - 1)];
+                        const uint32_t within = cs - e.x;
+                        rem = e.z - within;
+                        info = e.w;
+                        rabs = rdir ? e.y - within : e.y + within;
+                        if (wraps && rabs >= clen) rabs += wrap_fix;
+                    }
+                    uint32_t bad = 0;
+                    // three instantiations: plain, circular wrap, complementing (minus-strand genome pieces; keeps the wrap check)
+                    if (ref_comp) emit_chunk16<FASTQ, true, true>(ring, lut, cvt_tables, cbase, R, Q, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad);
+                    else if (wraps) emit_chunk16<FASTQ, true, false>(ring, lut, cvt_tables, cbase, R, Q, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad);
+                    else emit_chunk16<FASTQ, false, false>(ring, lut, cvt_tables, cbase, R, Q, k, rem, rabs, info, dir, clen, wrap_fix, tbl, sb, sq, bad);
+                    // ---- rare: IUPAC codes, one base at a time
+                    if (bad & 4u) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const bool need = (bad & 4u) || (FASTQ && ((sq[i >> 2] >> (8 * (i & 3))) & 0x80u));
-                        if (need) {
-                            const uint32_t rb = FASTQ ? W[i] : W[i >> 2] >> (8 * (i & 3));
-                            const uint32_t rp = FASTQ ? __byte_perm(W[i], W[(i + 1) & 15], 0x0444)
-                                                      : __byte_perm(W[i >> 2], W[((i + 1) & 15) >> 2],
-                                                                    ((i & 3) << 12) | ((4 + ((i + 1) & 3)) * 0x111));
-                            const uint32_t f = emit_fix_base<FASTQ>(a, pc, ring, w_ret, w_loaded, cs + i, rb, rp);
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t f = emit_fix_base(a, pc, ring, w_ret, w_loaded, cs + i, (R.RB >> (2 * i)) & 3u,
+                                                             mis_offset(R, Q.LB, (uint32_t)i));
                             const uint32_t m = 0xffu << (8 * (i & 3));
-                            sb[i >> 2] = (sb[i >> 2] & ~m) | ((f & 0xffu) << (8 * (i & 3)));
-                            if (FASTQ) sq[i >> 2] = (sq[i >> 2] & ~m) | ((f >> 8) << (8 * (i & 3)));
+                            sb[i >> 2] = (sb[i >> 2] & ~m) | (f << (8 * (i & 3)));
                         }
                     }
                 }

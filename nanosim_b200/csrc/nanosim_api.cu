@@ -75,11 +75,11 @@ struct NsContext {
 
     bool borrowed = false;          // ns_clone: reference + model buffers belong to the parent
     bool have_ref = false, have_model = false, have_cfg = false;
-    DevBuf ref_bases, ref_off;
+    DevBuf ref_bases, ref_off, ref_packed, ref_pk_off, ref_exc;
     DevRef dref{};
     std::vector<uint64_t> h_chrom_off;
 
-    DevBuf kde[5], alias, qlut, qcdf, ref_species, ref_circular, ref_sp_off, kde2d_x, kde2d_y, expr_alias, expr_chrom, chrom_polya;
+    DevBuf kde[5], alias, qlut, ref_species, ref_circular, ref_sp_off, kde2d_x, kde2d_y, expr_alias, expr_chrom, chrom_polya;
     bool have_expr = false;
     std::vector<uint32_t> h_sp_off;
     std::vector<double> abun, abun_inflated, species_bases;     // metagenome: dict_abun, dict_abun_inflated, running totals
@@ -153,6 +153,39 @@ __global__ void add_base_u64(uint64_t* v, uint32_t n, uint64_t base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += base;
 }
+// ns_set_reference: the 2-bit copy of the reference (DevRef::packed).  One thread per packed word; exceptions (bytes
+// that are not a/c/g/t in either case) are counted per 256-word block, other[0] counts bytes that are not even an IUPAC
+// nucleotide code (case_convert passes those through unchanged, so reads may then hold characters other than ACGT).
+__global__ void pack_reference_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ chrom_off,
+                                      const uint64_t* __restrict__ pk_off, uint32_t n_chrom, uint32_t* __restrict__ packed,
+                                      uint64_t n_words, uint32_t* __restrict__ exc_cnt, unsigned long long* other) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    // chromosome of this word: last c with pk_off[c] <= w
+    uint32_t lo = 0, hi = n_chrom;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pk_off[mid] <= w) lo = mid; else hi = mid;
+    }
+    const uint64_t cstart = chrom_off[lo], clen = chrom_off[lo + 1] - cstart;
+    const uint64_t first = (w - pk_off[lo]) * 16;
+    uint32_t word = 0, n_exc = 0, n_other = 0;
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (first + j >= clen) break;
+        uint32_t c = bases[cstart + first + j];
+        if (c - 'a' < 26u) c -= 32;
+        if (acgt_fast(c)) {
+            word |= base_idx(c) << (2 * j);
+        } else {
+            ++n_exc;
+            if (resolve_iupac(c, 0u, 0u) == c) ++n_other;      // not in case_convert's table: passes through unchanged
+        }
+    }
+    packed[w] = word;
+    if (n_exc) atomicAdd(&exc_cnt[w >> REF_EXC_BLOCK_SHIFT], n_exc);
+    if (n_other) atomicAdd(other, (unsigned long long)n_other);
+}
+
 // Bases leave the device as 2 bits each (the emit kernel only writes A C G T/U): 16 ASCII bytes -> one 32-bit word,
 // base j of a byte quadruple in bits [2j, 2j+1], code = (c >> 1) & 3 (A 0, C 1, T/U 2, G 3).  ns_fetch expands them again
 // on the host, so callers see the same ASCII buffers while the PCIe transfer of a FASTQ batch shrinks from 2 to 1.25 B/base.
@@ -311,33 +344,48 @@ cudaError_t upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, s);
 }
 
-// Bucket table over 24-bit quality uniforms; entry layout in device_common.cuh (qual_char_fast).
-// A draw u24 falls into bucket u24 >> QLUT_FRAC_BITS; when the bucket holds at most one cdf boundary the quality is
-// q_lo + (frac >= threshold); buckets with two or more boundaries (rare tail qualities) are flagged for an exact scan.
-void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut, std::vector<uint32_t>& cdf24) {
+// Base-quality sampler tables (emit_kernel.cuh:qual_pick).  The truncated log-normal of a state, floored to integers
+// (model_base_qualities.py:9-20, 120-130), arrives as a 32-bit cdf; it is rounded to a 24-bit pmf (masses sum to 2^24) and
+// laid out as a Walker alias table with QLUT_SIZE = 2048 slots of capacity 2^13: slot j holds a primary and an alias
+// quality and the primary's share t of the slot, so a 24-bit draw (11 bits slot, 13 bits u) returns the primary iff u < t.
+// All arithmetic is in integers: the table realises the 24-bit pmf exactly.  Entry: t << 19 | alias char << 8 | primary
+// char (ASCII = q + 33); a slot that holds one quality only stores it twice (t is then irrelevant).
+void build_qlut(const uint32_t cdf32[NS_N_QUAL_STATES][NS_QUAL_SLOTS], std::vector<uint32_t>& lut) {
     lut.assign((size_t)NS_N_QUAL_STATES * QLUT_SIZE, 0);
-    cdf24.assign((size_t)NS_N_QUAL_STATES * NS_QUAL_SLOTS, 0);
-    const uint32_t shift = QLUT_FRAC_BITS;
+    const uint32_t cap = 1u << (24 - QLUT_BITS);
     for (int s = 0; s < NS_N_QUAL_STATES; ++s) {
-        uint32_t* c = &cdf24[(size_t)s * NS_QUAL_SLOTS];
+        uint32_t c24[NS_QUAL_SLOTS];
         for (int q = 0; q < NS_QUAL_SLOTS; ++q) {
             uint64_t v = ((uint64_t)cdf32[s][q] + 128u) >> 8;
-            c[q] = (uint32_t)std::min<uint64_t>(v, 1u << 24);
+            c24[q] = (uint32_t)std::min<uint64_t>(v, 1u << 24);
+            if (q && c24[q] < c24[q - 1]) c24[q] = c24[q - 1];
         }
-        c[NS_QUAL_SLOTS - 1] = 1u << 24;
-        auto qof = [&](uint32_t u) {
-            uint32_t q = 0;
-            while (q < NS_QUAL_SLOTS - 1 && u >= c[q]) ++q;
-            return q;
-        };
-        for (uint32_t b = 0; b < QLUT_SIZE; ++b) {
-            uint32_t lo = b << shift, hi = lo + ((1u << shift) - 1u);
-            uint32_t qlo = qof(lo), qhi = qof(hi);
-            uint32_t e;
-            if (qhi == qlo) e = (qlo + 32u);                                   // threshold 0: always +1 (qlo >= 1)
-            else if (qhi == qlo + 1) e = (qlo + 33u) | ((c[qlo] - lo) << 19);   // 1 <= c[qlo] - lo < 2^13
-            else e = 0x80u | (qlo << 8);
-            lut[(size_t)s * QLUT_SIZE + b] = e;
+        c24[NS_QUAL_SLOTS - 1] = 1u << 24;
+        std::vector<uint32_t> mass(QLUT_SIZE, 0u), thr(QLUT_SIZE, 0u), prim(QLUT_SIZE), ali(QLUT_SIZE);
+        for (int q = 0; q < NS_QUAL_SLOTS; ++q) mass[q] = c24[q] - (q ? c24[q - 1] : 0u);
+        std::vector<uint32_t> small, large;
+        for (uint32_t j = 0; j < QLUT_SIZE; ++j) {
+            prim[j] = ali[j] = j;
+            (mass[j] < cap ? small : large).push_back(j);
+        }
+        while (!small.empty() && !large.empty()) {
+            const uint32_t a = small.back(), g = large.back();
+            small.pop_back();
+            large.pop_back();
+            thr[a] = mass[a];                   // the rest of slot a, cap - mass[a], is taken from g
+            ali[a] = g;
+            mass[g] -= cap - mass[a];
+            (mass[g] < cap ? small : large).push_back(g);
+        }
+        // what is left holds exactly `cap` (the masses are integers that sum to QLUT_SIZE * cap): pure slots
+        for (uint32_t j : small) { thr[j] = 0; ali[j] = prim[j]; }
+        for (uint32_t j : large) { thr[j] = 0; ali[j] = prim[j]; }
+        // a slot index >= 94 is not a quality: such slots had no mass and are aliased entirely (thr 0)
+        for (uint32_t j = 0; j < QLUT_SIZE; ++j) {
+            uint32_t pq = prim[j], aq = ali[j];
+            if (pq >= (uint32_t)NS_QUAL_SLOTS) pq = aq;
+            if (aq >= (uint32_t)NS_QUAL_SLOTS) aq = pq;           // cannot happen: only slots with mass are aliases
+            lut[(size_t)s * QLUT_SIZE + j] = (thr[j] << 19) | ((aq + 33u) << 8) | (pq + 33u);
         }
     }
 }
@@ -380,13 +428,13 @@ int ns_destroy(NsContext* ctx) {
     if (!ctx) return NS_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->reads, &ctx->pieces,
+    DevBuf* bufs[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->ref_packed, &ctx->ref_pk_off, &ctx->ref_exc, &ctx->alias, &ctx->qlut, &ctx->reads, &ctx->pieces,
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
                       &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev, &ctx->kde2d_x, &ctx->kde2d_y,
                       &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
-        DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->alias, &ctx->qlut, &ctx->qcdf, &ctx->ref_species,
+        DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->ref_packed, &ctx->ref_pk_off, &ctx->ref_exc, &ctx->alias, &ctx->qlut, &ctx->ref_species,
                             &ctx->ref_circular, &ctx->ref_sp_off, &ctx->kde2d_x, &ctx->kde2d_y, &ctx->expr_alias,
                             &ctx->expr_chrom, &ctx->chrom_polya};
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
@@ -418,9 +466,11 @@ int ns_clone(NsContext* parent, NsContext** out) {
     c->have_cfg = parent->have_cfg;
     c->ref_bases = parent->ref_bases;      // plain pointer copies; ns_destroy() of a clone does not free them
     c->ref_off = parent->ref_off;
+    c->ref_packed = parent->ref_packed;
+    c->ref_pk_off = parent->ref_pk_off;
+    c->ref_exc = parent->ref_exc;
     c->alias = parent->alias;
     c->qlut = parent->qlut;
-    c->qcdf = parent->qcdf;
     c->ref_species = parent->ref_species;
     c->ref_circular = parent->ref_circular;
     c->ref_sp_off = parent->ref_sp_off;
@@ -464,6 +514,38 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->dref.bases = ctx->ref_bases.as<uint8_t>();
     ctx->dref.chrom_off = ctx->ref_off.as<uint64_t>();
+    {   // 2-bit copy + exception counts for the emit kernel's fast path
+        std::vector<uint64_t> pk(ref->n_chrom + 1);
+        uint64_t words = 1;                                             // guard word in front
+        for (uint32_t i = 0; i < ref->n_chrom; ++i) {
+            pk[i] = words;
+            words += (ctx->h_chrom_off[i + 1] - ctx->h_chrom_off[i] + 15) / 16;
+        }
+        pk[ref->n_chrom] = words;
+        const uint64_t n_blocks = ((words + 2) >> REF_EXC_BLOCK_SHIFT) + 2;
+        CK(ctx->ref_packed.ensure((size_t)(words + 2) * 4));
+        CK(ctx->ref_exc.ensure((size_t)(2 * n_blocks + 2) * 4 + 16));
+        CK(upload(ctx->ref_pk_off, pk.data(), pk.size() * sizeof(uint64_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->ref_packed.p, 0, (size_t)(words + 2) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->ref_exc.p, 0, (size_t)(2 * n_blocks + 2) * 4 + 16, ctx->stream));
+        uint32_t* cnt = ctx->ref_exc.as<uint32_t>() + n_blocks + 1;     // counts behind the prefix array
+        unsigned long long* other = (unsigned long long*)(ctx->ref_exc.as<uint32_t>() + ((2 * n_blocks + 2 + 1) & ~1ull));
+        pack_reference_kernel<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->ref_bases.as<uint8_t>(), ctx->ref_off.as<uint64_t>(), ctx->ref_pk_off.as<uint64_t>(), ref->n_chrom,
+            ctx->ref_packed.as<uint32_t>(), words, cnt, other);
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, ctx->ref_exc.as<uint32_t>(), (int)(n_blocks + 1), ctx->stream));
+        CK(ctx->scan_tmp.ensure(tmp));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, cnt, ctx->ref_exc.as<uint32_t>(), (int)(n_blocks + 1), ctx->stream));
+        unsigned long long h_other = 0;
+        CK(cudaMemcpyAsync(&h_other, other, sizeof h_other, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->dref.packed = ctx->ref_packed.as<uint32_t>();
+        ctx->dref.pk_off = ctx->ref_pk_off.as<uint64_t>();
+        ctx->dref.exc_pre = ctx->ref_exc.as<uint32_t>();
+        ctx->dref.all_iupac = h_other == 0 ? 1u : 0u;
+    }
     ctx->dref.genome_len = ref->n_bases;
     ctx->dref.n_chrom = ref->n_chrom;
     ctx->dref.n_species = 0;
@@ -569,10 +651,9 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
     memcpy(d.trans, m->trans, sizeof d.trans);
     d.strandness = m->strandness_rate;
     d.seg_p = m->segment_mean > 1.0f ? 1.0 / (double)m->segment_mean : 1.0;
-    std::vector<uint32_t> lut, cdf24;
-    build_qlut(m->qual_cdf, lut, cdf24);
+    std::vector<uint32_t> lut;
+    build_qlut(m->qual_cdf, lut);
     CK(upload(ctx->qlut, lut.data(), lut.size() * 4, ctx->stream));
-    CK(upload(ctx->qcdf, cdf24.data(), cdf24.size() * 4, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_model = true;
     ctx->have_batch = false;
@@ -770,7 +851,7 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
     ea.seq = ctx->seq.as<uint8_t>();
     ea.qual = ctx->qual.as<uint8_t>();
     ea.qlut = ctx->qlut.as<uint32_t>();
-    ea.qcdf = ctx->qcdf.as<uint32_t>();
+    ea.force_exact = (ctx->hcfg.flags & NS_FLAG_EMIT_EXACT) ? 1u : 0u;
     ea.counter = ctx->counter.as<uint32_t>();
     ea.order = order;
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
@@ -1186,7 +1267,8 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
     cudaStream_t st = ctx->stream;
     if (bi.n_reads == 0) return NS_OK;
     if (qual && !ctx->hcfg.fastq) return fail(ctx, NS_ESTATE, "ns_fetch: qualities requested but the run is not --fastq");
-    const int nt = unpack_threads();
+    // 2 bits per base only when reads cannot hold anything but A C G T/U: every reference byte is an IUPAC nucleotide code
+    const int nt = ctx->dref.all_iupac ? unpack_threads() : 0;
     const bool packed = seq && nt > 0 && bi.seq_bytes >= (1u << 20);
     if (packed) {
         // bases: pack on the device, copy a quarter of the bytes, expand on the host while the other copies run
@@ -1226,6 +1308,14 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
     if (trace)
         fprintf(stderr, "ns_fetch: %.2f GB bases; packed copy done after %.1f ms, expansion %.1f ms (%d threads), everything after %.1f ms\n",
                 bi.seq_bytes / 1e9, t_packed, t_unpacked - t_packed, nt, ms_since());
+    return NS_OK;
+}
+
+int ns_transfer_info(NsContext* ctx, uint32_t* packed_bases, uint32_t* n_threads) {
+    if (!ctx) return NS_EINVAL;
+    const int nt = (!ctx->have_ref || ctx->dref.all_iupac) ? unpack_threads() : 0;
+    if (packed_bases) *packed_bases = nt > 0 ? 1u : 0u;
+    if (n_threads) *n_threads = (uint32_t)nt;
     return NS_OK;
 }
 

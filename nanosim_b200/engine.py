@@ -93,10 +93,19 @@ class Engine:
         i = np.ascontiguousarray(inflated, dtype=np.float64) if inflated is not None else None
         self._check(self._lib.ns_set_abundance(self._ctx, _ptr(a), _ptr(i), len(a)))
 
-    def set_reference_ptr(self, bases_ptr, n_bases, offsets):
+    def set_reference_ptr(self, bases_ptr, n_bases, offsets, chrom_species=None, chrom_circular=None, n_species=0):
+        """Reference whose bases already sit in device (or pinned host) memory, e.g. after an NCCL broadcast."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-        r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1, 0, None, None)
+        sp = np.ascontiguousarray(chrom_species, dtype=np.uint32) if n_species else None
+        circ = np.ascontiguousarray(chrom_circular, dtype=np.uint8) if n_species else None
+        r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1, int(n_species), _ptr(sp), _ptr(circ))
         self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
+
+    def fetch_packs_bases(self):
+        """True when ns_fetch sends the bases over PCIe as 2 bits each (ns_transfer_info)."""
+        packed, threads = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.ns_transfer_info(self._ctx, C.byref(packed), C.byref(threads)))
+        return bool(packed.value)
 
     def set_model(self, t: DeviceTables, perfect=False):
         m = L.NsModel()
@@ -157,10 +166,11 @@ class Engine:
 
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
                   max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False,
-                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0, trx_records=0):
+                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0, trx_records=0, emit_exact=False):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
-        flags = (L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0) | (L.NS_FLAG_URACIL if uracil else 0)
+        flags = (L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0) | (L.NS_FLAG_URACIL if uracil else 0) | \
+            (L.NS_FLAG_EMIT_EXACT if emit_exact else 0)
         cfg = L.NsRunConfig(2 if transcriptome else (1 if metagenome else 0), int(circular), int(perfect), int(fastq),
                             int(chimeric), int(kmer_bias or 0), int(min_len), int(min(max_len, 0x0fffffff)),
                             float(median_len or 0.0), float(sd_len or 0.0), flags, int(kde2d_sample), float(polya_scale or 0.0),

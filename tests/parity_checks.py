@@ -51,7 +51,7 @@ def load_tables(model, **kw):
 
 
 def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, min_len=50, max_len=None, circular=False,
-                device=0, unaligned_scripts=False, kmer_bias=0):
+                device=0, unaligned_scripts=False, kmer_bias=0, emit_exact=False):
     from nanosim_b200.engine import Engine
 
     cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect, homopolymer=bool(kmer_bias))
@@ -60,7 +60,7 @@ def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, m
     eng.set_model(t, perfect=perfect)
     eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
                   max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts,
-                  kmer_bias=kmer_bias)
+                  kmer_bias=kmer_bias, emit_exact=emit_exact)
     return eng, cm, t
 
 
@@ -474,10 +474,31 @@ def tags_to_ops(tags, middle_ref):
     return ops
 
 
-def script_stats(op_lists):
+def canonical_indels(ops):
+    """Inserted and deleted bases that touch each other have no defined order (the read is the same whether the gap is
+    written DEL INS DEL or INS DEL): every maximal run of INS / DEL ops becomes one INS followed by one DEL."""
+    out, ins, dele = [], 0, 0
+    for t, n in list(ops) + [(0, 0)]:
+        if t == 2:
+            ins += n
+        elif t == 3:
+            dele += n
+        else:
+            if ins:
+                out.append((2, ins))
+            if dele:
+                out.append((3, dele))
+            ins = dele = 0
+            out.append((t, n))
+    return out[:-1]
+
+
+def script_stats(op_lists, canonical=False):
     """Event statistics of a list of op lists [(type, len), ...]: the run_stats event keys."""
     s = rs.empty()
     for ops in op_lists:
+        if canonical:
+            ops = canonical_indels(ops)
         merged = []
         for t, n in ops:
             if n == 0:

@@ -82,6 +82,38 @@ def test_unaligned_fast_path_equals_scripted_path(model, fastq, mini_ref, L):
     assert bf.reads["attempts"].max() > 0
 
 
+def _reads_bytes(b, fastq):
+    out = []
+    for r in b.reads:
+        a, n = int(r["seq_off"]), int(r["seq_len"])
+        out.append((b.seq[a:a + n].tobytes(), b.qual[a:a + n].tobytes() if fastq else b""))
+    return out
+
+
+@pytest.mark.parametrize("model,kw", [("guppy", dict(fastq=True)), ("guppy", dict(fastq=False)),
+                                      ("dorado", dict(fastq=True, chimeric=True)), ("dorado", dict(fastq=True, chimeric=True, kmer_bias=6))])
+def test_emit_fast_route_equals_exact_route(model, kw, ecoli, mini_ref, L):
+    """The emit kernel reads plain-ACGT stretches from the 2-bit copy of the reference, 16 bases per entry (fast route), and
+    everything else byte by byte (exact route).  Same seed => same bytes on either route: on a pure-ACGT reference every
+    piece is fast, NS_FLAG_EMIT_EXACT forces the other route; on the IUPAC / lower-case mini reference the routes mix."""
+    fastq = kw.get("fastq", False)
+    for ref in (ecoli, mini_ref):
+        got = {}
+        for exact in (False, True):
+            eng, _, _ = pc.make_engine(model, ref, seed=314, emit_exact=exact, **kw)
+            eng.simulate(L.NS_KIND_ALIGNED, 11, 4000)
+            b = eng.fetch(want_ops=True)
+            if not exact:
+                assert pc.check_edit_scripts(b, ref, fastq, max_reads=300) > 0
+            rows = _reads_bytes(b, fastq)
+            eng.simulate(L.NS_KIND_UNALIGNED, 5, 800)
+            rows += _reads_bytes(eng.fetch(), fastq)
+            eng.close()
+            got[exact] = rows
+        n_diff = sum(x != y for x, y in zip(got[False], got[True]))
+        assert len(got[False]) == len(got[True]) == 4800 and n_diff == 0, "%d reads differ between the routes" % n_diff
+
+
 def test_unaligned_event_scripts_vs_oracle(ecoli, L, tmp_path):
     """unaligned_error_list (simulator.py:1784-1830: 0.4/0.3/0.15/0.15 step mix, insertions merged at pos+0.1) and what
     mutate_read makes of its e_dict (:1957-1995) against the pinned oracle: the device's scripted unaligned path on 2500
@@ -97,7 +129,7 @@ def test_unaligned_event_scripts_vs_oracle(ecoli, L, tmp_path):
     eng.close()
     assert pc.check_edit_scripts(b, ecoli, False) > 0
     dev_ops = [pc.device_piece_ops(b, pcs) for pcs in b.pieces]
-    s_dev = pc.script_stats(dev_ops)
+    s_dev = pc.script_stats(dev_ops, canonical=True)       # INS/DEL that touch have no order
     m = oracle_model(cm, tmp_path, fastq=False)
     random.seed(99)
     np.random.seed(99)
@@ -118,7 +150,7 @@ def test_unaligned_event_scripts_vs_oracle(ecoli, L, tmp_path):
         or_ops.append(pc.tags_to_ops(tags, middle_ref))
         d_len_or.append((len(tags) - m_ref, middle_ref - m_ref))
         d_len_dev.append((int(pcs["out_len"]) - m_ref, int(pcs["ref_len"]) - m_ref))
-    s_or = pc.script_stats(or_ops)
+    s_or = pc.script_stats(or_ops, canonical=True)
     rd, ro = pc.rates(s_dev), pc.rates(s_or)
     print("unaligned per-reference-base event bases device", rd, "oracle", ro)
     fails = pc.compare_stats(s_dev, s_or, rate_tol=0.02, p_min=1e-5, label="unaligned-scripts",
