@@ -315,10 +315,14 @@ def main():
         sref = build_reference(args.workload, local, args.ref_scale, torch.cuda.is_available())
         pool = OraclePool(args.workload, sref, n_procs)
         del sref
-        per_worker = args.cpu_reads or (400 if W["mode"] != "transcriptome" else 1500)
+        # a step = a bounded sample: sized from the first (untimed) step so that a timed step takes about 6 s of wall clock
+        probe = 16 if W["mode"] != "transcriptome" else 64
+        pool.step(probe)
+        _, pr_reads, pr_wall, _ = pool.step(probe)
+        per_worker = args.cpu_reads or int(min(4000, max(probe, 6.0 * probe / max(pr_wall, 1e-3))))
         vals = []
         for s in range(args.warmup + args.steps):
-            bases, nreads, wall, wsum = pool.step(per_worker if s >= args.warmup else max(8, per_worker // 10))
+            bases, nreads, wall, wsum = pool.step(per_worker if s >= args.warmup else max(8, per_worker // 8))
             if s >= args.warmup:
                 vals.append((bases, nreads, wall, wsum))
         pool.close()
@@ -340,6 +344,9 @@ def main():
     from nanosim_b200.engine import Engine
     from nanosim_b200.model import CompiledModel, DeviceTables, build_alias
 
+    from nanosim_b200 import hostbind
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    binding = hostbind.bind_to_gpu_node(local)       # this rank's threads and pinned buffers next to its GPU
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     dist = None
@@ -548,10 +555,14 @@ def main():
                                  "stretches every per-launch duration)" % (kernel, len(al1), n_al),
                      "whole_path_frac": algo_bytes * total_bases / (t_ms * 1e-3) / 1e9 / peak / max(world, 1)},
     }
+    line["host"] = {"cpus": cores, "cpus_allowed": len(all_cpus) if all_cpus else None, "numa_binding": binding}
     if keep_host:
+        hostbind.unbind(all_cpus)                                # the CPU baseline may use every core of the box
         pool = OraclePool(args.workload, sref, n_procs)
-        per_worker = args.cpu_reads or (1000 if W["mode"] != "transcriptome" else 3000)
-        pool.step(max(8, per_worker // 20))                      # the workers' first call (lazy imports, page faults)
+        probe = 16 if W["mode"] != "transcriptome" else 64
+        pool.step(probe)                                         # the workers' first call (lazy imports, page faults)
+        _, _, pr_wall, _ = pool.step(probe)
+        per_worker = args.cpu_reads or int(min(8000, max(probe, 15.0 * probe / max(pr_wall, 1e-3))))     # ~15 s of wall clock
         cb, cr, ct, cw = pool.step(per_worker)
         pool.close()
         line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": n_procs, "kind": "port", "per_core": cb / max(cw, 1e-9),

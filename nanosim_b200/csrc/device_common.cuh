@@ -46,12 +46,17 @@ struct DevRef {
     const uint32_t* expr_chrom;         // expressed transcript -> reference record
     uint32_t n_expressed;
     const uint8_t* chrom_has_polya;     // per reference record (nullptr: no polyA list)
+    // transcript records sorted by length (ns_configure, transcriptome mode): lengths ascending and the record of each
+    const uint32_t* trx_len_sorted;
+    const uint32_t* trx_len_idx;
+    uint32_t n_trx_sorted;
     // 2-bit copy of the reference for the emit kernel's fast path (built once by ns_set_reference): 16 bases per 32-bit
     // word, base j of a word in bits [2j+1:2j], code (c >> 1) & 3 of the upper-cased base (A 0, C 1, T 2, G 3); every
     // chromosome starts at a word boundary (pk_off[chrom], in words); one guard word in front, two behind.  Bytes that
     // case_convert does not map to exactly one of ACGT (IUPAC codes, anything else) are "exceptions" and get code 0:
     // exc_pre[b] = exceptions in packed words [0, 256 b) -- a piece whose words touch none takes the fast path.
     const uint32_t* packed;
+    uint64_t pk_words;                  // packed words incl. the guards (another 64 words of slack are allocated behind them)
     const uint64_t* pk_off;
     const uint32_t* exc_pre;
     uint32_t all_iupac;                 // every reference byte is a nucleotide code case_convert turns into A C G T

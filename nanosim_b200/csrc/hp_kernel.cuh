@@ -15,6 +15,16 @@
 //
 // The rewritten script uses COPY / DEL (reference skip) / LIT / HT ops only; the emit kernel needs no random draws for
 // its bases.  COUNT pass: new op count and output length per piece; WRITE pass: the scripts.
+//
+// Reads are taken longest first (the plan kernel's order), so the lanes of a warp walk segments of similar length.
+// A segment whose reference span holds plain a/c/g/t only (DevRef::exc_pre) is walked on the 2-bit copy of the reference:
+//   * copied stretches 16 bases per step: equal-neighbour bits of the packed word tell whether any run of >= K equal bases
+//     can start, end or continue inside it; if not -- the usual case -- the word is accounted for with a handful of integer
+//     operations (leading bases join the pending run, the middle becomes a COPY, the trailing run becomes the pending run);
+//     otherwise its 16 bases go through the base-by-base path;
+//   * the error filter reads the 32 reference bases around a position as one 64-bit word and counts the equal neighbours
+//     of the centre base with two count-leading/trailing-zeros.
+// NS_FLAG_EMIT_EXACT switches both shortcuts off (tests: identical scripts either way).
 #pragma once
 #include "device_common.cuh"
 
@@ -31,6 +41,9 @@ struct HpArgs {
     double hp[2][6];            // rows AT, CG: const, alpha1, beta1, breakpoint1, intercept, slope
     double hp_mis_rate;
     uint32_t* counter;
+    const uint32_t* order;      // read slots, longest first (nullptr: identity)
+    uint32_t n_reads;
+    uint32_t force_exact;       // NS_FLAG_EMIT_EXACT: no packed-word shortcuts
 };
 
 #define HP_MAX_SEG 12
@@ -76,8 +89,42 @@ struct HpWalker {
         uint32_t c = converted_ref_base(__ldg(&cb[ab]), seed, rid, piece_in_read, x);
         return acgt_fast(c) ? base_idx(c) : (4u + (c & 3u));            // non-ACGT leftovers never form ACGT runs
     }
+    // ---- 2-bit copy of the reference (only used when the segment's packed words hold no exception and it does not wrap)
+    const uint32_t* pk;       // first packed word of the chromosome
+    bool packed;
+    // 16 bases from segment offset x: base x + j in bits [2j+1:2j]
+    __device__ __forceinline__ uint32_t bases16(uint32_t x) const {
+        const uint32_t l = pos + x;
+        const uint32_t* q = pk + (l >> 4);
+        return __funnelshift_r(__ldg(q), __ldg(q + 1), (l + l) & 30u);
+    }
+    // in_hp on the packed copy (K <= 16): the 32 bases x-15 .. x+16 as 64 bits, fields outside [0, ref_len) and fields that
+    // differ from the centre base marked; the run through x = 1 + equal neighbours on either side
+    __device__ __forceinline__ bool in_hp_packed(int64_t x) const {
+        if (x < 0 || x >= (int64_t)ref_len) return false;
+        const uint32_t L = pos + (uint32_t)x + 1u;                         // window starts at base L - 16 (>= -15: guard word)
+        const uint32_t* q = pk + (L >> 4) - 1;
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), sh = (L + L) & 30u;
+        const uint64_t W = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+        const uint64_t c = (W >> 30) & 3u;                                 // centre = field 15
+        const uint64_t d = W ^ (c * 0x5555555555555555ull);
+        uint64_t ne = (d | (d >> 1)) & 0x5555555555555555ull;             // bit 2j: field j differs from the centre
+        const uint32_t jlo = x < 15 ? 15u - (uint32_t)x : 0u;              // fields below jlo lie before the segment
+        const uint64_t room = (uint64_t)ref_len - (uint64_t)x + 15u;       // fields from here on lie behind it
+        if (jlo) ne |= (1ull << (2u * jlo)) - 1ull;
+        if (room < 32u) ne |= ~((1ull << (2u * (uint32_t)room)) - 1ull);
+        const uint32_t below = (uint32_t)ne & 0x3fffffffu, above = (uint32_t)(ne >> 32);     // fields 0..14 / 16..31
+        const uint32_t right = above ? ((uint32_t)__ffs((int)above) - 1u) >> 1 : 16u;        // equal fields directly above 15
+        return 1u + left_count(below) + right >= K;
+    }
+    __device__ __forceinline__ static uint32_t left_count(uint32_t below) {     // equal fields directly below field 15
+        if (!below) return 15u;
+        const uint32_t top = 31u - (uint32_t)__clz((int)below);               // bit 2j of the nearest differing field j
+        return 14u - (top >> 1);
+    }
     // is offset x inside a run of >= K equal bases of the unmutated segment?
     __device__ __forceinline__ bool in_hp(int64_t x) const {
+        if (packed) return in_hp_packed(x);
         if (x < 0 || x >= (int64_t)ref_len) return false;
         const uint32_t b = base_at((uint32_t)x);
         if (b > 3u) return false;
@@ -92,15 +139,24 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs a) {
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     const uint32_t K = a.cfg.kmer_bias;
+    uint32_t pi = 0, pi_end = 0;
+    NsReadMeta rm;
     for (;;) {
-        const uint32_t pi = atomicAdd(a.counter, 1u);
-        if (pi >= a.n_pieces) break;
-        NsPieceMeta& pm = a.pieces[pi];
-        if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
-            if (!WRITE) a.out_n_ops[pi] = 0;           // untouched pieces keep their script
+        if (pi == pi_end) {                            // next read (longest first); its pieces are walked one after the other
+            uint32_t ri = atomicAdd(a.counter, 1u);
+            if (ri >= a.n_reads) break;
+            if (a.order) ri = a.order[ri];
+            rm = a.reads[ri];
+            pi = rm.piece_first;
+            pi_end = pi + rm.n_pieces;
             continue;
         }
-        const NsReadMeta rm = a.reads[pm.read_slot];
+        NsPieceMeta& pm = a.pieces[pi];
+        const uint32_t this_piece = pi++;
+        if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
+            if (!WRITE) a.out_n_ops[this_piece] = 0;   // untouched pieces keep their script
+            continue;
+        }
         const uint64_t rid = a.first_id + pm.read_slot;
         HpWalker w;
         const uint64_t cstart = a.ref.chrom_off[pm.chrom];
@@ -109,13 +165,23 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
         w.seed = a.cfg.seed;
         w.rid = rid;
         w.pos = pm.pos;
-        w.piece_in_read = pi - rm.piece_first;
+        w.piece_in_read = this_piece - rm.piece_first;
         w.ref_len = pm.ref_len;
         w.K = K;
+        {   // packed-word shortcuts: plain a/c/g/t span that stays inside the chromosome, K small enough for the 32-base window
+            const uint64_t pk0 = a.ref.pk_off[pm.chrom];
+            w.pk = a.ref.packed + pk0;
+            bool ok = !a.force_exact && K <= 16u && pm.ref_len > 0 && (uint64_t)pm.pos + pm.ref_len <= w.clen;
+            if (ok) {
+                const uint64_t w_lo = pk0 + (pm.pos >> 4), w_hi = pk0 + ((pm.pos + pm.ref_len - 1u) >> 4);
+                ok = __ldg(&a.ref.exc_pre[(w_hi >> REF_EXC_BLOCK_SHIFT) + 1]) == __ldg(&a.ref.exc_pre[w_lo >> REF_EXC_BLOCK_SHIFT]);
+            }
+            w.packed = ok;
+        }
         uint32_t* ev = a.ops + pm.ev_off;
         const uint32_t n_ev = pm.ev_n_ops;
         ScriptOut<WRITE> out;
-        out.begin(WRITE ? a.ops + a.out_off[pi] : nullptr);
+        out.begin(WRITE ? a.ops + a.out_off[this_piece] : nullptr);
 
         // ---- current run of equal bases in the mutated stream
         uint32_t run_base = 0xffu, run_len = 0, run_ref = 0, nseg = 0, n_runs = 0;
@@ -195,6 +261,18 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
             nseg = 0;
             run_base = 0xffu;
         };
+        auto add_seg = [&](uint32_t kind, uint32_t cnt) {     // cnt more bases of `kind` in the pending run
+            if (nseg > 0 && seg_kind[nseg - 1] == kind) {
+                seg_cnt[nseg - 1] += cnt;
+            } else if (nseg < HP_MAX_SEG) {
+                seg_kind[nseg] = kind;
+                seg_cnt[nseg] = cnt;
+                ++nseg;
+            } else {
+                seg_cnt[nseg - 1] += cnt;                          // pathological run: lump into the last segment
+                if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
+            }
+        };
         auto feed = [&](uint32_t b, uint32_t kind) {          // one base of the mutated stream
             if (b != run_base || b > 3u) {
                 flush_run();
@@ -202,16 +280,7 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
             }
             ++run_len;
             if (kind != 2) ++run_ref;
-            if (nseg > 0 && seg_kind[nseg - 1] == kind) {
-                ++seg_cnt[nseg - 1];
-            } else if (nseg < HP_MAX_SEG) {
-                seg_kind[nseg] = kind;
-                seg_cnt[nseg] = 1;
-                ++nseg;
-            } else {
-                ++seg_cnt[nseg - 1];                           // pathological run: lump into the last segment
-                if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
-            }
+            add_seg(kind, 1u);
         };
 
         // per-event random bases: Philox-7 block per op, one byte per base
@@ -244,7 +313,49 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 }
             }
             if (ty == NS_OP_COPY) {
-                for (uint32_t t = 0; t < len; ++t) feed(w.base_at(rpos + t), 0);
+                uint32_t t = 0;
+                if (w.packed) {
+                    // 16 copied bases per step.  ne: bit 2j set iff base j differs from base j-1 (j >= 1)
+                    for (; len - t >= 16u; t += 16u) {
+                        const uint32_t w16 = w.bases16(rpos + t);
+                        const uint32_t d = w16 ^ (w16 << 2);
+                        const uint32_t ne = (d | (d >> 1)) & 0x55555554u;
+                        // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
+                        uint32_t eq = ~ne & 0x55555554u, runs = eq;
+                        for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
+                        const uint32_t first = w16 & 3u;
+                        // leading bases that continue the pending run
+                        const uint32_t lead = (run_len && first == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : 16u) : 0u;
+                        if (runs || run_len + lead >= K) {         // a run reaches K here: base by base
+                            for (uint32_t j = 0; j < 16u; ++j) feed((w16 >> (2u * j)) & 3u, 0);
+                            continue;
+                        }
+                        if (lead == 16u) {                         // the whole word continues the pending run
+                            add_seg(0u, 16u);
+                            run_len += 16u;
+                            run_ref += 16u;
+                            continue;
+                        }
+                        if (lead) {
+                            add_seg(0u, lead);
+                            run_len += lead;
+                            run_ref += lead;
+                        }
+                        flush_run();                               // the pending run ends inside this word, shorter than K
+                        // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
+                        const uint32_t bound = ne | 1u;            // field 0 bounds the trailing run inside the word
+                        const uint32_t trail = 16u - ((31u - (uint32_t)__clz((int)bound)) >> 1);
+                        out.add(NS_OP_COPY << 28, 16u - lead - trail);
+                        run_base = w16 >> 30;
+                        run_len = run_ref = trail;
+                        nseg = 1;
+                        seg_kind[0] = 0;
+                        seg_cnt[0] = trail;
+                    }
+                    for (; t < len; ++t) feed((w.bases16(rpos + t)) & 3u, 0);
+                } else {
+                    for (; t < len; ++t) feed(w.base_at(rpos + t), 0);
+                }
                 rpos += len;
             } else if (ty == NS_OP_DEL) {
                 // deleted bases vanish from the read: their neighbours become adjacent and may join one run
@@ -270,7 +381,7 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                     const uint32_t r8 = (wd >> (8u * (t & 3u))) & 0xffu;
                     uint32_t b;
                     if (ty == NS_OP_MIS) {
-                        const uint32_t orig = w.base_at(rpos + t);
+                        const uint32_t orig = w.packed ? (w.bases16(rpos + t) & 3u) : w.base_at(rpos + t);
                         const uint32_t rr = r8 == 255u ? 0u : r8;
                         b = ((orig & 3u) + 1u + rr % 3u) & 3u;
                         feed(b, 1);
@@ -285,10 +396,10 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
         flush_run();
         out.flush();
         if (!WRITE) {
-            a.out_n_ops[pi] = out.n;
+            a.out_n_ops[this_piece] = out.n;
             pm.out_len = out.out_len;
         } else {
-            pm.op_off = a.out_off[pi];
+            pm.op_off = a.out_off[this_piece];
             pm.n_ops = out.n;
         }
     }

@@ -76,6 +76,8 @@ struct NsContext {
     bool borrowed = false;          // ns_clone: reference + model buffers belong to the parent
     bool have_ref = false, have_model = false, have_cfg = false;
     DevBuf ref_bases, ref_off, ref_packed, ref_pk_off, ref_exc;
+    DevBuf trx_sorted;              // transcript lengths ascending + their records (ns_configure, transcriptome mode)
+    bool trx_sorted_owned = false;  // false on a clone that still uses its parent's table
     DevRef dref{};
     std::vector<uint64_t> h_chrom_off;
 
@@ -440,6 +442,7 @@ int ns_destroy(NsContext* ctx) {
         for (DevBuf* b : shared) { b->p = nullptr; b->cap = 0; }
         for (auto& k : ctx->kde) { k.p = nullptr; k.cap = 0; }
     }
+    if (ctx->trx_sorted_owned) ctx->trx_sorted.release();
     for (DevBuf* b : bufs) b->release();
     for (auto& k : ctx->kde) k.release();
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -469,6 +472,7 @@ int ns_clone(NsContext* parent, NsContext** out) {
     c->ref_packed = parent->ref_packed;
     c->ref_pk_off = parent->ref_pk_off;
     c->ref_exc = parent->ref_exc;
+    c->trx_sorted = parent->trx_sorted;        // shared; trx_sorted_owned stays false
     c->alias = parent->alias;
     c->qlut = parent->qlut;
     c->ref_species = parent->ref_species;
@@ -523,10 +527,10 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
         }
         pk[ref->n_chrom] = words;
         const uint64_t n_blocks = ((words + 2) >> REF_EXC_BLOCK_SHIFT) + 2;
-        CK(ctx->ref_packed.ensure((size_t)(words + 2) * 4));
+        CK(ctx->ref_packed.ensure((size_t)(words + 2 + 64) * 4));      // + slack: a 64-word window copy may start at the last word
         CK(ctx->ref_exc.ensure((size_t)(2 * n_blocks + 2) * 4 + 16));
         CK(upload(ctx->ref_pk_off, pk.data(), pk.size() * sizeof(uint64_t), ctx->stream));
-        CK(cudaMemsetAsync(ctx->ref_packed.p, 0, (size_t)(words + 2) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->ref_packed.p, 0, (size_t)(words + 2 + 64) * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->ref_exc.p, 0, (size_t)(2 * n_blocks + 2) * 4 + 16, ctx->stream));
         uint32_t* cnt = ctx->ref_exc.as<uint32_t>() + n_blocks + 1;     // counts behind the prefix array
         unsigned long long* other = (unsigned long long*)(ctx->ref_exc.as<uint32_t>() + ((2 * n_blocks + 2 + 1) & ~1ull));
@@ -542,6 +546,7 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
         CK(cudaMemcpyAsync(&h_other, other, sizeof h_other, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->dref.packed = ctx->ref_packed.as<uint32_t>();
+        ctx->dref.pk_words = words + 2;
         ctx->dref.pk_off = ctx->ref_pk_off.as<uint64_t>();
         ctx->dref.exc_pre = ctx->ref_exc.as<uint32_t>();
         ctx->dref.all_iupac = h_other == 0 ? 1u : 0u;
@@ -556,6 +561,9 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     ctx->dref.expr_chrom = nullptr;
     ctx->dref.n_expressed = 0;
     ctx->dref.chrom_has_polya = nullptr;
+    ctx->dref.trx_len_sorted = nullptr;
+    ctx->dref.trx_len_idx = nullptr;
+    ctx->dref.n_trx_sorted = 0;
     ctx->have_expr = false;
     if (ref->n_species > 0) {
         if (!ref->chrom_species || !ref->chrom_circular)
@@ -689,6 +697,31 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.uracil = (cfg->flags & NS_FLAG_URACIL) ? 1u : 0u;
     ctx->dcfg.kde2d_n = cfg->kde2d_sample ? cfg->kde2d_sample : 1u;
     ctx->dcfg.trx_records = cfg->trx_records;
+    if (cfg->mode == 2 && ctx->have_ref) {
+        // records sorted by length for the unaligned reads' transcript draw (plan_kernel.cuh:draw_position_trx)
+        const uint32_t nrec = cfg->trx_records ? std::min(cfg->trx_records, ctx->dref.n_chrom) : ctx->dref.n_chrom;
+        if (ctx->dref.n_trx_sorted != nrec || !ctx->dref.trx_len_sorted) {
+            std::vector<uint32_t> idx(nrec), both(2 * (size_t)nrec);
+            for (uint32_t i = 0; i < nrec; ++i) idx[i] = i;
+            const std::vector<uint64_t>& off = ctx->h_chrom_off;
+            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] < off[y + 1] - off[y]; });
+            for (uint32_t i = 0; i < nrec; ++i) {
+                both[i] = (uint32_t)(off[idx[i] + 1] - off[idx[i]]);
+                both[nrec + i] = idx[i];
+            }
+            CK(cudaSetDevice(ctx->device));
+            if (!ctx->trx_sorted_owned) {          // a clone must not grow (= free) its parent's buffer
+                ctx->trx_sorted.p = nullptr;
+                ctx->trx_sorted.cap = 0;
+            }
+            CK(upload(ctx->trx_sorted, both.data(), both.size() * 4, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->trx_sorted_owned = true;
+            ctx->dref.trx_len_sorted = ctx->trx_sorted.as<uint32_t>();
+            ctx->dref.trx_len_idx = ctx->trx_sorted.as<uint32_t>() + nrec;
+            ctx->dref.n_trx_sorted = nrec;
+        }
+    }
     ctx->dcfg.polya_scale = cfg->polya_scale;
     ctx->dcfg.min_len = cfg->min_len;
     ctx->dcfg.max_len = cfg->max_len;
@@ -761,44 +794,71 @@ struct HostRng {       // splitmix64 stream keyed by (seed, batch id); only driv
 // quota[s] = total_bases * abun[s] / sum(abun) - current[s]; every segment takes a uniformly random species whose quota
 // still fits it (else any species with quota left); later segments of a chimeric read stay in the previous species with
 // probability abun_inflated[prev] % (:793-797).
-void assign_species_host(const std::vector<uint32_t>& n_seg, const std::vector<uint32_t>& piece_first,
-                         std::vector<NsPieceMeta>& pieces, const std::vector<double>& abun, const std::vector<double>& inflated,
-                         const std::vector<double>& current, HostRng& rng) {
+// seg_len[j]: drawn length of segment j (segments of read i are first[i] .. first[i] + n_seg[i]); by_len: read slots by
+// decreasing total drawn length (the device's stable radix sort, = decreasing segment length for single-segment reads).
+// The species whose quota exceeds a length are a PREFIX of the species sorted by quota, so a pick is a binary search + one
+// uniform draw, and charging a quota moves one species a few places down that order.
+void assign_species_host(const std::vector<uint32_t>& n_seg, const std::vector<uint32_t>& first, const std::vector<uint32_t>& seg_len,
+                         const std::vector<uint32_t>& by_len, std::vector<uint32_t>& seg_species, const std::vector<double>& abun,
+                         const std::vector<double>& inflated, const std::vector<double>& current, HostRng& rng) {
     const uint32_t n = (uint32_t)n_seg.size(), S = (uint32_t)abun.size();
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        if (n_seg[a] != n_seg[b]) return n_seg[a] > n_seg[b];
-        if (n_seg[a] > 1) return false;
-        return pieces[piece_first[a]].ref_req > pieces[piece_first[b]].ref_req;
-    });
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    for (uint32_t k = NS_MAX_SEGMENTS; k >= 2; --k)                        // most segments first, stable
+        for (uint32_t i = 0; i < n; ++i)
+            if (n_seg[i] == k) order.push_back(i);
+    for (uint32_t q = 0; q < n; ++q)
+        if (n_seg[by_len[q]] <= 1) order.push_back(by_len[q]);
     double to_add = 0, cur = 0, tot_abun = 0;
-    for (uint32_t i = 0; i < n; ++i)
-        for (uint32_t q = 0; q < n_seg[i]; ++q) to_add += pieces[piece_first[i] + 2 * q].ref_req;
+    for (uint32_t v : seg_len) to_add += v;
     for (uint32_t s = 0; s < S; ++s) {
         cur += current[s];
         tot_abun += abun[s];
     }
     std::vector<double> quota(S);
     for (uint32_t s = 0; s < S; ++s) quota[s] = (to_add + cur) * abun[s] / tot_abun - current[s];
-    std::vector<uint32_t> avail;
-    avail.reserve(S);
+    std::vector<uint32_t> ord(S), where(S);                                // species by decreasing quota, and its inverse
+    for (uint32_t s = 0; s < S; ++s) ord[s] = s;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return quota[x] > quota[y]; });
+    for (uint32_t k = 0; k < S; ++k) where[ord[k]] = k;
+    auto count_above = [&](double v) {                                      // species with quota > v
+        uint32_t lo = 0, hi = S;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (quota[ord[mid]] > v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    auto pick_above = [&](double v, int exclude) -> uint32_t {              // uniform among them, `exclude` left out
+        const uint32_t c = count_above(v);
+        const bool ex_in = exclude >= 0 && where[exclude] < c;
+        const uint32_t m = c - (ex_in ? 1u : 0u);
+        if (m == 0) return 0xffffffffu;
+        uint32_t r = rng.below(m);
+        if (ex_in && r >= where[exclude]) ++r;
+        return ord[r];
+    };
     auto pick = [&](double len, int exclude) -> uint32_t {
-        avail.clear();
-        for (uint32_t s = 0; s < S; ++s)
-            if (quota[s] - len > 0 && (int)s != exclude) avail.push_back(s);
-        if (avail.empty() && exclude < 0)
-            for (uint32_t s = 0; s < S; ++s)
-                if (quota[s] > 0) avail.push_back(s);
-        if (avail.empty()) return 0xffffffffu;
-        return avail[rng.below((uint32_t)avail.size())];
+        uint32_t sp = pick_above(len, exclude);                             // quota - len > 0
+        if (sp == 0xffffffffu && exclude < 0) sp = pick_above(0.0, -1);     // else any species with quota left
+        return sp;
+    };
+    auto charge = [&](uint32_t sp, double len) {
+        quota[sp] -= len;
+        uint32_t k = where[sp];
+        while (k + 1 < S && quota[ord[k + 1]] > quota[sp]) {               // keeps `ord` sorted
+            ord[k] = ord[k + 1];
+            where[ord[k]] = k;
+            ++k;
+        }
+        ord[k] = sp;
+        where[sp] = k;
     };
     for (uint32_t oi = 0; oi < n; ++oi) {
         const uint32_t i = order[oi];
         int pre = -1;
         for (uint32_t q = 0; q < n_seg[i]; ++q) {
-            NsPieceMeta& pm = pieces[piece_first[i] + 2 * q];
-            const double len = pm.ref_req;
+            const double len = seg_len[first[i] + q];
             uint32_t sp;
             if (q == 0) {
                 sp = pick(len, -1);
@@ -809,16 +869,28 @@ void assign_species_host(const std::vector<uint32_t>& n_seg, const std::vector<u
                 else if (p > inflated[pre] && other != 0xffffffffu) sp = other;
                 else sp = pick(len, -1);
             }
-            if (sp == 0xffffffffu) {                      // cannot happen while sum(quota) >= len; keep it total anyway
-                sp = 0;
-                for (uint32_t s = 1; s < S; ++s)
-                    if (quota[s] > quota[sp]) sp = s;
-            }
-            pm.chrom = sp;                                // species id travels in `chrom` until the position is drawn
-            quota[sp] -= len;
+            if (sp == 0xffffffffu) sp = ord[0];           // cannot happen while sum(quota) >= len; keep it total anyway
+            seg_species[first[i] + q] = sp;
+            charge(sp, len);
             pre = (int)sp;
         }
     }
+}
+
+// segment lengths down / species up: 4 bytes per segment instead of whole NsPieceMeta records
+__global__ void gather_segment_req(const NsPieceMeta* pieces, const uint32_t* piece_first, const uint32_t* n_seg, uint32_t n_reads,
+                                   const uint32_t* seg_first, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const uint32_t pf = piece_first ? piece_first[i] : i, ns = n_seg ? n_seg[i] : 1u, sf = seg_first ? seg_first[i] : i;
+    for (uint32_t q = 0; q < ns; ++q) out[sf + q] = pieces[pf + 2 * q].ref_req;
+}
+__global__ void scatter_segment_species(NsPieceMeta* pieces, const uint32_t* piece_first, const uint32_t* n_seg, uint32_t n_reads,
+                                        const uint32_t* seg_first, const uint32_t* species) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const uint32_t pf = piece_first ? piece_first[i] : i, ns = n_seg ? n_seg[i] : 1u, sf = seg_first ? seg_first[i] : i;
+    for (uint32_t q = 0; q < ns; ++q) pieces[pf + 2 * q].chrom = species[sf + q];    // species id travels in `chrom` until the position is drawn
 }
 
 __global__ void species_bases_kernel(const NsPieceMeta* pieces, uint32_t n, const uint32_t* chrom_species, double* acc) {
@@ -855,7 +927,7 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
     ea.counter = ctx->counter.as<uint32_t>();
     ea.order = order;
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-    const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 512;
+    const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 512 + EMIT_WINDOW_SMEM;
     if (ctx->hcfg.fastq) {
         size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
         CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -985,23 +1057,38 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
     uint32_t batch_reversed = 0;
     if (ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) {
-        // ---- assign_species (:758-811): sequential greedy quota fill over this batch's segments, on the host
+        // ---- assign_species (:758-811): sequential greedy quota fill over this batch's segments, on the host.  Down: the
+        //      drawn segment lengths and the reads' order by length (4 B each); up: one species per segment.
         if (ctx->abun.size() != ctx->dref.n_species) return fail(ctx, NS_ESTATE, "ns_simulate: call ns_set_abundance first");
-        std::vector<NsPieceMeta> hp((size_t)n_pieces);
-        std::vector<uint32_t> hseg(n, 1u), hfirst(n);
-        CK(cudaMemcpyAsync(hp.data(), ctx->pieces.p, (size_t)n_pieces * sizeof(NsPieceMeta), cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> hseg(n, 1u), hfirst(n), by_len(n);
+        uint32_t n_segs = n;
         if (chim) {
             CK(cudaMemcpyAsync(hseg.data(), ctx->nseg.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(hfirst.data(), ctx->piece_first.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        }
-        CK(cudaStreamSynchronize(st));
-        if (!chim)
+            CK(cudaStreamSynchronize(st));
+            n_segs = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                hfirst[i] = n_segs;
+                n_segs += hseg[i];
+            }
+        } else {
             for (uint32_t i = 0; i < n; ++i) hfirst[i] = i;
+        }
+        CK(ctx->hp_off.ensure((size_t)(n + n_segs) * 4));                 // scratch: segment starts + per-segment values
+        uint32_t* d_sfirst = ctx->hp_off.as<uint32_t>();
+        uint32_t* d_segval = d_sfirst + n;
+        if (chim) CK(cudaMemcpyAsync(d_sfirst, hfirst.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        gather_segment_req<<<gb, tb, 0, st>>>(ctx->pieces.as<NsPieceMeta>(), d_pfirst, d_nseg, n, chim ? d_sfirst : nullptr, d_segval);
+        std::vector<uint32_t> seg_len(n_segs), seg_species(n_segs, 0u);
+        CK(cudaMemcpyAsync(seg_len.data(), d_segval, (size_t)n_segs * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(by_len.data(), vals_out, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
         HostRng hr{ctx->seed * 0x9E3779B97F4A7C15ull ^ (first_read_id + 0x1234567ull)};
         batch_reversed = hr.uniform() > (double)ctx->dmodel.strandness ? 1u : 0u;      // once per batch (:860)
-        assign_species_host(hseg, hfirst, hp, ctx->abun, ctx->abun_inflated, ctx->species_bases, hr);
-        CK(cudaMemcpyAsync(ctx->pieces.p, hp.data(), (size_t)n_pieces * sizeof(NsPieceMeta), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        assign_species_host(hseg, hfirst, seg_len, by_len, seg_species, ctx->abun, ctx->abun_inflated, ctx->species_bases, hr);
+        CK(cudaMemcpyAsync(d_segval, seg_species.data(), (size_t)n_segs * 4, cudaMemcpyHostToDevice, st));
+        scatter_segment_species<<<gb, tb, 0, st>>>(ctx->pieces.as<NsPieceMeta>(), d_pfirst, d_nseg, n, chim ? d_sfirst : nullptr, d_segval);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));                                    // seg_species must outlive the copy
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     launches += 10;
@@ -1103,7 +1190,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         memcpy(ha.hp, ctx->hmodel.hp, sizeof ha.hp);
         ha.hp_mis_rate = ctx->hmodel.hp_mis_rate;
         ha.counter = ctx->counter.as<uint32_t>();
-        const unsigned hp_blocks = std::min<unsigned>((n_pieces + 127) / 128, (unsigned)ctx->sm_count * 16u);
+        ha.order = vals_out;                 // reads longest first: the lanes of a warp walk segments of similar length
+        ha.n_reads = n;
+        ha.force_exact = (ctx->hcfg.flags & NS_FLAG_EMIT_EXACT) ? 1u : 0u;
+        const unsigned hp_blocks = std::min<unsigned>((n + 127) / 128, (unsigned)ctx->sm_count * 16u);
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         hp_kernel<false><<<hp_blocks, 128, 0, st>>>(ha);
         CK(cudaGetLastError());

@@ -187,10 +187,28 @@ __device__ __forceinline__ void draw_position_meta(const DevRef& ref, Rng& rng, 
     }
 }
 
-// extract_read, transcriptome branch (:1695-1703, unaligned reads): uniform transcript until it is longer than the
-// read, uniform start.
+// extract_read, transcriptome branch (:1695-1703, unaligned reads): a uniformly chosen transcript, drawn again until it is
+// longer than the read, then a uniform start.  Redrawing until the condition holds == one uniform draw among the
+// transcripts that satisfy it: they are a suffix of the records sorted by length (DevRef::trx_len_sorted), so the
+// rejection loop (thousands of draws for a read close to the longest transcript) becomes one binary search.
 __device__ __forceinline__ void draw_position_trx(const DevRef& ref, uint32_t n_records, Rng& rng, uint32_t length, uint32_t& chrom,
                                                   uint32_t& pos) {
+    if (ref.trx_len_sorted && ref.n_trx_sorted == n_records) {
+        uint32_t lo = 0, hi = n_records;                     // first sorted record longer than the read
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&ref.trx_len_sorted[mid]) > length) hi = mid; else lo = mid + 1;
+        }
+        if (lo < n_records) {
+            const uint32_t j = lo + (uint32_t)__umul64hi(rng.next64(), (uint64_t)(n_records - lo));
+            chrom = __ldg(&ref.trx_len_idx[j]);
+            pos = (uint32_t)__umul64hi(rng.next64(), (uint64_t)(__ldg(&ref.trx_len_sorted[j]) - length + 1u));
+            return;
+        }
+        chrom = 0;                                           // no transcript is long enough (the reference would spin forever)
+        pos = 0;
+        return;
+    }
     for (int it = 0; it < 1000000; ++it) {
         const uint32_t c = (uint32_t)__umul64hi(rng.next64(), (uint64_t)n_records);
         const uint64_t clen = __ldg(&ref.chrom_off[c + 1]) - __ldg(&ref.chrom_off[c]);

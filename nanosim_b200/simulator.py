@@ -123,6 +123,9 @@ def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=
     prof.perfect = per
     _log("Read KDF of aligned reads")
     prof.seed = seed
+    # one process per GPU: keep its threads (record formatting, 2-bit expansion) and pinned buffers on the GPU's NUMA node
+    from .hostbind import bind_to_gpu_node
+    bind_to_gpu_node(device)
     prof.engine = Engine(device=device, seed=seed)
     prof.engine.set_reference(prof.ref)
     prof.engine.set_model(prof.tables, perfect=per)
