@@ -70,6 +70,7 @@ struct EmitArgs {
     const uint32_t* qlut;        // [5][QLUT_SIZE] alias table entries (built on the host from qual_cdf)
     uint32_t* counter;
     const uint32_t* order;       // piece processing order (longest first) or null
+    const uint32_t* abort;       // sync-free batches: non-zero = a capacity check failed upstream, do nothing (or null)
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
@@ -371,6 +372,7 @@ __device__ __forceinline__ void emit_chunk16_fast(uint32_t ring_s, const char* l
 
 template <bool FASTQ>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ EmitArgs a) {
+    if (a.abort && *a.abort) return;
     extern __shared__ uint4 smem4[];
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem4);                          // FASTQ only
     uint8_t* cvt_tables = reinterpret_cast<uint8_t*>(lut + (FASTQ ? NS_N_QUAL_STATES * QLUT_SIZE : 0));

@@ -315,25 +315,31 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
             if (ty == NS_OP_COPY) {
                 uint32_t t = 0;
                 if (w.packed) {
-                    // 16 copied bases per step.  ne: bit 2j set iff base j differs from base j-1 (j >= 1)
-                    for (; len - t >= 16u; t += 16u) {
-                        const uint32_t w16 = w.bases16(rpos + t);
-                        const uint32_t d = w16 ^ (w16 << 2);
-                        const uint32_t ne = (d | (d >> 1)) & 0x55555554u;
+                    // up to 16 copied bases per step (the next word is requested before this one is looked at).
+                    // ne: bit 2j set iff base j differs from base j-1 (1 <= j < n)
+                    uint32_t w16 = w.bases16(rpos);
+                    while (t < len) {
+                        const uint32_t n = len - t < 16u ? len - t : 16u;
+                        const uint32_t cur = w16;
+                        if (t + n < len) w16 = w.bases16(rpos + t + n);
+                        const uint32_t fields = (n == 16u ? 0xffffffffu : (1u << (2u * n)) - 1u) & 0x55555554u;   // fields 1 .. n-1
+                        const uint32_t d = cur ^ (cur << 2);
+                        const uint32_t ne = (d | (d >> 1)) & fields;
                         // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
-                        uint32_t eq = ~ne & 0x55555554u, runs = eq;
+                        const uint32_t eq = ~ne & fields;
+                        uint32_t runs = eq;
                         for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
-                        const uint32_t first = w16 & 3u;
                         // leading bases that continue the pending run
-                        const uint32_t lead = (run_len && first == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : 16u) : 0u;
+                        const uint32_t lead = (run_len && (cur & 3u) == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : n) : 0u;
+                        t += n;
                         if (runs || run_len + lead >= K) {         // a run reaches K here: base by base
-                            for (uint32_t j = 0; j < 16u; ++j) feed((w16 >> (2u * j)) & 3u, 0);
+                            for (uint32_t j = 0; j < n; ++j) feed((cur >> (2u * j)) & 3u, 0);
                             continue;
                         }
-                        if (lead == 16u) {                         // the whole word continues the pending run
-                            add_seg(0u, 16u);
-                            run_len += 16u;
-                            run_ref += 16u;
+                        if (lead == n) {                           // the whole word continues the pending run
+                            add_seg(0u, n);
+                            run_len += n;
+                            run_ref += n;
                             continue;
                         }
                         if (lead) {
@@ -344,15 +350,14 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                         flush_run();                               // the pending run ends inside this word, shorter than K
                         // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
                         const uint32_t bound = ne | 1u;            // field 0 bounds the trailing run inside the word
-                        const uint32_t trail = 16u - ((31u - (uint32_t)__clz((int)bound)) >> 1);
-                        out.add(NS_OP_COPY << 28, 16u - lead - trail);
-                        run_base = w16 >> 30;
+                        const uint32_t trail = n - ((31u - (uint32_t)__clz((int)bound)) >> 1);
+                        out.add(NS_OP_COPY << 28, n - lead - trail);
+                        run_base = (cur >> (2u * (n - 1u))) & 3u;
                         run_len = run_ref = trail;
                         nseg = 1;
                         seg_kind[0] = 0;
                         seg_cnt[0] = trail;
                     }
-                    for (; t < len; ++t) feed((w.bases16(rpos + t)) & 3u, 0);
                 } else {
                     for (; t < len; ++t) feed(w.base_at(rpos + t), 0);
                 }

@@ -101,6 +101,11 @@ struct NsContext {
     uint8_t* pack_host = nullptr;
     size_t pack_host_cap = 0;
     cudaEvent_t ev_pack = nullptr;
+    // Batches of one job have near-identical sizes: once a batch of a kind has run with host-sized buffers, the next ones
+    // are submitted in one go (no host round trip between the first and the last kernel) against those capacities; a
+    // kernel checks them on the device and a batch that does not fit is simply run again the sized way.
+    bool opt_ok[2] = {false, false};
+    uint32_t opt_n[2] = {0, 0};
     NsBatchInfo last{};
     int last_kind = 0;
     uint64_t last_first_id = 0;
@@ -204,8 +209,33 @@ __global__ void pack_bases_kernel(const uint4* __restrict__ seq, uint32_t* __res
 // The batch totals the host needs mid-pipeline are written straight into mapped pinned host memory: a cudaMemcpy
 // would queue behind another context's multi-GB device->host transfer on the copy engine and serialise the pipelines.
 __global__ void publish_totals(const uint64_t* totals, volatile uint64_t* host) {
-    if (threadIdx.x < 8) host[threadIdx.x] = totals[threadIdx.x];
+    if (threadIdx.x < 16) host[threadIdx.x] = totals[threadIdx.x];
     __threadfence_system();
+}
+// totals[] slots: 0 pieces, 1 overflow ops, 2 sequence bytes, 3 bases, 4 slot ops, 5 flagged reads, 6 hp ops, 7 pool cursor,
+// 8 pool base, 9 pool size, 10 primary ops, 11 abort flags (bit 0: script area too small, bit 1: with the overflow area,
+// bit 2: sequence buffers too small)
+#define NS_T_POOL 8
+#define NS_T_PRIMARY 10
+#define NS_T_ABORT 11
+// sync-free batches: what the host would compute from the scans, computed and checked against the capacities on the device
+__global__ void capacity_stage_a(uint64_t* totals, uint32_t fast_unaligned, uint64_t ops_cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    const uint64_t slot_ops = totals[4];
+    const uint64_t pool_ops = fast_unaligned ? slot_ops / 16 + (1u << 20) : 0;
+    totals[NS_T_POOL] = slot_ops;
+    totals[NS_T_POOL + 1] = pool_ops;
+    totals[NS_T_PRIMARY] = slot_ops + pool_ops;
+    if (slot_ops + pool_ops + 4 > ops_cap) totals[NS_T_ABORT] |= 1u;
+}
+__global__ void capacity_stage_b(uint64_t* totals, uint64_t ops_cap, uint64_t seq_cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (totals[NS_T_PRIMARY] + totals[1] + 4 > ops_cap) totals[NS_T_ABORT] |= 2u;
+    if (totals[2] + 16 > seq_cap) totals[NS_T_ABORT] |= 4u;
+}
+__global__ void scatter_flagged_off_dev(NsPieceMeta* pieces, const NsReadMeta* reads, uint32_t n, const uint64_t* off, const uint64_t* base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (reads[pieces[i].read_slot].flags & 1u)) pieces[i].op_off = *base + off[i];
 }
 __global__ void gather_read_bytes(const NsReadMeta* reads, uint32_t n, uint64_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -405,7 +435,7 @@ int ns_create(int device, uint64_t seed, NsContext** out) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_totals, 8 * sizeof(uint64_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_totals, 16 * sizeof(uint64_t), cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->h_totals_dev, ctx->h_totals, 0);
     if (e == cudaSuccess && device >= 0 && device < 64 && !g_base[device]) {
         e = cudaEventCreate(&g_base[device]);
@@ -593,6 +623,7 @@ int ns_set_reference(NsContext* ctx, const NsReference* ref) {
     }
     ctx->have_ref = true;
     ctx->have_batch = false;
+    ctx->opt_ok[0] = ctx->opt_ok[1] = false;
     return NS_OK;
 }
 
@@ -665,6 +696,7 @@ int ns_set_model(NsContext* ctx, const NsModel* m) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_model = true;
     ctx->have_batch = false;
+    ctx->opt_ok[0] = ctx->opt_ok[1] = false;
     return NS_OK;
 }
 
@@ -730,6 +762,7 @@ int ns_configure(NsContext* ctx, const NsRunConfig* cfg) {
     ctx->dcfg.sd_len = cfg->sd_len;
     ctx->have_cfg = true;
     ctx->have_batch = false;
+    ctx->opt_ok[0] = ctx->opt_ok[1] = false;
     return NS_OK;
 }
 
@@ -908,8 +941,15 @@ static int exclusive_scan_u64(NsContext* ctx, const uint64_t* in, uint64_t* out,
 }
 
 namespace {
+// Launch-geometry experiments: NANOSIM_B200_EMIT_BLOCKS_PER_SM / NANOSIM_B200_PLAN_BLOCKS_PER_SM cap the persistent grids
+// (0 / unset = as many blocks as fit), so that kernels of overlapped contexts can share an SM instead of queueing.
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
 // emit_kernel over `n_pieces` pieces of the context's current batch (all of them, or the ones `order` lists)
-int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order) {
+int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order,
+                const uint32_t* abort_flag = nullptr) {
     cudaStream_t st = ctx->stream;
     EmitArgs ea;
     ea.ref = ctx->dref;
@@ -924,6 +964,7 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
     ea.qual = ctx->qual.as<uint8_t>();
     ea.qlut = ctx->qlut.as<uint32_t>();
     ea.force_exact = (ctx->hcfg.flags & NS_FLAG_EMIT_EXACT) ? 1u : 0u;
+    ea.abort = abort_flag;
     ea.counter = ctx->counter.as<uint32_t>();
     ea.order = order;
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
@@ -933,12 +974,16 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
         CK(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<true>, EMIT_WARPS * 32, smem));
+        static const int cap_sm = env_int("NANOSIM_B200_EMIT_BLOCKS_PER_SM", 0);
+        if (cap_sm > 0) per_sm = std::min(per_sm, cap_sm);
         unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
         emit_kernel<true><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
     } else {
         size_t smem = ring_bytes;
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emit_kernel<false>, EMIT_WARPS * 32, smem));
+        static const int cap_sm = env_int("NANOSIM_B200_EMIT_BLOCKS_PER_SM", 0);
+        if (cap_sm > 0) per_sm = std::min(per_sm, cap_sm);
         unsigned blocks = std::min<unsigned>((n_pieces + EMIT_WARPS - 1) / EMIT_WARPS, (unsigned)(ctx->sm_count * std::max(per_sm, 1)));
         emit_kernel<false><<<blocks, EMIT_WARPS * 32, smem, st>>>(ea);
     }
@@ -990,14 +1035,23 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     const unsigned tb = 256, gb = (n + tb - 1) / tb;
     CK(ctx->reads.ensure((size_t)n * sizeof(NsReadMeta)));
     CK(ctx->counter.ensure(64));
-    CK(ctx->totals.ensure(8 * sizeof(uint64_t)));
+    CK(ctx->totals.ensure(16 * sizeof(uint64_t)));
     CK(ctx->scan_in.ensure((size_t)n * (2 * NS_MAX_SEGMENTS) * sizeof(uint64_t)));
     CK(ctx->scan_out.ensure((size_t)n * (2 * NS_MAX_SEGMENTS) * sizeof(uint64_t)));
-    CK(cudaMemsetAsync(ctx->totals.p, 0, 8 * sizeof(uint64_t), st));
+    CK(cudaMemsetAsync(ctx->totals.p, 0, 16 * sizeof(uint64_t), st));
     CK(cudaEventRecord(ctx->ev[0], st));
 
     // ---- pieces per read
     const bool chim = (kind == NS_KIND_ALIGNED) && ctx->hcfg.chimeric;
+    // one submission, no host round trip: same kind of batch as one already sized, no chimeric piece count, species
+    // assignment, homopolymer pass or scripted unaligned reads in the way
+    static const bool no_opt = getenv("NANOSIM_B200_SYNC_BATCHES") != nullptr;
+    const bool optimistic = !no_opt && ctx->opt_ok[kind] && n <= ctx->opt_n[kind] && !chim && !(ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) &&
+                            !(ctx->hcfg.kmer_bias > 0 && kind == NS_KIND_ALIGNED) && (kind == NS_KIND_ALIGNED || fast_unaligned) &&
+                            ctx->ops.cap > 64 && ctx->seq.cap > 64 && (!ctx->hcfg.fastq || ctx->qual.cap >= ctx->seq.cap);
+    const uint64_t ops_cap = ctx->ops.cap / sizeof(uint32_t), seq_cap = ctx->seq.cap;
+    uint64_t* d_totals = ctx->totals.as<uint64_t>();
+    const uint32_t* d_abort = optimistic ? (const uint32_t*)(d_totals + NS_T_ABORT) : nullptr;
     uint32_t n_pieces = n;
     const uint32_t* d_nseg = nullptr;
     const uint32_t* d_pfirst = nullptr;
@@ -1048,13 +1102,17 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(ctx->sort_tmp.ensure(tmp));
         CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, st));
     }
-    publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
-    CK(cudaStreamSynchronize(st));
     // primary script area = the capped slots (+ a bump pool for re-drawn unaligned reads, uread_kernel.cuh)
-    const uint64_t slot_ops = ctx->h_totals[4];
-    const uint64_t pool_ops = fast_unaligned ? slot_ops / 16 + (1u << 20) : 0;
-    const uint64_t primary_ops = slot_ops + pool_ops;
-    CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
+    uint64_t slot_ops = 0, pool_ops = 0, primary_ops = 0;
+    capacity_stage_a<<<1, 32, 0, st>>>(d_totals, fast_unaligned ? 1u : 0u, optimistic ? ops_cap : ~0ull);
+    if (!optimistic) {
+        publish_totals<<<1, 32, 0, st>>>(d_totals, ctx->h_totals_dev);
+        CK(cudaStreamSynchronize(st));
+        slot_ops = ctx->h_totals[4];
+        pool_ops = ctx->h_totals[NS_T_POOL + 1];
+        primary_ops = ctx->h_totals[NS_T_PRIMARY];
+        CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
+    }
     uint32_t batch_reversed = 0;
     if (ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED) {
         // ---- assign_species (:758-811): sequential greedy quota fill over this batch's segments, on the host.  Down: the
@@ -1110,8 +1168,10 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     pa.counter = ctx->counter.as<uint32_t>();
     pa.n_flagged = (uint32_t*)(ctx->totals.as<uint64_t>() + 5);
     pa.batch_reversed = batch_reversed;
+    pa.abort = d_abort;
     const unsigned plan_tb = 128;
-    unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * 16u);
+    static const int plan_per_sm = env_int("NANOSIM_B200_PLAN_BLOCKS_PER_SM", 16);
+    unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * (unsigned)std::max(1, plan_per_sm));
     // unaligned reads without NS_FLAG_UNALIGNED_SCRIPTS: warp-per-read evaluation (uread_kernel.cuh), same outputs
     UreadArgs ua;
     ua.m = ctx->dmodel;
@@ -1126,8 +1186,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ua.counter = pa.counter;
     ua.n_flagged = pa.n_flagged;
     ua.pool_cursor = (unsigned long long*)(ctx->totals.as<uint64_t>() + 7);
-    ua.pool_base = slot_ops;
-    ua.pool_size = pool_ops;
+    ua.pool = d_totals + NS_T_POOL;             // {base, size} of the bump pool, written by capacity_stage_a
+    ua.abort = d_abort;
     const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
     if (fast_unaligned) uread_kernel<false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
@@ -1151,20 +1211,28 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         if (rc) return rc;
     }
     last_total<<<1, 32, 0, st>>>(ctx->scan_in.as<uint64_t>(), ctx->scan_out.as<uint64_t>(), n_pieces, ctx->totals.as<uint64_t>(), 1);
-    publish_totals<<<1, 32, 0, st>>>(ctx->totals.as<uint64_t>(), ctx->h_totals_dev);
-    CK(cudaStreamSynchronize(st));
-    const uint64_t overflow_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
-    const uint32_t n_flagged = (uint32_t)(ctx->h_totals[5] & 0xffffffffull);
-    const uint64_t n_ops = primary_ops + overflow_ops;
-    CK(ctx->seq.ensure((size_t)seq_bytes + 16));
-    if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes + 16));
+    uint64_t overflow_ops = 0, seq_bytes = 0, total_bases = 0, n_ops = 0;
+    uint32_t n_flagged = 0;
+    if (optimistic) {
+        capacity_stage_b<<<1, 32, 0, st>>>(d_totals, ops_cap, seq_cap);
+        n_flagged = 1;                     // unknown without a round trip: the (normally empty) replay is always submitted
+    } else {
+        publish_totals<<<1, 32, 0, st>>>(d_totals, ctx->h_totals_dev);
+        CK(cudaStreamSynchronize(st));
+        overflow_ops = ctx->h_totals[1], seq_bytes = ctx->h_totals[2], total_bases = ctx->h_totals[3];
+        n_flagged = (uint32_t)(ctx->h_totals[5] & 0xffffffffull);
+        n_ops = primary_ops + overflow_ops;
+        CK(ctx->seq.ensure((size_t)seq_bytes + 16));
+        if (ctx->hcfg.fastq) CK(ctx->qual.ensure((size_t)seq_bytes + 16));
+    }
     CK(cudaEventRecord(ctx->ev[3], st));
     launches += 9;
     if (n_flagged > 0) {
         // ---- rare: replay the flagged reads and write their scripts behind the primary area
-        CK(ctx->ops.ensure_keep((size_t)(n_ops + 4) * sizeof(uint32_t), (size_t)primary_ops * sizeof(uint32_t), st));
+        if (!optimistic) CK(ctx->ops.ensure_keep((size_t)(n_ops + 4) * sizeof(uint32_t), (size_t)primary_ops * sizeof(uint32_t), st));
         pa.ops = ctx->ops.as<uint32_t>();
-        scatter_flagged_off<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_out.as<uint64_t>(), primary_ops);
+        if (optimistic) scatter_flagged_off_dev<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_out.as<uint64_t>(), d_totals + NS_T_PRIMARY);
+        else scatter_flagged_off<<<gp, tb, 0, st>>>(pa.pieces, pa.reads, n_pieces, ctx->scan_out.as<uint64_t>(), primary_ops);
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         ua.ops = pa.ops;
         if (fast_unaligned) uread_kernel<true><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
@@ -1235,7 +1303,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
 
     // ---- emit
     {
-        int rc = launch_emit(ctx, kind, first_read_id, n_pieces, chim ? nullptr : vals_out);   // one piece per read: the plan's
+        int rc = launch_emit(ctx, kind, first_read_id, n_pieces, chim ? nullptr : vals_out, d_abort);   // one piece per read: the plan's
         if (rc) return rc;                                                                       // longest-first order serves the emit too
     }
     CK(cudaGetLastError());
@@ -1251,7 +1319,22 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(cudaStreamSynchronize(st));
         for (uint32_t k = 0; k < S; ++k) ctx->species_bases[k] += add[k];
     }
+    if (optimistic) publish_totals<<<1, 32, 0, st>>>(d_totals, ctx->h_totals_dev);
     CK(cudaStreamSynchronize(st));
+    if (optimistic) {
+        if (ctx->h_totals[NS_T_ABORT]) {
+            // a buffer was too small for this batch: nothing was written past a capacity (the kernels saw the flag and
+            // returned); run it again the sized way, which also re-establishes the capacities
+            ctx->opt_ok[kind] = false;
+            return ns_simulate(ctx, kind, first_read_id, n_reads, info);
+        }
+        n_ops_total = ctx->h_totals[NS_T_PRIMARY] + ctx->h_totals[1];
+        seq_bytes_final = ctx->h_totals[2];
+        total_bases_final = ctx->h_totals[3];
+    } else if (!chim && !(ctx->dcfg.metagenome && kind == NS_KIND_ALIGNED)) {
+        ctx->opt_ok[kind] = true;
+        ctx->opt_n[kind] = n;
+    }
 
     NsBatchInfo& bi = ctx->last;
     bi.seq_bytes = seq_bytes_final;

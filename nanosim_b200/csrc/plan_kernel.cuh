@@ -35,6 +35,7 @@ struct PlanArgs {
     uint32_t* counter;          // work-fetch counter (zeroed before launch)
     uint32_t* n_flagged;        // REPLAY=false: number of reads whose script overflowed its slot
     uint32_t batch_reversed;    // metagenome: is_reversed is drawn once per batch (:860)
+    const uint32_t* abort;      // sync-free batches: non-zero = the script area is too small, do nothing (or null)
 };
 
 #define NS_MAX_SAME_LEN_RETRIES 64
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const bool unal_kind = (a.kind == NS_KIND_UNALIGNED);
+    if (a.abort && *a.abort) return;
     __shared__ uint8_t bin_lut[BIN_LUT_SIZE];
     for (uint32_t i = threadIdx.x; i < BIN_LUT_SIZE; i += blockDim.x) bin_lut[i] = (uint8_t)match_bin_scan(m, i);
     __syncthreads();

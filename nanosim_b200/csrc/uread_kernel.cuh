@@ -40,7 +40,8 @@ struct UreadArgs {
     uint32_t* n_flagged;
     // slots for re-drawn reads (a rejected attempt draws a new length, :1503): bump-allocated behind the primary area
     unsigned long long* pool_cursor;
-    uint64_t pool_base, pool_size;
+    const uint64_t* pool;    // {base, size} of the pool, in ops (device memory: written by capacity_stage_a)
+    const uint32_t* abort;   // sync-free batches: non-zero = the script area is too small, do nothing (or null)
 };
 
 #define UREAD_WARPS 8
@@ -52,6 +53,8 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
     const int lane = threadIdx.x & 31;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const uint2 key = make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+    if (a.abort && *a.abort) return;
+    const uint64_t pool_base = a.pool[0], pool_size = a.pool[1];
 
     for (;;) {
         uint32_t idx = 0;
@@ -85,8 +88,8 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 unsigned long long off = 0;
                 if (lane == 0) off = atomicAdd(a.pool_cursor, (unsigned long long)need);
                 off = __shfl_sync(0xffffffffu, off, 0);
-                if (off + need <= a.pool_size) {
-                    op_off = a.pool_base + off;
+                if (off + need <= pool_size) {
+                    op_off = pool_base + off;
                     cap = need;
                 } else {
                     cap = 0;                                     // pool exhausted: count only, replay later
@@ -96,11 +99,19 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             uint32_t base = 0, pos_base = 0, carry_a = 0, middle_ref = m_ref, n_draws = 0, n_ops = 0;
             int64_t l_new = (int64_t)m_ref;
             bool done = false;
+            // draw `d` of the attempt: its type and step length (independent of everything before it: the next 32 draws are
+            // issued before the scans of the current 32, so that the Philox rounds and the table loads overlap the shuffles)
+            auto draw = [&](uint32_t d, uint32_t& kd, uint32_t& sd) {
+                const uint4 r = philox4x32_10(make_uint4(id_lo, id_hi, sw, d + 1u), key);
+                kd = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
+                sd = 1;
+                if (kd != 0) sd = alias_draw(m, kd == 1 ? 1u : (kd == 2 ? 2u : 3u), r.y);
+            };
+            uint32_t kind_next, s_next;
+            draw(lane, kind_next, s_next);
             while (!done) {
-                const uint4 r = philox4x32_10(make_uint4(id_lo, id_hi, sw, base + lane + 1u), key);
-                const uint32_t kind = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
-                uint32_t s = 1;
-                if (kind != 0) s = alias_draw(m, kind == 1 ? 1u : (kind == 2 ? 2u : 3u), r.y);
+                const uint32_t kind = kind_next, s = s_next;
+                draw(base + 32u + lane, kind_next, s_next);
                 const bool nonins = kind != 2;
                 const uint32_t adv = nonins ? s : 0u;
                 const uint32_t P = pos_base + warp_incl_scan(adv, lane);

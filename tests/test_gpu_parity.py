@@ -1080,3 +1080,174 @@ def test_cli_end_to_end_config1(tmp_path, L):
                     "--fastq", "--chimeric", "-t", "4"])
     s2 = rs.stats_from_prefix(out2, True)
     assert s2["n_aligned"] + s2["n_unaligned"] == 300 and s2["qual_middle"].sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4 and 5 on their named synthetic references (SURVEY.md 8d generators, tests/synth.py), small N
+# against the pinned oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_files(prefix, sink, fastq):
+    with open(prefix + "_aligned_reads" + (".fastq" if fastq else ".fasta"), "w") as f:
+        import nanosim_oracle as no
+        f.write(no.format_records(sink.records, fastq))
+    with open(prefix + "_aligned_error_profile", "w") as f:
+        f.write("Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
+        f.writelines(r + "\n" for r in sink.error_rows)
+    return rs.stats_from_prefix(prefix, fastq)
+
+
+def test_config3_transcriptome_200k_transcripts_vs_oracle(L, tmp_path):
+    """BASELINE config 3: transcriptome directRNA, dRNA_Bham1_guppy model, FASTA, --no_model_ir, on the 200k-transcript
+    synthetic reference with its expression profile (simulator.py:1043-1263).  Aligned reads: length laws, error rates, the
+    aligned share of the chosen transcript, the lengths of the chosen transcripts.  Unaligned reads: a uniformly chosen
+    transcript longer than the read (:1695-1703) -- on the device one draw among the records sorted by length."""
+    import random
+    import nanosim_oracle as no
+    from conftest import oracle_model
+    from nanosim_b200.reference_fasta import PackedReference
+    names, lengths, bases, tpm = synth.config3_transcriptome()
+    keys = [n.split(".")[0] for n in names]
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    ref = PackedReference(keys, bases, offs)
+    N = 500
+    eng, cm, t = pc.make_trx_engine(ref, np.arange(len(keys), dtype=np.uint32), tpm, None, fastq=False, seed=303, kde2d_sample=N)
+    s_dev = rs.empty()
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 60000)
+    b = eng.fetch(want_ops=True)
+    assert pc.check_edit_scripts(b, ref, False, max_reads=400) > 0
+    pc.meta_stats(b, s_dev)
+    pc.merge_op_stats(s_dev, eng.op_stats())
+    tl_dev = ref.lengths[b.pieces["chrom"]]
+    frac_dev = b.pieces["ref_len"] / tl_dev
+    eng.simulate(L.NS_KIND_UNALIGNED, 0, 40000)
+    bu = eng.fetch()
+    pc.meta_stats(bu, s_dev)
+    tlu_dev = ref.lengths[bu.pieces["chrom"]]
+    assert (bu.pieces["ref_len"] < tlu_dev).all() and (bu.pieces["pos"].astype(np.int64) + bu.pieces["ref_len"] <= tlu_dev).all()
+    eng.close()
+    seqs = [bases[int(offs[i]):int(offs[i + 1])].tobytes().decode() for i in range(len(keys))]
+    oref = no.OracleTrxReference(list(zip(keys, seqs)), dict(zip(keys, tpm.tolist())))
+    m = oracle_model(cm, tmp_path, fastq=False)
+    s_or = rs.empty()
+    tl_or, frac_or, tlu_or = [], [], []
+    index = {k: i for i, k in enumerate(keys)}
+    for rep in range(2):
+        random.seed(700 + rep)
+        np.random.seed(700 + rep)
+        sink = no.ReadSink()
+        no.simulation_aligned_transcriptome(oref, m, sink, None, "guppy", N, False, False, False, False, False)
+        rs.merge(s_or, _oracle_files(os.path.join(str(tmp_path), "o3_%d" % rep), sink, False))
+        for name, seq, q in sink.records:
+            i = index[name.split("_")[0]]
+            tl_or.append(lengths[i])
+            frac_or.append(int(name.rsplit("_", 4)[3]) / lengths[i])
+    random.seed(710)
+    np.random.seed(710)
+    sink_u = no.ReadSink()
+    no.simulation_unaligned_transcriptome(oref, m, sink_u, 50, oref.max_chrom, False, 1200)
+    for name, seq, q in sink_u.records:
+        tlu_or.append(lengths[index[name.split("_")[0]]])
+        s_or["len_unaligned"][rs._bin(rs.LEN_EDGES, len(seq))] += 1
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.06, p_min=1e-5, label="config3",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match", "len_unaligned"])
+    ledges = np.unique(np.round(np.logspace(np.log10(300), np.log10(20001), 25)))
+    for label, x, y, edges in (("length of the chosen transcript (aligned)", tl_dev, tl_or, ledges),
+                               ("length of the chosen transcript (unaligned)", tlu_dev, tlu_or, ledges),
+                               ("aligned share of the transcript", frac_dev, frac_or, np.linspace(0, 1.0001, 21))):
+        st, dof, p = pc.chi2_two_sample(np.histogram(x, edges)[0], np.histogram(y, edges)[0])
+        print("config3 %s: chi2 %.1f dof %d p %.3g" % (label, st, dof, p))
+        if p < 1e-5:
+            fails.append("config3 %s: chi2 %.1f dof %d p %.3g" % (label, st, dof, p))
+    assert not fails, "\n".join(fails)
+
+
+def test_config4_metagenome_50_species_vs_oracle(L, tmp_path):
+    """BASELINE config 4: metagenome, ERR3152364_Even model, FASTQ --chimeric, 50 species x 1-3 circular chromosomes, Even
+    abundance (simulator.py:814-1040, assign_species :758-811): device vs the pinned oracle on the same reference, and the
+    species base shares against the abundance the quotas enforce."""
+    import random
+    import nanosim_oracle as no
+    from conftest import oracle_model
+    from nanosim_b200.reference_fasta import MetaReference
+    genomes = synth.config4_metagenome()
+    ref = MetaReference.from_genomes(genomes)
+    abun = [100.0 / len(ref.species)] * len(ref.species)
+    eng, cm, t = pc.make_meta_engine(ref, abun, fastq=True, chimeric=True, seed=404)
+    s_dev = rs.empty()
+    fr = np.zeros(len(ref.species))
+    for k in range(3):
+        eng.simulate(L.NS_KIND_ALIGNED, k * 12000, 12000)
+        b = eng.fetch(want_ops=(k == 0))
+        if k == 0:
+            assert pc.check_edit_scripts(b, ref, True, max_reads=300) > 0
+            b.ops = None                                  # event histograms come from the device (ns_op_stats)
+        pc.batch_stats(b, ref, True, s_dev)               # lengths, strands, quality histograms
+        pc.merge_op_stats(s_dev, eng.op_stats())
+        fr += _species_base_fractions(b, ref, L) / 3
+    eng.close()
+    print("config4 species base shares: min %.4f max %.4f (target %.4f)" % (fr.min(), fr.max(), 1.0 / len(ref.species)))
+    assert np.abs(fr - 1.0 / len(ref.species)).max() < 2e-3             # quota fill: every species gets its share of the bases
+    oref = no.OracleMetaReference({MetaReference.species_key(sp): [(k2, a.tobytes().decode()) for k2, a in recs] for sp, recs in genomes})
+    m = oracle_model(cm, tmp_path, fastq=True, chimeric=True, mode="metagenome")
+    oabun = {sp: a for sp, a in zip(ref.species, abun)}
+    infl = {sp: no.inflate_abun(oabun, sp, m.abun_inflation) for sp in oabun}
+    random.seed(44)
+    np.random.seed(44)
+    sink = no.ReadSink()
+    no.simulation_aligned_metagenome(oref, m, sink, oabun, infl, 50, max(oref.max_chrom.values()), None, True, 500, False, True)
+    s_or = _oracle_files(os.path.join(str(tmp_path), "o4"), sink, True)
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.05, p_min=1e-5, label="config4",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s_dev[k], s_or[k])
+        print("config4", k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-5:
+            fails.append("config4 %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    fc_d, fc_o = s_dev["n_chimeric"] / s_dev["n_aligned"], s_or["n_chimeric"] / s_or["n_aligned"]
+    assert abs(fc_d - fc_o) < 0.035, (fc_d, fc_o)
+    assert not fails, "\n".join(fails)
+
+
+def test_config5_dorado_hp_chimeric_on_3gb_reference_vs_oracle(L, tmp_path):
+    """BASELINE config 5 (and the reference of config 2): genome, dorado kit-v14 model, FASTQ -hp -k 6 --chimeric on the 3.09 Gb
+    synthetic reference (24 chromosomes with hg38 lengths).  Device vs the pinned oracle: lengths, error rates after the
+    homopolymer filter (simulator.py:1920-1947), run lengths after mutate_homo (:618-705), qualities; plus the bit-exact
+    script check on chromosomes of hundreds of Mb (offsets beyond 2^31)."""
+    import torch
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(1)
+    lens = synth.HG38_LENGTHS
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(1)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda:0")
+    total = sum(lens)
+    dev = torch.empty(total, dtype=torch.uint8, device="cuda:0")
+    for s0 in range(0, total, 1 << 28):
+        e0 = min(total, s0 + (1 << 28))
+        dev[s0:e0] = lut[torch.randint(0, 4, (e0 - s0,), generator=g, device="cuda:0", dtype=torch.uint8).long()]
+    bases = dev.cpu().numpy()
+    del dev
+    torch.cuda.empty_cache()
+    ref = PackedReference(list(synth.HG38_NAMES), bases, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64))
+    eng, cm, t = pc.make_engine("dorado", ref, fastq=True, chimeric=True, kmer_bias=6, seed=505)
+    s_dev = rs.empty()
+    eng.simulate(L.NS_KIND_ALIGNED, 0, 3000)
+    b = eng.fetch(want_ops=True)
+    assert pc.check_edit_scripts(b, ref, True, max_reads=150) > 0
+    assert (b.pieces["chrom"] > 10).any() and int((ref.offsets[b.pieces["chrom"]].astype(np.int64) + b.pieces["pos"]).max()) > 2 ** 31
+    pc.batch_stats(b, ref, True, s_dev)
+    eng.close()
+    recs = [(n, bases[int(ref.offsets[i]):int(ref.offsets[i + 1])].tobytes().decode()) for i, n in enumerate(ref.names)]
+    s_or = pc.oracle_stats(cm, recs, 160, 0, True, chimeric=True, tmpdir=str(tmp_path), kmer_bias=6)
+    fails = pc.compare_stats(s_dev, s_or, rate_tol=0.08, p_min=1e-5, label="config5",
+                             keys=["len_aligned", "len_middle_ref", "len_head", "len_tail", "match_run", "first_match"])
+    for k in ("hp_runs", "qual_middle", "qual_ht"):
+        st, dof, p = pc.chi2_two_sample(s_dev[k], s_or[k])
+        print("config5", k, "chi2 %.1f dof %d p %.3g" % (st, dof, p))
+        if p < 1e-5:
+            fails.append("config5 %s chi2 %.1f dof %d p %.3g" % (k, st, dof, p))
+    rd = (s_dev["aligned_bases"] - s_dev["head_bases"] - s_dev["tail_bases"]) / s_dev["ref_bases"]
+    ro = (s_or["aligned_bases"] - s_or["head_bases"] - s_or["tail_bases"]) / s_or["ref_bases"]
+    print("config5 middle bases per reference base: device %.5f oracle %.5f" % (rd, ro))
+    assert abs(rd / ro - 1) < 3e-3, (rd, ro)
+    assert not fails, "\n".join(fails)
