@@ -555,6 +555,34 @@ def main():
                                  "stretches every per-launch duration)" % (kernel, len(al1), n_al),
                      "whole_path_frac": algo_bytes * total_bases / (t_ms * 1e-3) / 1e9 / peak / max(world, 1)},
     }
+    if keep_host:
+        # ---- to-file arm: the drop-in driver's simulation() (nanosim_b200/simulator.py: names, FASTA/FASTQ records and the
+        #      error profile formatted and pwrite()n by library threads) into RAM-backed files, on a bounded number of reads
+        import shutil
+        from types import SimpleNamespace
+        from nanosim_b200 import simulator
+        out_dir = tempfile.mkdtemp(prefix="bench_to_file_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        host_ref = SimpleNamespace(names=list(sref.names), bases=sref.bases, offsets=sref.offsets)
+        nthr = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else cores))
+        tf = {}
+        try:
+            for label, errp, nsteps in (("with_error_profile", True, 1), ("reads_only", False, 2)):
+                prof = SimpleNamespace(ref=host_ref, tables=tables, engine=eng, number_aligned=n_al * nsteps, number_unaligned=n_un * nsteps,
+                                       seed=20260924, ir=None, n_trx=0)
+                t0 = time.perf_counter()
+                tot = simulator.simulation(prof, W["mode"], os.path.join(out_dir, label), "linear", False, W["kmer_bias"] or None, "guppy",
+                                           sref.max_chrom, 50, nthr, W["fastq"], chimeric=W["chimeric"], batch_reads=batch_reads,
+                                           error_profile=errp)
+                dt = time.perf_counter() - t0
+                tf[label] = {"value": tot["bases"] / dt, "unit": "bases/s", "reads": tot["reads"], "file_gb": tot["bytes"] / 1e9,
+                             "gb_per_s": tot["bytes"] / dt / 1e9, "seconds": dt}
+                for fn in os.listdir(out_dir):
+                    os.remove(os.path.join(out_dir, fn))
+        finally:
+            shutil.rmtree(out_dir, ignore_errors=True)
+        tf["note"] = "simulator.simulation() of the drop-in CLI writing into %s, %d formatter / writer threads (-t), pipeline depth 2, " \
+                     "first batch included" % (os.path.dirname(out_dir), nthr)
+        line["to_file"] = tf
     line["host"] = {"cpus": cores, "cpus_allowed": len(all_cpus) if all_cpus else None, "numa_binding": binding}
     if keep_host:
         hostbind.unbind(all_cpus)                                # the CPU baseline may use every core of the box

@@ -240,6 +240,26 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
  * (cores / LOCAL_WORLD_SIZE), else 0 = plain ASCII copies). */
 int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsPieceMeta* pieces, uint32_t* ops);
 
+/* Multi-GPU init (one process per GPU): the reference's forked workers inherit seq_dict from the parent
+ * (simulator.py:1588-1622); here rank `root` reads the FASTA, calls ns_set_reference, and ONE NCCL broadcast hands bases,
+ * chromosome offsets and the metagenome tables to the other ranks' HBM, where each rank builds its own 2-bit copy.  Rank
+ * `root` obtains a communicator id with ns_nccl_unique_id() and passes it to the others by any host channel (the driver
+ * uses torch.distributed's store); every rank then calls ns_bcast_nccl() (collective).  libnccl.so.2 is loaded at run time. */
+/* Host copy of the resident reference bytes (ranks that received them by broadcast format the error profile's reference
+ * column from it). */
+int ns_get_reference(NsContext* ctx, uint8_t* bases, uint64_t cap);
+#define NS_NCCL_ID_BYTES 128
+int ns_nccl_unique_id(uint8_t* id /* NS_NCCL_ID_BYTES */);
+int ns_bcast_nccl(NsContext* ctx, const uint8_t* id, int rank, int world, int root);
+
+/* read_profile's reference reader (simulator.py:341-349, readfq :709-740) for FASTA and FASTQ files: sequence bytes of all
+ * records back to back exactly as in the file (case and IUPAC codes kept, line ends dropped), record offsets, header lines.
+ * Multi-threaded over an mmap of the file.  Two calls: with bases == NULL only the three counts are set (the caller sizes
+ * its buffers: n_bases bytes, n_records + 1 offsets, header_bytes bytes, n_records header offsets), then the fill.  Returns
+ * the number of bases or a negative NS_E* code. */
+int64_t ns_read_fasta(const char* path, uint8_t* bases, uint64_t bases_cap, uint64_t* rec_off, char* headers, uint64_t headers_cap,
+                      uint64_t* header_off, uint32_t* n_records, uint64_t* n_bases, uint64_t* header_bytes, int n_threads);
+
 /* How ns_fetch moves the bases of large batches: *packed_bases = 1 when they cross PCIe as 2 bits each (every byte of the
  * reference is an IUPAC nucleotide code, so reads hold A C G T/U only, and the host has threads to expand them),
  * *unpack_threads = host threads ns_fetch uses for the expansion.  (No reference counterpart: its workers write files.) */
@@ -293,6 +313,16 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
                                 uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
                                 const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
                                 int n_threads);
+
+/* The two formatters above writing straight into a file (what the reference's workers do with out_reads.write /
+ * out_error.write, simulator.py:1437-1443, 2006-2008): every thread formats its stretch of records into a private chunk and
+ * pwrite()s it at byte `file_off` + its position, so no text buffer of the whole batch exists and the copy into the page
+ * cache runs on n_threads cores.  Returns the bytes written (the caller advances its offset by it) or a negative NS_E*. */
+int64_t ns_write_records(int fd, uint64_t file_off, const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads,
+                         uint32_t n_reads, const char* names, const uint64_t* name_off, int fastq, int n_threads);
+int64_t ns_write_error_profile(int fd, uint64_t file_off, const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces,
+                               const uint32_t* ops, uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off,
+                               const char* names, const uint64_t* name_off, uint64_t seed, uint64_t first_id, int n_threads);
 
 /* Host-side read names of a fetched batch in the reference's formats (genome :1390-1402, metagenome :965-969,
  * transcriptome :1188-1219, perfect :1332-1343, unaligned :1511/:1529-1534), written as NUL-terminated strings back to

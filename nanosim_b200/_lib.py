@@ -23,7 +23,7 @@ NS_STATS_COMP_OFF = NS_STATS_INS_OFF + 4
 NS_STATS_WORDS = NS_STATS_COMP_OFF + 4
 
 EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
-           "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names", "ns_transfer_info"]
+           "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names", "ns_transfer_info", "ns_write_records", "ns_write_error_profile", "ns_read_fasta", "ns_nccl_unique_id", "ns_bcast_nccl", "ns_get_reference"]
 
 
 class NsReference(C.Structure):
@@ -146,6 +146,19 @@ def lib():
     L.ns_format_error_profile.restype = C.c_int64
     L.ns_format_names.argtypes = [P, P, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, P, P, P, C.c_uint64, P]
     L.ns_format_names.restype = C.c_int64
+    L.ns_get_reference.argtypes = [P, P, C.c_uint64]
+    L.ns_get_reference.restype = C.c_int
+    L.ns_nccl_unique_id.argtypes = [P]
+    L.ns_nccl_unique_id.restype = C.c_int
+    L.ns_bcast_nccl.argtypes = [P, P, C.c_int, C.c_int, C.c_int]
+    L.ns_bcast_nccl.restype = C.c_int
+    L.ns_read_fasta.argtypes = [C.c_char_p, P, C.c_uint64, P, P, C.c_uint64, P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                C.POINTER(C.c_uint64), C.c_int]
+    L.ns_read_fasta.restype = C.c_int64
+    L.ns_write_records.argtypes = [C.c_int, C.c_uint64, P, P, P, C.c_uint32, P, P, C.c_int, C.c_int]
+    L.ns_write_records.restype = C.c_int64
+    L.ns_write_error_profile.argtypes = [C.c_int, C.c_uint64, P, P, P, P, C.c_uint32, P, P, P, P, C.c_uint64, C.c_uint64, C.c_int]
+    L.ns_write_error_profile.restype = C.c_int64
     L.ns_transfer_info.argtypes = [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.ns_transfer_info.restype = C.c_int
     L.ns_reemit.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, C.c_uint64]

@@ -12,10 +12,22 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <string>
 #include <mutex>
 #include <thread>
 #include <vector>
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define NS_HAVE_NCCL 1
+#else
+#define NS_HAVE_NCCL 0
+#endif
 
 #include "nanosim_b200.h"
 #include "device_common.cuh"
@@ -1578,9 +1590,48 @@ int ns_op_stats(NsContext* ctx, uint64_t* out) {
 // ---------------------------------------------------------------------------------------------------------
 // host-side FASTA/FASTQ record formatting (simulator.py:1437-1443), multi-threaded memcpy-style assembly
 // ---------------------------------------------------------------------------------------------------------
-int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads, uint32_t n_reads,
-                          const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
-                          int n_threads) {
+namespace {
+// Sink of a formatter thread: either the caller's buffer, or a private chunk that is written with pwrite() at the right
+// file position whenever it fills up (the records of one thread are contiguous in the output).
+struct ChunkSink {
+    char* out;                // buffer mode: start of the whole output
+    int fd;                   // file mode: descriptor + offset of the output's first byte in the file
+    uint64_t file_off;
+    std::vector<char> buf;
+    size_t used = 0;
+    uint64_t start = 0;       // output position of buf[0]
+    bool ok = true;
+    ChunkSink(char* o, int f, uint64_t fo) : out(o), fd(f), file_off(fo) {
+        if (fd >= 0) buf.resize(size_t(8) << 20);
+    }
+    char* reserve(uint64_t at, size_t n) {       // n bytes at output position `at` (positions only grow within a thread)
+        if (fd < 0) return out + at;
+        if (used + n > buf.size()) {
+            flush();
+            if (n > buf.size()) buf.resize(n);
+        }
+        if (used == 0) start = at;
+        char* p = buf.data() + used;
+        used += n;
+        return p;
+    }
+    void flush() {
+        size_t done = 0;
+        while (fd >= 0 && done < used) {
+            const ssize_t w = pwrite(fd, buf.data() + done, used - done, (off_t)(file_off + start + done));
+            if (w <= 0) {
+                ok = false;
+                break;
+            }
+            done += (size_t)w;
+        }
+        used = 0;
+    }
+};
+
+int64_t format_records_impl(const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads, uint32_t n_reads,
+                            const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
+                            int n_threads, int fd, uint64_t file_off) {
     if (!seq || !reads || !names || !name_off || (fastq && !qual)) return NS_EINVAL;
     std::vector<uint64_t> off((size_t)n_reads + 1, 0);
     for (uint32_t i = 0; i < n_reads; ++i) {
@@ -1589,12 +1640,16 @@ int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadM
         if (fastq) rec += 2 + reads[i].seq_len + 1;
         off[i + 1] = off[i] + rec;
     }
-    if (!out) return (int64_t)off[n_reads];
-    if (off[n_reads] > out_cap) return NS_ENOMEM;
+    if (fd < 0) {
+        if (!out) return (int64_t)off[n_reads];
+        if (off[n_reads] > out_cap) return NS_ENOMEM;
+    }
     int nt = std::max(1, std::min(n_threads, 64));
-    auto work = [&](uint32_t lo, uint32_t hi) {
+    std::vector<char> failed((size_t)nt, 0);
+    auto work = [&](uint32_t lo, uint32_t hi, int tid) {
+        ChunkSink sink(out, fd, file_off);
         for (uint32_t i = lo; i < hi; ++i) {
-            char* p = out + off[i];
+            char* p = sink.reserve(off[i], (size_t)(off[i + 1] - off[i]));
             const char* nm = names + name_off[i];
             size_t nl = strlen(nm);
             *p++ = fastq ? '@' : '>';
@@ -1612,9 +1667,11 @@ int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadM
                 *p++ = '\n';
             }
         }
+        sink.flush();
+        if (!sink.ok) failed[tid] = 1;
     };
     if (nt == 1 || n_reads < 64) {
-        work(0, n_reads);
+        work(0, n_reads, 0);
     } else {
         std::vector<std::thread> th;
         // split by bytes, not by reads, so threads carry equal copy volume
@@ -1624,12 +1681,27 @@ int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadM
             uint32_t hi = (uint32_t)(std::upper_bound(off.begin(), off.end(), goal) - off.begin());
             hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_reads);
             if (t == nt - 1) hi = n_reads;
-            if (hi > lo) th.emplace_back(work, lo, hi);
+            if (hi > lo) th.emplace_back(work, lo, hi, t);
             lo = hi;
         }
         for (auto& x : th) x.join();
     }
+    for (char f : failed)
+        if (f) return NS_EINVAL;
     return (int64_t)off[n_reads];
+}
+}  // namespace
+
+int64_t ns_format_records(const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads, uint32_t n_reads,
+                          const char* names, const uint64_t* name_off, int fastq, char* out, uint64_t out_cap,
+                          int n_threads) {
+    return format_records_impl(seq, qual, reads, n_reads, names, name_off, fastq, out, out_cap, n_threads, -1, 0);
+}
+
+int64_t ns_write_records(int fd, uint64_t file_off, const uint8_t* seq, const uint8_t* qual, const NsReadMeta* reads,
+                         uint32_t n_reads, const char* names, const uint64_t* name_off, int fastq, int n_threads) {
+    if (fd < 0) return NS_EINVAL;
+    return format_records_impl(seq, qual, reads, n_reads, names, name_off, fastq, nullptr, 0, n_threads, fd, file_off);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1665,10 +1737,10 @@ struct EvRow {
 };
 }  // namespace
 
-int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces, const uint32_t* ops,
-                                uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
-                                const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
-                                int n_threads) {
+static int64_t format_error_profile_impl(const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces, const uint32_t* ops,
+                                         uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
+                                         const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
+                                         int n_threads, int fd, uint64_t file_off) {
     if (!seq || !reads || !pieces || !ops || !ref_bases || !chrom_off || !names || !name_off) return NS_EINVAL;
     static const char kTypes[3][4] = {"mis", "ins", "del"};
     uint8_t comp[256];
@@ -1792,13 +1864,21 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
         }
         for (uint32_t i = 0; i < n_reads; ++i) off[i + 1] += off[i];
     }
-    if (!out) return (int64_t)off[n_reads];
-    if (off[n_reads] > out_cap) return NS_ENOMEM;
-    auto fill = [&](uint32_t lo, uint32_t hi) {
-        for (uint32_t i = lo; i < hi; ++i) do_read(i, out + off[i]);
+    if (fd < 0) {
+        if (!out) return (int64_t)off[n_reads];
+        if (off[n_reads] > out_cap) return NS_ENOMEM;
+    }
+    std::vector<char> failed((size_t)nt + 1, 0);
+    int next_tid = 0;
+    auto fill = [&](uint32_t lo, uint32_t hi, int tid) {
+        ChunkSink sink(out, fd, file_off);
+        for (uint32_t i = lo; i < hi; ++i)
+            if (off[i + 1] > off[i]) do_read(i, sink.reserve(off[i], (size_t)(off[i + 1] - off[i])));
+        sink.flush();
+        if (!sink.ok) failed[tid] = 1;
     };
     if (nt == 1 || n_reads < 64) {
-        fill(0, n_reads);
+        fill(0, n_reads, 0);
     } else {
         std::vector<std::thread> th;
         uint32_t lo = 0;
@@ -1807,13 +1887,32 @@ int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, con
             uint32_t hi = (uint32_t)(std::upper_bound(off.begin(), off.end(), goal) - off.begin());
             hi = std::min<uint32_t>(std::max<uint32_t>(hi, lo), n_reads);
             if (t == nt - 1) hi = n_reads;
-            if (hi > lo) th.emplace_back(fill, lo, hi);
+            if (hi > lo) th.emplace_back(fill, lo, hi, next_tid++);
             lo = hi;
         }
         for (auto& x : th) x.join();
     }
+    for (char f : failed)
+        if (f) return NS_EINVAL;
     return (int64_t)off[n_reads];
 }
+
+int64_t ns_format_error_profile(const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces, const uint32_t* ops,
+                                uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off, const char* names,
+                                const uint64_t* name_off, uint64_t seed, uint64_t first_id, char* out, uint64_t out_cap,
+                                int n_threads) {
+    return format_error_profile_impl(seq, reads, pieces, ops, n_reads, ref_bases, chrom_off, names, name_off, seed, first_id, out,
+                                     out_cap, n_threads, -1, 0);
+}
+
+int64_t ns_write_error_profile(int fd, uint64_t file_off, const uint8_t* seq, const NsReadMeta* reads, const NsPieceMeta* pieces,
+                               const uint32_t* ops, uint32_t n_reads, const uint8_t* ref_bases, const uint64_t* chrom_off,
+                               const char* names, const uint64_t* name_off, uint64_t seed, uint64_t first_id, int n_threads) {
+    if (fd < 0) return NS_EINVAL;
+    return format_error_profile_impl(seq, reads, pieces, ops, n_reads, ref_bases, chrom_off, names, name_off, seed, first_id, nullptr,
+                                     0, n_threads, fd, file_off);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------
 // host-side read names (simulator.py:1390-1402 genome, :965-969 metagenome, :1188-1219 transcriptome, :1332-1343 perfect,
@@ -1949,6 +2048,265 @@ int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint
         total += nm.size() + 1;
     }
     return (int64_t)total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FASTA / FASTQ reader of read_profile (simulator.py:341-349 with readfq :709-740): the file is mmap()ed and cut into
+// line-aligned chunks; every thread finds the record headers of its chunk and counts its sequence bytes (pass 1), a prefix
+// sum places the chunks, and the threads copy their sequence lines behind one another (pass 2).  Bytes are kept as they are
+// (case, IUPAC codes); line ends (\n, \r\n) are dropped.  A FASTQ file (first byte '@') is read by one thread: its
+// quality lines can begin with '>' or '@'.
+// Two-call protocol: with bases == NULL only *n_records, *n_bases and *header_bytes are set.  rec_off gets n_records + 1
+// offsets into bases; headers gets the header lines (without the marker) NUL-terminated back to back, header_off their starts.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct FaChunk {
+    const char* lo;
+    const char* hi;
+    uint64_t n_bases = 0;
+    std::vector<std::pair<const char*, uint64_t>> heads;      // header line start (at the marker), sequence bytes of the chunk before it
+};
+inline const char* line_end(const char* p, const char* end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    return nl ? nl : end;
+}
+inline size_t trimmed(const char* p, const char* e) {         // line length without a trailing \r
+    return (e > p && e[-1] == '\r') ? (size_t)(e - p - 1) : (size_t)(e - p);
+}
+}  // namespace
+
+int64_t ns_read_fasta(const char* path, uint8_t* bases, uint64_t bases_cap, uint64_t* rec_off, char* headers, uint64_t headers_cap,
+                      uint64_t* header_off, uint32_t* n_records, uint64_t* n_bases, uint64_t* header_bytes, int n_threads) {
+    if (!path || !n_records || !n_bases || !header_bytes) return NS_EINVAL;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return NS_EINVAL;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        close(fd);
+        return NS_EINVAL;
+    }
+    const size_t size = (size_t)sb.st_size;
+    *n_records = 0;
+    *n_bases = *header_bytes = 0;
+    if (size == 0) {
+        close(fd);
+        return 0;
+    }
+    const char* base = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) return NS_ENOMEM;
+    madvise((void*)base, size, MADV_SEQUENTIAL);
+    const char* end = base + size;
+    const bool fastq = base[0] == '@';
+    int nt = fastq ? 1 : std::max(1, std::min(n_threads, 64));
+    if (size < (size_t(1) << 22)) nt = 1;
+    std::vector<FaChunk> ch((size_t)nt);
+    for (int t = 0; t < nt; ++t) {                             // line-aligned chunk boundaries
+        const char* p = base + size * (size_t)t / (size_t)nt;
+        if (t > 0) {
+            p = line_end(p - 1, end);
+            if (p < end) ++p;
+        }
+        ch[t].lo = p;
+        if (t > 0) ch[t - 1].hi = p;
+    }
+    ch[nt - 1].hi = end;
+    const bool fill = bases != nullptr;
+    // pass 1 / pass 2 over one chunk; FASTQ: sequence lines run to the '+' line, then as many quality bytes are skipped
+    auto walk = [&](FaChunk& c, uint8_t* dst) {
+        const char* p = c.lo;
+        uint64_t count = 0;
+        bool in_qual = false;
+        uint64_t qual_left = 0, rec_bases = 0;
+        while (p < c.hi) {
+            const char* e = line_end(p, c.hi);
+            const size_t len = trimmed(p, e);
+            if (fastq && in_qual) {
+                if (qual_left <= len) in_qual = false; else qual_left -= len;
+            } else if (len && (p[0] == '>' || (fastq && p[0] == '@'))) {
+                if (!dst) c.heads.emplace_back(p, count);
+                rec_bases = 0;
+            } else if (fastq && len && p[0] == '+') {
+                in_qual = rec_bases > 0;
+                qual_left = rec_bases;
+            } else if (len) {
+                if (dst) memcpy(dst + count, p, len);
+                count += len;
+                rec_bases += len;
+            }
+            p = e < c.hi ? e + 1 : c.hi;
+        }
+        if (!dst) c.n_bases = count;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { walk(ch[t], nullptr); });
+        walk(ch[0], nullptr);
+        for (auto& x : th) x.join();
+    }
+    uint64_t total = 0, n_rec = 0, hbytes = 0;
+    std::vector<uint64_t> chunk_off((size_t)nt);
+    for (int t = 0; t < nt; ++t) {
+        chunk_off[t] = total;
+        total += ch[t].n_bases;
+        n_rec += ch[t].heads.size();
+        for (auto& h : ch[t].heads) hbytes += trimmed(h.first, line_end(h.first, end));       // marker dropped, NUL added
+    }
+    *n_records = (uint32_t)n_rec;
+    *n_bases = total;
+    *header_bytes = hbytes;
+    int64_t rc = (int64_t)total;
+    if (fill) {
+        if (total > bases_cap || hbytes > headers_cap || !rec_off || !headers || !header_off) {
+            rc = NS_ENOMEM;
+        } else {
+            uint64_t r = 0, hpos = 0;
+            for (int t = 0; t < nt; ++t)
+                for (auto& h : ch[t].heads) {
+                    rec_off[r] = chunk_off[t] + h.second;
+                    const size_t hl = trimmed(h.first, line_end(h.first, end)) - 1;
+                    header_off[r] = hpos;
+                    memcpy(headers + hpos, h.first + 1, hl);
+                    headers[hpos + hl] = 0;
+                    hpos += hl + 1;
+                    ++r;
+                }
+            rec_off[n_rec] = total;
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { walk(ch[t], bases + chunk_off[t]); });
+            walk(ch[0], bases + chunk_off[0]);
+            for (auto& x : th) x.join();
+        }
+    }
+    munmap((void*)base, size);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One NCCL broadcast of the reference at init (the reference's workers inherit the parent's seq_dict through fork(),
+// simulator.py:1588-1622; ranks on different GPUs get it over NVLink instead of each parsing the FASTA).  NCCL is
+// loaded at run time (dlopen), so the library has no link-time dependency on it.
+// ---------------------------------------------------------------------------------------------------------
+#if NS_HAVE_NCCL
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* override_path = getenv("NANOSIM_B200_NCCL_LIB");
+        const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            a.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (a.h) break;
+        }
+        if (!a.h) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(a.h, "ncclBroadcast");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.Broadcast && a.CommDestroy;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+#endif
+
+int ns_get_reference(NsContext* ctx, uint8_t* bases, uint64_t cap) {
+    if (!ctx || !bases) return NS_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, NS_ESTATE, "ns_get_reference: no reference set");
+    if (cap < ctx->dref.genome_len) return fail(ctx, NS_ENOMEM, "ns_get_reference: buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(bases, ctx->dref.bases, ctx->dref.genome_len, cudaMemcpyDeviceToHost));
+    return NS_OK;
+}
+
+int ns_nccl_unique_id(uint8_t* id) {
+#if NS_HAVE_NCCL
+    if (!id) return NS_EINVAL;
+    NcclApi& api = nccl_api();
+    if (!api.ok) return NS_ESTATE;
+    ncclUniqueId u;
+    if (api.GetUniqueId(&u) != ncclSuccess) return NS_ECUDA;
+    static_assert(sizeof(ncclUniqueId) == NS_NCCL_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &u, sizeof u);
+    return NS_OK;
+#else
+    (void)id;
+    return NS_ESTATE;
+#endif
+}
+
+int ns_bcast_nccl(NsContext* ctx, const uint8_t* id, int rank, int world, int root) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world || root < 0 || root >= world) return fail(ctx, NS_EINVAL, "ns_bcast_nccl: bad argument");
+#if NS_HAVE_NCCL
+    if (ctx->borrowed) return fail(ctx, NS_ESTATE, "ns_bcast_nccl: a cloned context shares its parent's reference");
+    if (rank == root && !ctx->have_ref) return fail(ctx, NS_ESTATE, "ns_bcast_nccl: the root rank sets its reference first (ns_set_reference)");
+    if (world == 1) return NS_OK;
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(ctx, NS_ESTATE, "ns_bcast_nccl: libnccl.so.2 could not be loaded (NANOSIM_B200_NCCL_LIB overrides the path)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    ncclComm_t comm = nullptr;
+    ncclResult_t nr = api.CommInitRank(&comm, world, u, rank);
+    if (nr != ncclSuccess) return fail(ctx, NS_ECUDA, "ns_bcast_nccl: ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(nr) : "?");
+    auto bc = [&](void* p, size_t bytes) { return bytes ? api.Broadcast(p, p, bytes, ncclUint8, root, comm, st) : ncclSuccess; };
+    int rc = NS_OK;
+    uint64_t* d_head = nullptr;
+    void *t_bases = nullptr, *t_off = nullptr, *t_sp = nullptr, *t_circ = nullptr;
+    do {
+        uint64_t head[4] = {ctx->dref.genome_len, ctx->dref.n_chrom, ctx->dref.n_species, 0};
+        if (cudaMalloc((void**)&d_head, sizeof head) != cudaSuccess) { rc = NS_ENOMEM; break; }
+        cudaMemcpyAsync(d_head, head, sizeof head, cudaMemcpyHostToDevice, st);
+        if (bc(d_head, sizeof head) != ncclSuccess) { rc = NS_ECUDA; break; }
+        cudaMemcpyAsync(head, d_head, sizeof head, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = NS_ECUDA; break; }
+        const uint64_t n_bases = head[0];
+        const uint32_t n_chrom = (uint32_t)head[1], n_species = (uint32_t)head[2];
+        if (rank == root) {
+            t_bases = ctx->ref_bases.p; t_off = ctx->ref_off.p; t_sp = ctx->ref_species.p; t_circ = ctx->ref_circular.p;
+        } else {
+            if (cudaMalloc(&t_bases, n_bases ? n_bases : 16) != cudaSuccess || cudaMalloc(&t_off, (n_chrom + 1) * sizeof(uint64_t)) != cudaSuccess ||
+                (n_species && (cudaMalloc(&t_sp, n_chrom * 4) != cudaSuccess || cudaMalloc(&t_circ, n_chrom) != cudaSuccess))) { rc = NS_ENOMEM; break; }
+        }
+        if (bc(t_bases, n_bases) != ncclSuccess || bc(t_off, (n_chrom + 1) * sizeof(uint64_t)) != ncclSuccess ||
+            (n_species && (bc(t_sp, (size_t)n_chrom * 4) != ncclSuccess || bc(t_circ, n_chrom) != ncclSuccess))) { rc = NS_ECUDA; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = NS_ECUDA; break; }
+        if (rank != root) {
+            NsReference r;
+            r.bases = (const uint8_t*)t_bases;            // device pointers: ns_set_reference copies from them
+            r.n_bases = n_bases;
+            r.chrom_off = (const uint64_t*)t_off;
+            r.n_chrom = n_chrom;
+            r.n_species = n_species;
+            r.chrom_species = (const uint32_t*)t_sp;
+            r.chrom_circular = (const uint8_t*)t_circ;
+            rc = ns_set_reference(ctx, &r);
+        }
+    } while (0);
+    if (rank != root) {
+        cudaFree(t_bases); cudaFree(t_off); cudaFree(t_sp); cudaFree(t_circ);
+    }
+    cudaFree(d_head);
+    api.CommDestroy(comm);
+    if (rc != NS_OK && ctx->err.empty()) ctx->err = "ns_bcast_nccl: broadcast failed";
+    return rc;
+#else
+    (void)rank; (void)world; (void)root;
+    return fail(ctx, NS_ESTATE, "ns_bcast_nccl: built without nccl.h");
+#endif
 }
 
 }  // extern "C"

@@ -101,6 +101,24 @@ class Engine:
         r = L.NsReference(C.c_void_p(int(bases_ptr)), int(n_bases), _ptr(offsets), len(offsets) - 1, int(n_species), _ptr(sp), _ptr(circ))
         self._check(self._lib.ns_set_reference(self._ctx, C.byref(r)))
 
+    # ---- multi-GPU init: one NCCL broadcast of the reference (ns_bcast_nccl)
+    def nccl_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        rc = self._lib.ns_nccl_unique_id(buf)
+        if rc != 0:
+            raise NanoSimError("ns_nccl_unique_id failed (rc=%d): libnccl.so.2 not loadable?" % rc)
+        return bytes(buf)
+
+    def bcast_reference(self, nccl_id, rank, world, root=0):
+        """Collective over the ranks of a job: rank `root` (which has set its reference) sends it to the others' HBM."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
+        self._check(self._lib.ns_bcast_nccl(self._ctx, buf, int(rank), int(world), int(root)))
+
+    def reference_bases(self, n_bases):
+        out = np.empty(int(n_bases), dtype=np.uint8)
+        self._check(self._lib.ns_get_reference(self._ctx, _ptr(out), C.c_uint64(len(out))))
+        return out
+
     def fetch_packs_bases(self):
         """True when ns_fetch sends the bases over PCIe as 2 bits each (ns_transfer_info)."""
         packed, threads = C.c_uint32(), C.c_uint32()

@@ -86,6 +86,38 @@ def format_records(batch, names, fastq, n_threads=8, as_array=False):
     return out if as_array else out.tobytes()
 
 
+def write_records(fd, file_off, batch, names, fastq, n_threads=8):
+    """format_records() straight into file descriptor ``fd`` at byte ``file_off`` (ns_write_records: every formatter thread
+    pwrite()s its own stretch).  Returns the number of bytes written."""
+    lib = L.lib()
+    blob, offs = _name_blob(names)
+    reads = np.ascontiguousarray(batch.reads)
+    qual_ptr = batch.qual.ctypes.data_as(C.c_void_p) if fastq else None
+    got = lib.ns_write_records(int(fd), C.c_uint64(int(file_off)), batch.seq.ctypes.data_as(C.c_void_p), qual_ptr,
+                               reads.ctypes.data_as(C.c_void_p), len(names), blob, offs.ctypes.data_as(C.c_void_p), int(fastq), n_threads)
+    if got < 0:
+        raise OSError("ns_write_records failed: %d" % got)
+    return int(got)
+
+
+def write_error_profile(fd, file_off, batch, names, ref, seed=0, n_threads=8):
+    """format_error_profile() straight into file descriptor ``fd`` at byte ``file_off`` (ns_write_error_profile)."""
+    lib = L.lib()
+    blob, offs = _name_blob(names)
+    reads = np.ascontiguousarray(batch.reads)
+    pieces = np.ascontiguousarray(batch.pieces)
+    ops = np.ascontiguousarray(batch.ops, dtype=np.uint32)
+    bases = np.ascontiguousarray(ref.bases)
+    coff = np.ascontiguousarray(ref.offsets, dtype=np.uint64)
+    got = lib.ns_write_error_profile(int(fd), C.c_uint64(int(file_off)), batch.seq.ctypes.data_as(C.c_void_p),
+                                     reads.ctypes.data_as(C.c_void_p), pieces.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_void_p),
+                                     len(names), bases.ctypes.data_as(C.c_void_p), coff.ctypes.data_as(C.c_void_p), blob,
+                                     offs.ctypes.data_as(C.c_void_p), C.c_uint64(int(seed)), C.c_uint64(int(batch.first_id)), n_threads)
+    if got < 0:
+        raise OSError("ns_write_error_profile failed: %d" % got)
+    return int(got)
+
+
 class NameTable:
     """Read names as the formatters take them: NUL-terminated strings back to back + the offset of each."""
 

@@ -67,7 +67,48 @@ class PackedReference:
         return PackedReference(a.names + b.names, np.concatenate([a.bases, b.bases]), offs, a.raw_names + b.raw_names)
 
     @staticmethod
-    def from_fasta(path):
+    def from_fasta(path, n_threads=None):
+        """FASTA (or FASTQ) file -> PackedReference.  The bytes are read by the library's multi-threaded mmap reader
+        (ns_read_fasta); the pure-Python reader below is the fallback when the library is not built and for files with a
+        repeated record key (a later record then replaces the earlier one, as seq_dict[key] = ... does, :346)."""
+        try:
+            ref = PackedReference._from_fasta_native(path, n_threads)
+            if ref is not None:
+                return ref
+        except (OSError, RuntimeError):
+            pass
+        return PackedReference._from_fasta_python(path)
+
+    @staticmethod
+    def _from_fasta_native(path, n_threads=None):
+        import ctypes as C
+        import os
+
+        from . import _lib
+        lib = _lib.lib()
+        nt = int(n_threads or min(32, os.cpu_count() or 1))
+        n_rec, n_bases, hbytes = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        rc = lib.ns_read_fasta(os.fsencode(path), None, 0, None, None, 0, None, C.byref(n_rec), C.byref(n_bases), C.byref(hbytes), nt)
+        if rc < 0:
+            raise OSError("ns_read_fasta(%s) failed: %d" % (path, rc))
+        bases = np.empty(n_bases.value, dtype=np.uint8)
+        offs = np.zeros(n_rec.value + 1, dtype=np.uint64)
+        hdr = np.zeros(max(hbytes.value, 1), dtype=np.uint8)
+        hoff = np.zeros(max(n_rec.value, 1), dtype=np.uint64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.ns_read_fasta(os.fsencode(path), vp(bases), len(bases), vp(offs), vp(hdr), len(hdr), vp(hoff), C.byref(n_rec),
+                               C.byref(n_bases), C.byref(hbytes), nt)
+        if rc < 0:
+            raise OSError("ns_read_fasta(%s) failed: %d" % (path, rc))
+        headers = [h.decode() for h in hdr.tobytes()[:hbytes.value].split(b"\0")[:n_rec.value]]
+        names = [normalise_name(h) for h in headers]
+        if len(set(names)) != len(names) or (n_rec.value and int(offs[0]) != 0):
+            return None                       # repeated keys / bytes before the first record: the general path sorts it out
+        raws = [h.split()[0] if h.split() else h for h in headers]
+        return PackedReference(names, bases, offs, raws)
+
+    @staticmethod
+    def _from_fasta_python(path):
         with open(path, "rb") as f:
             blob = f.read()
         recs = []

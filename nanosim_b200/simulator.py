@@ -23,7 +23,7 @@ from . import _lib as L
 from .engine import Engine
 from .model import DeviceTables, load_model
 from .pipeline import BatchPipeline
-from .records import format_error_profile, format_records, name_table
+from .records import name_table, write_error_profile, write_records
 from .reference_fasta import (POLYA_SCALE, MetaReference, PackedReference, read_abundance, read_expression,
                               read_polya_list)
 from .model import build_alias
@@ -49,9 +49,97 @@ class Profile:
         self.perfect = False
 
 
+def _dist_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _dist_init():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")       # host-side plumbing only (objects, barriers); the reference travels over NCCL
+    return dist
+
+
+class _RemoteReference(PackedReference):
+    """The reference as a rank other than 0 sees it before the broadcast: names and offsets, no bases yet."""
+
+    def __init__(self, names, offsets, raw_names):
+        self.names, self.raw_names = list(names), list(raw_names)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.bases = None
+
+
 def read_profile(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
                  polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
                  device=0, seed=0, ir_files=None):
+    """read_profile (:244-591).  Under torchrun (WORLD_SIZE > 1) only rank 0 reads the reference files; the other ranks get
+    names and offsets through torch.distributed and the bases through ONE NCCL broadcast into their HBM (ns_bcast_nccl)."""
+    rank, world = _dist_world()
+    if world > 1:
+        return _read_profile_distributed(rank, world, ref_g, number_list, model_prefix, per, mode, strandness, ref_t, dna_type, abun,
+                                         polya, exp, model_ir, chimeric, homopolymer, fastq, device, seed, ir_files)
+    return _read_profile_local(ref_g, number_list, model_prefix, per, mode, strandness, ref_t, dna_type, abun, polya, exp, model_ir,
+                               chimeric, homopolymer, fastq, device, seed, ir_files)
+
+
+def _read_profile_distributed(rank, world, ref_g, number_list, model_prefix, per, mode, strandness, ref_t, dna_type, abun, polya, exp,
+                              model_ir, chimeric, homopolymer, fastq, device, seed, ir_files):
+    dist = _dist_init()
+    box = [None]
+    if rank == 0:
+        prof = _read_profile_local(ref_g, number_list, model_prefix, per, mode, strandness, ref_t, dna_type, abun, polya, exp, model_ir,
+                                   chimeric, homopolymer, fastq, device, seed, ir_files)
+        r = prof.ref
+        box[0] = {"names": r.names, "raw": r.raw_names, "offsets": r.offsets,
+                  "meta": (r.species, r.chrom_species, r.chrom_circular, r.chrom_keys) if mode == "metagenome" else None,
+                  "nccl_id": prof.engine.nccl_unique_id(),
+                  "extra": {k: getattr(prof, k) for k in ("samples", "number_list", "expr_chrom", "expr_weights", "polya_flags", "max_chrom",
+                                                          "n_trx", "coverage_ref_len", "counts", "number_aligned", "number_unaligned")
+                            if hasattr(prof, k)}}
+    dist.broadcast_object_list(box, src=0)
+    info = box[0]
+    if rank != 0:
+        # everything of read_profile that is not the reference: model tables, counts, expression / abundance (from rank 0)
+        prof = Profile()
+        prof.ir, prof.n_trx = None, 0
+        for k, v in info["extra"].items():
+            setattr(prof, k, v)
+        if info["meta"] is not None:
+            sp, csp, circ, keys = info["meta"]
+            prof.ref = MetaReference.__new__(MetaReference)
+            _RemoteReference.__init__(prof.ref, info["names"], info["offsets"], info["raw"])
+            prof.ref.species, prof.ref.chrom_species, prof.ref.chrom_circular, prof.ref.chrom_keys = sp, csp, circ, keys
+        else:
+            prof.ref = _RemoteReference(info["names"], info["offsets"], info["raw"])
+        if mode == "transcriptome" and model_ir:
+            from .intron_retention import IntronRetention, TranscriptStructures, read_ir_markov_model
+            ir_files = ir_files or {}
+            base = model_prefix[:-4] if model_prefix.endswith(".npz") else model_prefix
+            n_trx = prof.n_trx
+            trx_names, genome_raw = prof.ref.names[:n_trx], prof.ref.raw_names[n_trx:]
+            st = TranscriptStructures.from_gff3(ir_files.get("gff3") or base + "_added_intron_final.gff3", trx_names, genome_raw)
+            prof.ir = IntronRetention(read_ir_markov_model(ir_files.get("markov") or base + "_IR_markov_model"), st,
+                                      prof.ref.lengths[:n_trx], n_trx)
+        cm = load_model(model_prefix)
+        prof.tables = DeviceTables(cm, fastq=fastq, homopolymer=homopolymer, chimeric=chimeric, perfect=per, strandness=strandness, mode=mode)
+        prof.perfect, prof.seed = per, seed
+        from .hostbind import bind_to_gpu_node
+        bind_to_gpu_node(device)
+        prof.engine = Engine(device=device, seed=seed)
+    prof.engine.bcast_reference(info["nccl_id"], rank, world, 0)          # the one NCCL broadcast of the job
+    if rank != 0:
+        prof.ref.bases = prof.engine.reference_bases(int(prof.ref.offsets[-1]))   # host copy for the error profile's reference column
+        prof.engine.ref = prof.ref
+        prof.engine.set_model(prof.tables, perfect=per)
+        if mode == "transcriptome":
+            pr, al = build_alias(prof.expr_weights)
+            prof.engine.set_expression(pr, al, prof.expr_chrom, prof.polya_flags)
+    return prof
+
+
+def _read_profile_local(ref_g, number_list, model_prefix, per, mode, strandness, ref_t=None, dna_type=None, abun=None,
+                        polya=None, exp=None, model_ir=False, chimeric=False, homopolymer=False, fastq=False,
+                        device=0, seed=0, ir_files=None):
     prof = Profile()
     prof.ir = None
     prof.n_trx = 0
@@ -161,28 +249,43 @@ def simulation(prof, mode, out, dna_type, per, kmer_bias, basecaller, max_l, min
     suffix = "" if world == 1 else str(rank)
     want_err = error_profile and not per
     pipe = BatchPipeline(eng, depth=2, fetch=True, want_ops=want_err)
+    totals = {"reads": 0, "bases": 0, "bytes": 0}
     try:
-        _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads)
+        _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads, totals)
     finally:
         pipe.close()         # the cloned contexts own device batch buffers and pinned staging
+    return totals            # what this rank simulated and wrote (the reference returns nothing)
 
 
-def _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads):
+def _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, want_err, world, rank, batch_reads, fmt_threads, totals):
     def jobs(kind, lo, hi):
         return [(kind, start, min(batch_reads, hi - start)) for start in range(lo, hi, batch_reads)]
 
+    class _Out:
+        """An output file written at explicit offsets: the library's formatter threads pwrite() into it."""
+
+        def __init__(self, path, header=b""):
+            self.fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            self.pos = 0
+            if header:
+                self.pos = os.pwrite(self.fd, header, 0)
+
+        def close(self):
+            os.close(self.fd)
+
     _log("Start simulation of aligned reads")
     lo, hi = _shard(prof.number_aligned, rank, world)
-    with open(out + "_aligned_reads" + suffix + ext, "wb") as f_reads, \
-            open(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix), "wb") as f_err:
-        if world == 1:
-            f_err.write(b"Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n")
-
+    f_reads = _Out(out + "_aligned_reads" + suffix + ext)
+    f_err = _Out(out + ("_aligned_error_profile" if world == 1 else "_error_profile" + suffix),
+                 b"Seq_name\tSeq_pos\terror_type\terror_length\tref_base\tseq_base\n" if world == 1 else b"")
+    try:
         def sink_aligned(info, b, job):
             names = name_table(b, prof.ref.names, job[1], perfect=per, metagenome=meta, transcriptome=trx)
-            f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads, as_array=True))
+            f_reads.pos += write_records(f_reads.fd, f_reads.pos, b, names, fastq, n_threads=fmt_threads)
+            totals["reads"] += int(info.n_reads)
+            totals["bases"] += int(info.total_bases)
             if want_err:
-                f_err.write(format_error_profile(b, names, prof.ref, seed=prof.seed, n_threads=fmt_threads, as_array=True))
+                f_err.pos += write_error_profile(f_err.fd, f_err.pos, b, names, prof.ref, seed=prof.seed, n_threads=fmt_threads)
 
         def retain_introns(engine, info, job):
             # intron retention (:1156-1183): decided on the host from the batch's metadata, the few affected reads are laid
@@ -194,18 +297,27 @@ def _simulation_body(prof, pipe, mode, out, per, fastq, meta, trx, ext, suffix, 
 
         pipe.run(jobs(L.NS_KIND_ALIGNED, lo, hi), sink_aligned, static_assign=meta,
                  after_simulate=retain_introns if (trx and prof.ir is not None and not per) else None)
+    finally:
+        totals["bytes"] += f_reads.pos + f_err.pos
+        f_reads.close()
+        f_err.close()
     if not per:
         _log("Start simulation of random reads")
         lo, hi = _shard(prof.number_unaligned, rank, world)
         pipe.want_ops = False                              # unaligned reads are not logged (:1482-1549)
-        with open(out + "_unaligned_reads" + suffix + ext, "wb") as f_reads:
-
+        f_un = _Out(out + "_unaligned_reads" + suffix + ext)
+        try:
             def sink_unaligned(info, b, job):
                 # the reference's read index keeps counting after the aligned reads (shared total_simulated, :1574)
                 names = name_table(b, prof.ref.names, prof.number_aligned + job[1])
-                f_reads.write(format_records(b, names, fastq, n_threads=fmt_threads, as_array=True))
+                f_un.pos += write_records(f_un.fd, f_un.pos, b, names, fastq, n_threads=fmt_threads)
+                totals["reads"] += int(info.n_reads)
+                totals["bases"] += int(info.total_bases)
 
             pipe.run(jobs(L.NS_KIND_UNALIGNED, lo, hi), sink_unaligned, static_assign=meta)
+        finally:
+            totals["bytes"] += f_un.pos
+            f_un.close()
 
 
 def merge_rank_files(out, fastq, per, world):

@@ -18,6 +18,7 @@ MODEL_FILES = {"guppy": "guppy_fab49712_plusq.npz", "dorado": "dorado_kitv14_v3.
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs at least two CUDA devices (gpurun --gpus 2); not selected by -m gpu")
 
 
 @pytest.fixture(scope="session")

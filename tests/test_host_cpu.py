@@ -500,3 +500,67 @@ def test_coverage_counts_the_transcriptome_only_and_abundance_rows_may_be_missin
     numbers, samples = read_abundance(ab, ref.species)
     missing = MetaReference.species_key(lines[-1].split("\t")[0])
     assert samples[0][ref.species.index(missing)] == 0.0 and sum(samples[0]) > 0
+
+
+def test_file_sinks_write_what_the_formatters_return(tmp_path):
+    """ns_write_records / ns_write_error_profile (formatter threads pwrite() their own stretch of the file at the given
+    offset) leave exactly the bytes ns_format_records / ns_format_error_profile return, behind whatever precedes them."""
+    from nanosim_b200.records import format_error_profile, format_records, write_error_profile, write_records
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(15)
+    ref = PackedReference.from_records([("chrT", "".join(rng.choice(list("ACGTacgtN"), 3000)))])
+    b = _synthetic_batch(rng, ref, 400, False)
+    b.qual = (33 + rng.integers(1, 94, len(b.seq))).astype(np.uint8)
+    names = ["chrT_%d_aligned_%d_F_0_1_0" % (i * 7, i) for i in range(400)]
+    for fastq in (False, True):
+        want = format_records(b, names, fastq, n_threads=1)
+        for nt in (1, 7):
+            path = os.path.join(str(tmp_path), "r%d_%d" % (fastq, nt))
+            fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            pos = os.pwrite(fd, b"HEADER\n", 0)
+            pos += write_records(fd, pos, b, names, fastq, n_threads=nt)
+            os.close(fd)
+            assert open(path, "rb").read() == b"HEADER\n" + want and pos == 7 + len(want)
+    want = format_error_profile(b, names, ref, seed=3, n_threads=1)
+    for nt in (1, 6):
+        path = os.path.join(str(tmp_path), "e%d" % nt)
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        n = write_error_profile(fd, 0, b, names, ref, seed=3, n_threads=nt)
+        os.close(fd)
+        assert n == len(want) > 1000 and open(path, "rb").read() == want
+
+
+def test_native_fasta_reader_matches_python_reader(tmp_path):
+    """ns_read_fasta (mmap, line-aligned chunks over threads) against the pure-Python reader: the repository's fixtures,
+    a multi-MB file with CRLF line ends and ragged line lengths that the threads cut anywhere, and a FASTQ reference
+    (readfq, simulator.py:709-740) whose quality lines start with '>' and '@'."""
+    from nanosim_b200.reference_fasta import PackedReference
+    rng = np.random.default_rng(21)
+    paths = [os.path.join(GOLDEN, "mini_ref.fa"), os.path.join(GOLDEN, "mini_circular.fa"), os.path.join(GOLDEN, "trx", "transcripts.fa")]
+    big = os.path.join(str(tmp_path), "big.fa")
+    with open(big, "wb") as f:
+        for r in range(40):
+            f.write(b">rec_%d some description\r\n" % r)
+            seq = np.frombuffer(b"ACGTNacgtRY", dtype=np.uint8)[rng.integers(0, 11, int(rng.integers(1000, 400000)))].tobytes()
+            pos = 0
+            while pos < len(seq):
+                w = int(rng.integers(1, 120))
+                f.write(seq[pos:pos + w] + (b"\r\n" if r % 2 else b"\n"))
+                pos += w
+            if r % 7 == 0:
+                f.write(b"\n")
+    paths.append(big)
+    for path in paths:
+        a = PackedReference._from_fasta_python(path)
+        for nt in (1, 3, 16):
+            b = PackedReference._from_fasta_native(path, nt)
+            assert b is not None and a.names == b.names and a.raw_names == b.raw_names
+            assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.bases, b.bases), (path, nt)
+    fq = os.path.join(str(tmp_path), "ref.fq")
+    recs = [("chrA", "ACGTACGTAC" * 30, ">@+!" * 75), ("chrB extra", "GGGTTTAAAC", "@>@>@>@>@>")]
+    with open(fq, "w") as f:
+        for name, seq, q in recs:
+            f.write("@%s\n%s\n%s\n+\n%s\n%s\n" % (name, seq[:150], seq[150:], q[:200], q[200:]) if len(seq) > 150 else "@%s\n%s\n+\n%s\n" % (name, seq, q))
+    b = PackedReference._from_fasta_native(fq, 4)
+    assert b.names == ["chrA", "chrB"] and b.bases.tobytes().decode() == recs[0][1] + recs[1][1]
+    assert b.lengths.tolist() == [300, 10]
