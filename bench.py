@@ -63,6 +63,19 @@ WORKLOADS = {
 }
 
 
+def effective_cores():
+    """CPUs this process can actually use: the affinity mask, capped by the cgroup CPU quota (cpu.max) of the container."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(round(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,7 +312,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     n_procs = args.cpu_procs or cores
     W = WORKLOADS[args.workload]
     batch_reads = args.batch_reads or W["batch"]
@@ -563,16 +576,18 @@ def main():
         from nanosim_b200 import simulator
         out_dir = tempfile.mkdtemp(prefix="bench_to_file_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         host_ref = SimpleNamespace(names=list(sref.names), bases=sref.bases, offsets=sref.offsets)
-        nthr = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else cores))
+        nthr = max(1, min(32, cores))
         tf = {}
+        import contextlib
         try:
-            for label, errp, nsteps in (("with_error_profile", True, 1), ("reads_only", False, 2)):
+            for label, errp, nsteps in (("with_error_profile", True, 2), ("reads_only", False, 4)):
                 prof = SimpleNamespace(ref=host_ref, tables=tables, engine=eng, number_aligned=n_al * nsteps, number_unaligned=n_un * nsteps,
                                        seed=20260924, ir=None, n_trx=0)
                 t0 = time.perf_counter()
-                tot = simulator.simulation(prof, W["mode"], os.path.join(out_dir, label), "linear", False, W["kmer_bias"] or None, "guppy",
-                                           sref.max_chrom, 50, nthr, W["fastq"], chimeric=W["chimeric"], batch_reads=batch_reads,
-                                           error_profile=errp)
+                with contextlib.redirect_stdout(sys.stderr):           # the driver's progress lines are not part of the JSON line
+                    tot = simulator.simulation(prof, W["mode"], os.path.join(out_dir, label), "linear", False, W["kmer_bias"] or None, "guppy",
+                                               sref.max_chrom, 50, nthr, W["fastq"], chimeric=W["chimeric"], batch_reads=batch_reads,
+                                               error_profile=errp)
                 dt = time.perf_counter() - t0
                 tf[label] = {"value": tot["bases"] / dt, "unit": "bases/s", "reads": tot["reads"], "file_gb": tot["bytes"] / 1e9,
                              "gb_per_s": tot["bytes"] / dt / 1e9, "seconds": dt}
@@ -583,7 +598,8 @@ def main():
         tf["note"] = "simulator.simulation() of the drop-in CLI writing into %s, %d formatter / writer threads (-t), pipeline depth 2, " \
                      "first batch included" % (os.path.dirname(out_dir), nthr)
         line["to_file"] = tf
-    line["host"] = {"cpus": cores, "cpus_allowed": len(all_cpus) if all_cpus else None, "numa_binding": binding}
+    line["host"] = {"cpus": os.cpu_count(), "cpus_allowed": len(all_cpus) if all_cpus else None, "cpus_effective": cores,
+                    "note": "cpus_effective = affinity mask capped by the container's cgroup CPU quota (cpu.max)", "numa_binding": binding}
     if keep_host:
         hostbind.unbind(all_cpus)                                # the CPU baseline may use every core of the box
         pool = OraclePool(args.workload, sref, n_procs)

@@ -139,156 +139,191 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs a) {
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     const uint32_t K = a.cfg.kmer_bias;
-    uint32_t pi = 0, pi_end = 0;
+    // A lane walks one segment at a time, as a FLAT state machine: one loop iteration = one micro-step of every lane --
+    // a 16-base word of a copied stretch (the common case, which the lanes of a warp therefore execute together), one op of
+    // the script, or the hand-over to the next segment.  (Nested per-lane loops would leave ~2 of 32 lanes active.)
+    enum : int { ST_FETCH = 0, ST_OP = 1, ST_WORD = 2 };
+    int st = ST_FETCH;
+    uint32_t pi = 0, pi_end = 0, this_piece = 0;
     NsReadMeta rm;
-    for (;;) {
-        if (pi == pi_end) {                            // next read (longest first); its pieces are walked one after the other
-            uint32_t ri = atomicAdd(a.counter, 1u);
-            if (ri >= a.n_reads) break;
-            if (a.order) ri = a.order[ri];
-            rm = a.reads[ri];
-            pi = rm.piece_first;
-            pi_end = pi + rm.n_pieces;
-            continue;
-        }
-        NsPieceMeta& pm = a.pieces[pi];
-        const uint32_t this_piece = pi++;
-        if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
-            if (!WRITE) a.out_n_ops[this_piece] = 0;   // untouched pieces keep their script
-            continue;
-        }
-        const uint64_t rid = a.first_id + pm.read_slot;
-        HpWalker w;
-        const uint64_t cstart = a.ref.chrom_off[pm.chrom];
-        w.cb = a.ref.bases + cstart;
-        w.clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
-        w.seed = a.cfg.seed;
-        w.rid = rid;
-        w.pos = pm.pos;
-        w.piece_in_read = this_piece - rm.piece_first;
-        w.ref_len = pm.ref_len;
-        w.K = K;
-        {   // packed-word shortcuts: plain a/c/g/t span that stays inside the chromosome, K small enough for the 32-base window
-            const uint64_t pk0 = a.ref.pk_off[pm.chrom];
-            w.pk = a.ref.packed + pk0;
-            bool ok = !a.force_exact && K <= 16u && pm.ref_len > 0 && (uint64_t)pm.pos + pm.ref_len <= w.clen;
-            if (ok) {
-                const uint64_t w_lo = pk0 + (pm.pos >> 4), w_hi = pk0 + ((pm.pos + pm.ref_len - 1u) >> 4);
-                ok = __ldg(&a.ref.exc_pre[(w_hi >> REF_EXC_BLOCK_SHIFT) + 1]) == __ldg(&a.ref.exc_pre[w_lo >> REF_EXC_BLOCK_SHIFT]);
-            }
-            w.packed = ok;
-        }
-        uint32_t* ev = a.ops + pm.ev_off;
-        const uint32_t n_ev = pm.ev_n_ops;
-        ScriptOut<WRITE> out;
-        out.begin(WRITE ? a.ops + a.out_off[this_piece] : nullptr);
+    NsPieceMeta* pmp = nullptr;
+    uint64_t rid = 0;
+    HpWalker w = {};
+    uint32_t* ev = nullptr;
+    uint32_t n_ev = 0, k = 0, rpos = 0;
+    uint32_t len = 0, t = 0, w16 = 0;                      // the copied stretch being walked word by word
+    ScriptOut<WRITE> out;
+    out.begin(nullptr);
+    // ---- current run of equal bases in the mutated stream
+    uint32_t run_base = 0xffu, run_len = 0, run_ref = 0, nseg = 0, n_runs = 0;
+    uint32_t seg_kind[HP_MAX_SEG], seg_cnt[HP_MAX_SEG];     // in order: 0 copy, 1 mis, 2 ins, 3 deleted reference bases
 
-        // ---- current run of equal bases in the mutated stream
-        uint32_t run_base = 0xffu, run_len = 0, run_ref = 0, nseg = 0, n_runs = 0;
-        uint32_t seg_kind[HP_MAX_SEG], seg_cnt[HP_MAX_SEG];     // in order: 0 copy, 1 mis, 2 ins, 3 deleted reference bases
-
-        auto flush_run = [&]() {
-            if (run_len == 0) return;
-            if (run_len >= K && run_base < 4u) {
-                // new length ~ N(mu(L), sigma(L)), clipped at 0, Python round()
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_HP, 0, w.piece_in_read), n_runs), key);
-                const uint32_t cls = (run_base == 0u || run_base == 2u) ? 0u : 1u;      // A,T -> "AT" ; C,G -> "CG"
-                const double* p = a.hp[cls];
-                const double L = (double)run_len;
-                const double mu = p[0] + p[1] * L + p[2] * fmax(L - p[3], 0.0);
-                const double sigma = p[4] + p[5] * L;
-                const float z = sqrtf(-2.0f * logf(u01_open_low(r.x))) * cospif(2.0f * ((float)(r.y >> 8) * (1.0f / 16777216.0f)));
-                double x = mu + sigma * (double)z;
-                if (x < 0.0) x = 0.0;
-                const uint32_t nn = (uint32_t)rint(x);
-                // states of the new bases: last nn members (contraction) / all members + ins (expansion)
-                uint32_t skip = run_len > nn ? run_len - nn : 0u;
-                bool mis_q_used = false;
-                Rng mr;
-                if (a.hp_mis_rate > 0.0) mr.init(a.cfg.seed, rid, stream_word(ST_HP, 1, w.piece_in_read) ^ (n_runs << 4));
-                uint32_t produced = 0;
-                for (uint32_t s = 0; s <= nseg && produced < nn; ++s) {
-                    uint32_t cnt, state;
-                    if (s < nseg) {
-                        if (seg_kind[s] == 3) continue;       // deleted reference bases carry no quality
-                        cnt = seg_cnt[s];
-                        state = seg_kind[s] == 0 ? 2u : (seg_kind[s] == 1 ? 0u : 1u);
-                        if (skip >= cnt) {
-                            skip -= cnt;
-                            continue;
-                        }
-                        cnt -= skip;
-                        skip = 0;
-                    } else {
-                        cnt = nn - produced;                  // expansion: inserted-base qualities (:692-695)
-                        state = 1u;
+    auto flush_run = [&]() {
+        if (run_len == 0) return;
+        if (run_len >= K && run_base < 4u) {
+            // new length ~ N(mu(L), sigma(L)), clipped at 0, Python round()
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_HP, 0, w.piece_in_read), n_runs), key);
+            const uint32_t cls = (run_base == 0u || run_base == 2u) ? 0u : 1u;      // A,T -> "AT" ; C,G -> "CG"
+            const double* p = a.hp[cls];
+            const double L = (double)run_len;
+            const double mu = p[0] + p[1] * L + p[2] * fmax(L - p[3], 0.0);
+            const double sigma = p[4] + p[5] * L;
+            const float z = sqrtf(-2.0f * logf(u01_open_low(r.x))) * cospif(2.0f * ((float)(r.y >> 8) * (1.0f / 16777216.0f)));
+            double x = mu + sigma * (double)z;
+            if (x < 0.0) x = 0.0;
+            const uint32_t nn = (uint32_t)rint(x);
+            // states of the new bases: last nn members (contraction) / all members + ins (expansion)
+            uint32_t skip = run_len > nn ? run_len - nn : 0u;
+            bool mis_q_used = false;
+            Rng mr;
+            if (a.hp_mis_rate > 0.0) mr.init(a.cfg.seed, rid, stream_word(ST_HP, 1, w.piece_in_read) ^ (n_runs << 4));
+            uint32_t produced = 0;
+            for (uint32_t s = 0; s <= nseg && produced < nn; ++s) {
+                uint32_t cnt, state;
+                if (s < nseg) {
+                    if (seg_kind[s] == 3) continue;       // deleted reference bases carry no quality
+                    cnt = seg_cnt[s];
+                    state = seg_kind[s] == 0 ? 2u : (seg_kind[s] == 1 ? 0u : 1u);
+                    if (skip >= cnt) {
+                        skip -= cnt;
+                        continue;
                     }
-                    if (cnt > nn - produced) cnt = nn - produced;
-                    if (a.hp_mis_rate > 0.0) {
-                        for (uint32_t t = 0; t < cnt; ++t) {
-                            const double pr = u01_double(mr.next64());
-                            uint32_t b = run_base, st = state;
-                            if (pr > 0.0 && pr <= a.hp_mis_rate) {
-                                b = (run_base + 1u + (mr.next() % 3u)) & 3u;
-                                if (!mis_q_used) {
-                                    st = 0u;
-                                    mis_q_used = true;
-                                }
+                    cnt -= skip;
+                    skip = 0;
+                } else {
+                    cnt = nn - produced;                  // expansion: inserted-base qualities (:692-695)
+                    state = 1u;
+                }
+                if (cnt > nn - produced) cnt = nn - produced;
+                if (a.hp_mis_rate > 0.0) {
+                    for (uint32_t t = 0; t < cnt; ++t) {
+                        const double pr = u01_double(mr.next64());
+                        uint32_t b = run_base, st = state;
+                        if (pr > 0.0 && pr <= a.hp_mis_rate) {
+                            b = (run_base + 1u + (mr.next() % 3u)) & 3u;
+                            if (!mis_q_used) {
+                                st = 0u;
+                                mis_q_used = true;
                             }
-                            out.add((NS_OP_LIT << 28) | (b << 26) | (st << 24), 1);
                         }
-                    } else {
-                        out.add((NS_OP_LIT << 28) | (run_base << 26) | (state << 24), cnt);
+                        out.add((NS_OP_LIT << 28) | (b << 26) | (st << 24), 1);
                     }
-                    produced += cnt;
+                } else {
+                    out.add((NS_OP_LIT << 28) | (run_base << 26) | (state << 24), cnt);
                 }
-                out.add(NS_OP_DEL << 28, run_ref);            // the reference bases the run stood on
-                ++n_runs;
-            } else {
-                for (uint32_t s = 0; s < nseg; ++s) {
-                    if (seg_kind[s] == 0) {
-                        out.add(NS_OP_COPY << 28, seg_cnt[s]);
-                    } else if (seg_kind[s] == 3) {
-                        out.add(NS_OP_DEL << 28, seg_cnt[s]);
-                    } else {
-                        out.add((NS_OP_LIT << 28) | ((run_base & 3u) << 26) | ((seg_kind[s] == 1 ? 0u : 1u) << 24), seg_cnt[s]);
-                        if (seg_kind[s] == 1) out.add(NS_OP_DEL << 28, seg_cnt[s]);
-                    }
+                produced += cnt;
+            }
+            out.add(NS_OP_DEL << 28, run_ref);            // the reference bases the run stood on
+            ++n_runs;
+        } else {
+            for (uint32_t s = 0; s < nseg; ++s) {
+                if (seg_kind[s] == 0) {
+                    out.add(NS_OP_COPY << 28, seg_cnt[s]);
+                } else if (seg_kind[s] == 3) {
+                    out.add(NS_OP_DEL << 28, seg_cnt[s]);
+                } else {
+                    out.add((NS_OP_LIT << 28) | ((run_base & 3u) << 26) | ((seg_kind[s] == 1 ? 0u : 1u) << 24), seg_cnt[s]);
+                    if (seg_kind[s] == 1) out.add(NS_OP_DEL << 28, seg_cnt[s]);
                 }
             }
-            run_len = 0;
-            run_ref = 0;
-            nseg = 0;
-            run_base = 0xffu;
-        };
-        auto add_seg = [&](uint32_t kind, uint32_t cnt) {     // cnt more bases of `kind` in the pending run
-            if (nseg > 0 && seg_kind[nseg - 1] == kind) {
-                seg_cnt[nseg - 1] += cnt;
-            } else if (nseg < HP_MAX_SEG) {
-                seg_kind[nseg] = kind;
-                seg_cnt[nseg] = cnt;
-                ++nseg;
-            } else {
-                seg_cnt[nseg - 1] += cnt;                          // pathological run: lump into the last segment
-                if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
-            }
-        };
-        auto feed = [&](uint32_t b, uint32_t kind) {          // one base of the mutated stream
-            if (b != run_base || b > 3u) {
-                flush_run();
-                run_base = b;
-            }
-            ++run_len;
-            if (kind != 2) ++run_ref;
-            add_seg(kind, 1u);
-        };
+        }
+        run_len = 0;
+        run_ref = 0;
+        nseg = 0;
+        run_base = 0xffu;
+    };
+    auto add_seg = [&](uint32_t kind, uint32_t cnt) {     // cnt more bases of `kind` in the pending run
+        if (nseg > 0 && seg_kind[nseg - 1] == kind) {
+            seg_cnt[nseg - 1] += cnt;
+        } else if (nseg < HP_MAX_SEG) {
+            seg_kind[nseg] = kind;
+            seg_cnt[nseg] = cnt;
+            ++nseg;
+        } else {
+            seg_cnt[nseg - 1] += cnt;                          // pathological run: lump into the last segment
+            if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
+        }
+    };
+    auto feed = [&](uint32_t b, uint32_t kind) {          // one base of the mutated stream
+        if (b != run_base || b > 3u) {
+            flush_run();
+            run_base = b;
+        }
+        ++run_len;
+        if (kind != 2) ++run_ref;
+        add_seg(kind, 1u);
+    };
 
-        // per-event random bases: Philox-7 block per op, one byte per base
-        uint32_t rpos = 0;
-        for (uint32_t k = 0; k < n_ev; ++k) {
+
+    for (;;) {
+        if (st == ST_WORD) {
+            // ---- up to 16 copied bases (the next word is requested before this one is looked at).
+            //      ne: bit 2j set iff base j differs from base j-1 (1 <= j < n)
+            do {
+                const uint32_t n = len - t < 16u ? len - t : 16u;
+                const uint32_t cur = w16;
+                if (t + n < len) w16 = w.bases16(rpos + t + n);
+                const uint32_t fields = (n == 16u ? 0xffffffffu : (1u << (2u * n)) - 1u) & 0x55555554u;   // fields 1 .. n-1
+                const uint32_t d = cur ^ (cur << 2);
+                const uint32_t ne = (d | (d >> 1)) & fields;
+                // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
+                const uint32_t eq = ~ne & fields;
+                uint32_t runs = eq;
+                for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
+                // leading bases that continue the pending run
+                const uint32_t lead = (run_len && (cur & 3u) == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : n) : 0u;
+                t += n;
+                if (runs || run_len + lead >= K) {         // a run reaches K here: base by base
+                    for (uint32_t j = 0; j < n; ++j) feed((cur >> (2u * j)) & 3u, 0);
+                    break;
+                }
+                if (lead == n) {                           // the whole word continues the pending run
+                    add_seg(0u, n);
+                    run_len += n;
+                    run_ref += n;
+                    break;
+                }
+                if (lead) {
+                    add_seg(0u, lead);
+                    run_len += lead;
+                    run_ref += lead;
+                }
+                flush_run();                               // the pending run ends inside this word, shorter than K
+                // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
+                const uint32_t bound = ne | 1u;            // field 0 bounds the trailing run inside the word
+                const uint32_t trail = n - ((31u - (uint32_t)__clz((int)bound)) >> 1);
+                out.add(NS_OP_COPY << 28, n - lead - trail);
+                run_base = (cur >> (2u * (n - 1u))) & 3u;
+                run_len = run_ref = trail;
+                nseg = 1;
+                seg_kind[0] = 0;
+                seg_cnt[0] = trail;
+                    
+            } while (0);
+            if (t >= len) {
+                rpos += len;
+                st = ST_OP;
+            }
+        } else if (st == ST_OP) {
+            NsPieceMeta& pm = *pmp;
+            if (k >= n_ev) {                                   // end of the segment's script
+                flush_run();
+                out.flush();
+                if (!WRITE) {
+                    a.out_n_ops[this_piece] = out.n;
+                    pm.out_len = out.out_len;
+                } else {
+                    pm.op_off = a.out_off[this_piece];
+                    pm.n_ops = out.n;
+                }
+                st = ST_FETCH;
+                continue;
+            }
             uint32_t op = ev[k];
             uint32_t ty = op >> 28;
-            const uint32_t len = op & 0x0fffffffu;
+            len = op & 0x0fffffffu;
+            const uint32_t kk = k;
+            ++k;
             if (ty == NS_OP_HT) {
                 flush_run();
                 out.add(NS_OP_HT << 28, len);
@@ -307,61 +342,20 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 for (int64_t x = lo; x <= hi && !drop; ++x) drop = w.in_hp(x);
                 if (drop) {
                     op = ty == NS_OP_INS ? (NS_OP_COPY << 28) : ((NS_OP_COPY << 28) | len);
-                    if (WRITE) ev[k] = op;
+                    if (WRITE) ev[kk] = op;
                     ty = NS_OP_COPY;
                     if ((op & 0x0fffffffu) == 0) continue;
                 }
             }
             if (ty == NS_OP_COPY) {
-                uint32_t t = 0;
                 if (w.packed) {
-                    // up to 16 copied bases per step (the next word is requested before this one is looked at).
-                    // ne: bit 2j set iff base j differs from base j-1 (1 <= j < n)
-                    uint32_t w16 = w.bases16(rpos);
-                    while (t < len) {
-                        const uint32_t n = len - t < 16u ? len - t : 16u;
-                        const uint32_t cur = w16;
-                        if (t + n < len) w16 = w.bases16(rpos + t + n);
-                        const uint32_t fields = (n == 16u ? 0xffffffffu : (1u << (2u * n)) - 1u) & 0x55555554u;   // fields 1 .. n-1
-                        const uint32_t d = cur ^ (cur << 2);
-                        const uint32_t ne = (d | (d >> 1)) & fields;
-                        // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
-                        const uint32_t eq = ~ne & fields;
-                        uint32_t runs = eq;
-                        for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
-                        // leading bases that continue the pending run
-                        const uint32_t lead = (run_len && (cur & 3u) == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : n) : 0u;
-                        t += n;
-                        if (runs || run_len + lead >= K) {         // a run reaches K here: base by base
-                            for (uint32_t j = 0; j < n; ++j) feed((cur >> (2u * j)) & 3u, 0);
-                            continue;
-                        }
-                        if (lead == n) {                           // the whole word continues the pending run
-                            add_seg(0u, n);
-                            run_len += n;
-                            run_ref += n;
-                            continue;
-                        }
-                        if (lead) {
-                            add_seg(0u, lead);
-                            run_len += lead;
-                            run_ref += lead;
-                        }
-                        flush_run();                               // the pending run ends inside this word, shorter than K
-                        // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
-                        const uint32_t bound = ne | 1u;            // field 0 bounds the trailing run inside the word
-                        const uint32_t trail = n - ((31u - (uint32_t)__clz((int)bound)) >> 1);
-                        out.add(NS_OP_COPY << 28, n - lead - trail);
-                        run_base = (cur >> (2u * (n - 1u))) & 3u;
-                        run_len = run_ref = trail;
-                        nseg = 1;
-                        seg_kind[0] = 0;
-                        seg_cnt[0] = trail;
-                    }
+                    t = 0;
+                    w16 = w.bases16(rpos);
+                    st = ST_WORD;
                 } else {
-                    for (; t < len; ++t) feed(w.base_at(rpos + t), 0);
+                    for (uint32_t tt = 0; tt < len; ++tt) feed(w.base_at(rpos + tt), 0);
+                    rpos += len;
                 }
-                rpos += len;
             } else if (ty == NS_OP_DEL) {
                 // deleted bases vanish from the read: their neighbours become adjacent and may join one run
                 if (run_len == 0) {
@@ -380,13 +374,13 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 }
                 rpos += len;
             } else {
-                for (uint32_t t = 0; t < len; ++t) {
-                    const uint4 r = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece_in_read), (k << 8) + (t >> 4)), key);
-                    const uint32_t wd = (t & 8u) ? ((t & 4u) ? r.w : r.z) : ((t & 4u) ? r.y : r.x);
-                    const uint32_t r8 = (wd >> (8u * (t & 3u))) & 0xffu;
+                for (uint32_t tt = 0; tt < len; ++tt) {
+                    const uint4 r = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece_in_read), (kk << 8) + (tt >> 4)), key);
+                    const uint32_t wd = (tt & 8u) ? ((tt & 4u) ? r.w : r.z) : ((tt & 4u) ? r.y : r.x);
+                    const uint32_t r8 = (wd >> (8u * (tt & 3u))) & 0xffu;
                     uint32_t b;
                     if (ty == NS_OP_MIS) {
-                        const uint32_t orig = w.packed ? (w.bases16(rpos + t) & 3u) : w.base_at(rpos + t);
+                        const uint32_t orig = w.packed ? (w.bases16(rpos + tt) & 3u) : w.base_at(rpos + tt);
                         const uint32_t rr = r8 == 255u ? 0u : r8;
                         b = ((orig & 3u) + 1u + rr % 3u) & 3u;
                         feed(b, 1);
@@ -397,15 +391,52 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 }
                 if (ty == NS_OP_MIS) rpos += len;
             }
-        }
-        flush_run();
-        out.flush();
-        if (!WRITE) {
-            a.out_n_ops[this_piece] = out.n;
-            pm.out_len = out.out_len;
         } else {
-            pm.op_off = a.out_off[this_piece];
-            pm.n_ops = out.n;
+            // ---- next segment: pieces of the current read, then the next read (longest first)
+            if (pi == pi_end) {
+                uint32_t ri = atomicAdd(a.counter, 1u);
+                if (ri >= a.n_reads) break;
+                if (a.order) ri = a.order[ri];
+                rm = a.reads[ri];
+                pi = rm.piece_first;
+                pi_end = pi + rm.n_pieces;
+                continue;
+            }
+            pmp = &a.pieces[pi];
+            NsPieceMeta& pm = *pmp;
+            this_piece = pi++;
+            if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
+                if (!WRITE) a.out_n_ops[this_piece] = 0;   // untouched pieces keep their script
+                continue;
+            }
+            rid = a.first_id + pm.read_slot;
+            const uint64_t cstart = a.ref.chrom_off[pm.chrom];
+            w.cb = a.ref.bases + cstart;
+            w.clen = a.ref.chrom_off[pm.chrom + 1] - cstart;
+            w.seed = a.cfg.seed;
+            w.rid = rid;
+            w.pos = pm.pos;
+            w.piece_in_read = this_piece - rm.piece_first;
+            w.ref_len = pm.ref_len;
+            w.K = K;
+            {   // packed-word shortcuts: plain a/c/g/t span that stays inside the chromosome, K small enough for the 32-base window
+                const uint64_t pk0 = a.ref.pk_off[pm.chrom];
+                w.pk = a.ref.packed + pk0;
+                bool ok = !a.force_exact && K <= 16u && pm.ref_len > 0 && (uint64_t)pm.pos + pm.ref_len <= w.clen;
+                if (ok) {
+                    const uint64_t w_lo = pk0 + (pm.pos >> 4), w_hi = pk0 + ((pm.pos + pm.ref_len - 1u) >> 4);
+                    ok = __ldg(&a.ref.exc_pre[(w_hi >> REF_EXC_BLOCK_SHIFT) + 1]) == __ldg(&a.ref.exc_pre[w_lo >> REF_EXC_BLOCK_SHIFT]);
+                }
+                w.packed = ok;
+            }
+            ev = a.ops + pm.ev_off;
+            n_ev = pm.ev_n_ops;
+            k = 0;
+            rpos = 0;
+            out.begin(WRITE ? a.ops + a.out_off[this_piece] : nullptr);
+            run_base = 0xffu;
+            run_len = run_ref = nseg = n_runs = 0;
+            st = ST_OP;
         }
     }
 }

@@ -128,6 +128,11 @@ namespace {
 
 cudaEvent_t g_base[64] = {};      // per device: origin of the device timeline reported in NsBatchInfo
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 int fail(NsContext* c, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -953,12 +958,8 @@ static int exclusive_scan_u64(NsContext* ctx, const uint64_t* in, uint64_t* out,
 }
 
 namespace {
-// Launch-geometry experiments: NANOSIM_B200_EMIT_BLOCKS_PER_SM / NANOSIM_B200_PLAN_BLOCKS_PER_SM cap the persistent grids
-// (0 / unset = as many blocks as fit), so that kernels of overlapped contexts can share an SM instead of queueing.
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
+// Launch geometry: NANOSIM_B200_EMIT_BLOCKS_PER_SM / NANOSIM_B200_PLAN_BLOCKS_PER_SM cap the persistent grids (0 / unset =
+// as many blocks as fit), so that kernels of overlapped contexts can share an SM instead of queueing.
 // emit_kernel over `n_pieces` pieces of the context's current batch (all of them, or the ones `order` lists)
 int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order,
                 const uint32_t* abort_flag = nullptr) {
@@ -1182,7 +1183,9 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     pa.batch_reversed = batch_reversed;
     pa.abort = d_abort;
     const unsigned plan_tb = 128;
-    static const int plan_per_sm = env_int("NANOSIM_B200_PLAN_BLOCKS_PER_SM", 16);
+    // 2 resident blocks per SM: measured faster than 4 (the register limit) both alone (6.3-6.8 vs 8.2-8.6 ms on the config-2
+    // batch) and next to another context's emit kernel, which then still finds room on every SM
+    static const int plan_per_sm = env_int("NANOSIM_B200_PLAN_BLOCKS_PER_SM", 2);
     unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * (unsigned)std::max(1, plan_per_sm));
     // unaligned reads without NS_FLAG_UNALIGNED_SCRIPTS: warp-per-read evaluation (uread_kernel.cuh), same outputs
     UreadArgs ua;
@@ -1201,6 +1204,25 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ua.pool = d_totals + NS_T_POOL;             // {base, size} of the bump pool, written by capacity_stage_a
     ua.abort = d_abort;
     const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
+    if (chim && !ctx->hcfg.perfect) {
+        // chimeric gaps of every read's first attempt, a warp per read (uread_kernel.cuh:gap_kernel)
+        GapArgs ga;
+        ga.m = ctx->dmodel;
+        ga.cfg = ctx->dcfg;
+        ga.kind = (uint32_t)kind;
+        ga.first_id = first_read_id;
+        ga.n_reads = n;
+        ga.n_seg = d_nseg;
+        ga.piece_first = d_pfirst;
+        ga.pieces = pa.pieces;
+        ga.ops = pa.ops;
+        ga.counter = pa.counter;
+        ga.abort = d_abort;
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        gap_kernel<<<ublocks, UREAD_WARPS * 32, 0, st>>>(ga);
+        CK(cudaGetLastError());
+        launches += 1;
+    }
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
     if (fast_unaligned) uread_kernel<false><<<ublocks, UREAD_WARPS * 32, 0, st>>>(ua);
     else plan_kernel<false><<<plan_blocks, plan_tb, 0, st>>>(pa);
@@ -1924,14 +1946,24 @@ int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint
                         uint64_t out_cap, uint64_t* name_off) {
     if (!reads || !pieces || !chrom_names || !chrom_name_off) return NS_EINVAL;
     const bool perfect = flags & 1u, meta = flags & 2u, trx = flags & 4u;
+    // the reads are cut into ranges, one per thread; every thread builds the names of its range back to back in its own blob
+    static const int name_threads = std::max(1, std::min(env_int("NANOSIM_B200_NAME_THREADS", 8), 64));
+    const int nt = n_reads < 4096 ? 1 : name_threads;
+    std::vector<std::string> blobs((size_t)nt);
+    std::vector<std::vector<uint32_t>> lens((size_t)nt);
+    auto work = [&](int tid) {
+    const uint32_t lo = (uint32_t)((uint64_t)n_reads * tid / nt), hi = (uint32_t)((uint64_t)n_reads * (tid + 1) / nt);
+    std::string& blob = blobs[tid];
+    std::vector<uint32_t>& ln = lens[tid];
+    blob.reserve((size_t)(hi - lo) * 64);
+    ln.reserve(hi - lo);
     std::string nm;
-    uint64_t total = 0;
     char num[32];
     auto add_num = [&](uint64_t v) {
         char* e = put_dec(num, v);
         nm.append(num, (size_t)(e - num));
     };
-    for (uint32_t i = 0; i < n_reads; ++i) {
+    for (uint32_t i = lo; i < hi; ++i) {
         const NsReadMeta& r = reads[i];
         const NsPieceMeta* pc = pieces + r.piece_first;
         const char strand = r.reversed ? 'R' : 'F';
@@ -2040,12 +2072,33 @@ int64_t ns_format_names(const NsReadMeta* reads, const NsPieceMeta* pieces, uint
             nm += '_';
             add_num(r.tail);
         }
-        if (out) {
-            if (total + nm.size() + 1 > out_cap) return NS_ENOMEM;
-            memcpy(out + total, nm.c_str(), nm.size() + 1);
-            if (name_off) name_off[i] = total;
-        }
-        total += nm.size() + 1;
+        blob.append(nm.c_str(), nm.size() + 1);
+        ln.push_back((uint32_t)nm.size() + 1);
+    }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    uint64_t total = 0;
+    for (const std::string& bl : blobs) total += bl.size();
+    if (!out) return (int64_t)total;
+    if (total > out_cap) return NS_ENOMEM;
+    uint64_t pos = 0;
+    uint32_t i = 0;
+    for (int t = 0; t < nt; ++t) {
+        memcpy(out + pos, blobs[t].data(), blobs[t].size());
+        if (name_off)
+            for (uint32_t l : lens[t]) {
+                name_off[i++] = pos;
+                pos += l;
+            }
+        else
+            pos += blobs[t].size();
     }
     return (int64_t)total;
 }

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     uint32_t pos = 0, middle_ref = 0, prev_match = 0, err_state = 0, last_err = 3;
     int64_t l_new = 0;
     uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
+    uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap: its own stream (shared with gap_kernel), draw k = Philox block k + 1
     bool last_op_was_ins_same_pos = false;
     uint32_t last_ins_len = 0;
     OpSink<true> sink;
@@ -512,6 +513,22 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
             last_op_was_ins_same_pos = false;
             bool is_gap = unal_kind || (p & 1u);
             if (!unal_kind && p == 0 && head > 0) sink.put(NS_OP_HT, head);
+            if (is_gap && !unal_kind) {
+                // a chimeric gap draws from its own stream (device_common.cuh ST_GAP); the first attempt was already walked
+                // by gap_kernel, 32 draws at a time, and left its result in the piece record
+                gap_sw = stream_word(ST_GAP, a.kind, (attempt << 5) | (p & 31u));
+                gap_draw = 0;
+                if (!REPLAY && attempt == 0 && pm.polya_len == 1u) {
+                    pm.polya_len = 0;
+                    sink.n = pm.n_ops;
+                    sink.out_len = pm.out_len;
+                    middle_ref = pm.ref_len;
+                    l_new = (int64_t)pm.out_len;
+                    phase = PH_PIECE_END;
+                    break;
+                }
+                pm.polya_len = 0;
+            }
             if (is_gap) {
                 phase = (m_ref == 0) ? PH_PIECE_END : PH_UEVENT;
             } else if (cfg.perfect) {
@@ -572,7 +589,12 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
             break;
         }
         case PH_UEVENT: {  // one pass of unaligned_error_list's loop (:1794-1828) + its effect in mutate_read
-            uint4 r = rng.next4();
+            uint4 r;
+            if (unal_kind) {
+                r = rng.next4();
+            } else {               // chimeric gap: block k + 1 of the gap's stream for draw k, as gap_kernel / uread_kernel count them
+                r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, ++gap_draw), rng.key);
+            }
             // fixed type cdf 0.4 / 0.7 / 0.85 / 1 (:1787)
             uint32_t kind_u = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
             if (kind_u == 2) {                       // ins: merged at key pos+0.1 (:1808-1815)
@@ -639,6 +661,8 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                 pm.out_rel = (uint32_t)actual;
                 pm.l_new = (uint32_t)(l_new < 0 ? 0 : l_new);
             }
+            // a replayed gap was first walked by gap_kernel, whose script merges less: the exact slot is at least as large
+            if (REPLAY && is_gap && !unal_kind) pm.n_ops = sink.n;
             actual += sink.out_len;
             if (cfg.metagenome && !unal_kind) {
                 // metagenome: total = remainder + middle_ref of the segments + mutated gap lengths (:924-943)

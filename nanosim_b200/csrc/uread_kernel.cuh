@@ -46,12 +46,126 @@ struct UreadArgs {
 
 #define UREAD_WARPS 8
 
+// unaligned_error_list (:1784-1830) + its effect in mutate_read for ONE read / chimeric gap of drawn length m_ref, evaluated by
+// a whole warp 32 draws at a time (see the header comment).  Draw k uses Philox block k + 1 of stream `sw`.  Ops go to
+// ops[0 .. cap) (counted beyond that).
+struct UChain {
+    uint32_t n_ops, middle_ref, n_draws;
+    int64_t l_new;
+};
+__device__ __forceinline__ UChain unaligned_chain_warp(const DevModel& m, uint2 key, uint32_t id_lo, uint32_t id_hi, uint32_t sw,
+                                                       uint32_t m_ref, uint32_t* ops, uint32_t cap, int lane) {
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint32_t base = 0, pos_base = 0, carry_a = 0, middle_ref = m_ref, n_draws = 0, n_ops = 0;
+    int64_t l_new = (int64_t)m_ref;
+    bool done = false;
+    // draw `d` of the attempt: its type and step length (independent of everything before it: the next 32 draws are
+    // issued before the scans of the current 32, so that the Philox rounds and the table loads overlap the shuffles)
+    auto draw = [&](uint32_t d, uint32_t& kd, uint32_t& sd) {
+        const uint4 r = philox4x32_10(make_uint4(id_lo, id_hi, sw, d + 1u), key);
+        kd = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
+        sd = 1;
+        if (kd != 0) sd = alias_draw(m, kd == 1 ? 1u : (kd == 2 ? 2u : 3u), r.y);
+    };
+    uint32_t kind_next, s_next;
+    draw(lane, kind_next, s_next);
+    while (!done) {
+        const uint32_t kind = kind_next, s = s_next;
+        draw(base + 32u + lane, kind_next, s_next);
+        const bool nonins = kind != 2;
+        const uint32_t adv = nonins ? s : 0u;
+        const uint32_t P = pos_base + warp_incl_scan(adv, lane);
+        const uint32_t I = warp_incl_scan(nonins ? 0u : s, lane);
+        const uint32_t stop_mask = __ballot_sync(0xffffffffu, nonins && P >= m_ref);
+        const int jstop = stop_mask ? __ffs(stop_mask) - 1 : 32;
+        const bool valid = lane <= jstop;
+        const uint32_t nonins_mask = __ballot_sync(0xffffffffu, nonins);
+        // inserted bases pending in front of a non-insertion draw = I - I(previous non-insertion draw)
+        const uint32_t below = nonins_mask & lane_lt;
+        const int pn = below ? 31 - __clz(below) : -1;
+        const uint32_t I_pn = __shfl_sync(0xffffffffu, I, pn < 0 ? 0 : pn);
+        const uint32_t a_ins = nonins ? (pn >= 0 ? I - I_pn : I + carry_a) : 0u;
+        int32_t delta = 0;
+        if (valid) delta = kind == 2 ? (int32_t)s : (kind == 3 ? -(int32_t)s : 0);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
+        l_new += delta;
+
+        // ---- this draw's ops (at most four), empty ones dropped and equal neighbours merged
+        uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;          // an empty op is the zero word (COPY of length 0)
+        const bool emits = valid && nonins;
+        // a run of plain matches (no pending insertion) is written once, by its first lane
+        const uint32_t plain_mask = __ballot_sync(0xffffffffu, emits && kind == 0 && a_ins == 0);
+        if (emits) {
+            if (kind == 0) {
+                if (a_ins == 0) {
+                    if (!(lane > 0 && ((plain_mask >> (lane - 1)) & 1u))) {
+                        const uint32_t run = __ffs(~(plain_mask >> lane)) - 1;       // consecutive set bits from `lane`
+                        o0 = (NS_OP_COPY << 28) | (run == 0xffffffffu ? 32u - lane : run);
+                    }
+                } else {
+                    o0 = (NS_OP_COPY << 28) | 1u;
+                    o1 = (NS_OP_INS << 28) | a_ins;
+                }
+            } else {
+                const uint32_t covered = a_ins < s - 1 ? a_ins : s - 1;
+                const uint32_t rest = s - 1 - covered;
+                const uint32_t T = kind == 1 ? NS_OP_MIS : NS_OP_DEL;
+                const uint32_t n_ins = kind == 1 ? a_ins : a_ins - covered;
+                if (n_ins == 0) {
+                    o0 = (T << 28) | (1u + rest);
+                } else {
+                    o0 = (T << 28) | 1u;
+                    o1 = (NS_OP_INS << 28) | n_ins;
+                    if (rest) o2 = (T << 28) | rest;
+                }
+                if (covered) o3 = (NS_OP_COPY << 28) | covered;
+            }
+        }
+        const uint32_t p1 = o0 ? 1u : 0u, p2 = p1 + (o1 ? 1u : 0u), p3 = p2 + (o2 ? 1u : 0u);
+        const uint32_t cnt = p3 + (o3 ? 1u : 0u);
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        const uint32_t at = n_ops + incl - cnt;
+        if (o0 && at < cap) ops[at] = o0;
+        if (o1 && at + p1 < cap) ops[at + p1] = o1;
+        if (o2 && at + p2 < cap) ops[at + p2] = o2;
+        if (o3 && at + p3 < cap) ops[at + p3] = o3;
+        n_ops += __shfl_sync(0xffffffffu, incl, 31);
+
+        if (jstop < 32) {
+            const uint32_t Pstop = __shfl_sync(0xffffffffu, P, jstop);
+            if (Pstop > middle_ref) {                      // overrun extends the segment (:1826-1828)
+                l_new += Pstop - middle_ref;
+                middle_ref = Pstop;
+            }
+            n_draws = base + (uint32_t)jstop + 1u;
+            done = true;
+        } else {
+            pos_base = __shfl_sync(0xffffffffu, P, 31);
+            const uint32_t I31 = __shfl_sync(0xffffffffu, I, 31);
+            if (nonins_mask) {
+                const int last = 31 - __clz(nonins_mask);
+                carry_a = I31 - __shfl_sync(0xffffffffu, I, last);
+            } else {
+                carry_a += I31;
+            }
+            base += 32;
+        }
+    }
+    UChain c;
+    c.n_ops = n_ops;
+    c.middle_ref = middle_ref;
+    c.n_draws = n_draws;
+    c.l_new = l_new;
+    return c;
+}
+
+
 template <bool REPLAY>
 __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_constant__ UreadArgs a) {
     const DevModel& m = a.m;
     const DevCfg& cfg = a.cfg;
     const int lane = threadIdx.x & 31;
-    const uint32_t lane_lt = (1u << lane) - 1u;
     const uint2 key = make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
     if (a.abort && *a.abort) return;
     const uint64_t pool_base = a.pool[0], pool_size = a.pool[1];
@@ -96,102 +210,9 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 }
                 ops = a.ops + op_off;
             }
-            uint32_t base = 0, pos_base = 0, carry_a = 0, middle_ref = m_ref, n_draws = 0, n_ops = 0;
-            int64_t l_new = (int64_t)m_ref;
-            bool done = false;
-            // draw `d` of the attempt: its type and step length (independent of everything before it: the next 32 draws are
-            // issued before the scans of the current 32, so that the Philox rounds and the table loads overlap the shuffles)
-            auto draw = [&](uint32_t d, uint32_t& kd, uint32_t& sd) {
-                const uint4 r = philox4x32_10(make_uint4(id_lo, id_hi, sw, d + 1u), key);
-                kd = r.x < 1717986918u ? 0u : (r.x < 3006477107u ? 1u : (r.x < 3650722201u ? 2u : 3u));
-                sd = 1;
-                if (kd != 0) sd = alias_draw(m, kd == 1 ? 1u : (kd == 2 ? 2u : 3u), r.y);
-            };
-            uint32_t kind_next, s_next;
-            draw(lane, kind_next, s_next);
-            while (!done) {
-                const uint32_t kind = kind_next, s = s_next;
-                draw(base + 32u + lane, kind_next, s_next);
-                const bool nonins = kind != 2;
-                const uint32_t adv = nonins ? s : 0u;
-                const uint32_t P = pos_base + warp_incl_scan(adv, lane);
-                const uint32_t I = warp_incl_scan(nonins ? 0u : s, lane);
-                const uint32_t stop_mask = __ballot_sync(0xffffffffu, nonins && P >= m_ref);
-                const int jstop = stop_mask ? __ffs(stop_mask) - 1 : 32;
-                const bool valid = lane <= jstop;
-                const uint32_t nonins_mask = __ballot_sync(0xffffffffu, nonins);
-                // inserted bases pending in front of a non-insertion draw = I - I(previous non-insertion draw)
-                const uint32_t below = nonins_mask & lane_lt;
-                const int pn = below ? 31 - __clz(below) : -1;
-                const uint32_t I_pn = __shfl_sync(0xffffffffu, I, pn < 0 ? 0 : pn);
-                const uint32_t a_ins = nonins ? (pn >= 0 ? I - I_pn : I + carry_a) : 0u;
-                int32_t delta = 0;
-                if (valid) delta = kind == 2 ? (int32_t)s : (kind == 3 ? -(int32_t)s : 0);
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
-                l_new += delta;
-
-                // ---- this draw's ops (at most four), empty ones dropped and equal neighbours merged
-                uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;          // an empty op is the zero word (COPY of length 0)
-                const bool emits = valid && nonins;
-                // a run of plain matches (no pending insertion) is written once, by its first lane
-                const uint32_t plain_mask = __ballot_sync(0xffffffffu, emits && kind == 0 && a_ins == 0);
-                if (emits) {
-                    if (kind == 0) {
-                        if (a_ins == 0) {
-                            if (!(lane > 0 && ((plain_mask >> (lane - 1)) & 1u))) {
-                                const uint32_t run = __ffs(~(plain_mask >> lane)) - 1;       // consecutive set bits from `lane`
-                                o0 = (NS_OP_COPY << 28) | (run == 0xffffffffu ? 32u - lane : run);
-                            }
-                        } else {
-                            o0 = (NS_OP_COPY << 28) | 1u;
-                            o1 = (NS_OP_INS << 28) | a_ins;
-                        }
-                    } else {
-                        const uint32_t covered = a_ins < s - 1 ? a_ins : s - 1;
-                        const uint32_t rest = s - 1 - covered;
-                        const uint32_t T = kind == 1 ? NS_OP_MIS : NS_OP_DEL;
-                        const uint32_t n_ins = kind == 1 ? a_ins : a_ins - covered;
-                        if (n_ins == 0) {
-                            o0 = (T << 28) | (1u + rest);
-                        } else {
-                            o0 = (T << 28) | 1u;
-                            o1 = (NS_OP_INS << 28) | n_ins;
-                            if (rest) o2 = (T << 28) | rest;
-                        }
-                        if (covered) o3 = (NS_OP_COPY << 28) | covered;
-                    }
-                }
-                const uint32_t p1 = o0 ? 1u : 0u, p2 = p1 + (o1 ? 1u : 0u), p3 = p2 + (o2 ? 1u : 0u);
-                const uint32_t cnt = p3 + (o3 ? 1u : 0u);
-                const uint32_t incl = warp_incl_scan(cnt, lane);
-                const uint32_t at = n_ops + incl - cnt;
-                if (o0 && at < cap) ops[at] = o0;
-                if (o1 && at + p1 < cap) ops[at + p1] = o1;
-                if (o2 && at + p2 < cap) ops[at + p2] = o2;
-                if (o3 && at + p3 < cap) ops[at + p3] = o3;
-                n_ops += __shfl_sync(0xffffffffu, incl, 31);
-
-                if (jstop < 32) {
-                    const uint32_t Pstop = __shfl_sync(0xffffffffu, P, jstop);
-                    if (Pstop > middle_ref) {                      // overrun extends the segment (:1826-1828)
-                        l_new += Pstop - middle_ref;
-                        middle_ref = Pstop;
-                    }
-                    n_draws = base + (uint32_t)jstop + 1u;
-                    done = true;
-                } else {
-                    pos_base = __shfl_sync(0xffffffffu, P, 31);
-                    const uint32_t I31 = __shfl_sync(0xffffffffu, I, 31);
-                    if (nonins_mask) {
-                        const int last = 31 - __clz(nonins_mask);
-                        carry_a = I31 - __shfl_sync(0xffffffffu, I, last);
-                    } else {
-                        carry_a += I31;
-                    }
-                    base += 32;
-                }
-            }
+            const UChain ch = unaligned_chain_warp(m, key, id_lo, id_hi, sw, m_ref, ops, cap, lane);
+            const uint32_t middle_ref = ch.middle_ref, n_draws = ch.n_draws, n_ops = ch.n_ops;
+            const int64_t l_new = ch.l_new;
             if (REPLAY) break;
             const bool ok = middle_ref >= cfg.min_len && middle_ref <= cfg.max_len && l_new >= (int64_t)cfg.min_len &&
                             l_new <= (int64_t)cfg.max_len;
@@ -240,6 +261,59 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
                 if (overflow) atomicAdd(a.n_flagged, 1u);
             }
             break;
+        }
+    }
+}
+
+// Chimeric gaps (simulation_gap :1552-1568: "an unaligned read of gap_len") of the first attempt of every read, one WARP per
+// read, before the plan kernel: the same 32-draws-at-a-time evaluation, so that a 50 kb gap is not 50 000 iterations of ONE
+// lane of the plan kernel's state machine.  Stream ST_GAP keyed by (attempt 0, piece): the plan kernel's own sequential gap
+// walk (later attempts, replays) draws from the same stream, block k + 1 for draw k, and gets the same lengths.
+// Results travel in the gap's piece record: n_ops, ref_len (middle_ref), out_len = l_new, polya_len = 1 as "precomputed" mark.
+struct GapArgs {
+    DevModel m;
+    DevCfg cfg;
+    uint32_t kind;
+    uint64_t first_id;
+    uint32_t n_reads;
+    const uint32_t* n_seg;
+    const uint32_t* piece_first;
+    NsPieceMeta* pieces;
+    uint32_t* ops;
+    uint32_t* counter;
+    const uint32_t* abort;
+};
+__device__ __forceinline__ uint32_t gap_stream_word(uint32_t kind, uint32_t attempt, uint32_t piece_in_read) {
+    return stream_word(ST_GAP, kind, (attempt << 5) | (piece_in_read & 31u));
+}
+__global__ void __launch_bounds__(UREAD_WARPS * 32) gap_kernel(const __grid_constant__ GapArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
+    if (a.abort && *a.abort) return;
+    for (;;) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(a.counter, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= a.n_reads) break;
+        const uint32_t ns = a.n_seg[slot];
+        if (ns < 2) continue;
+        const uint32_t pf = a.piece_first[slot];
+        const uint64_t rid = a.first_id + slot;
+        for (uint32_t q = 1; q < 2 * ns - 1; q += 2) {
+            NsPieceMeta& pm = a.pieces[pf + q];
+            const uint32_t m_ref = pm.ref_req;
+            if (m_ref == 0) continue;                                  // nothing to walk (plan handles it)
+            const uint64_t op_off = pm.op_off;
+            const uint32_t cap = (uint32_t)(a.pieces[pf + q + 1].op_off - op_off);
+            const UChain ch = unaligned_chain_warp(a.m, key, (uint32_t)rid, (uint32_t)(rid >> 32), gap_stream_word(a.kind, 0, q), m_ref,
+                                                   a.ops + op_off, cap, lane);
+            if (lane == 0) {
+                pm.n_ops = ch.n_ops;
+                pm.ref_len = ch.middle_ref;
+                pm.out_len = (uint32_t)(ch.l_new < 0 ? 0 : ch.l_new);
+                pm.l_new = pm.out_len;
+                pm.polya_len = 1;
+            }
         }
     }
 }

@@ -155,15 +155,19 @@ def name_table(batch, ref_names, index_base, perfect=False, metagenome=False, tr
         return lib.ns_format_names(reads.ctypes.data_as(C.c_void_p), pieces.ctypes.data_as(C.c_void_p), n, int(batch.kind), flags,
                                    C.c_uint64(int(index_base)), cblob, coffs.ctypes.data_as(C.c_void_p), out_ptr, cap, off_ptr)
 
-    need = call(None, 0, None)
-    if need < 0:
-        raise RuntimeError("ns_format_names failed: %d" % need)
-    out = np.empty(int(need), dtype=np.uint8)
     offs = np.zeros(n, dtype=np.uint64)
-    got = call(out.ctypes.data_as(C.c_void_p), int(need), offs.ctypes.data_as(C.c_void_p))
-    if got != need:
+    # one call with a buffer that almost always suffices (names are ~60 characters); sized exactly when it does not
+    out = np.empty(max(n, 1) * 160, dtype=np.uint8)
+    got = call(out.ctypes.data_as(C.c_void_p), len(out), offs.ctypes.data_as(C.c_void_p))
+    if got == -4:                                    # NS_ENOMEM
+        need = call(None, 0, None)
+        if need < 0:
+            raise RuntimeError("ns_format_names failed: %d" % need)
+        out = np.empty(int(need), dtype=np.uint8)
+        got = call(out.ctypes.data_as(C.c_void_p), int(need), offs.ctypes.data_as(C.c_void_p))
+    if got < 0:
         raise RuntimeError("ns_format_names failed: %d" % got)
-    return NameTable(out.tobytes(), offs)
+    return NameTable(out[:int(got)].tobytes(), offs)
 
 
 def _name_blob(names):
