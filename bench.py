@@ -332,7 +332,7 @@ def main():
         probe = 16 if W["mode"] != "transcriptome" else 64
         pool.step(probe)
         _, pr_reads, pr_wall, _ = pool.step(probe)
-        per_worker = args.cpu_reads or int(min(4000, max(probe, 6.0 * probe / max(pr_wall, 1e-3))))
+        per_worker = args.cpu_reads or int(min(4000, max(1000, 6.0 * probe / max(pr_wall, 1e-3))))
         vals = []
         for s in range(args.warmup + args.steps):
             bases, nreads, wall, wsum = pool.step(per_worker if s >= args.warmup else max(8, per_worker // 8))
@@ -606,7 +606,7 @@ def main():
         probe = 16 if W["mode"] != "transcriptome" else 64
         pool.step(probe)                                         # the workers' first call (lazy imports, page faults)
         _, _, pr_wall, _ = pool.step(probe)
-        per_worker = args.cpu_reads or int(min(8000, max(probe, 15.0 * probe / max(pr_wall, 1e-3))))     # ~15 s of wall clock
+        per_worker = args.cpu_reads or int(min(8000, max(1000, 15.0 * probe / max(pr_wall, 1e-3))))      # >= 1000 reads per worker, ~15 s of wall clock
         cb, cr, ct, cw = pool.step(per_worker)
         pool.close()
         line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": n_procs, "kind": "port", "per_core": cb / max(cw, 1e-9),
