@@ -137,6 +137,10 @@ typedef struct {
  * byte (exact route: IUPAC codes, circular wrap-around, minus-strand genome pieces).  Both give the same bytes; this flag
  * sends every piece down the exact route (tests compare the two). */
 #define NS_FLAG_EMIT_EXACT 4u
+/* Pieces longer than 16 kb are emitted as several work items (each resuming the script walk from a checkpoint), so that the
+ * longest read of a batch does not keep one warp busy long after the rest has finished.  This flag emits every piece as one
+ * item (tests compare the two: same bytes). */
+#define NS_FLAG_EMIT_WHOLE 8u
 
 #define NS_KIND_ALIGNED 0
 #define NS_KIND_UNALIGNED 1

@@ -66,6 +66,7 @@ class NsExpression(C.Structure):
 NS_FLAG_UNALIGNED_SCRIPTS = 1
 NS_FLAG_URACIL = 2
 NS_FLAG_EMIT_EXACT = 4
+NS_FLAG_EMIT_WHOLE = 8
 
 
 class NsReadMeta(C.Structure):

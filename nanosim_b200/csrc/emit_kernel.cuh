@@ -71,7 +71,18 @@ struct EmitArgs {
     uint32_t* counter;
     const uint32_t* order;       // piece processing order (longest first) or null
     const uint32_t* abort;       // sync-free batches: non-zero = a capacity check failed upstream, do nothing (or null)
+    // long pieces are emitted EMIT_SPLIT bases per work item (split_kernel below): a piece's later stretches are extra work
+    // items, taken before everything else, each starting from a checkpoint of the script walk
+    const uint32_t* split_base;  // [n_pieces] first checkpoint of the piece, 0xffffffff = not split (null: nothing is split)
+    const uint2* extra;          // {piece, stretch >= 1}, piece 0xffffffff = unused slot
+    const uint4* ckpt;           // {op index in walking order, output start of that op, reference bases before it, -}
+    const uint32_t* n_extra;     // number of extra work items (device counter written by split_kernel)
+    uint32_t cap_extra;
 };
+
+// Output bases per work item of a long piece.  One warp emits ~512 bases per step; the longest read of a batch (100-600 kb)
+// would keep one warp busy for milliseconds after every other warp has run out of work.
+#define EMIT_SPLIT 16384u
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -404,12 +415,22 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     const uint32_t lane_lt = (1u << lane) - 1u;
 
+    uint32_t n_extra = a.split_base ? *a.n_extra : 0u;
+    if (n_extra > a.cap_extra) n_extra = a.cap_extra;
     for (;;) {
-        uint32_t piece = 0;
+        uint32_t piece = 0, sub = 0;
         if (lane == 0) piece = atomicAdd(a.counter, 1u);
         piece = __shfl_sync(0xffffffffu, piece, 0);
-        if (piece >= a.n_pieces) break;
-        if (a.order) piece = __ldg(&a.order[piece]);
+        if (piece >= n_extra + a.n_pieces) break;
+        if (piece < n_extra) {                   // a later stretch of a long piece
+            const uint2 x = a.extra[piece];
+            if (x.x == 0xffffffffu) continue;
+            piece = x.x;
+            sub = x.y;
+        } else {
+            piece -= n_extra;
+            if (a.order) piece = __ldg(&a.order[piece]);
+        }
         const NsPieceMeta pm = a.pieces[piece];
         if (pm.out_len == 0) continue;
         const NsReadMeta rm = a.reads[pm.read_slot];
@@ -420,8 +441,25 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         const bool rdir = rev != ref_comp;
         const uint32_t n_ops = pm.n_ops, ref_len = pm.ref_len;
         const uint32_t A = rev ? rm.seq_len - pm.out_rel - pm.out_len : pm.out_rel;    // piece start in read coordinates
-        const uint32_t pad = A & 15u, P0 = A - pad;          // x = read coordinate - P0: chunks are x/16
-        const uint32_t x_end = pad + pm.out_len;
+        uint32_t pad = A & 15u;                              // x = read coordinate - P0: chunks are x/16
+        const uint32_t P0 = A - pad;
+        uint32_t x_end = pad + pm.out_len;
+        // a stretch of a split piece: [sub * EMIT_SPLIT, (sub + 1) * EMIT_SPLIT) of x, the walk resumed from its checkpoint
+        uint32_t t_first = 0, out_first = pad, ref_first = 0, x_first = 0;
+        {
+            const uint32_t sbase = a.split_base ? __ldg(&a.split_base[piece]) : 0xffffffffu;
+            if (sbase != 0xffffffffu) {
+                if (sub) {
+                    const uint4 ck = a.ckpt[sbase + sub - 1u];
+                    t_first = ck.x;
+                    out_first = ck.y;
+                    ref_first = ck.z;
+                    x_first = sub * EMIT_SPLIT;
+                    pad = 0;
+                }
+                if (x_end > (sub + 1u) * EMIT_SPLIT) x_end = (sub + 1u) * EMIT_SPLIT;
+            }
+        }
         const uint64_t cstart = a.ref.chrom_off[pm.chrom];
         EmitPiece pc;
         pc.cbase = a.ref.bases + cstart;
@@ -455,7 +493,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
         }
         const char* lut_s = reinterpret_cast<const char*>(lut) + (unmapped ? 4u * QLUT_SIZE * 4u : 0u);
 
-        uint32_t t_loaded = 0, w_loaded = 0, w_ret = 0, out_loaded = pad, ref_loaded = 0, prog = 0;
+        uint32_t t_loaded = t_first, w_loaded = 0, w_ret = 0, out_loaded = out_first, ref_loaded = ref_first, prog = x_first;
         bool closed = false;
         if (pad) {
             if (lane == 0) ring[0] = make_uint4(0u, 0u, 2u * pad, info_pad);
@@ -598,6 +636,82 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, EMIT_MIN_BLOCKS) emit_kernel(
 #if EMIT_TMA_WINDOW
             if (win_on) win_phase ^= 1u;           // every lane is past the window: the next step may overwrite it
 #endif
+        }
+    }
+}
+
+// ---- long pieces -> extra work items + checkpoints (one warp per long piece; everything else costs one 64-byte read)
+struct SplitArgs {
+    const NsReadMeta* reads;
+    const NsPieceMeta* pieces;
+    const uint32_t* ops;
+    uint32_t n_pieces;
+    uint32_t* split_base;
+    uint2* extra;
+    uint4* ckpt;
+    uint32_t* n_extra;
+    uint32_t cap_extra;
+    const uint32_t* abort;
+};
+
+__global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ SplitArgs a) {
+    if (a.abort && *a.abort) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    (void)lane_lt;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t piece = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); piece < a.n_pieces; piece += n_warps) {
+        const NsPieceMeta* pmp = a.pieces + piece;
+        const uint32_t out_len = pmp->out_len;
+        if (out_len <= EMIT_SPLIT - 16u) {                    // pad < 16: fits one work item
+            if (lane == 0) a.split_base[piece] = 0xffffffffu;
+            continue;
+        }
+        const NsPieceMeta pm = *pmp;
+        const NsReadMeta rm = a.reads[pm.read_slot];
+        const bool rev = rm.reversed != 0;
+        const uint32_t A = rev ? rm.seq_len - pm.out_rel - pm.out_len : pm.out_rel;
+        const uint32_t pad = A & 15u, x_end = pad + out_len;
+        const uint32_t n_sub = (x_end + EMIT_SPLIT - 1u) / EMIT_SPLIT;
+        if (n_sub < 2u) {
+            if (lane == 0) a.split_base[piece] = 0xffffffffu;
+            continue;
+        }
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.n_extra, n_sub - 1u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + (n_sub - 1u) > a.cap_extra) {              // cannot happen with the capacity launch_emit reserves; stay whole
+            if (lane == 0) a.split_base[piece] = 0xffffffffu;
+            continue;
+        }
+        if (lane == 0) a.split_base[piece] = base;
+        for (uint32_t j = 1u + lane; j < n_sub; j += 32u) a.extra[base + j - 1u] = make_uint2(piece, j);
+        // the same walk as the emit kernel's ring build: two ops per lane, output / reference prefix sums
+        const uint32_t* __restrict__ ops = a.ops + pm.op_off;
+        const uint32_t n_ops = pm.n_ops;
+        uint32_t out_loaded = pad, ref_loaded = 0;
+        for (uint32_t t_loaded = 0; t_loaded < n_ops && out_loaded < x_end; t_loaded += 64u) {
+            const uint32_t t = t_loaded + 2u * lane;
+            uint32_t op0 = 0, op1 = 0;
+            if (t < n_ops) op0 = __ldg(&ops[rev ? n_ops - 1u - t : t]);
+            if (t + 1u < n_ops) op1 = __ldg(&ops[rev ? n_ops - 2u - t : t + 1u]);
+            const uint32_t ty0 = op0 >> 28, len0 = op_len(op0), ty1 = op1 >> 28, len1 = op_len(op1);
+            const uint32_t o0 = (ty0 == NS_OP_DEL) ? 0u : len0, o1 = (ty1 == NS_OP_DEL) ? 0u : len1;
+            const uint32_t r0 = (ty0 < 2u || ty0 == NS_OP_DEL) ? len0 : 0u, r1 = (ty1 < 2u || ty1 == NS_OP_DEL) ? len1 : 0u;
+            const uint32_t so = warp_incl_scan(o0 + o1, lane), sr = warp_incl_scan(r0 + r1, lane);
+            const uint32_t xo = out_loaded + so - (o0 + o1), rs = ref_loaded + sr - (r0 + r1);
+            // boundaries j * EMIT_SPLIT inside [xo, xo + o0) and [xo + o0, xo + o0 + o1)
+            if (o0) {
+                for (uint32_t j = (xo + EMIT_SPLIT - 1u) / EMIT_SPLIT; j < n_sub && j * EMIT_SPLIT < xo + o0; ++j)
+                    if (j) a.ckpt[base + j - 1u] = make_uint4(t, xo, rs, 0u);
+            }
+            if (o1) {
+                const uint32_t x1 = xo + o0;
+                for (uint32_t j = (x1 + EMIT_SPLIT - 1u) / EMIT_SPLIT; j < n_sub && j * EMIT_SPLIT < x1 + o1; ++j)
+                    if (j) a.ckpt[base + j - 1u] = make_uint4(t + 1u, x1, rs + r0, 0u);
+            }
+            out_loaded += __shfl_sync(0xffffffffu, so, 31);
+            ref_loaded += __shfl_sync(0xffffffffu, sr, 31);
         }
     }
 }

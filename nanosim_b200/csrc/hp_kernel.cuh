@@ -139,19 +139,26 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs a) {
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     const uint32_t K = a.cfg.kmer_bias;
-    // A lane walks one segment at a time, as a FLAT state machine: one loop iteration = one micro-step of every lane --
-    // a 16-base word of a copied stretch (the common case, which the lanes of a warp therefore execute together), one op of
-    // the script, or the hand-over to the next segment.  (Nested per-lane loops would leave ~2 of 32 lanes active.)
-    enum : int { ST_FETCH = 0, ST_OP = 1, ST_WORD = 2 };
-    int st = ST_FETCH;
+    // A lane walks one segment at a time, as a FLAT state machine.  One loop iteration = one micro-step of every lane: a
+    // 16-base word of a copied stretch (ST_WORD, the common case), one base of a stretch that has to be looked at base by
+    // base (ST_BASE: a word in which a run reaches K, substituted / inserted bases, the byte-exact route), one op of the
+    // script (ST_OP), or the hand-over to the next segment (ST_FETCH).  Every micro-step is split into a part that looks at
+    // its input (A), ONE shared place where the pending run is closed if the step asks for it (B: the only copy of
+    // flush_run in the kernel -- it is by far the largest piece of code), and a part that applies the step (C).  Nested
+    // per-lane loops left 2-5 of 32 lanes active and a kernel that mostly waited for its instruction cache.
+    enum : int { ST_FETCH = 0, ST_OP = 1, ST_WORD = 2, ST_BASE = 3 };
+    enum : int { SRC_WORD = 0, SRC_EXACT = 1, SRC_MIS = 2, SRC_INS = 3 };
+    enum : int { P_NONE = 0, P_END, P_HT, P_LIT, P_COPY, P_DEL, P_BASES, P_SLOW, P_ALL, P_MID };
+    int st = ST_FETCH, bsrc = SRC_WORD;
     uint32_t pi = 0, pi_end = 0, this_piece = 0;
     NsReadMeta rm;
     NsPieceMeta* pmp = nullptr;
     uint64_t rid = 0;
     HpWalker w = {};
     uint32_t* ev = nullptr;
-    uint32_t n_ev = 0, k = 0, rpos = 0;
-    uint32_t len = 0, t = 0, w16 = 0;                      // the copied stretch being walked word by word
+    uint32_t n_ev = 0, k = 0, kk = 0, rpos = 0;
+    uint32_t len = 0, t = 0, w16 = 0, cur = 0, n = 0;      // the stretch being walked: t of len done; cur / n = rest of its current word
+    uint4 rblk = make_uint4(0, 0, 0, 0);                    // random block of the substituted / inserted bases being walked
     ScriptOut<WRITE> out;
     out.begin(nullptr);
     // ---- current run of equal bases in the mutated stream
@@ -196,17 +203,17 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 }
                 if (cnt > nn - produced) cnt = nn - produced;
                 if (a.hp_mis_rate > 0.0) {
-                    for (uint32_t t = 0; t < cnt; ++t) {
+                    for (uint32_t q = 0; q < cnt; ++q) {
                         const double pr = u01_double(mr.next64());
-                        uint32_t b = run_base, st = state;
+                        uint32_t b = run_base, sq = state;
                         if (pr > 0.0 && pr <= a.hp_mis_rate) {
                             b = (run_base + 1u + (mr.next() % 3u)) & 3u;
                             if (!mis_q_used) {
-                                st = 0u;
+                                sq = 0u;
                                 mis_q_used = true;
                             }
                         }
-                        out.add((NS_OP_LIT << 28) | (b << 26) | (st << 24), 1);
+                        out.add((NS_OP_LIT << 28) | (b << 26) | (sq << 24), 1);
                     }
                 } else {
                     out.add((NS_OP_LIT << 28) | (run_base << 26) | (state << 24), cnt);
@@ -244,70 +251,152 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
             if (kind != 2 && seg_kind[nseg - 1] == 2) seg_kind[nseg - 1] = kind;
         }
     };
-    auto feed = [&](uint32_t b, uint32_t kind) {          // one base of the mutated stream
-        if (b != run_base || b > 3u) {
-            flush_run();
-            run_base = b;
-        }
-        ++run_len;
-        if (kind != 2) ++run_ref;
-        add_seg(kind, 1u);
-    };
-
 
     for (;;) {
+        // ================= A: look at the micro-step's input; does the pending run have to be closed before it?
+        int path = P_NONE;
+        bool need_flush = false;
+        uint32_t b = 0, bkind = 0;                          // ST_BASE: the base and its kind (0 copy, 1 mis, 2 ins)
+        uint32_t ne = 0, lead = 0;                          // ST_WORD
+        uint32_t op = 0, ty = 0;                            // ST_OP
         if (st == ST_WORD) {
-            // ---- up to 16 copied bases (the next word is requested before this one is looked at).
-            //      ne: bit 2j set iff base j differs from base j-1 (1 <= j < n)
-            do {
-                const uint32_t n = len - t < 16u ? len - t : 16u;
-                const uint32_t cur = w16;
+            if (n == 0) {                                   // next word of the stretch (the one after it is requested now)
+                n = len - t < 16u ? len - t : 16u;
+                cur = w16;
                 if (t + n < len) w16 = w.bases16(rpos + t + n);
-                const uint32_t fields = (n == 16u ? 0xffffffffu : (1u << (2u * n)) - 1u) & 0x55555554u;   // fields 1 .. n-1
-                const uint32_t d = cur ^ (cur << 2);
-                const uint32_t ne = (d | (d >> 1)) & fields;
-                // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
-                const uint32_t eq = ~ne & fields;
-                uint32_t runs = eq;
-                for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
-                // leading bases that continue the pending run
-                const uint32_t lead = (run_len && (cur & 3u) == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : n) : 0u;
-                t += n;
-                if (runs || run_len + lead >= K) {         // a run reaches K here: base by base
-                    for (uint32_t j = 0; j < n; ++j) feed((cur >> (2u * j)) & 3u, 0);
-                    break;
-                }
-                if (lead == n) {                           // the whole word continues the pending run
-                    add_seg(0u, n);
-                    run_len += n;
-                    run_ref += n;
-                    break;
-                }
+            }
+            // ne: bit 2j set iff base j differs from base j-1 (1 <= j < n)
+            const uint32_t fields = (n == 16u ? 0xffffffffu : (1u << (2u * n)) - 1u) & 0x55555554u;   // fields 1 .. n-1
+            const uint32_t d = cur ^ (cur << 2);
+            ne = (d | (d >> 1)) & fields;
+            // a run of >= K equal bases inside the word <=> K-1 consecutive "equal to the previous base" fields
+            const uint32_t eq = ~ne & fields;
+            uint32_t runs = eq;
+            for (uint32_t j = 1; j + 1 < K; ++j) runs &= eq << (2u * j);
+            // leading bases that continue the pending run
+            lead = (run_len && (cur & 3u) == run_base) ? (ne ? ((uint32_t)__ffs((int)ne) - 1u) >> 1 : n) : 0u;
+            if (runs || run_len + lead >= K) {
+                path = P_SLOW;                              // a run reaches K here: base by base
+            } else {
                 if (lead) {
                     add_seg(0u, lead);
                     run_len += lead;
                     run_ref += lead;
                 }
-                flush_run();                               // the pending run ends inside this word, shorter than K
-                // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
-                const uint32_t bound = ne | 1u;            // field 0 bounds the trailing run inside the word
-                const uint32_t trail = n - ((31u - (uint32_t)__clz((int)bound)) >> 1);
-                out.add(NS_OP_COPY << 28, n - lead - trail);
-                run_base = (cur >> (2u * (n - 1u))) & 3u;
-                run_len = run_ref = trail;
-                nseg = 1;
-                seg_kind[0] = 0;
-                seg_cnt[0] = trail;
-                    
-            } while (0);
-            if (t >= len) {
-                rpos += len;
+                path = lead == n ? P_ALL : P_MID;           // P_MID: the pending run ends inside this word, shorter than K
+                need_flush = path == P_MID;
+            }
+        } else if (st == ST_BASE) {
+            if (bsrc == SRC_WORD) {
+                b = cur & 3u;
+            } else if (bsrc == SRC_EXACT) {
+                b = w.base_at(rpos + t);
+            } else {
+                if ((t & 15u) == 0)
+                    rblk = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece_in_read), (kk << 8) + (t >> 4)), key);
+                const uint32_t wd = (t & 8u) ? ((t & 4u) ? rblk.w : rblk.z) : ((t & 4u) ? rblk.y : rblk.x);
+                const uint32_t r8 = (wd >> (8u * (t & 3u))) & 0xffu;
+                if (bsrc == SRC_MIS) {
+                    const uint32_t orig = w.packed ? (w.bases16(rpos + t) & 3u) : w.base_at(rpos + t);
+                    const uint32_t rr = r8 == 255u ? 0u : r8;
+                    b = ((orig & 3u) + 1u + rr % 3u) & 3u;
+                    bkind = 1;
+                } else {
+                    b = r8 & 3u;
+                    bkind = 2;
+                }
+            }
+            need_flush = b != run_base || b > 3u;
+        } else if (st == ST_OP) {
+            if (k >= n_ev) {                                // end of the segment's script
+                path = P_END;
+                need_flush = true;
+            } else {
+                op = ev[k];
+                ty = op >> 28;
+                len = op & 0x0fffffffu;
+                kk = k++;
+                if (ty == NS_OP_HT) {
+                    path = P_HT;
+                    need_flush = true;
+                } else if (ty == NS_OP_LIT) {               // polyA tail (appended after mutate_homo, :1229-1230)
+                    path = P_LIT;
+                    need_flush = true;
+                } else {
+                    if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && len > 0) {
+                        // ---- error filter (:1929-1947)
+                        const int64_t lo = ty == NS_OP_INS ? (int64_t)rpos - 1 : (int64_t)rpos;
+                        const int64_t hi = (int64_t)rpos + (int64_t)len - 1;
+                        bool drop = false;
+                        for (int64_t x = lo; x <= hi && !drop; ++x) drop = w.in_hp(x);
+                        if (drop) {
+                            if (ty == NS_OP_INS) len = 0;
+                            if (WRITE) ev[kk] = (NS_OP_COPY << 28) | len;
+                            ty = NS_OP_COPY;
+                        }
+                    }
+                    if (len == 0) {
+                        path = P_NONE;
+                    } else if (ty == NS_OP_COPY) {
+                        path = P_COPY;
+                    } else if (ty == NS_OP_DEL) {
+                        path = P_DEL;                       // pathological run (no room for another part): closed here
+                        need_flush = run_len != 0 && !(nseg > 0 && seg_kind[nseg - 1] == 3) && nseg >= HP_MAX_SEG;
+                    } else {
+                        path = P_BASES;
+                    }
+                }
+            }
+        }
+        // ================= B
+        if (need_flush) flush_run();
+        // ================= C: apply the micro-step
+        if (st == ST_WORD) {
+            if (path == P_SLOW) {
+                bsrc = SRC_WORD;
+                st = ST_BASE;
+            } else {
+                if (path == P_MID) {
+                    // the trailing run (bases equal to the last one) becomes the pending run, what lies between is copied
+                    const uint32_t bound = ne | 1u;        // field 0 bounds the trailing run inside the word
+                    const uint32_t trail = n - ((31u - (uint32_t)__clz((int)bound)) >> 1);
+                    out.add(NS_OP_COPY << 28, n - lead - trail);
+                    run_base = (cur >> (2u * (n - 1u))) & 3u;
+                    run_len = run_ref = trail;
+                    nseg = 1;
+                    seg_kind[0] = 0;
+                    seg_cnt[0] = trail;
+                }
+                t += n;
+                n = 0;
+                if (t >= len) {
+                    rpos += len;
+                    st = ST_OP;
+                }
+            }
+        } else if (st == ST_BASE) {
+            if (need_flush) run_base = b;
+            ++run_len;
+            if (bkind != 2) ++run_ref;
+            add_seg(bkind, 1u);
+            ++t;
+            if (bsrc == SRC_WORD) {
+                cur >>= 2;
+                if (--n == 0) {
+                    if (t >= len) {
+                        rpos += len;
+                        st = ST_OP;
+                    } else {
+                        st = ST_WORD;
+                    }
+                }
+            } else if (t >= len) {
+                if (bsrc != SRC_INS) rpos += len;
                 st = ST_OP;
             }
         } else if (st == ST_OP) {
-            NsPieceMeta& pm = *pmp;
-            if (k >= n_ev) {                                   // end of the segment's script
-                flush_run();
+            if (path == P_END) {
+                NsPieceMeta& pm = *pmp;
                 out.flush();
                 if (!WRITE) {
                     a.out_n_ops[this_piece] = out.n;
@@ -317,79 +406,39 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                     pm.n_ops = out.n;
                 }
                 st = ST_FETCH;
-                continue;
-            }
-            uint32_t op = ev[k];
-            uint32_t ty = op >> 28;
-            len = op & 0x0fffffffu;
-            const uint32_t kk = k;
-            ++k;
-            if (ty == NS_OP_HT) {
-                flush_run();
+            } else if (path == P_HT) {
                 out.add(NS_OP_HT << 28, len);
-                continue;
-            }
-            if (ty == NS_OP_LIT) {                         // polyA tail (appended after mutate_homo, :1229-1230)
-                flush_run();
+            } else if (path == P_LIT) {
                 out.add(op & 0xff000000u, op & 0x00ffffffu);
-                continue;
-            }
-            if (ty >= NS_OP_MIS && ty <= NS_OP_DEL && len > 0) {
-                // ---- error filter (:1929-1947)
-                const int64_t lo = ty == NS_OP_INS ? (int64_t)rpos - 1 : (int64_t)rpos;
-                const int64_t hi = (int64_t)rpos + (int64_t)len - 1;
-                bool drop = false;
-                for (int64_t x = lo; x <= hi && !drop; ++x) drop = w.in_hp(x);
-                if (drop) {
-                    op = ty == NS_OP_INS ? (NS_OP_COPY << 28) : ((NS_OP_COPY << 28) | len);
-                    if (WRITE) ev[kk] = op;
-                    ty = NS_OP_COPY;
-                    if ((op & 0x0fffffffu) == 0) continue;
-                }
-            }
-            if (ty == NS_OP_COPY) {
+            } else if (path == P_COPY) {
+                t = 0;
                 if (w.packed) {
-                    t = 0;
+                    n = 0;
                     w16 = w.bases16(rpos);
                     st = ST_WORD;
                 } else {
-                    for (uint32_t tt = 0; tt < len; ++tt) feed(w.base_at(rpos + tt), 0);
-                    rpos += len;
+                    bsrc = SRC_EXACT;
+                    st = ST_BASE;
                 }
-            } else if (ty == NS_OP_DEL) {
+            } else if (path == P_DEL) {
                 // deleted bases vanish from the read: their neighbours become adjacent and may join one run
                 if (run_len == 0) {
                     out.add(NS_OP_DEL << 28, len);
                 } else {
                     run_ref += len;
-                    if (nseg > 0 && seg_kind[nseg - 1] == 3) seg_cnt[nseg - 1] += len;
-                    else if (nseg < HP_MAX_SEG) {
+                    if (nseg > 0 && seg_kind[nseg - 1] == 3) {
+                        seg_cnt[nseg - 1] += len;
+                    } else {
                         seg_kind[nseg] = 3;
                         seg_cnt[nseg] = len;
                         ++nseg;
-                    } else {                                   // pathological: close the run here
-                        flush_run();
-                        out.add(NS_OP_DEL << 28, len);
                     }
                 }
                 rpos += len;
-            } else {
-                for (uint32_t tt = 0; tt < len; ++tt) {
-                    const uint4 r = philox4x32_7(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), stream_word(ST_EMIT_B, 0, w.piece_in_read), (kk << 8) + (tt >> 4)), key);
-                    const uint32_t wd = (tt & 8u) ? ((tt & 4u) ? r.w : r.z) : ((tt & 4u) ? r.y : r.x);
-                    const uint32_t r8 = (wd >> (8u * (tt & 3u))) & 0xffu;
-                    uint32_t b;
-                    if (ty == NS_OP_MIS) {
-                        const uint32_t orig = w.packed ? (w.bases16(rpos + tt) & 3u) : w.base_at(rpos + tt);
-                        const uint32_t rr = r8 == 255u ? 0u : r8;
-                        b = ((orig & 3u) + 1u + rr % 3u) & 3u;
-                        feed(b, 1);
-                    } else {
-                        b = r8 & 3u;
-                        feed(b, 2);
-                    }
-                }
-                if (ty == NS_OP_MIS) rpos += len;
+            } else if (path == P_BASES) {
+                t = 0;
+                bsrc = ty == NS_OP_MIS ? SRC_MIS : SRC_INS;
+                st = ST_BASE;
             }
         } else {
             // ---- next segment: pieces of the current read, then the next read (longest first)

@@ -104,6 +104,7 @@ struct NsContext {
     DevCfg dcfg{};
 
     // batch state
+    DevBuf split_base, split_extra, split_ckpt;     // long pieces -> extra emit work items (emit_kernel.cuh:split_kernel)
     DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
         stats, sort_keys, sort_vals, sort_tmp, hp_off;
     uint64_t* h_totals = nullptr;   // pinned + mapped
@@ -481,7 +482,7 @@ int ns_destroy(NsContext* ctx) {
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
                       &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev, &ctx->kde2d_x, &ctx->kde2d_y,
-                      &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya};
+                      &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya, &ctx->split_base, &ctx->split_extra, &ctx->split_ckpt};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
         DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->ref_packed, &ctx->ref_pk_off, &ctx->ref_exc, &ctx->alias, &ctx->qlut, &ctx->ref_species,
                             &ctx->ref_circular, &ctx->ref_sp_off, &ctx->kde2d_x, &ctx->kde2d_y, &ctx->expr_alias,
@@ -962,7 +963,7 @@ namespace {
 // as many blocks as fit), so that kernels of overlapped contexts can share an SM instead of queueing.
 // emit_kernel over `n_pieces` pieces of the context's current batch (all of them, or the ones `order` lists)
 int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order,
-                const uint32_t* abort_flag = nullptr) {
+                const uint32_t* abort_flag = nullptr, bool split = true) {
     cudaStream_t st = ctx->stream;
     EmitArgs ea;
     ea.ref = ctx->dref;
@@ -981,6 +982,38 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
     ea.counter = ctx->counter.as<uint32_t>();
     ea.order = order;
     CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+    {   // long pieces become several work items.  Capacity: every extra item stands for EMIT_SPLIT - 16 or more output bytes
+        // of its piece, and a batch's output fits the sequence buffer (checked on the device for sync-free batches).
+        static const int no_split = env_int("NANOSIM_B200_NO_SPLIT", 0);
+        const uint32_t cap_extra = (uint32_t)std::min<size_t>(ctx->seq.cap / (EMIT_SPLIT - 16u) + 64u, 0x7fffffffu);
+        ea.split_base = nullptr;
+        ea.extra = nullptr;
+        ea.ckpt = nullptr;
+        ea.n_extra = ctx->counter.as<uint32_t>() + 4;
+        ea.cap_extra = cap_extra;
+        if (split && !no_split && n_pieces && !(ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE)) {     // (`order` lists pieces below n_pieces whenever split is asked for)
+            CK(ctx->split_base.ensure((size_t)n_pieces * sizeof(uint32_t)));
+            CK(ctx->split_extra.ensure((size_t)cap_extra * sizeof(uint2)));
+            CK(ctx->split_ckpt.ensure((size_t)cap_extra * sizeof(uint4)));
+            CK(cudaMemsetAsync(ctx->split_extra.p, 0xff, (size_t)cap_extra * sizeof(uint2), st));
+            SplitArgs sa;
+            sa.reads = ea.reads;
+            sa.pieces = ea.pieces;
+            sa.ops = ea.ops;
+            sa.n_pieces = n_pieces;
+            sa.split_base = ctx->split_base.as<uint32_t>();
+            sa.extra = ctx->split_extra.as<uint2>();
+            sa.ckpt = ctx->split_ckpt.as<uint4>();
+            sa.n_extra = ctx->counter.as<uint32_t>() + 4;
+            sa.cap_extra = cap_extra;
+            sa.abort = abort_flag;
+            const unsigned sblocks = std::min<unsigned>((n_pieces + 7u) / 8u, (unsigned)ctx->sm_count * 8u);
+            split_kernel<<<sblocks, 256, 0, st>>>(sa);
+            ea.split_base = sa.split_base;
+            ea.extra = sa.extra;
+            ea.ckpt = sa.ckpt;
+        }
+    }
     const size_t ring_bytes = (size_t)EMIT_WARPS * EMIT_RING * sizeof(uint4) + 512 + EMIT_WINDOW_SMEM;
     if (ctx->hcfg.fastq) {
         size_t smem = ring_bytes + (size_t)NS_N_QUAL_STATES * QLUT_SIZE * 4;
@@ -1333,7 +1366,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         launches += 14;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
-    launches += 2;    // ev copy + emit
+    launches += 3;    // ev copy + split + emit
 
     // ---- emit
     {
@@ -1564,7 +1597,7 @@ int ns_reemit(NsContext* ctx, const uint32_t* read_slots, const NsReadMeta* new_
     iota_from<<<(n_new_pieces + 255) / 256, 256, 0, st>>>(ctx->sort_vals.as<uint32_t>(), n_new_pieces, old_np);
     CK(cudaGetLastError());
     {
-        int rc = launch_emit(ctx, NS_KIND_ALIGNED, ctx->last_first_id, n_new_pieces, ctx->sort_vals.as<uint32_t>());
+        int rc = launch_emit(ctx, NS_KIND_ALIGNED, ctx->last_first_id, n_new_pieces, ctx->sort_vals.as<uint32_t>(), nullptr, false);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(st));

@@ -184,11 +184,11 @@ class Engine:
 
     def configure(self, circular=False, perfect=False, fastq=False, chimeric=False, kmer_bias=0, min_len=50,
                   max_len=None, median_len=0.0, sd_len=0.0, unaligned_scripts=False, metagenome=False,
-                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0, trx_records=0, emit_exact=False):
+                  transcriptome=False, uracil=False, polya_scale=0.0, kde2d_sample=0, trx_records=0, emit_exact=False, emit_whole=False):
         if max_len is None or max_len == float("inf"):
             max_len = 0x0fffffff
         flags = (L.NS_FLAG_UNALIGNED_SCRIPTS if unaligned_scripts else 0) | (L.NS_FLAG_URACIL if uracil else 0) | \
-            (L.NS_FLAG_EMIT_EXACT if emit_exact else 0)
+            (L.NS_FLAG_EMIT_EXACT if emit_exact else 0) | (L.NS_FLAG_EMIT_WHOLE if emit_whole else 0)
         cfg = L.NsRunConfig(2 if transcriptome else (1 if metagenome else 0), int(circular), int(perfect), int(fastq),
                             int(chimeric), int(kmer_bias or 0), int(min_len), int(min(max_len, 0x0fffffff)),
                             float(median_len or 0.0), float(sd_len or 0.0), flags, int(kde2d_sample), float(polya_scale or 0.0),

@@ -51,7 +51,7 @@ def load_tables(model, **kw):
 
 
 def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, min_len=50, max_len=None, circular=False,
-                device=0, unaligned_scripts=False, kmer_bias=0, emit_exact=False):
+                device=0, unaligned_scripts=False, kmer_bias=0, emit_exact=False, emit_whole=False):
     from nanosim_b200.engine import Engine
 
     cm, t = load_tables(model, fastq=fastq, chimeric=chimeric, perfect=perfect, homopolymer=bool(kmer_bias))
@@ -60,7 +60,7 @@ def make_engine(model, ref, fastq=True, chimeric=False, perfect=False, seed=1, m
     eng.set_model(t, perfect=perfect)
     eng.configure(circular=circular, perfect=perfect, fastq=fastq, chimeric=chimeric, min_len=min_len,
                   max_len=min(max_len or ref.max_chrom, ref.max_chrom), unaligned_scripts=unaligned_scripts,
-                  kmer_bias=kmer_bias, emit_exact=emit_exact)
+                  kmer_bias=kmer_bias, emit_exact=emit_exact, emit_whole=emit_whole)
     return eng, cm, t
 
 

@@ -114,6 +114,33 @@ def test_emit_fast_route_equals_exact_route(model, kw, ecoli, mini_ref, L):
         assert len(got[False]) == len(got[True]) == 4800 and n_diff == 0, "%d reads differ between the routes" % n_diff
 
 
+@pytest.mark.parametrize("model,kw", [("guppy", dict(fastq=True)), ("dorado", dict(fastq=False, chimeric=True)),
+                                      ("dorado", dict(fastq=True, chimeric=True, kmer_bias=6))])
+def test_emit_split_pieces_equal_whole_pieces(model, kw, ecoli, mini_ref, L):
+    """Pieces longer than 16 kb are emitted as several work items, each resuming the script walk from a checkpoint
+    (emit_kernel.cuh:split_kernel); NS_FLAG_EMIT_WHOLE emits every piece in one go.  Same bytes either way, on both routes
+    (pure-ACGT reference: fast; IUPAC / lower-case mini reference: mixed), forward and reverse reads, aligned and unaligned."""
+    fastq = kw.get("fastq", False)
+    for ref, exact in ((ecoli, False), (ecoli, True), (mini_ref, False)):
+        got, n_long = {}, 0
+        for whole in (False, True):
+            eng, _, _ = pc.make_engine(model, ref, seed=2718, emit_whole=whole, emit_exact=exact, **kw)
+            eng.simulate(L.NS_KIND_ALIGNED, 3, 3000)
+            b = eng.fetch(want_ops=True)
+            if not whole:
+                assert pc.check_edit_scripts(b, ref, fastq, max_reads=200) > 0
+                n_long = int((b.pieces["out_len"] > 40000).sum())
+            rows = _reads_bytes(b, fastq)
+            eng.simulate(L.NS_KIND_UNALIGNED, 9, 1500)
+            rows += _reads_bytes(eng.fetch(), fastq)
+            eng.close()
+            got[whole] = rows
+        if ref is ecoli:
+            assert n_long > 0, "no piece long enough to be split three ways: the test does not test anything"
+        n_diff = sum(x != y for x, y in zip(got[False], got[True]))
+        assert len(got[False]) == len(got[True]) == 4500 and n_diff == 0, "%d reads differ between split and whole emission" % n_diff
+
+
 def test_unaligned_event_scripts_vs_oracle(ecoli, L, tmp_path):
     """unaligned_error_list (simulator.py:1784-1830: 0.4/0.3/0.15/0.15 step mix, insertions merged at pos+0.1) and what
     mutate_read makes of its e_dict (:1957-1995) against the pinned oracle: the device's scripted unaligned path on 2500
