@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--ref_scale", type=float, default=1.0, help="scale the synthetic reference (tests only)")
     ap.add_argument("--depth", type=int, default=4, help="overlapped contexts per GPU")
     ap.add_argument("--timeline", default=None, help="write the per-batch phase intervals of the timed steps to this file")
+    ap.add_argument("--max_len", type=int, default=0, help="experiments only: cap the read length (-max); 0 = the reference's default")
     ap.add_argument("--cpu_reads", type=int, default=0, help="reads PER WORKER in a CPU-baseline step (0 = auto)")
     ap.add_argument("--cpu_procs", type=int, default=0, help="CPU-baseline worker processes (0 = all host cores)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
@@ -402,7 +403,7 @@ def main():
     if W["mode"] == "metagenome":
         abun = [100.0 / len(sref.species)] * len(sref.species)
         eng.set_abundance(abun, [1 - (1 - a) * tables.abun_inflation for a in abun] if W["chimeric"] else None)
-    eng.configure(fastq=W["fastq"], chimeric=W["chimeric"], kmer_bias=W["kmer_bias"], min_len=50, max_len=sref.max_chrom,
+    eng.configure(fastq=W["fastq"], chimeric=W["chimeric"], kmer_bias=W["kmer_bias"], min_len=50, max_len=min(sref.max_chrom, args.max_len) if args.max_len else sref.max_chrom,
                   metagenome=W["mode"] == "metagenome", transcriptome=W["mode"] == "transcriptome",
                   # the reference's 2-D KDE sample has one row per aligned read of a worker (simulator.py:1072): 5M-read job / cores
                   kde2d_sample=max(1, int(5000000 * n_al / max(batch_reads, 1)) // cores) if W["mode"] == "transcriptome" else 0)

@@ -94,7 +94,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox
 __host__ __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) { return philox4x32<7>(c, k); }
 
 // stream word layout: [31:28] purpose, [27] kind, [26:0] attempt / generation
-enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6, ST_IUPAC = 7, ST_HP = 8, ST_GAP = 9 };
+enum : uint32_t { ST_SEG = 1, ST_LEN = 2, ST_ATT = 3, ST_POS = 4, ST_EMIT_Q = 5, ST_EMIT_B = 6, ST_IUPAC = 7, ST_HP = 8, ST_GAP = 9, ST_CHAIN = 10 };
 
 __host__ __device__ __forceinline__ uint32_t stream_word(uint32_t purpose, uint32_t kind, uint32_t sub) {
     return (purpose << 28) | ((kind & 1u) << 27) | (sub & 0x07ffffffu);

@@ -686,32 +686,39 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
         }
         if (lane == 0) a.split_base[piece] = base;
         for (uint32_t j = 1u + lane; j < n_sub; j += 32u) a.extra[base + j - 1u] = make_uint2(piece, j);
-        // the same walk as the emit kernel's ring build: two ops per lane, output / reference prefix sums
+        // The walk of the emit kernel's ring build (ops in walking order, output / reference prefix sums), 2048 ops per step:
+        // every lane adds up 64 consecutive ops, one warp scan gives each lane its start, and a lane looks at its ops again
+        // only when a boundary falls among them (a boundary every 16 kb, a lane's ops span a few hundred bases).
         const uint32_t* __restrict__ ops = a.ops + pm.op_off;
         const uint32_t n_ops = pm.n_ops;
         uint32_t out_loaded = pad, ref_loaded = 0;
-        for (uint32_t t_loaded = 0; t_loaded < n_ops && out_loaded < x_end; t_loaded += 64u) {
-            const uint32_t t = t_loaded + 2u * lane;
-            uint32_t op0 = 0, op1 = 0;
-            if (t < n_ops) op0 = __ldg(&ops[rev ? n_ops - 1u - t : t]);
-            if (t + 1u < n_ops) op1 = __ldg(&ops[rev ? n_ops - 2u - t : t + 1u]);
-            const uint32_t ty0 = op0 >> 28, len0 = op_len(op0), ty1 = op1 >> 28, len1 = op_len(op1);
-            const uint32_t o0 = (ty0 == NS_OP_DEL) ? 0u : len0, o1 = (ty1 == NS_OP_DEL) ? 0u : len1;
-            const uint32_t r0 = (ty0 < 2u || ty0 == NS_OP_DEL) ? len0 : 0u, r1 = (ty1 < 2u || ty1 == NS_OP_DEL) ? len1 : 0u;
-            const uint32_t so = warp_incl_scan(o0 + o1, lane), sr = warp_incl_scan(r0 + r1, lane);
-            const uint32_t xo = out_loaded + so - (o0 + o1), rs = ref_loaded + sr - (r0 + r1);
-            // boundaries j * EMIT_SPLIT inside [xo, xo + o0) and [xo + o0, xo + o0 + o1)
-            if (o0) {
-                for (uint32_t j = (xo + EMIT_SPLIT - 1u) / EMIT_SPLIT; j < n_sub && j * EMIT_SPLIT < xo + o0; ++j)
-                    if (j) a.ckpt[base + j - 1u] = make_uint4(t, xo, rs, 0u);
+        for (uint32_t t_tile = 0; t_tile < n_ops && out_loaded < x_end; t_tile += 2048u) {
+            const uint32_t t0 = t_tile + 64u * lane, t1 = t0 + 64u < n_ops ? t0 + 64u : n_ops;
+            uint32_t so = 0, sr = 0;
+            for (uint32_t t = t0; t < t1; ++t) {
+                const uint32_t op = __ldg(&ops[rev ? n_ops - 1u - t : t]);
+                const uint32_t ty = op >> 28, len = op_len(op);
+                so += (ty == NS_OP_DEL) ? 0u : len;
+                sr += (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
             }
-            if (o1) {
-                const uint32_t x1 = xo + o0;
-                for (uint32_t j = (x1 + EMIT_SPLIT - 1u) / EMIT_SPLIT; j < n_sub && j * EMIT_SPLIT < x1 + o1; ++j)
-                    if (j) a.ckpt[base + j - 1u] = make_uint4(t + 1u, x1, rs + r0, 0u);
+            const uint32_t io = warp_incl_scan(so, lane), ir = warp_incl_scan(sr, lane);
+            uint32_t xo = out_loaded + io - so, rs = ref_loaded + ir - sr;
+            // boundaries j * EMIT_SPLIT in [xo, xo + so)
+            if (so && (xo + so - 1u) / EMIT_SPLIT != (xo ? (xo - 1u) / EMIT_SPLIT : 0u)) {
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const uint32_t op = __ldg(&ops[rev ? n_ops - 1u - t : t]);
+                    const uint32_t ty = op >> 28, len = op_len(op);
+                    const uint32_t o = (ty == NS_OP_DEL) ? 0u : len;
+                    if (o) {
+                        for (uint32_t j = (xo + EMIT_SPLIT - 1u) / EMIT_SPLIT; j < n_sub && j * EMIT_SPLIT < xo + o; ++j)
+                            if (j) a.ckpt[base + j - 1u] = make_uint4(t, xo, rs, 0u);
+                    }
+                    xo += o;
+                    rs += (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
+                }
             }
-            out_loaded += __shfl_sync(0xffffffffu, so, 31);
-            ref_loaded += __shfl_sync(0xffffffffu, sr, 31);
+            out_loaded += __shfl_sync(0xffffffffu, io, 31);
+            ref_loaded += __shfl_sync(0xffffffffu, ir, 31);
         }
     }
 }

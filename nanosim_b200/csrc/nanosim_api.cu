@@ -34,6 +34,7 @@
 #include "plan_kernel.cuh"
 #include "emit_kernel.cuh"
 #include "uread_kernel.cuh"
+#include "chain_kernel.cuh"
 #include "hp_kernel.cuh"
 
 namespace {
@@ -963,7 +964,7 @@ namespace {
 // as many blocks as fit), so that kernels of overlapped contexts can share an SM instead of queueing.
 // emit_kernel over `n_pieces` pieces of the context's current batch (all of them, or the ones `order` lists)
 int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pieces, const uint32_t* order,
-                const uint32_t* abort_flag = nullptr, bool split = true) {
+                const uint32_t* abort_flag = nullptr, bool split = true, cudaEvent_t emit_begin = nullptr) {
     cudaStream_t st = ctx->stream;
     EmitArgs ea;
     ea.ref = ctx->dref;
@@ -1009,6 +1010,7 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
             sa.abort = abort_flag;
             const unsigned sblocks = std::min<unsigned>((n_pieces + 7u) / 8u, (unsigned)ctx->sm_count * 8u);
             split_kernel<<<sblocks, 256, 0, st>>>(sa);
+            if (emit_begin) CK(cudaEventRecord(emit_begin, st));     // the emit phase of the batch timings starts after the split
             ea.split_base = sa.split_base;
             ea.extra = sa.extra;
             ea.ckpt = sa.ckpt;
@@ -1236,6 +1238,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ua.pool_cursor = (unsigned long long*)(ctx->totals.as<uint64_t>() + 7);
     ua.pool = d_totals + NS_T_POOL;             // {base, size} of the bump pool, written by capacity_stage_a
     ua.abort = d_abort;
+    ua.no_cta = (ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE) ? 1u : 0u;
     const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
     if (chim && !ctx->hcfg.perfect) {
         // chimeric gaps of every read's first attempt, a warp per read (uread_kernel.cuh:gap_kernel)
@@ -1253,6 +1256,27 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         ga.abort = d_abort;
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         gap_kernel<<<ublocks, UREAD_WARPS * 32, 0, st>>>(ga);
+        CK(cudaGetLastError());
+        launches += 1;
+    }
+    if (kind == NS_KIND_ALIGNED && !ctx->hcfg.perfect && !ctx->dcfg.transcriptome && !(ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE)) {
+        // the error chains of the longest segments, a warp each (chain_kernel.cuh); the plan kernel picks the results up
+        ChainArgs ca;
+        ca.m = ctx->dmodel;
+        ca.cfg = ctx->dcfg;
+        ca.kind = (uint32_t)kind;
+        ca.first_id = first_read_id;
+        ca.n_reads = n;
+        ca.n_seg = d_nseg;
+        ca.piece_first = d_pfirst;
+        ca.pieces = pa.pieces;
+        ca.ops = pa.ops;
+        ca.order = vals_out;
+        ca.counter = pa.counter;
+        ca.abort = d_abort;
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
+        const unsigned cblocks = std::min<unsigned>((n + CHAIN_WARPS - 1) / CHAIN_WARPS, (unsigned)ctx->sm_count * 4u);
+        chain_kernel<<<cblocks, CHAIN_WARPS * 32, 0, st>>>(ca);
         CK(cudaGetLastError());
         launches += 1;
     }
@@ -1370,7 +1394,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
 
     // ---- emit
     {
-        int rc = launch_emit(ctx, kind, first_read_id, n_pieces, chim ? nullptr : vals_out, d_abort);   // one piece per read: the plan's
+        int rc = launch_emit(ctx, kind, first_read_id, n_pieces, chim ? nullptr : vals_out, d_abort, true, ctx->ev[4]);   // one piece per read: the plan's
         if (rc) return rc;                                                                       // longest-first order serves the emit too
     }
     CK(cudaGetLastError());

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     uint32_t pos = 0, middle_ref = 0, prev_match = 0, err_state = 0, last_err = 3;
     int64_t l_new = 0;
     uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
-    uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap: its own stream (shared with gap_kernel), draw k = Philox block k + 1
+    uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap / segment chain: its own stream (shared with gap_kernel / chain_kernel), draw k = Philox block k + 1
     bool last_op_was_ins_same_pos = false;
     uint32_t last_ins_len = 0;
     OpSink<true> sink;
@@ -535,8 +535,33 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                 sink.put(NS_OP_COPY, m_ref);
                 phase = PH_PIECE_END;
             } else {
+                // the error chain of a segment draws from its own stream, keyed by (attempt, piece): block 0 = first match,
+                // block k + 1 = event k.  The longest segments of a batch were already walked by chain_kernel (a warp each,
+                // chain_kernel.cuh) from the same blocks; their result waits in the piece record, the ops in the slot (behind
+                // a free word for the head op when this is the read's first piece).
+                gap_sw = stream_word(ST_CHAIN, a.kind, (attempt << 5) | (p & 31u));
+                gap_draw = 0;
+                const bool walked = !REPLAY && !cfg.transcriptome && pm.polya_len == 1u;
+                if (!REPLAY && !cfg.transcriptome) pm.polya_len = 0;
+                if (walked && attempt == 0) {
+                    uint32_t n_pre = pm.n_ops;
+                    if (p == 0) {
+                        if (head > 0) {
+                            ++n_pre;                         // sink.put above wrote the head op into the free word
+                        } else {
+                            pm.op_off += 1;
+                            sink.begin(a.ops + pm.op_off, sink.cap ? sink.cap - 1u : 0u);
+                        }
+                    }
+                    sink.n = n_pre;
+                    sink.out_len = pm.out_len + ((p == 0) ? head : 0u);
+                    middle_ref = pm.ref_len;
+                    l_new = (int64_t)pm.l_new;
+                    phase = PH_PIECE_END;
+                    break;
+                }
                 // first match from _first_match.hist, floor 2 (:1843-1850); no extension when it overshoots
-                uint32_t fm = alias_draw(m, 0, rng.next());
+                uint32_t fm = alias_draw(m, 0, philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, 0u), rng.key).x);
                 prev_match = fm;
                 err_state = 0;     // "start"
                 last_err = 3;
@@ -547,7 +572,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
             break;
         }
         case PH_EVENT: {   // one pass of the while-loop body of error_list (:1858-1914)
-            uint4 r = rng.next4();
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, ++gap_draw), rng.key);
             // the next match length only depends on the previous one (:1891-1903): its table lookup is issued first so
             // that it overlaps the error-length lookup below
             const uint32_t b = match_bin(m, bin_lut, prev_match);
