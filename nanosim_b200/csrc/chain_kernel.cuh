@@ -171,6 +171,7 @@ struct ChainArgs {
     const uint32_t* order;          // read slots by decreasing total drawn length
     uint32_t* counter;
     const uint32_t* abort;
+    uint32_t min_len;               // segments whose drawn reference length exceeds this are walked here
 };
 
 // Results travel in the piece record: n_ops, ref_len (middle_ref), out_len, l_new, polya_len = 1 as "walked" mark (the field is
@@ -196,11 +197,11 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_kernel(const __grid_co
         const uint64_t rid = a.first_id + slot;
         uint64_t total = 0;
         for (uint32_t q = 0; q < 2u * ns - 1u; ++q) total += a.pieces[pf + q].ref_req;
-        if (total <= CHAIN_MIN_LEN) break;                 // reads come by decreasing total length: nothing long is left
+        if (total <= a.min_len) break;                 // reads come by decreasing total length: nothing long is left
         for (uint32_t q = 0; q < 2u * ns - 1u; q += 2u) {
             NsPieceMeta& pm = a.pieces[pf + q];
             const uint32_t m_ref = pm.ref_req;
-            if (m_ref <= CHAIN_MIN_LEN) continue;
+            if (m_ref <= a.min_len) continue;
             const uint32_t shift = q == 0 ? 1u : 0u;
             const uint64_t op_off = pm.op_off;
             const uint32_t room = (uint32_t)(a.pieces[pf + q + 1].op_off - op_off);

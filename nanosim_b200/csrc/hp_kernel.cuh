@@ -41,8 +41,7 @@ struct HpArgs {
     double hp[2][6];            // rows AT, CG: const, alpha1, beta1, breakpoint1, intercept, slope
     double hp_mis_rate;
     uint32_t* counter;
-    const uint32_t* order;      // read slots, longest first (nullptr: identity)
-    uint32_t n_reads;
+    const uint32_t* order;      // pieces, longest reference span first (nullptr: identity)
     uint32_t force_exact;       // NS_FLAG_EMIT_EXACT: no packed-word shortcuts
 };
 
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
     enum : int { SRC_WORD = 0, SRC_EXACT = 1, SRC_MIS = 2, SRC_INS = 3 };
     enum : int { P_NONE = 0, P_END, P_HT, P_LIT, P_COPY, P_DEL, P_BASES, P_SLOW, P_ALL, P_MID };
     int st = ST_FETCH, bsrc = SRC_WORD;
-    uint32_t pi = 0, pi_end = 0, this_piece = 0;
+    uint32_t this_piece = 0;
     NsReadMeta rm;
     NsPieceMeta* pmp = nullptr;
     uint64_t rid = 0;
@@ -441,23 +440,18 @@ __global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs 
                 st = ST_BASE;
             }
         } else {
-            // ---- next segment: pieces of the current read, then the next read (longest first)
-            if (pi == pi_end) {
-                uint32_t ri = atomicAdd(a.counter, 1u);
-                if (ri >= a.n_reads) break;
-                if (a.order) ri = a.order[ri];
-                rm = a.reads[ri];
-                pi = rm.piece_first;
-                pi_end = pi + rm.n_pieces;
-                continue;
-            }
-            pmp = &a.pieces[pi];
+            // ---- next segment, longest first (a read's segments go to different lanes: a chimeric read of five 100 kb segments
+            //      would otherwise keep one lane busy five times as long as any other)
+            const uint32_t wi = atomicAdd(a.counter, 1u);
+            if (wi >= a.n_pieces) break;
+            this_piece = a.order ? a.order[wi] : wi;
+            pmp = &a.pieces[this_piece];
             NsPieceMeta& pm = *pmp;
-            this_piece = pi++;
             if (NS_PIECE_KIND(pm.kind) != NS_PIECE_SEGMENT) {
                 if (!WRITE) a.out_n_ops[this_piece] = 0;   // untouched pieces keep their script
                 continue;
             }
+            rm = a.reads[pm.read_slot];
             rid = a.first_id + pm.read_slot;
             const uint64_t cstart = a.ref.chrom_off[pm.chrom];
             w.cb = a.ref.bases + cstart;

@@ -105,7 +105,7 @@ struct NsContext {
     DevCfg dcfg{};
 
     // batch state
-    DevBuf split_base, split_extra, split_ckpt;     // long pieces -> extra emit work items (emit_kernel.cuh:split_kernel)
+    DevBuf split_base, split_extra, split_ckpt, hp_keys;     // long pieces -> extra emit work items (emit_kernel.cuh:split_kernel)
     DevBuf reads, pieces, ops, seq, qual, nseg, npieces, piece_first, scan_in, scan_out, scan_tmp, counter, totals,
         stats, sort_keys, sort_vals, sort_tmp, hp_off;
     uint64_t* h_totals = nullptr;   // pinned + mapped
@@ -483,7 +483,7 @@ int ns_destroy(NsContext* ctx) {
                       &ctx->ops, &ctx->seq, &ctx->qual, &ctx->nseg, &ctx->npieces, &ctx->piece_first, &ctx->scan_in,
                       &ctx->scan_out, &ctx->scan_tmp, &ctx->counter, &ctx->totals, &ctx->stats, &ctx->sort_keys, &ctx->sort_vals,
                       &ctx->sort_tmp, &ctx->hp_off, &ctx->ref_species, &ctx->ref_circular, &ctx->ref_sp_off, &ctx->sp_bases_dev, &ctx->kde2d_x, &ctx->kde2d_y,
-                      &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya, &ctx->split_base, &ctx->split_extra, &ctx->split_ckpt};
+                      &ctx->expr_alias, &ctx->expr_chrom, &ctx->chrom_polya, &ctx->split_base, &ctx->split_extra, &ctx->split_ckpt, &ctx->hp_keys};
     if (ctx->borrowed) {            // shared with the parent: drop the pointers without freeing
         DevBuf* shared[] = {&ctx->ref_bases, &ctx->ref_off, &ctx->ref_packed, &ctx->ref_pk_off, &ctx->ref_exc, &ctx->alias, &ctx->qlut, &ctx->ref_species,
                             &ctx->ref_circular, &ctx->ref_sp_off, &ctx->kde2d_x, &ctx->kde2d_y, &ctx->expr_alias,
@@ -1039,6 +1039,13 @@ int launch_emit(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_pie
     return NS_OK;
 }
 
+__global__ void hp_piece_keys(const NsPieceMeta* pieces, uint32_t n, uint32_t* keys, uint32_t* vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = NS_PIECE_KIND(pieces[i].kind) == NS_PIECE_SEGMENT ? pieces[i].ref_len : 0u;
+    vals[i] = i;
+}
+
 __global__ void replace_reads(NsReadMeta* reads, const uint32_t* slots, const NsReadMeta* repl, uint32_t n, uint32_t n_reads) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && slots[i] < n_reads) {
@@ -1238,7 +1245,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     ua.pool_cursor = (unsigned long long*)(ctx->totals.as<uint64_t>() + 7);
     ua.pool = d_totals + NS_T_POOL;             // {base, size} of the bump pool, written by capacity_stage_a
     ua.abort = d_abort;
-    ua.no_cta = (ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE) ? 1u : 0u;
+    static const int cta_min = env_int("NANOSIM_B200_UREAD_CTA_MIN", (int)UREAD_CTA_MIN_LEN);
+    ua.cta_min_len = (ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE) ? 0u : (uint32_t)std::max(cta_min, 0);
     const unsigned ublocks = std::min<unsigned>((n + UREAD_WARPS - 1) / UREAD_WARPS, (unsigned)ctx->sm_count * 8u);
     if (chim && !ctx->hcfg.perfect) {
         // chimeric gaps of every read's first attempt, a warp per read (uread_kernel.cuh:gap_kernel)
@@ -1274,6 +1282,8 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         ca.order = vals_out;
         ca.counter = pa.counter;
         ca.abort = d_abort;
+        static const int chain_min = env_int("NANOSIM_B200_CHAIN_MIN", (int)CHAIN_MIN_LEN);
+        ca.min_len = (uint32_t)std::max(chain_min, 1024);
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         const unsigned cblocks = std::min<unsigned>((n + CHAIN_WARPS - 1) / CHAIN_WARPS, (unsigned)ctx->sm_count * 4u);
         chain_kernel<<<cblocks, CHAIN_WARPS * 32, 0, st>>>(ca);
@@ -1349,10 +1359,19 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         memcpy(ha.hp, ctx->hmodel.hp, sizeof ha.hp);
         ha.hp_mis_rate = ctx->hmodel.hp_mis_rate;
         ha.counter = ctx->counter.as<uint32_t>();
-        ha.order = vals_out;                 // reads longest first: the lanes of a warp walk segments of similar length
-        ha.n_reads = n;
+        {   // segments longest first: the lanes of a warp walk segments of similar length, and the longest one starts first
+            CK(ctx->hp_keys.ensure((size_t)n_pieces * 16));
+            uint32_t* k_in = ctx->hp_keys.as<uint32_t>();
+            uint32_t *k_out = k_in + n_pieces, *v_in = k_out + n_pieces, *v_out = v_in + n_pieces;
+            hp_piece_keys<<<gp, tb, 0, st>>>(pa.pieces, n_pieces, k_in, v_in);
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n_pieces, 0, 32, st));
+            CK(ctx->sort_tmp.ensure(tmp));
+            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)n_pieces, 0, 32, st));
+            ha.order = v_out;
+        }
         ha.force_exact = (ctx->hcfg.flags & NS_FLAG_EMIT_EXACT) ? 1u : 0u;
-        const unsigned hp_blocks = std::min<unsigned>((n + 127) / 128, (unsigned)ctx->sm_count * 16u);
+        const unsigned hp_blocks = std::min<unsigned>((n_pieces + 127) / 128, (unsigned)ctx->sm_count * 16u);
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         hp_kernel<false><<<hp_blocks, 128, 0, st>>>(ha);
         CK(cudaGetLastError());
@@ -1387,7 +1406,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         hp_kernel<true><<<hp_blocks, 128, 0, st>>>(ha);
         CK(cudaGetLastError());
-        launches += 14;
+        launches += 17;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     launches += 3;    // ev copy + split + emit

@@ -42,7 +42,7 @@ struct UreadArgs {
     unsigned long long* pool_cursor;
     const uint64_t* pool;    // {base, size} of the pool, in ops (device memory: written by capacity_stage_a)
     const uint32_t* abort;   // sync-free batches: non-zero = the script area is too small, do nothing (or null)
-    uint32_t no_cta;         // tests: every read by one warp (NS_FLAG_EMIT_WHOLE)
+    uint32_t cta_min_len;    // reads whose first drawn length exceeds this are walked by a whole block (0: none, NS_FLAG_EMIT_WHOLE)
 };
 
 #define UREAD_WARPS 8
@@ -317,8 +317,9 @@ __device__ __forceinline__ UChain unaligned_chain_cta(const DevModel& m, uint2 k
     return c;
 }
 
-// reads whose first drawn length exceeds this are walked by a whole block, the rest by one warp each
-#define UREAD_CTA_MIN_LEN 6144u
+// reads whose first drawn length exceeds this are walked by a whole block, the rest by one warp each: a block covers 256
+// draws per round but pays two barriers for it, so per draw it is slower than eight independent warps
+#define UREAD_CTA_MIN_LEN 32768u
 
 // One read (its rejection loop :1503, :1517), by one warp (CTA = false) or by the whole block (CTA = true); every thread runs
 // it redundantly on uniform values.  Returns the length drawn for attempt 0.
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
     __shared__ UCtaShared sh;
 
     // ---- the long reads come first in `order`: the whole block walks them, one at a time, until it meets a short one
-    if (!REPLAY && a.order && !a.no_cta) {
+    if (!REPLAY && a.order && a.cta_min_len) {
         for (;;) {
             if (threadIdx.x == 0) sh.bc32 = atomicAdd(a.counter, 1u);
             __syncthreads();
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_co
             __syncthreads();
             if (idx >= a.n_reads) return;
             const uint32_t first_len = uread_one<REPLAY, true>(a, key, a.order[idx], pool_base, pool_size, sh);
-            if (first_len <= UREAD_CTA_MIN_LEN) break;
+            if (first_len <= a.cta_min_len) break;
         }
     }
     // ---- one warp per read
