@@ -104,7 +104,8 @@ typedef struct {
     uint32_t has_hp;
     float strandness_rate;
     float segment_mean;
-    float mean_ref_per_event; /* sizing hint for op slots */
+    float mean_ref_per_event; /* sizing hint for op slots: reference bases per error event ... */
+    float ref_per_event_cv;   /* ... and their coefficient of variation (slots hold mean + 6 sigma events) */
 } NsModel;
 
 /* The scalar arguments of simulation()/simulation_aligned_genome()/simulation_unaligned(). */

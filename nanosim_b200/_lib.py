@@ -48,6 +48,7 @@ class NsModel(C.Structure):
         ("hp", (C.c_double * 6) * 2), ("hp_mis_rate", C.c_double),
         ("has_hp", C.c_uint32), ("strandness_rate", C.c_float), ("segment_mean", C.c_float),
         ("mean_ref_per_event", C.c_float),
+        ("ref_per_event_cv", C.c_float),
     ]
 
 

@@ -1142,6 +1142,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     const bool exact_only = (kind == NS_KIND_UNALIGNED) && !fast_unaligned;
     lengths_kernel<<<gb, tb, 0, st>>>(ctx->dmodel, ctx->dcfg, (uint32_t)kind, first_read_id, n, d_nseg, d_pfirst,
                                       ctx->pieces.as<NsPieceMeta>(), 1.0f / std::max(1.0f, ctx->hmodel.mean_ref_per_event),
+                                      std::min(8.0f, std::max(1.0f, ctx->hmodel.ref_per_event_cv)),
                                       exact_only ? 1u : 0u, ctx->scan_in.as<uint64_t>(), keys_in, vals_in);
     CK(cudaGetLastError());
     {

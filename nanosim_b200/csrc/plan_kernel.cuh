@@ -318,9 +318,10 @@ __device__ __forceinline__ void draw_lengths(const DevModel& m, const DevCfg& cf
 }
 
 // Generation-0 lengths of every read of the batch, op-slot capacities per piece and the sort key (total drawn length).
-// cap = 2 * (E + 6 sqrt(E) + 8) + 4 ops for a segment expected to hold E = m_ref / mean_ref_per_event error events.
+// cap = 2 * (E + 6 cv sqrt(E) + 8) + 4 ops for a segment expected to hold E = m_ref / mean_ref_per_event error events
+// (cv = coefficient of variation of the reference advance per event: the event count of a renewal process has variance E cv^2).
 __global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t first_id, uint32_t n, const uint32_t* n_seg,
-                               const uint32_t* piece_first, NsPieceMeta* pieces, float ev_per_base, uint32_t exact_only,
+                               const uint32_t* piece_first, NsPieceMeta* pieces, float ev_per_base, float ev_cv, uint32_t exact_only,
                                uint64_t* caps, uint32_t* keys, uint32_t* vals) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -339,7 +340,7 @@ __global__ void lengths_kernel(DevModel m, DevCfg cfg, uint32_t kind, uint64_t f
             else if (cfg.perfect) cap = 4;
             else {
                 float e = (float)len * ev_per_base;
-                cap = (uint64_t)(2.0f * (e + 6.0f * sqrtf(e) + 8.0f)) + 4;
+                cap = (uint64_t)(2.0f * (e + 6.0f * ev_cv * sqrtf(e) + 8.0f)) + 4;
             }
             caps[pf + q] = exact_only ? 0 : cap;
         }

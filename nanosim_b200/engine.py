@@ -170,6 +170,7 @@ class Engine:
         m.strandness_rate = float(t.strandness)
         m.segment_mean = float(t.segment_mean)
         m.mean_ref_per_event = float(t.mean_ref_per_event)
+        m.ref_per_event_cv = float(getattr(t, "ref_per_event_cv", 1.0))
         self._check(self._lib.ns_set_model(self._ctx, C.byref(m)))
         self.tables = t
 

@@ -451,15 +451,16 @@ class DeviceTables:
         elif homopolymer:
             raise FileNotFoundError("model has no _hp_lengths_model_parameters.tsv (needed for -hp)")
         # ---- expected ops/base, used to size the per-read op slots
-        self.mean_ref_per_event = self._mean_ref_advance_per_event()
+        self.mean_ref_per_event, self.ref_per_event_cv = self._mean_ref_advance_per_event()
 
     def _mean_ref_advance_per_event(self, n_events=20000):
         """Reference bases consumed per error event in the stationary regime of the
-        error/match renewal chain (simulator.py:1858-1914), estimated by running the chain on the
-        tabulated pmfs with a private generator.  Only used to size per-read op slots."""
+        error/match renewal chain (simulator.py:1858-1914): mean and coefficient of variation, estimated by running
+        the chain on the tabulated pmfs with a private generator.  Only used to size per-read op slots: the number of
+        events in a segment of L bases has mean L / mean and variance ~ (L / mean) * cv^2 (renewal process)."""
         rng = np.random.default_rng(20240917)
         cdfs = [np.cumsum(pm) for pm in self.pmfs]
-        state, prev_match, ref = 0, 10, 0
+        state, prev_match, ref, ref2 = 0, 10, 0, 0
         u = rng.random((n_events, 3))
         for e in range(n_events):
             pm, pi, pd = self.trans_rows[ERR_STATES[state]]
@@ -479,9 +480,13 @@ class DeviceTables:
             if prev_match == 0 and m == 0:
                 m = 1
             prev_match = m
+            adv = m + (step if kind != 2 else 0)
             ref += m
+            ref2 += adv * adv
             state = kind + (3 if m == 0 else 0)
-        return max(1.0, ref / float(n_events))
+        mean = ref / float(n_events)
+        var = max(ref2 / float(n_events) - mean * mean, 0.0)
+        return max(1.0, mean), max(1.0, math.sqrt(var) / max(mean, 1e-9))
 
     def split_counts(self, number, perfect=False):
         """simulator.py:465-468, 538-542."""
