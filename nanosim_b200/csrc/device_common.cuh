@@ -153,6 +153,16 @@ __device__ __forceinline__ uint32_t alias_draw(const DevModel& m, uint32_t t, ui
     return (frac < e.x || e.x == 0xffffffffu) ? j : e.y;
 }
 
+// The same draw with the table directory (offsets, sizes) in shared memory: a warp whose lanes index the directory
+// differently pays one constant-cache replay per distinct index when it sits in the kernel parameters.
+__device__ __forceinline__ uint32_t alias_draw_s(const uint2* __restrict__ alias, const uint32_t* tab_off, const uint32_t* tab_n, uint32_t t,
+                                                 uint32_t r) {
+    const uint64_t p = (uint64_t)r * tab_n[t];
+    const uint32_t j = (uint32_t)(p >> 32);
+    const uint2 e = __ldg(&alias[tab_off[t] + j]);
+    return ((uint32_t)p < e.x || e.x == 0xffffffffu) ? j : e.y;
+}
+
 // sklearn KernelDensity.sample (gaussian): data[floor(u*N)] + N(0, bw)
 __device__ __forceinline__ double kde_draw(const DevKde& k, Rng& rng) {
     uint64_t r0 = rng.next64();

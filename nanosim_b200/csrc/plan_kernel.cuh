@@ -370,7 +370,15 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     const bool unal_kind = (a.kind == NS_KIND_UNALIGNED);
     if (a.abort && *a.abort) return;
     __shared__ uint8_t bin_lut[BIN_LUT_SIZE];
+    // table directory and error-type thresholds: the lanes of a warp index them differently (bin of the previous match, error
+    // state), which costs one constant-cache replay per distinct index when read from the kernel parameters
+    __shared__ uint32_t s_tab_off[NS_MAX_TABLES], s_tab_n[NS_MAX_TABLES], s_trans[NS_N_ERR_STATES * 3];
     for (uint32_t i = threadIdx.x; i < BIN_LUT_SIZE; i += blockDim.x) bin_lut[i] = (uint8_t)match_bin_scan(m, i);
+    for (uint32_t i = threadIdx.x; i < NS_MAX_TABLES; i += blockDim.x) {
+        s_tab_off[i] = m.tab_off[i];
+        s_tab_n[i] = m.tab_n[i];
+    }
+    for (uint32_t i = threadIdx.x; i < NS_N_ERR_STATES * 3; i += blockDim.x) s_trans[i] = m.trans[i / 3][i % 3];
     __syncthreads();
 
     int phase = PH_FETCH;
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     uint32_t pos = 0, middle_ref = 0, prev_match = 0, err_state = 0, last_err = 3;
     int64_t l_new = 0;
     uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
+    uint4 ev_r = make_uint4(0, 0, 0, 0);  // random block of the next error event (PH_EVENT)
     uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap / segment chain: its own stream (shared with gap_kernel / chain_kernel), draw k = Philox block k + 1
     bool last_op_was_ins_same_pos = false;
     uint32_t last_ins_len = 0;
@@ -563,6 +572,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                 }
                 // first match from _first_match.hist, floor 2 (:1843-1850); no extension when it overshoots
                 uint32_t fm = alias_draw(m, 0, philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, 0u), rng.key).x);
+                ev_r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, 1u), rng.key);
                 prev_match = fm;
                 err_state = 0;     // "start"
                 last_err = 3;
@@ -573,19 +583,23 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
             break;
         }
         case PH_EVENT: {   // one pass of the while-loop body of error_list (:1858-1914)
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, ++gap_draw), rng.key);
+            // this event's random block was computed during the previous event; the next one's is requested now, so that its
+            // ten rounds run while this event waits for its table lookups (the lookups, not the arithmetic, are the chain)
+            const uint4 r = ev_r;
+            ++gap_draw;
+            ev_r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, gap_draw + 1u), rng.key);
             // the next match length only depends on the previous one (:1891-1903): its table lookup is issued first so
             // that it overlaps the error-length lookup below
             const uint32_t b = match_bin(m, bin_lut, prev_match);
-            uint32_t mt = alias_draw(m, 4 + b, r.z);
+            uint32_t mt = alias_draw_s(m.alias, s_tab_off, s_tab_n, 4 + b, r.z);
             // error type from the Markov chain keyed by prev_error[+"0"] (:1860-1864)
             uint32_t e;
-            if (r.x < m.trans[err_state][0]) e = 1;
-            else if (r.x < m.trans[err_state][1]) e = 2;
-            else if (r.x >= m.trans[err_state][2]) e = 3;
+            if (r.x < s_trans[3 * err_state]) e = 1;
+            else if (r.x < s_trans[3 * err_state + 1]) e = 2;
+            else if (r.x >= s_trans[3 * err_state + 2]) e = 3;
             else e = last_err;                        // dead gap of the (1-p_del, 1) interval: stale value
             last_err = e;
-            uint32_t step = alias_draw(m, e, r.y);    // tables 1..3: mis / ins / del lengths (:1866-1873)
+            uint32_t step = alias_draw_s(m.alias, s_tab_off, s_tab_n, e, r.y);    // tables 1..3: mis / ins / del lengths (:1866-1873)
             if (e == 2) {
                 l_new += step;
                 if (last_op_was_ins_same_pos) sink.replace_last_ins(last_ins_len, step);
@@ -600,7 +614,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                     middle_ref = pos;
                 }
             }
-            if (mt == m.tab_n[4 + b] - 1) mt = step;  // ECDF miss: `step` keeps the error length (:1895-1898)
+            if (mt == s_tab_n[4 + b] - 1) mt = step;  // ECDF miss: `step` keeps the error length (:1895-1898)
             if (prev_match == 0 && mt == 0) mt = 1;
             prev_match = mt;
             if (pos + mt > middle_ref) {
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                 sink.push(NS_OP_COPY, 1, true);
                 sink.push(NS_OP_INS, a_ins, true);
             } else {
-                s = alias_draw(m, kind_u == 1 ? 1 : 3, r.y);
+                s = alias_draw_s(m.alias, s_tab_off, s_tab_n, kind_u == 1 ? 1 : 3, r.y);
                 uint32_t covered = a_ins < s - 1 ? a_ins : s - 1;     // inserted bases inside [pos, pos+s)
                 uint32_t rest = (s - 1) - covered;                     // reference bases still hit after them
                 if (kind_u == 1) {
