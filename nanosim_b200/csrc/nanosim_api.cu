@@ -34,7 +34,6 @@
 #include "plan_kernel.cuh"
 #include "emit_kernel.cuh"
 #include "uread_kernel.cuh"
-#include "chain_kernel.cuh"
 #include "hp_kernel.cuh"
 
 namespace {
@@ -1228,7 +1227,9 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
     const unsigned plan_tb = 128;
     // 2 resident blocks per SM: measured faster than 4 (the register limit) both alone (6.3-6.8 vs 8.2-8.6 ms on the config-2
     // batch) and next to another context's emit kernel, which then still finds room on every SM
-    static const int plan_per_sm = env_int("NANOSIM_B200_PLAN_BLOCKS_PER_SM", 2);
+    // (transcripts are short -- 1-2 kb reads, no long tail, two passes: there the register limit of 4 blocks is better)
+    static const int plan_per_sm_env = env_int("NANOSIM_B200_PLAN_BLOCKS_PER_SM", 0);
+    const int plan_per_sm = plan_per_sm_env > 0 ? plan_per_sm_env : (ctx->dcfg.transcriptome ? 4 : 2);
     unsigned plan_blocks = std::min<unsigned>((n + plan_tb - 1) / plan_tb, (unsigned)ctx->sm_count * (unsigned)std::max(1, plan_per_sm));
     // unaligned reads without NS_FLAG_UNALIGNED_SCRIPTS: warp-per-read evaluation (uread_kernel.cuh), same outputs
     UreadArgs ua;
@@ -1265,29 +1266,6 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         ga.abort = d_abort;
         CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
         gap_kernel<<<ublocks, UREAD_WARPS * 32, 0, st>>>(ga);
-        CK(cudaGetLastError());
-        launches += 1;
-    }
-    if (kind == NS_KIND_ALIGNED && !ctx->hcfg.perfect && !ctx->dcfg.transcriptome && !(ctx->hcfg.flags & NS_FLAG_EMIT_WHOLE)) {
-        // the error chains of the longest segments, a warp each (chain_kernel.cuh); the plan kernel picks the results up
-        ChainArgs ca;
-        ca.m = ctx->dmodel;
-        ca.cfg = ctx->dcfg;
-        ca.kind = (uint32_t)kind;
-        ca.first_id = first_read_id;
-        ca.n_reads = n;
-        ca.n_seg = d_nseg;
-        ca.piece_first = d_pfirst;
-        ca.pieces = pa.pieces;
-        ca.ops = pa.ops;
-        ca.order = vals_out;
-        ca.counter = pa.counter;
-        ca.abort = d_abort;
-        static const int chain_min = env_int("NANOSIM_B200_CHAIN_MIN", (int)CHAIN_MIN_LEN);
-        ca.min_len = (uint32_t)std::max(chain_min, 1024);
-        CK(cudaMemsetAsync(ctx->counter.p, 0, 64, st));
-        const unsigned cblocks = std::min<unsigned>((n + CHAIN_WARPS - 1) / CHAIN_WARPS, (unsigned)ctx->sm_count * 4u);
-        chain_kernel<<<cblocks, CHAIN_WARPS * 32, 0, st>>>(ca);
         CK(cudaGetLastError());
         launches += 1;
     }

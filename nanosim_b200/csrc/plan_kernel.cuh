@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
     int64_t l_new = 0;
     uint32_t pending_ins = 0;     // unaligned chain: insertion waiting for the next non-ins step
     uint4 ev_r = make_uint4(0, 0, 0, 0);  // random block of the next error event (PH_EVENT)
-    uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap / segment chain: its own stream (shared with gap_kernel / chain_kernel), draw k = Philox block k + 1
+    uint32_t gap_sw = 0, gap_draw = 0;   // chimeric gap / segment chain: its own stream (a gap's is shared with gap_kernel), draw k = Philox block k + 1
     bool last_op_was_ins_same_pos = false;
     uint32_t last_ins_len = 0;
     OpSink<true> sink;
@@ -546,30 +546,10 @@ __global__ void __launch_bounds__(128, PLAN_MIN_BLOCKS) plan_kernel(const __grid
                 phase = PH_PIECE_END;
             } else {
                 // the error chain of a segment draws from its own stream, keyed by (attempt, piece): block 0 = first match,
-                // block k + 1 = event k.  The longest segments of a batch were already walked by chain_kernel (a warp each,
-                // chain_kernel.cuh) from the same blocks; their result waits in the piece record, the ops in the slot (behind
-                // a free word for the head op when this is the read's first piece).
+                // block k + 1 = event k (so that an event's block can be computed while the previous event is still waiting
+                // for its table lookups)
                 gap_sw = stream_word(ST_CHAIN, a.kind, (attempt << 5) | (p & 31u));
                 gap_draw = 0;
-                const bool walked = !REPLAY && !cfg.transcriptome && pm.polya_len == 1u;
-                if (!REPLAY && !cfg.transcriptome) pm.polya_len = 0;
-                if (walked && attempt == 0) {
-                    uint32_t n_pre = pm.n_ops;
-                    if (p == 0) {
-                        if (head > 0) {
-                            ++n_pre;                         // sink.put above wrote the head op into the free word
-                        } else {
-                            pm.op_off += 1;
-                            sink.begin(a.ops + pm.op_off, sink.cap ? sink.cap - 1u : 0u);
-                        }
-                    }
-                    sink.n = n_pre;
-                    sink.out_len = pm.out_len + ((p == 0) ? head : 0u);
-                    middle_ref = pm.ref_len;
-                    l_new = (int64_t)pm.l_new;
-                    phase = PH_PIECE_END;
-                    break;
-                }
                 // first match from _first_match.hist, floor 2 (:1843-1850); no extension when it overshoots
                 uint32_t fm = alias_draw(m, 0, philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, 0u), rng.key).x);
                 ev_r = philox4x32_10(make_uint4((uint32_t)rid, (uint32_t)(rid >> 32), gap_sw, 1u), rng.key);

@@ -428,8 +428,11 @@ __device__ __forceinline__ uint32_t uread_one(const UreadArgs& a, uint2 key, uin
     return first_len;
 }
 
+#ifndef UREAD_MIN_BLOCKS
+#define UREAD_MIN_BLOCKS 3          // 80 registers: 24 warps per SM hide the shuffle chains better than 16 (-7 % measured)
+#endif
 template <bool REPLAY>
-__global__ void __launch_bounds__(UREAD_WARPS * 32) uread_kernel(const __grid_constant__ UreadArgs a) {
+__global__ void __launch_bounds__(UREAD_WARPS * 32, UREAD_MIN_BLOCKS) uread_kernel(const __grid_constant__ UreadArgs a) {
     const int lane = threadIdx.x & 31;
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     if (a.abort && *a.abort) return;
