@@ -134,8 +134,11 @@ struct HpWalker {
     }
 };
 
+#ifndef HP_MIN_BLOCKS
+#define HP_MIN_BLOCKS 4
+#endif
 template <bool WRITE>
-__global__ void __launch_bounds__(128) hp_kernel(const __grid_constant__ HpArgs a) {
+__global__ void __launch_bounds__(128, HP_MIN_BLOCKS) hp_kernel(const __grid_constant__ HpArgs a) {
     const uint2 key = make_uint2((uint32_t)a.cfg.seed, (uint32_t)(a.cfg.seed >> 32));
     const uint32_t K = a.cfg.kmer_bias;
     // A lane walks one segment at a time, as a FLAT state machine.  One loop iteration = one micro-step of every lane: a

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -1506,16 +1507,35 @@ void unpack_bases(const uint8_t* packed, uint8_t* seq, uint64_t seq_bytes, bool 
     for (uint64_t k = whole * 8; k < seq_bytes; ++k) seq[k] = (uint8_t)abc[(packed[k >> 2] >> (2 * (k & 3))) & 3u];
 }
 
+// CPUs this process can really use: the affinity mask, capped by the container's cgroup CPU quota (cpu.max) -- the boxes of
+// this pool show 128 logical CPUs and grant 16-24 cores of CPU time
+unsigned effective_cpus() {
+    unsigned n = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = (unsigned)CPU_COUNT(&set);
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64] = {0};
+        unsigned long long period = 0;
+        if (fscanf(f, "%63s %llu", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            const unsigned long long quota = strtoull(q, nullptr, 10);
+            const unsigned cores = (unsigned)((quota + period / 2) / period);
+            if (cores >= 1 && cores < n) n = cores;
+        }
+        fclose(f);
+    }
+    return n ? n : 4u;
+}
+
 int unpack_threads() {
     static const int n = [] {
         const char* e = getenv("NANOSIM_B200_UNPACK_THREADS");     // 0: copy the bases as ASCII (no packing)
         if (e && *e) return std::max(0, atoi(e));
-        // packing only pays when the host can expand faster than PCIe delivers: with fewer than 48 cores per GPU process
-        // (torchrun exports LOCAL_WORLD_SIZE) every GPU's own PCIe link is the better deal and the bases travel as ASCII
-        const unsigned hc = std::thread::hardware_concurrency();
+        // packing only pays when the host can expand faster than PCIe delivers: one expanding thread per core this GPU
+        // process can count on (torchrun exports LOCAL_WORLD_SIZE), at most 16; with fewer than 6 the bases travel as ASCII
         const char* lw = getenv("LOCAL_WORLD_SIZE");
         const unsigned ranks = (lw && *lw) ? (unsigned)std::max(1, atoi(lw)) : 1u;
-        return ((hc ? hc : 4u) / ranks >= 48u) ? 16 : 0;
+        const unsigned per_rank = effective_cpus() / ranks;
+        return per_rank >= 6u ? (int)std::min(per_rank, 16u) : 0;
     }();
     return n;
 }

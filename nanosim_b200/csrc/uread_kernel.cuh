@@ -50,6 +50,19 @@ struct UreadArgs {
 // unaligned_error_list (:1784-1830) + its effect in mutate_read for ONE read / chimeric gap of drawn length m_ref, evaluated by
 // a whole warp 32 draws at a time (see the header comment).  Draw k uses Philox block k + 1 of stream `sw`.  Ops go to
 // ops[0 .. cap) (counted beyond that).
+// inclusive warp prefix sums of the reference advance (non-insertion steps) and of the inserted bases of 32 draws: one scan
+// over both packed in a word when every step is short enough for the sums to fit 16 bits (always, with the shipped models)
+__device__ __forceinline__ void scan_advance_and_insertions(bool nonins, uint32_t s, int lane, uint32_t& adv_incl, uint32_t& ins_incl) {
+    if (__all_sync(0xffffffffu, s < 2048u)) {
+        const uint32_t both = warp_incl_scan(nonins ? s : (s << 16), lane);
+        adv_incl = both & 0xffffu;
+        ins_incl = both >> 16;
+    } else {
+        adv_incl = warp_incl_scan(nonins ? s : 0u, lane);
+        ins_incl = warp_incl_scan(nonins ? 0u : s, lane);
+    }
+}
+
 struct UChain {
     uint32_t n_ops, middle_ref, n_draws;
     int64_t l_new;
@@ -74,9 +87,9 @@ __device__ __forceinline__ UChain unaligned_chain_warp(const DevModel& m, uint2 
         const uint32_t kind = kind_next, s = s_next;
         draw(base + 32u + lane, kind_next, s_next);
         const bool nonins = kind != 2;
-        const uint32_t adv = nonins ? s : 0u;
-        const uint32_t P = pos_base + warp_incl_scan(adv, lane);
-        const uint32_t I = warp_incl_scan(nonins ? 0u : s, lane);
+        uint32_t Pl, I;
+        scan_advance_and_insertions(nonins, s, lane, Pl, I);
+        const uint32_t P = pos_base + Pl;
         const uint32_t stop_mask = __ballot_sync(0xffffffffu, nonins && P >= m_ref);
         const int jstop = stop_mask ? __ffs(stop_mask) - 1 : 32;
         const bool valid = lane <= jstop;
@@ -88,8 +101,7 @@ __device__ __forceinline__ UChain unaligned_chain_warp(const DevModel& m, uint2 
         const uint32_t a_ins = nonins ? (pn >= 0 ? I - I_pn : I + carry_a) : 0u;
         int32_t delta = 0;
         if (valid) delta = kind == 2 ? (int32_t)s : (kind == 3 ? -(int32_t)s : 0);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
+        delta = __reduce_add_sync(0xffffffffu, delta);
         l_new += delta;
 
         // ---- this draw's ops (at most four), empty ones dropped and equal neighbours merged
@@ -192,8 +204,8 @@ __device__ __forceinline__ UChain unaligned_chain_cta(const DevModel& m, uint2 k
         const uint32_t kind = kind_next, s = s_next;
         draw(base + 32u * UREAD_WARPS + 32u * (uint32_t)w + lane, kind_next, s_next);
         const bool nonins = kind != 2;
-        const uint32_t Pl = warp_incl_scan(nonins ? s : 0u, lane);
-        const uint32_t I = warp_incl_scan(nonins ? 0u : s, lane);
+        uint32_t Pl, I;
+        scan_advance_and_insertions(nonins, s, lane, Pl, I);
         const uint32_t nonins_mask = __ballot_sync(0xffffffffu, nonins);
         const uint32_t P31 = __shfl_sync(0xffffffffu, Pl, 31), I31 = __shfl_sync(0xffffffffu, I, 31);
         const uint32_t I_last = __shfl_sync(0xffffffffu, I, nonins_mask ? 31 - __clz(nonins_mask) : 0);
@@ -227,8 +239,7 @@ __device__ __forceinline__ UChain unaligned_chain_cta(const DevModel& m, uint2 k
         const uint32_t a_ins = nonins ? (pn >= 0 ? I - I_pn : I + carry_in) : 0u;
         int32_t delta = 0;
         if (valid) delta = kind == 2 ? (int32_t)s : (kind == 3 ? -(int32_t)s : 0);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
+        delta = __reduce_add_sync(0xffffffffu, delta);
 
         // ---- this draw's ops (at most four), exactly as in unaligned_chain_warp
         uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
