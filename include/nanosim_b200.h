@@ -271,6 +271,11 @@ int64_t ns_read_fasta(const char* path, uint8_t* bases, uint64_t bases_cap, uint
  * *unpack_threads = host threads ns_fetch uses for the expansion.  (No reference counterpart: its workers write files.) */
 int ns_transfer_info(NsContext* ctx, uint32_t* packed_bases, uint32_t* unpack_threads);
 
+/* The host half of that transfer, for consumers that copy the packed bases themselves: expands n_bases bases, 2 bits each
+ * (base k in bits [2(k&3)+1 : 2(k&3)] of packed[k >> 2]; A C T G = 0 1 2 3, U for T when uracil), into ASCII with `threads`
+ * host threads (AVX2 when the CPU has it).  Replaces nothing in the reference: its workers hold Python strings. */
+int ns_unpack_bases(const uint8_t* packed, uint8_t* seq, uint64_t n_bases, int uracil, int threads);
+
 /* Intron retention (simulator.py:1156-1183), second half: replaces the piece lists of `n_slots` reads of the last batch and
  * emits those reads again.  The host decides which reads retain introns (nanosim_b200/intron_retention.py) and lays each of
  * them out as pieces on the GENOME records of the reference, one per exon / retained-intron interval (NS_PIECE_REF_REV,

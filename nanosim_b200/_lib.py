@@ -23,7 +23,7 @@ NS_STATS_COMP_OFF = NS_STATS_INS_OFF + 4
 NS_STATS_WORDS = NS_STATS_COMP_OFF + 4
 
 EXPORTS = ["ns_create", "ns_destroy", "ns_last_error", "ns_clone", "ns_set_abundance", "ns_set_expression", "ns_set_reference", "ns_set_model", "ns_configure",
-           "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names", "ns_transfer_info", "ns_write_records", "ns_write_error_profile", "ns_read_fasta", "ns_nccl_unique_id", "ns_bcast_nccl", "ns_get_reference"]
+           "ns_simulate", "ns_fetch", "ns_reemit", "ns_device_buffers", "ns_op_stats", "ns_format_records", "ns_format_error_profile", "ns_format_names", "ns_transfer_info", "ns_write_records", "ns_write_error_profile", "ns_read_fasta", "ns_nccl_unique_id", "ns_bcast_nccl", "ns_get_reference", "ns_unpack_bases"]
 
 
 class NsReference(C.Structure):
@@ -163,6 +163,8 @@ def lib():
     L.ns_write_error_profile.restype = C.c_int64
     L.ns_transfer_info.argtypes = [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.ns_transfer_info.restype = C.c_int
+    L.ns_unpack_bases.argtypes = [P, P, C.c_uint64, C.c_int, C.c_int]
+    L.ns_unpack_bases.restype = C.c_int
     L.ns_reemit.argtypes = [P, P, P, C.c_uint32, P, C.c_uint32, P, C.c_uint64]
     L.ns_reemit.restype = C.c_int
     _lib = L

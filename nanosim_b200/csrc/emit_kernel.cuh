@@ -695,11 +695,16 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
         for (uint32_t t_tile = 0; t_tile < n_ops && out_loaded < x_end; t_tile += 2048u) {
             const uint32_t t0 = t_tile + 64u * lane, t1 = t0 + 64u < n_ops ? t0 + 64u : n_ops;
             uint32_t so = 0, sr = 0;
-            for (uint32_t t = t0; t < t1; ++t) {
-                const uint32_t op = __ldg(&ops[rev ? n_ops - 1u - t : t]);
-                const uint32_t ty = op >> 28, len = op_len(op);
-                so += (ty == NS_OP_DEL) ? 0u : len;
-                sr += (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
+            for (uint32_t t = t0; t < t1; t += 8u) {            // eight loads in flight (an empty op counts for nothing)
+                uint32_t v[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 8u; ++q) v[q] = t + q < t1 ? __ldg(&ops[rev ? n_ops - 1u - (t + q) : t + q]) : 0u;
+#pragma unroll
+                for (uint32_t q = 0; q < 8u; ++q) {
+                    const uint32_t ty = v[q] >> 28, len = op_len(v[q]);
+                    so += (ty == NS_OP_DEL) ? 0u : len;
+                    sr += (ty < 2u || ty == NS_OP_DEL) ? len : 0u;
+                }
             }
             const uint32_t io = warp_incl_scan(so, lane), ir = warp_incl_scan(sr, lane);
             uint32_t xo = out_loaded + io - so, rs = ref_loaded + ir - sr;

@@ -1109,6 +1109,50 @@ def test_cli_end_to_end_config1(tmp_path, L):
     assert s2["n_aligned"] + s2["n_unaligned"] == 300 and s2["qual_middle"].sum() > 0
 
 
+_FETCH_DIGEST = """
+import hashlib, os, sys
+sys.path[:0] = [%r, %r, %r]
+import parity_checks as pc
+from nanosim_b200 import _lib as L
+from nanosim_b200.reference_fasta import PackedReference
+import synth
+refs = [PackedReference.from_records(synth.ecoli5m()), PackedReference.from_fasta(os.path.join(%r, "mini_ref.fa"))]
+h = hashlib.sha256()
+packs = []
+for ref in refs:
+    eng, _, _ = pc.make_engine("guppy", ref, seed=99, fastq=True)
+    packs.append(int(eng.fetch_packs_bases()))
+    for kind, n in ((L.NS_KIND_ALIGNED, 1500), (L.NS_KIND_UNALIGNED, 300)):
+        eng.simulate(kind, 7, n)
+        b = eng.fetch()
+        for r in b.reads:
+            a, m = int(r["seq_off"]), int(r["seq_len"])
+            h.update(b.seq[a:a + m].tobytes())
+            h.update(b.qual[a:a + m].tobytes())
+    eng.close()
+print("DIGEST", h.hexdigest(), packs)
+"""
+
+
+def test_fetch_two_bit_transfer_equals_ascii_transfer():
+    """ns_fetch sends the bases over PCIe as 2 bits each and expands them on the host (AVX2 / table) when the reference holds
+    nucleotide codes only and the process has CPU cores for it; otherwise as ASCII.  Same seed => same bytes either way:
+    NANOSIM_B200_UNPACK_THREADS=0 forces ASCII, =3 forces three expanding threads (the choice is made once per process, hence
+    the subprocesses).  References: pure ACGT, and the IUPAC / lower-case mini reference."""
+    import subprocess
+    from conftest import ROOT
+    code = _FETCH_DIGEST % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), GOLDEN)
+    out = {}
+    for nt in ("0", "3"):
+        env = dict(os.environ, NANOSIM_B200_UNPACK_THREADS=nt, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1].split(None, 2)
+        out[nt] = (line[1], line[2])
+    assert out["0"][1] == "[0, 0]" and out["3"][1] == "[1, 1]", out       # ASCII / packed on both references
+    assert out["0"][0] == out["3"][0], "2-bit transfer and ASCII transfer give different reads"
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE configs 3, 4 and 5 on their named synthetic references (SURVEY.md 8d generators, tests/synth.py), small N
 # against the pinned oracle

@@ -564,3 +564,40 @@ def test_native_fasta_reader_matches_python_reader(tmp_path):
     b = PackedReference._from_fasta_native(fq, 4)
     assert b.names == ["chrA", "chrB"] and b.bases.tobytes().decode() == recs[0][1] + recs[1][1]
     assert b.lengths.tolist() == [300, 10]
+
+
+def test_unpack_bases_matches_bit_definition(tmp_path):
+    """ns_unpack_bases (the host half of ns_fetch's 2-bit transfer): base k sits in bits [2(k&3)+1 : 2(k&3)] of packed[k >> 2],
+    A C T G = 0 1 2 3.  AVX2 path (when the CPU has it) and the table path (NANOSIM_B200_NO_AVX2=1, in a subprocess: the
+    choice is made once per process), 1 and 5 threads, lengths around the 32-base step, a destination that is not 32-byte
+    aligned, both alphabets."""
+    import ctypes as C
+    import subprocess
+    import sys
+    from nanosim_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(5)
+
+    def check():
+        for n in (0, 1, 31, 32, 33, 100, 4097, (1 << 20) + 13):
+            for uracil in (0, 1):
+                for threads in (1, 5):
+                    for shift in (0, 8):
+                        packed = rng.integers(0, 256, (n + 3) // 4 + 8, dtype=np.uint8)
+                        k = np.arange(n)
+                        want = np.frombuffer(b"ACUG" if uracil else b"ACTG", dtype=np.uint8)[(packed[k >> 2] >> (2 * (k & 3))) & 3]
+                        buf = np.zeros(n + 64 + shift, dtype=np.uint8)
+                        base = buf.ctypes.data
+                        off = (-base) % 32 + shift                      # 32-byte aligned, or 8 past it
+                        assert lib.ns_unpack_bases(packed.ctypes.data, base + off, n, uracil, threads) == 0
+                        assert np.array_equal(buf[off:off + n], want), (n, uracil, threads, shift)
+                        assert not buf[off + n:].any() and not buf[:off].any()
+
+    check()
+    if os.environ.get("NANOSIM_B200_NO_AVX2") is None:
+        env = dict(os.environ, NANOSIM_B200_NO_AVX2="1", PYTHONPATH=ROOT)
+        src = ("import os, sys\nsys.path[:0] = [%r, %r]\nimport pytest\n"
+               "sys.exit(pytest.main(['-q', '-x', %r, '-k', 'unpack_bases', '-p', 'no:cacheprovider']))\n"
+               % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "test_host_cpu.py")))
+        r = subprocess.run([sys.executable, "-c", src], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
