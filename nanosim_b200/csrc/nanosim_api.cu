@@ -1159,13 +1159,11 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         CK(cub::DeviceRadixSort::SortPairsDescending(ctx->sort_tmp.p, tmp, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 32, st));
     }
     // primary script area = the capped slots (+ a bump pool for re-drawn unaligned reads, uread_kernel.cuh)
-    uint64_t slot_ops = 0, pool_ops = 0, primary_ops = 0;
+    uint64_t primary_ops = 0;
     capacity_stage_a<<<1, 32, 0, st>>>(d_totals, fast_unaligned ? 1u : 0u, optimistic ? ops_cap : ~0ull);
     if (!optimistic) {
         publish_totals<<<1, 32, 0, st>>>(d_totals, ctx->h_totals_dev);
         CK(cudaStreamSynchronize(st));
-        slot_ops = ctx->h_totals[4];
-        pool_ops = ctx->h_totals[NS_T_POOL + 1];
         primary_ops = ctx->h_totals[NS_T_PRIMARY];
         CK(ctx->ops.ensure((size_t)(primary_ops + 4) * sizeof(uint32_t)));
     }
