@@ -115,6 +115,7 @@ struct NsContext {
     uint8_t* pack_host = nullptr;
     size_t pack_host_cap = 0;
     cudaEvent_t ev_pack = nullptr;
+    cudaEvent_t ev_block = nullptr;     // cudaEventBlockingSync: long waits sleep instead of spinning (wait_stream)
     // Batches of one job have near-identical sizes: once a batch of a kind has run with host-sized buffers, the next ones
     // are submitted in one go (no host round trip between the first and the last kernel) against those capacities; a
     // kernel checks them on the device and a batch that does not fit is simply run again the sized way.
@@ -125,6 +126,31 @@ struct NsContext {
     uint64_t last_first_id = 0;
     bool have_batch = false;
 };
+
+// Wait for everything queued on the context's stream.  cudaStreamSynchronize spins: a host thread per overlapped context then
+// burns a core for the whole 20-100 ms of a big batch.  The boxes of this pool grant their GPU processes a CPU quota (16 cores
+// for 1 GPU, 24 for 2, 96 logical for 8), and per-GPU end-to-end throughput fell with the number of GPU processes (39 / 30 /
+// 16 Gbases/s) although no PCIe link was saturated and the expansion of the 2-bit bases takes 19 ms of a 100 ms fetch: four
+// spinning threads per process are the largest CPU consumer left.  With several GPU processes on the host (torchrun's
+// LOCAL_WORLD_SIZE > 1, or NANOSIM_B200_BLOCKING_SYNC=1) long waits therefore sleep on a cudaEventBlockingSync event; a single
+// process, and every short wait, spins as before.  (Written after the round's GPU minutes were spent: not measured.)
+static bool blocking_sync_wanted() {
+    static const bool want = [] {
+        if (const char* e = getenv("NANOSIM_B200_BLOCKING_SYNC")) return atoi(e) != 0;
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        return lw && atoi(lw) > 1;
+    }();
+    return want;
+}
+static cudaError_t wait_stream(NsContext* ctx, bool long_wait) {
+    if (!long_wait || !blocking_sync_wanted()) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaSuccess;
+    if (!ctx->ev_block) e = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_block, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_block);
+    return e;
+}
+
 
 namespace {
 
@@ -498,6 +524,7 @@ int ns_destroy(NsContext* ctx) {
     if (ctx->pack_host) cudaFreeHost(ctx->pack_host);
     ctx->pack_dev.release();
     if (ctx->ev_pack) cudaEventDestroy(ctx->ev_pack);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1408,7 +1435,7 @@ int ns_simulate(NsContext* ctx, int kind, uint64_t first_read_id, uint32_t n_rea
         for (uint32_t k = 0; k < S; ++k) ctx->species_bases[k] += add[k];
     }
     if (optimistic) publish_totals<<<1, 32, 0, st>>>(d_totals, ctx->h_totals_dev);
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, n >= 16384u));
     if (optimistic) {
         if (ctx->h_totals[NS_T_ABORT]) {
             // a buffer was too small for this batch: nothing was written past a capacity (the kernels saw the flag and
@@ -1613,7 +1640,7 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
             CK(cudaHostAlloc((void**)&ctx->pack_host, want, cudaHostAllocDefault));
             ctx->pack_host_cap = want;
         }
-        if (!ctx->ev_pack) CK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+        if (!ctx->ev_pack) CK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming | (blocking_sync_wanted() ? (unsigned)cudaEventBlockingSync : 0u)));
         pack_bases_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(ctx->seq.as<uint4>(), ctx->pack_dev.as<uint32_t>(), n16);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctx->pack_host, ctx->pack_dev.p, (size_t)n16 * 4, cudaMemcpyDeviceToHost, st));
@@ -1635,7 +1662,7 @@ int ns_fetch(NsContext* ctx, uint8_t* seq, uint8_t* qual, NsReadMeta* reads, NsP
         unpack_bases(ctx->pack_host, seq, bi.seq_bytes, ctx->dcfg.uracil != 0, nt);
         t_unpacked = ms_since();
     }
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, bi.seq_bytes >= (64u << 20)));
     if (trace)
         fprintf(stderr, "ns_fetch: %.2f GB bases; packed copy done after %.1f ms, expansion %.1f ms (%d threads), everything after %.1f ms\n",
                 bi.seq_bytes / 1e9, t_packed, t_unpacked - t_packed, nt, ms_since());
